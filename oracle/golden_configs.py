@@ -1,0 +1,28 @@
+"""Named configurations shared by oracle/make_golden.py and the tests (TEST INFRASTRUCTURE ONLY)."""
+from .ao_oracle import AOConfig, DetectorConfig
+
+RAZOR_DETECTOR = dict(photonNoise=True, readoutNoise=14.0, darkCurrent=5.0, QE=0.56, FWC=10000, bits=10,
+                      sensor="CMOS")        # MAIN_CODE/OOPAOEnv/OOPAOEnvRazor.py:243-250,332-333
+
+
+def tiny():
+    return AOConfig(nSubap=8, windSpeed=[10.0, 12.0], windDirection=[0.0, 72.0], fractionalR0=[0.6, 0.4],
+                    altitude=[0.0, 0.0], nZernike=20, nLoop=64)
+
+
+def tiny_noise():
+    c = tiny()
+    c.magnitude = 6.0
+    c.detector = DetectorConfig(**RAZOR_DETECTOR)
+    return c
+
+
+def cfg1():
+    """BASELINE.json configs[0]: 8 m, 20x20 SH, 21x21 DM, one layer (SURVEY.md section 8 d)."""
+    return AOConfig(nSubap=20, windSpeed=[10.0], windDirection=[0.0], fractionalR0=[1.0], altitude=[0.0],
+                    nZernike=50, nLoop=64)
+
+
+CONFIGS = {"tiny": tiny, "tiny_noise": tiny_noise, "cfg1": cfg1}
+STEPS = {"tiny": 30, "tiny_noise": 12, "cfg1": 24}
+EPISODE_SEED = 17          # MAIN_CODE/integrator_oopao_razor.py:46
