@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py — closed-loop AO env-steps/s (batched environments) on N B200s, next to the CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg3|cfg2|cfg1|tiny]
+
+A "step" is one `env.step` of every environment on every GPU (integrator policy action = gainCL * obs).
+Default workload (BASELINE.json configs[2], the one the 1e6 env-steps/s target is quoted on): 8 m telescope,
+40x40 SH-WFS, 41x41 DM, 3-layer von Karman atmosphere, 1024 environments PER GPU (8192 on 8 GPUs, weak scaling).
+Prints ONE JSON line (see the task contract): value = device-timed throughput with inputs resident in HBM,
+e2e = same metric through the host-facing TorchWrapper (pinned host action in, host obs/reward/Strehl out,
+copies inside the timed region), roofline of the dominant kernel, cpu_baseline (oracle port on host cores).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nSubap, nLayers, envs per GPU, description)
+    "cfg3": (40, 3, 1024, "8m 40x40 SH-WFS, 41x41 DM (1353 act), 3-layer VK atmosphere, integrator, noise off"),
+    "cfg2": (20, 1, 1024, "8m 20x20 SH-WFS, 21x21 DM (357 act), 1-layer VK atmosphere, integrator, noise off"),
+    "cfg1": (20, 1, 1, "8m 20x20 SH-WFS, 21x21 DM, 1 layer, single env"),
+    "tiny": (8, 2, 64, "8m 8x8 SH-WFS test system"),
+}
+
+
+def make_args(nSubap, nLayers):
+    from rlao_b200.Conf.parameter_file_synthetic_SHWFS import layer_profile
+    prof = layer_profile(nLayers)
+    return types.SimpleNamespace(r0=0.13, L0=25, nSubaperture=nSubap, nLoop=None, gainCL=0.5, **prof)
+
+
+def oracle_config(nSubap, nLayers):
+    from oracle.ao_oracle import AOConfig
+    from rlao_b200.Conf.parameter_file_synthetic_SHWFS import layer_profile
+    prof = layer_profile(nLayers)
+    return AOConfig(nSubap=nSubap, windSpeed=[float(v) for v in prof["windSpeed"]],
+                    windDirection=[float(v) for v in prof["windDirection"]], fractionalR0=prof["fractionalR0"],
+                    altitude=[0.0] * nLayers, nZernike=50, nLoop=4096)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows, self.gpu, self.proc = [], gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.15] or [r for t, r in self.rows][-3:]
+        sm, mx, reasons = [], None, set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference step)
+# ---------------------------------------------------------------------------------------------------------
+def _cpu_worker(env, seed, n_steps, q):
+    import numpy as np
+    try:
+        from threadpoolctl import threadpool_limits
+        ctx = threadpool_limits(1)
+    except Exception:
+        import contextlib
+        ctx = contextlib.nullcontext()
+    with ctx:
+        obs = env.new_episode(seed)
+        for i in range(3):
+            obs, *_ = env.step(i, env.gainCL * obs)
+        t0 = time.perf_counter()
+        for i in range(n_steps):
+            obs, *_ = env.step(3 + i, env.gainCL * obs)
+        q.put((time.perf_counter() - t0, float(np.abs(obs).max())))
+
+
+def cpu_env(nSubap, nLayers, reconstructor=None):
+    from oracle.ao_oracle import EnvOracle
+    return EnvOracle(oracle_config(nSubap, nLayers), reconstructor=reconstructor)
+
+
+def time_cpu(env, n_procs, n_steps):
+    """`n_procs` forked workers (read-only operators shared copy-on-write), one environment each, one BLAS
+    thread each; returns env-steps/s summed over workers."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_cpu_worker, args=(env, 100 + r, n_steps, q)) for r in range(n_procs)]
+    t0 = time.perf_counter()
+    for p in procs:
+        p.start()
+    res = [q.get() for _ in procs]
+    for p in procs:
+        p.join()
+    wall = time.perf_counter() - t0
+    worst = max(r[0] for r in res)
+    return n_procs * n_steps / worst, worst, wall
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Python reference itself cannot travel to
+    the GPU box) on all host cores, same metric/config keys."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nS, nL, B, desc = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    n_procs = max(1, min(cores, 64))
+    t_init = time.perf_counter()
+    env = cpu_env(nS, nL)
+    t_init = time.perf_counter() - t_init
+    per_step = 0.12 if nS >= 40 else 0.02
+    n_steps = max(3, int(min(20.0, 8.0 * max(1, args.steps)) / per_step / 4))
+    for _ in range(max(1, args.warmup // 3)):
+        time_cpu(env, n_procs, 2)
+    value, worst, wall = time_cpu(env, n_procs, n_steps)
+    line = {
+        "impl": "reference", "metric": "closed-loop AO env-steps/sec (batched envs)", "value": value, "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * worst / n_steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "description": desc, "envs": n_procs,
+                   "note": "oracle port (numpy float64) of the OOPAO/drl4ao step, one env per host process"},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": n_procs, "kind": "port",
+                         "sample": f"{n_procs} processes x {n_steps} steps of one env each (1 BLAS thread), init {t_init:.1f}s excluded"},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+class KernelTimer:
+    """Wraps the C-ABI entry points with CUDA events on the launching stream (used in a separate pass after the
+    timed region) to attribute device time to each kernel family."""
+
+    def __init__(self, lib, torch):
+        self.lib, self.torch, self.events, self.saved = lib, torch, [], {}
+
+    def __enter__(self):
+        from rlao_b200 import _lib
+        for name in _lib.PROTOTYPES:
+            fn = getattr(self.lib, name)
+            self.saved[name] = fn
+            setattr(self.lib, name, self._wrap(name, fn))
+        return self
+
+    def _wrap(self, name, fn):
+        torch = self.torch
+
+        def call(*a):
+            key = name
+            if name == "aoenv_gemm_tn":
+                key = f"aoenv_gemm_tn[N={a[7]},K={a[8]}]"
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*a)
+            e1.record()
+            self.events.append((key, e0, e1))
+            return rc
+        return call
+
+    def __exit__(self, *exc):
+        for name, fn in self.saved.items():
+            setattr(self.lib, name, fn)
+
+    def summary(self, n_steps):
+        self.torch.cuda.synchronize()
+        out = {}
+        for key, e0, e1 in self.events:
+            d = out.setdefault(key, [0.0, 0])
+            d[0] += e0.elapsed_time(e1)
+            d[1] += 1
+        return {k: {"ms_per_step": v[0] / n_steps, "calls_per_step": v[1] / n_steps, "ms_per_call": v[0] / v[1]} for k, v in out.items()}
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from rlao_b200 import _lib
+    from rlao_b200.OOPAOEnv.OOPAOEnvRazor import OOPAO
+    from rlao_b200.PO4AO.util_simple import TorchWrapper
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nS, nL, B, desc = WORKLOADS[args.workload]
+    if args.envs:
+        B = args.envs
+    env = OOPAO()
+    env.set_params_file("rlao_b200.Conf.parameter_file_synthetic_SHWFS", "")
+    env.set_params(make_args(nS, nL), "shackhartmann", gainCL=0.5, n_envs=B, device=dev, rng="philox", seed=1,
+                   env_offset=rank * B)
+    env.atm.generateNewPhaseScreen(17)
+    env.dm.coefs = 0
+    env.tel * env.dm * env.wfs
+    obs = env.reset_soft()
+    gain = env.gainCL
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident loop ------------------------------------------------------------------------
+    for i in range(args.warmup):
+        obs, reward, strehl, _, _ = env.step(None, gain * obs)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        obs, reward, strehl, _, _ = env.step(None, gain * obs)
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t[0])
+    value = world * B * args.steps / (ms_max * 1e-3)
+    sr_mean = float(strehl.float().mean())
+
+    # ---- end-to-end through the host-facing wrapper (pinned host buffers, copies inside the timed region) ----
+    wrapped = TorchWrapper(env, host_io=True)
+    obs_h = wrapped.reset_soft()
+    act_h = torch.empty(obs_h.shape, dtype=torch.float32, pin_memory=True)
+    for i in range(max(3, args.warmup)):
+        torch.mul(obs_h, gain, out=act_h)
+        obs_h, reward_h, strehl_h, _, _ = wrapped.step(None, act_h)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        torch.mul(obs_h, gain, out=act_h)
+        obs_h, reward_h, strehl_h, _, _ = wrapped.step(None, act_h)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t[0]) * 1e-3)
+    nAct2 = env.nActuator ** 2
+    h2d, d2h = B * nAct2 * 4, B * nAct2 * 4 + 2 * B * 4
+
+    # ---- per-kernel attribution + roofline of the dominant kernel (rank 0) -----------------------------------
+    roofline, kernels = None, None
+    if rank == 0:
+        n_prof = min(args.steps, 10)
+        with KernelTimer(_lib.load(), torch) as kt:
+            o = env._sq(env._obs).clone()
+            for i in range(n_prof):
+                o, *_ = env.step(None, gain * o)
+        kernels = kt.summary(n_prof)
+        roofline = dominant_roofline(kernels, env, B)
+    if world > 1:
+        dist.barrier()
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            t0 = time.perf_counter()
+            orc = cpu_env(nS, nL, reconstructor=env.reconstructor.cpu().numpy())
+            n_cpu = 100 if nS >= 40 else 400
+            v, worst, wall = time_cpu(orc, 1, n_cpu)
+            cpu_baseline = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
+                            "sample": f"{n_cpu} steps of one environment of the same optical configuration, one process, one BLAS thread "
+                                      f"(oracle port, float64; setup {time.perf_counter() - t0 - wall:.1f}s excluded)"}
+        except Exception as ex:          # the baseline must never take the GPU number down with it
+            cpu_baseline = {"value": None, "unit": "env-steps/s", "cores": 1, "kind": "port", "sample": f"failed: {ex!r}"}
+
+    if rank == 0:
+        line = {
+            "metric": "closed-loop AO env-steps/sec (batched envs)", "value": value, "unit": "env-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "description": desc, "envs_per_gpu": B, "total_envs": world * B,
+                       "policy": "integrator gainCL=0.5, leak=0.99", "rng": "philox",
+                       "l2": "per-step working set (layer maps) %.0f MB per GPU exceeds the 126 MB L2" % (
+                           env.atm._maps.numel() * 4 / 2 / 1e6),
+                       "mean_strehl_last_step": sr_mean},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "kernels": kernels,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def dominant_roofline(kernels, env, B):
+    """Algorithmic bytes / flops per launch (SURVEY.md section 8 d; DESIGN.md 'Kernels') of the kernel family with
+    the largest share of the step, against the measured peaks."""
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    R, L, M = env.tel.resolution, env.atm.nLayer, env.atm._M
+    P, nA, nSig = R * R, env.dm.nValidAct, env.wfs.nSignal
+    top = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    ms = kernels[top]["ms_per_call"]
+    if top.startswith("aoenv_gemm_tn"):
+        N = int(top.split("N=")[1].split(",")[0])
+        K = {P: nA, nA: nSig}.get(N, env.atm._nI + env.atm._nO)
+        flops = 2.0 * B * N * K
+        ach = flops / (ms * 1e-3) / 1e12
+        return {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak,
+                "traffic": None, "peak_source": src + ", bf16 dense sustained; this kernel runs FP32 SIMT"}
+    per_env = {
+        "aoenv_atm_phase": L * M * M * 4 + P * 4,
+        "aoenv_shwfs_frame": 3 * P * 4,
+        "aoenv_shwfs_slopes": P * 4 + nSig * 4,
+        "aoenv_atm_scatter": 2 * M * M * 4,
+        "aoenv_atm_gather": 2 * (env.atm._nI + env.atm._nO) * 4,
+        "aoenv_command_update": 3 * nA * 4 + env.nActuator ** 2 * 4,
+        "aoenv_observe": nA * 4 + env.nActuator ** 2 * 4,
+    }.get(top, 0)
+    ach = per_env * B / (ms * 1e-3) / 1e9
+    return {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+            "traffic": None, "peak_source": src}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=0, help="environments per GPU (default: the workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,157 @@
+/*
+ * aoenv.h — C ABI of libaoenv_b200.so: the closed-loop adaptive-optics environment step on B200 (sm_100a).
+ *
+ * The reference (artiom-matvei/RLAO, drl4ao + OOPAO) has no FFI: its boundary is the Python object protocol
+ * (Telescope / Atmosphere / DeformableMirror / ShackHartmann / Detector objects and the gym-style
+ * OOPAO.step).  rlao_b200 keeps that protocol in Python and calls the entry points below through ctypes.
+ * Each entry point names the reference code it replaces (paths under /root/reference/drl4ao/:
+ * OOPAO/ = AO_OOPAO/OOPAO/, MAIN/ = MAIN_CODE/).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with h_ (host);
+ *   - all arrays are dense row-major float32 unless stated otherwise; "B" is the number of environments
+ *     stepped in lock-step on this GPU, and is always the slowest-varying (leading) dimension;
+ *   - `stream` is a cudaStream_t passed as void*; no entry point synchronises the device or the stream;
+ *   - the caller owns every buffer; return value 0 = success, otherwise a negative error code whose text
+ *     is available (per calling thread) from aoenv_last_error().
+ */
+#ifndef AOENV_H_
+#define AOENV_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AOENV_MAX_LAYERS 8
+#define AOENV_ABI_VERSION 1
+
+int aoenv_abi_version(void);
+const char* aoenv_last_error(void);
+/* Number of kernels launched by this library in the calling process since load (bench.py's gpu_launches). */
+uint64_t aoenv_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Atmosphere — OOPAO/Atmosphere.py
+ *
+ * State per layer l: `map` [B][M][pitch] (M = R + 6 = layer.mapShift side, pitch >= M floats per row) and the
+ * per-environment extrema `minmax` [B][2] of that map (the clip range of skimage.warp, tools.py:215-217).
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* add_row, step 1 (Atmosphere.py:303-307): gathers, for every environment, the two inner rings Z of the map
+ * shifted by (sx, sy) in {-1,0,1}^2 pixels (tx = sx along columns, ty = sy along rows) into zx[b][0..nI), and
+ * the innovation xi ~ N(0,1) into zx[b][nI..nI+nO): injected from `xi` [B][nO] when non-null, else Philox
+ * (seed, stream_id, b).  zx rows have `ldz` floats (ldz >= nI+nO; the tail is zero-filled).
+ * inner_rc [nI][2] holds (row, col) of the inner-ring pixels in MAP coordinates, in the reference's boolean-
+ * mask (row-major) order. */
+int aoenv_atm_gather(const float* map, int B, int M, int pitch, int sx, int sy,
+                     const int32_t* inner_rc, int nI, int nO, const float* xi,
+                     uint64_t seed, uint64_t stream_id, float* zx, int ldz, void* stream);
+
+/* add_row, step 3 (Atmosphere.py:309-310): map_out interior <- map_in shifted by (sx, sy); map_out outer ring
+ * <- X [B][ldx] (X = A Z + B xi, computed by aoenv_gemm_tn on zx and the stacked operator [A | B]), ring pixels
+ * taken in the order of numpy's boolean mask `outerMask` (row 0, then the (r,0),(r,M-1) pairs, then row M-1;
+ * nO must equal 4M-4).  Also refreshes minmax[b] = {min, max} of map_out, stored as monotone int32 encodings
+ * of the float values (see aoenv_map_minmax). */
+int aoenv_atm_scatter(const float* map_in, float* map_out, int B, int M, int pitch, int sx, int sy, int nO,
+                      const float* X, int ldx, int32_t* minmax, void* stream);
+
+/* minmax[b] = {min, max} over map[b] (used after (re)initialising the screens).  Encoding: the float's bit
+ * pattern i, or i ^ 0x7fffffff when i < 0, so that integer order equals float order. */
+int aoenv_map_minmax(const float* map, int B, int M, int pitch, int32_t* minmax, void* stream);
+
+/* updateLayer tail + fill_phase_support + set_OPD (Atmosphere.py:406-407,439-450,474-478): for each layer the
+ * bicubic (4x4 tap) sub-pixel shift of the map, clipped to the map's [min,max], cropped to the R x R pupil
+ * footprint, weighted by sqrt(fractionalR0) and summed; opd_out [B][R][R] = sum * opd_scale (lambda/2pi).
+ * h_map / h_minmax: host arrays of nLayer device pointers.  h_row_off / h_col_off: first tap offset relative
+ * to the output pixel's own map row / column (so tap k reads row i + fp_off + h_row_off[l] + k).
+ * h_wrow / h_wcol [nLayer][4]: tap weights (computed by the host in float64 from layer.buff).
+ * h_weight [nLayer] = sqrt(fractionalR0).  fp_off = map index of footprint pixel 0 (3 for fov = 0). */
+int aoenv_atm_phase(const float* const* h_map, const int32_t* const* h_minmax, int nLayer, int B, int R, int M,
+                    int pitch, int fp_off, const int32_t* h_row_off, const int32_t* h_col_off,
+                    const float* h_wrow, const float* h_wcol, const float* h_weight, float opd_scale,
+                    float* opd_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Dense contractions — DeformableMirror.coefs setter (OOPAO/DeformableMirror.py:534-570: OPD = modes @ coefs),
+ * add_row's X = A Z + B xi (OOPAO/Atmosphere.py:308), reconstruction (MAIN/OOPAOEnv/OOPAOEnvRazor.py:496-499).
+ * D[m][n] = alpha * sum_k X[m][k] * W[n][k]     (both operands K-contiguous; D row-major, ldd floats/row)
+ * ------------------------------------------------------------------------------------------------------- */
+int aoenv_gemm_tn(const float* X, int ldx, const float* W, int ldw, float* D, int ldd,
+                  int M, int N, int K, float alpha, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Shack-Hartmann WFS + detector — OOPAO/ShackHartmann.py:511-601 (and :605-674), OOPAO/Detector.py:190-301
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t photon_noise;    /* Detector.photonNoise: Poisson(frame)                       (Detector.py:204) */
+  int32_t sensor_emccd;    /* 1: gain applied before the read noise (EMCCD), else after  (:249-266)        */
+  int32_t has_fwc;         /* FWC is not None: clip to [0, FWC]                           (:177-181)        */
+  int32_t bits;            /* 0 = no ADC; else quantise frame/FWC*(2^bits-1), truncate    (:190-201)        */
+  float qe;                /* quantum efficiency                                          (:172-174)        */
+  float dark_electrons;    /* darkCurrent * integrationTime, Poisson mean per pixel       (:224-229)        */
+  float fwc;
+  float gain;
+  float readout_noise;     /* e- rms; round(N(0,1) * RON)                                 (:218-221)        */
+  uint32_t reserved;
+  uint64_t seed;           /* Philox key                                                                    */
+  uint64_t frame_counter;  /* advances once per call: independent draws per step                            */
+} aoenv_detector_t;
+
+/* wfs_measure, diffractive branch up to the detector: per lenslet, the transposed n x n tile of
+ * phase = (opd_a + opd_b) * pupil * phase_scale is zero-padded to 2n x 2n, multiplied by sqrt(flux) and the
+ * half-pixel phasor, Fourier transformed, |.|^2 / (2n)^2, binned 2x2 -> n x n spot, written at tile (i, j) of
+ * frame [B][R][R] after the detector chain `det` (det == NULL: ideal detector).  Lenslets with valid[k] == 0
+ * contribute zero light (their pixels still see dark/read noise).  opd_b may be NULL.
+ * amp [R][R] = sqrt(fluxMap).  envmax [B] receives max over the environment's valid-lenslet pixels (float bits
+ * in a monotone int32 encoding, initialised by this call); shared_max != 0 -> one max for the whole batch in
+ * envmax[0] (the interaction-matrix branch, ShackHartmann.py:659).
+ * stats [B][4] (float64): sums over pupil pixels of {opd_a, opd_a^2, opd, opd^2} in metres, for
+ * env.total / env.residual / get_strehl (MAIN/OOPAOEnv/OOPAOEnvRazor.py:484,502,604-605). May be NULL.
+ * n (pixels per lenslet) must be one of the compiled sizes (4, 6, 8). */
+int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil, const float* amp,
+                      const uint8_t* valid, int B, int nS, int n, float phase_scale,
+                      const aoenv_detector_t* det, int shared_max,
+                      float* frame, int32_t* envmax, double* stats, void* stream);
+
+/* centroid + slopes (ShackHartmann.py:314-324,580-601): threshold at thr * max, first moments along the
+ * lenslet map's axis 1 -> X and axis 2 -> Y, NaN/Inf -> 0, minus reference, divided by slopes_units.
+ * valid_idx [nV]: lenslet numbers k = i*nS + j of the valid lenslets (row-major); ref_xy [2][nV].
+ * slopes [B][lds]: first nV entries X, next nV entries Y (= wfs.signal). */
+int aoenv_shwfs_slopes(const float* frame, const int32_t* envmax, int shared_max, const int32_t* valid_idx,
+                       int nV, const float* ref_xy, float inv_units, float threshold_cog, int B, int nS, int n,
+                       float* slopes, int lds, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Command update and observation — MAIN/OOPAOEnv/OOPAOEnvRazor.py:479,492-500,514,621-641
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* coefs = dm_prev * leak + img_to_vec(action) * 1e-6 ; dm_prev = coefs.   action [B][nAct][nAct] (micrometres),
+ * act_idx [nA]: flat index xvalid*nAct + yvalid of each valid actuator. coefs/dm_prev [B][ldc]. */
+int aoenv_command_update(const float* action, const int32_t* act_idx, int B, int nA, int nAct2, float leak,
+                         float* coefs, float* dm_prev, int ldc, void* stream);
+
+/* obs = vec_to_img(-rec) * 1e6 with rec [B][ldr] = reconstructor @ signal (from aoenv_gemm_tn);
+ * reward = -||obs||_2; strehl = exp(-var(phase[pupil])) ; total / residual = std(OPD[pupil]) * 1e9, from `stats`
+ * (see aoenv_shwfs_frame) and n_pupil = number of pupil pixels.  obs [B][nAct2] is fully overwritten. */
+int aoenv_observe(const float* rec, int ldr, const int32_t* act_idx, int B, int nA, int nAct2,
+                  const double* stats, double n_pupil, float phase_scale,
+                  float* obs, float* reward, float* strehl, float* total, float* residual, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Science-path PSF Strehl — OOPAO/Telescope.py:260-360 (computePSF(zp) -> PropagateField), PSF.max()
+ * The reference pads the pupil field to N = os*zp*R (os = 2 for even image sizes), takes |FFT/N|^2 and bins
+ * os x os.  This entry point evaluates that PSF on the central `win` x `win` binned pixels only (pruned DFT)
+ * and returns their maximum in psf_max [B]; psf_win [B][win][win] may be NULL.
+ * tw [2N][2] = (cos, sin)(-pi m / N), m = 0..2N-1 (float32, host-computed in float64);
+ * scratch: at least B * os*win * R * 2 floats.
+ * ------------------------------------------------------------------------------------------------------- */
+int aoenv_psf_peak(const float* opd_a, const float* opd_b, const float* pupil, const float* amp, const float* tw,
+                   int B, int R, int N, int os, int win, float phase_scale, float* scratch, float* psf_win,
+                   float* psf_max, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AOENV_H_ */

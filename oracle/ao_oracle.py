@@ -696,7 +696,10 @@ def compute_psf(pupil, fluxMap, phase, zeroPaddingFactor):
 class EnvOracle:
     """MAIN/OOPAOEnv/OOPAOEnvRazor.py: set_params (:91-339, SH branch) and step (:474-514), one environment."""
 
-    def __init__(self, cfg: AOConfig, atm_ops=None, act_mask=None, detector_seed=0, verbose=False):
+    def __init__(self, cfg: AOConfig, atm_ops=None, act_mask=None, detector_seed=0, verbose=False,
+                 reconstructor=None):
+        """`atm_ops` / `reconstructor`: pre-computed operators (e.g. from a previous oracle instance) to skip the
+        covariance and interaction-matrix computations when only the step itself is being timed."""
         self.cfg = cfg
         R = cfg.resolution
         self.pupil = telescope_pupil(R, cfg.centralObstruction)
@@ -714,16 +717,19 @@ class EnvOracle:
         self.cam = DetectorOracle(DetectorConfig(), cfg.samplingTime, seed=detector_seed)
         self.wfs = ShackHartmannOracle(cfg, self.pupil, self.fluxMap, self.wavelength, self.cam)
         self.cam.c = DetectorConfig(**{**cfg.detector.__dict__, "photonNoise": False, "readoutNoise": 0.0})
-        if cfg.nZernike > 0:
-            Z = zernike_modes(self.pupil, cfg.diameter, cfg.nZernike)
-            self.M2C = np.linalg.pinv(self.modes[self.pupil.reshape(-1), :]) @ Z      # :261
+        if reconstructor is not None:
+            self.reconstructor = np.asarray(reconstructor, dtype=float)
         else:
-            self.M2C = np.eye(self.nValidAct)
-        self.D_zonal = interaction_matrix(self.wfs, self.modes, np.eye(self.nValidAct), cfg.stroke,
-                                          cfg.nMeasurements, self.wavelength)
-        self.calib = calibration_vault(self.D_zonal @ self.M2C)                       # :290
-        self.reconstructor = self.M2C @ self.calib["M"]                               # :336
-        self.F = self.M2C @ np.linalg.pinv(self.M2C)                                  # :337
+            if cfg.nZernike > 0:
+                Z = zernike_modes(self.pupil, cfg.diameter, cfg.nZernike)
+                self.M2C = np.linalg.pinv(self.modes[self.pupil.reshape(-1), :]) @ Z      # :261
+            else:
+                self.M2C = np.eye(self.nValidAct)
+            self.D_zonal = interaction_matrix(self.wfs, self.modes, np.eye(self.nValidAct), cfg.stroke,
+                                              cfg.nMeasurements, self.wavelength)
+            self.calib = calibration_vault(self.D_zonal @ self.M2C)                       # :290
+            self.reconstructor = self.M2C @ self.calib["M"]                               # :336
+            self.F = self.M2C @ np.linalg.pinv(self.M2C)                                  # :337
         self.cam.c.photonNoise = cfg.detector.photonNoise                             # :332-333
         self.cam.c.readoutNoise = cfg.detector.readoutNoise
         self.leak = cfg.leak

@@ -1,0 +1,343 @@
+"""Atmosphere — mirror of OOPAO/Atmosphere.py (on-axis NGS, fov = 0), batched over environments.
+
+Every environment owns its own set of layer maps (independent turbulence realisations); the wind vector,
+r0, L0 and the Cn2 profile belong to the Atmosphere object and are therefore shared by all environments, so
+the integer-pixel extrusions (`add_row`) fire on the same step for the whole batch and become one GEMM
+X[B, nO] = [Z | xi][B, nI+nO] @ [A | B]^T.
+
+HBM layout: maps[layer][2][B][M][pitch] float32 (M = R + 6, ping-pong pair per layer), minmax[layer][B][2]
+(monotone-int encoded extrema for the interpolation clip), opd[B][R][R] (OPD_no_pupil in metres).
+"""
+import ctypes as C
+import math
+import time
+
+import numpy as np
+import torch
+from numpy.random import RandomState
+
+from . import _lib
+from .tools import vonkarman as vk
+
+
+class _LayerView:
+    """`atm.layer_k` — the handful of per-layer attributes callers poke at (Atmosphere.py:192-298)."""
+
+    def __init__(self, atm, index):
+        self._atm, self._i = atm, index
+        self.altitude = atm.altitude[index]
+        self.windSpeed = atm._windSpeed[index]
+        self.direction = atm._windDirection[index]
+        self.vY = self.windSpeed * np.cos(np.deg2rad(self.direction))
+        self.vX = self.windSpeed * np.sin(np.deg2rad(self.direction))
+        self.ratio = np.zeros(2)
+        self.buff = np.zeros(2)
+        self.notDoneOnce = True
+        self.resolution = atm._ops.layer_res
+        self.D = atm._ops.layer_D
+        self.seed = index
+        self.events = 0           # number of add_row calls so far (Philox stream id)
+
+    @property
+    def mapShift(self):
+        a = self._atm
+        m = a._maps[self._i, a._cur[self._i], :, :, :a._M]
+        return m[0] if a.n_envs == 1 else m
+
+    @property
+    def A(self):
+        return self._atm._ops.A
+
+    @property
+    def B(self):
+        return self._atm._ops.B
+
+
+class Atmosphere:
+    def __init__(self, telescope, r0, L0, windSpeed, fractionalR0, windDirection, altitude, mode=2, param=None,
+                 asterism=None, rng="philox", seed=0, warp_kernel="lagrange018", env_offset=0):
+        """`rng`: 'philox' — device counter-based streams (production); 'reference' — the reference's MT19937
+        streams for environment 0 (RandomState(42 + 1000*layer) etc., Atmosphere.py:201,579), offset by
+        104729*env for the others: host-generated, for parity runs and small batches.
+        `env_offset`: global index of this shard's first environment (multi-GPU sharding)."""
+        if asterism is not None or mode != 2:
+            raise NotImplementedError("asterisms / screen modes other than 2 are out of scope")
+        if telescope.src is None:
+            raise AttributeError("The telescope was not coupled to any source object! Make sure to couple it with an src object using src*tel")
+        if rng not in ("philox", "reference"):
+            raise ValueError("rng must be 'philox' or 'reference'")
+        self.hasNotBeenInitialized = True
+        self.telescope = telescope
+        self.device = telescope.device
+        self.n_envs = telescope.n_envs
+        self.r0_def = 0.15
+        self._r0 = r0
+        self._L0 = L0
+        self.fractionalR0 = list(fractionalR0)
+        self.altitude = list(altitude)
+        self.nLayer = len(self.fractionalR0)
+        if self.nLayer > 8:
+            raise ValueError("at most 8 layers (AOENV_MAX_LAYERS)")
+        self._windSpeed = list(windSpeed)
+        self._windDirection = list(windDirection)
+        self.tag = "atmosphere"
+        self.nExtra = 2
+        self.wavelength = 500e-9
+        self.user_defined_opd = False
+        self.mode = mode
+        self.seeingArcsec = 206265 * (self.wavelength / r0)
+        self.rng = rng
+        self.seed = int(seed)
+        self.env_offset = int(env_offset)
+        self.warp_kernel = warp_kernel
+        self.xi_queue = None        # optional iterator of [B, nO] tensors: injected innovations (parity runs)
+        self.xi_log = None          # set to [] to record every innovation block used
+
+    # ------------------------------------------------------------------------------------------------
+    def initializeAtmosphere(self, telescope):
+        """Atmosphere.py:145-190."""
+        tel = telescope
+        self.fov, self.fov_rad = tel.fov, tel.fov_rad
+        if tel.fov != 0:
+            raise NotImplementedError("fov > 0 is out of scope")
+        dev, B, R = self.device, self.n_envs, tel.resolution
+        if self.hasNotBeenInitialized:
+            self.initial_r0 = self._r0
+            self._ops = vk.VKOperators(R, tel.D, self._L0, self._r0, self.r0_def, dev)
+            ops = self._ops
+            self._M = ops.layer_res + self.nExtra
+            self._pitch = (self._M + 3) // 4 * 4
+            self._nO, self._nI = ops.outer_rc.shape[0], ops.inner_rc.shape[0]
+            self._K = (self._nI + self._nO + 15) // 16 * 16
+            self._ldx = (self._nO + 3) // 4 * 4
+            self._W = torch.zeros((self._nO, self._K), dtype=torch.float32, device=dev)
+            self._W[:, :self._nI] = ops.A.to(torch.float32)
+            self._upload_B()
+            self._inner_rc = torch.as_tensor(ops.inner_rc, dtype=torch.int32, device=dev).contiguous()
+            self._maps = torch.zeros((self.nLayer, 2, B, self._M, self._pitch), dtype=torch.float32, device=dev)
+            self._cur = [0] * self.nLayer
+            self._minmax = torch.zeros((self.nLayer, B, 2), dtype=torch.int32, device=dev)
+            self._zx = torch.zeros((B, self._K), dtype=torch.float32, device=dev)
+            self._X = torch.zeros((B, self._ldx), dtype=torch.float32, device=dev)
+            self._opd = torch.zeros((B, R, R), dtype=torch.float32, device=dev)
+            self._fp_off = 1 + (ops.layer_res // 2 - R // 2)         # crop [1:-1] + centred footprint (:231-232)
+            self.ps_loop = ops.layer_D / ops.layer_res
+            self._layers = [_LayerView(self, i) for i in range(self.nLayer)]
+            for i, ly in enumerate(self._layers):
+                setattr(self, "layer_" + str(i + 1), ly)
+            # first screens (Atmosphere.py:251-293): phase seeded with the layer index, ring from RandomState(42+1000 i)
+            self._new_screens(screen_seed=lambda i: i, ring_seed=lambda i: 42 + i * 1000)
+        else:
+            raise NotImplementedError("re-initialising an Atmosphere is not supported; build a new one")
+        self.hasNotBeenInitialized = False
+        self.generateNewPhaseScreen(seed=0)        # Atmosphere.py:185
+        self.update()                              # :188
+
+    def _upload_B(self):
+        self._W[:, self._nI:self._nI + self._nO] = self._ops.B.to(torch.float32)
+
+    # ---- random streams -----------------------------------------------------------------------------
+    def _host_xi(self, layer_index):
+        ly = self._layers[layer_index]
+        xi = np.stack([rs.normal(size=self._nO) for rs in ly.host_rng])
+        return torch.as_tensor(xi, dtype=torch.float32, device=self.device)
+
+    def _new_screens(self, screen_seed, ring_seed):
+        ops, B, dev = self._ops, self.n_envs, self.device
+        N, delta = ops.layer_res, ops.layer_D / ops.layer_res
+        for i, ly in enumerate(self._layers):
+            if self.rng == "reference":
+                ph = np.stack([vk.screen_reference_rng(self._r0, self._L0, N, delta, screen_seed(i) + 104729 * (self.env_offset + e))
+                               for e in range(B)])
+                phase = torch.as_tensor(ph, dtype=torch.float32, device=dev)
+                ly.host_rng = [RandomState(ring_seed(i) + 104729 * (self.env_offset + e)) for e in range(B)]
+            else:
+                g = torch.Generator(device=dev)
+                g.manual_seed((self.seed * 1000003 + screen_seed(i) * 7919 + self.env_offset * 104729 + 12345) % (2 ** 63))
+                phase = vk.screens_device_rng(self._r0, self._L0, N, delta, B, g, dev)
+                ly.philox_seed = (self.seed * 1000003 + ring_seed(i)) & 0xFFFFFFFFFFFFFFFF
+                ly.events = 0
+            cur = self._cur[i]
+            self._maps[i, cur, :, 1:-1, 1:self._M - 1] = phase
+            self._extrude(i, 0, 0)
+            ly.notDoneOnce = True
+
+    # ---- device steps -------------------------------------------------------------------------------
+    def _extrude(self, i, sx, sy):
+        """add_row (Atmosphere.py:301-311) for layer i and every environment."""
+        lib, ly = _lib.load(), self._layers[i]
+        B, M, pitch = self.n_envs, self._M, self._pitch
+        cur = self._cur[i]
+        src, dst = self._maps[i, cur], self._maps[i, 1 - cur]
+        st = _lib.stream_ptr(self.device)
+        xi = None
+        if self.xi_queue is not None:
+            xi = torch.as_tensor(next(self.xi_queue), dtype=torch.float32, device=self.device).reshape(B, self._nO).contiguous()
+        elif self.rng == "reference":
+            xi = self._host_xi(i)
+        if self.xi_log is not None:
+            self.xi_log.append(None if xi is None else xi.clone())
+        seed = getattr(ly, "philox_seed", 0)
+        stream_id = ((ly.events << 8) | i) + (self.env_offset << 40)
+        ly.events += 1
+        _lib.check(lib.aoenv_atm_gather(_lib.ptr(src), B, M, pitch, int(sx), int(sy), _lib.ptr(self._inner_rc), self._nI,
+                                        self._nO, _lib.ptr(xi), C.c_uint64(seed), C.c_uint64(stream_id),
+                                        _lib.ptr(self._zx), self._K, st), "atm_gather")
+        self._gemm(self._zx, self._W, self._X, B, self._nO, self._K)
+        _lib.check(lib.aoenv_atm_scatter(_lib.ptr(src), _lib.ptr(dst), B, M, pitch, int(sx), int(sy), self._nO,
+                                         _lib.ptr(self._X), self._ldx, _lib.ptr(self._minmax[i]), st), "atm_scatter")
+        self._cur[i] = 1 - cur
+
+    def _gemm(self, X, W, D, M, N, K):
+        _lib.check(_lib.load().aoenv_gemm_tn(_lib.ptr(X), X.stride(0), _lib.ptr(W), W.stride(0), _lib.ptr(D), D.stride(0),
+                                             M, N, K, 1.0, _lib.stream_ptr(self.device)), "gemm_tn")
+
+    def _update_layer(self, i):
+        """Integer part of updateLayer (Atmosphere.py:350-404); returns nothing, leaves ly.buff ready."""
+        ly = self._layers[i]
+        if ly.vX == 0 and ly.vY == 0:
+            return
+        if ly.notDoneOnce:
+            ly.notDoneOnce = False
+            ly.ratio = np.array([ly.vX * self.telescope.samplingTime / self.ps_loop,
+                                 ly.vY * self.telescope.samplingTime / self.ps_loop])
+            ly.buff = np.zeros(2)
+        ratio = ly.ratio
+        n = np.abs(ratio)
+        n[np.isinf(n)] = 0
+        n = n.astype(int)
+        sgn = np.sign(ratio)
+        for _ in range(n.min()):
+            self._extrude(i, sgn[0], sgn[1])
+        for _ in range(n.max() - n.min()):
+            step = sgn.copy()
+            step[n == n.min()] = 0
+            self._extrude(i, step[0], step[1])
+        ly.buff = ly.buff + (np.abs(ratio) % 1) * sgn
+        if abs(ly.buff[0]) >= 1 or abs(ly.buff[1]) >= 1:
+            step = np.sign(ly.buff)
+            step[np.abs(ly.buff) < 1] = 0
+            self._extrude(i, step[0], step[1])
+        ly.buff = (np.abs(ly.buff) % 1) * np.sign(ly.buff)
+
+    def _publish(self):
+        """Sub-pixel shift of every layer + Cn2-weighted sum -> OPD_no_pupil (Atmosphere.py:406-407,439-478)."""
+        L = self.nLayer
+        maps = (C.c_void_p * L)(*[self._maps[i, self._cur[i]].data_ptr() for i in range(L)])
+        mms = (C.c_void_p * L)(*[self._minmax[i].data_ptr() for i in range(L)])
+        roff, coff = (C.c_int32 * L)(), (C.c_int32 * L)()
+        wr, wc, wt = (C.c_float * (4 * L))(), (C.c_float * (4 * L))(), (C.c_float * L)()
+        for i, ly in enumerate(self._layers):
+            oc, wcol = vk.cubic_tap_weights(float(ly.buff[0]), self.warp_kernel)      # x -> columns
+            orow, wrow = vk.cubic_tap_weights(float(ly.buff[1]), self.warp_kernel)    # y -> rows
+            roff[i], coff[i] = orow, oc
+            for k in range(4):
+                wr[4 * i + k], wc[4 * i + k] = wrow[k], wcol[k]
+            wt[i] = math.sqrt(self.fractionalR0[i])
+        _lib.check(_lib.load().aoenv_atm_phase(maps, mms, L, self.n_envs, self.telescope.resolution, self._M, self._pitch,
+                                               self._fp_off, roff, coff, wr, wc, wt,
+                                               C.c_float(self.wavelength / 2 / math.pi), _lib.ptr(self._opd),
+                                               _lib.stream_ptr(self.device)), "atm_phase")
+
+    # ---- public API -----------------------------------------------------------------------------------
+    def update(self, OPD=None):
+        """Atmosphere.py:409-428."""
+        if OPD is None:
+            self.user_defined_opd = False
+            for i in range(self.nLayer):
+                self._update_layer(i)
+            self._publish()
+        else:
+            self.user_defined_opd = True
+            t = torch.as_tensor(OPD, dtype=torch.float32, device=self.device)
+            self._opd = (t if t.ndim == 3 else t.unsqueeze(0).expand(self.n_envs, -1, -1)).contiguous().clone()
+        if self.telescope.isPaired:
+            self * self.telescope
+
+    def generateNewPhaseScreen(self, seed=None):
+        """Atmosphere.py:560-592."""
+        if seed is None:
+            t = time.localtime()
+            seed = t.tm_hour * 3600 + t.tm_min * 60 + t.tm_sec
+        self._new_screens(screen_seed=lambda i: seed + i, ring_seed=lambda i: seed + i * 1000)
+        # the reference publishes layer.phase (the un-shifted screen) here; buff is reset by notDoneOnce
+        for ly in self._layers:
+            ly.buff = np.zeros(2)
+        self._publish()
+        if self.telescope.isPaired:
+            self * self.telescope
+
+    def __mul__(self, obj):
+        """atm*tel (Atmosphere.py:632-668)."""
+        if getattr(obj, "tag", None) != "telescope":
+            raise AttributeError("The atmosphere can be multiplied only with a Telescope or a Source object!")
+        self.telescope = obj
+        obj._set_lazy(self._opd, None)
+        obj.isPaired = True
+        return obj
+
+    @property
+    def OPD_no_pupil(self):
+        return self._opd[0] if self.n_envs == 1 else self._opd
+
+    @property
+    def OPD(self):
+        o = self._opd * self.telescope._pupil_f
+        return o[0] if self.n_envs == 1 else o
+
+    # ---- live parameter changes (Atmosphere.py:792-870) -----------------------------------------------------
+    @property
+    def r0(self):
+        return self._r0
+
+    @r0.setter
+    def r0(self, val):
+        self._r0 = val
+        if not self.hasNotBeenInitialized:
+            self.seeingArcsec = 206265 * (self.wavelength / val)
+            self._ops.B = self._ops.innovation_factor(val)
+            self._upload_B()
+
+    @property
+    def L0(self):
+        return self._L0
+
+    @L0.setter
+    def L0(self, val):
+        if not self.hasNotBeenInitialized and val != self._L0:
+            raise NotImplementedError("changing L0 rebuilds every operator: construct a new Atmosphere")
+        self._L0 = val
+
+    def _refresh_wind(self):
+        for i, ly in enumerate(self._layers):
+            ly.windSpeed, ly.direction = self._windSpeed[i], self._windDirection[i]
+            ly.vY = ly.windSpeed * np.cos(np.deg2rad(ly.direction))
+            ly.vX = ly.windSpeed * np.sin(np.deg2rad(ly.direction))
+            ly.ratio[0] = ly.vX * self.telescope.samplingTime / self.ps_loop
+            ly.ratio[1] = ly.vY * self.telescope.samplingTime / self.ps_loop
+
+    @property
+    def windSpeed(self):
+        return self._windSpeed
+
+    @windSpeed.setter
+    def windSpeed(self, val):
+        if not self.hasNotBeenInitialized and len(val) != self.nLayer:
+            print("Error! Wrong value for the wind-speed! Make sure that you inpute a wind-speed for each layer")
+            return
+        self._windSpeed = list(val)
+        if not self.hasNotBeenInitialized:
+            self._refresh_wind()
+
+    @property
+    def windDirection(self):
+        return self._windDirection
+
+    @windDirection.setter
+    def windDirection(self, val):
+        if not self.hasNotBeenInitialized and len(val) != self.nLayer:
+            print("Error! Wrong value for the wind-speed! Make sure that you inpute a wind-speed for each layer")
+            return
+        self._windDirection = list(val)
+        if not self.hasNotBeenInitialized:
+            self._refresh_wind()

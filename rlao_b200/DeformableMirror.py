@@ -1,0 +1,213 @@
+"""DeformableMirror — mirror of OOPAO/DeformableMirror.py (zonal Gaussian influence functions or user modes),
+batched over environments.  `dm.coefs = c` has the reference's side effect: dm.OPD = modes @ c, here a
+[n_frames, nValidAct] x [R*R, nValidAct]^T contraction on the GPU (include/aoenv.h: aoenv_gemm_tn).
+
+HBM layout: modes[R*R][Kp] float32, Kp = nValidAct rounded up to 16 with zero padding, K-contiguous, so the
+DM surface of every environment is one "TN" GEMM  OPD[B][R*R] = coefs[B][Kp] . modes[R*R][Kp]^T.
+"""
+import math
+import sys
+
+import numpy as np
+import torch
+
+from . import _lib
+from .MisRegistration import MisRegistration
+
+
+class DeformableMirror:
+    def __init__(self, telescope, nSubap, mechCoupling=0.35, coordinates=None, pitch=None, modes=None, misReg=None,
+                 M4_param=None, nJobs=30, nThreads=20, print_dm_properties=True, floating_precision=64, altitude=None):
+        if M4_param is not None and M4_param.get("isM4", False):
+            raise NotImplementedError("M4 influence functions are out of scope")
+        if altitude is not None:
+            raise NotImplementedError("DM in altitude is out of scope")
+        if mechCoupling <= 0:
+            raise ValueError("The value of mechanical coupling should be positive.")
+        self.telescope = telescope
+        self.device = telescope.device
+        self.n_envs = telescope.n_envs
+        self.altitude = None
+        self.isM4 = False
+        self.resolution = telescope.resolution
+        self.mechCoupling = mechCoupling
+        self.tag = "deformableMirror"
+        self.D = telescope.D
+        self.floating_precision = floating_precision
+        self.pitch = self.D / nSubap if pitch is None else pitch          # DeformableMirror.py:266-270
+        self.misReg = MisRegistration() if misReg is None else misReg
+        R = self.resolution
+
+        if coordinates is None:                                           # :286-305 Cartesian (Fried) geometry
+            self.nAct = nSubap + 1
+            self.nActAlongDiameter = self.nAct - 1
+            x = np.linspace(-self.D / 2, self.D / 2, self.nAct)
+            X, Y = np.meshgrid(x, x)
+            self.xIF0, self.yIF0 = X.reshape(-1), Y.reshape(-1)
+            r = np.sqrt(self.xIF0 ** 2 + self.yIF0 ** 2)
+            inner = r > (telescope.centralObstruction * self.D / 2 - 0.5 * self.pitch)
+            outer = r <= (self.D / 2 + 0.7533 * self.pitch)
+            self.validAct = inner * outer
+            self.nValidAct = int(self.validAct.sum())
+        else:                                                             # :309-321 explicit coordinates
+            coordinates = np.asarray(coordinates)
+            if coordinates.ndim != 2 or coordinates.shape[1] != 2:
+                raise AttributeError("Wrong size for the DM coordinates, the (x,y) coordinates should be input as a 2D array of dimension [nAct,2]")
+            self.xIF0, self.yIF0 = coordinates[:, 0], coordinates[:, 1]
+            self.nAct = len(self.xIF0)
+            self.nActAlongDiameter = self.D / self.pitch
+            self.validAct = np.arange(self.nAct).astype(int)
+            self.nValidAct = self.nAct
+
+        x0, y0 = self.xIF0[self.validAct], self.yIF0[self.validAct]
+        mr = self.misReg
+        x3, y3 = self.anamorphosis(x0, y0, mr.anamorphosisAngle * np.pi / 180, mr.tangentialScaling, mr.radialScaling)
+        x4, y4 = self.rotateDM(x3, y3, mr.rotationAngle * np.pi / 180)
+        self.xIF, self.yIF = x4 - mr.shiftX, y4 - mr.shiftY
+        self.nIF = len(self.xIF)
+        self.coordinates = np.stack([self.xIF, self.yIF], axis=1)
+
+        if modes is None:
+            modes64 = self._gaussian_modes()
+        else:
+            modes64 = torch.as_tensor(np.asarray(modes), dtype=torch.float64, device=self.device)
+            self.nValidAct = modes64.shape[1]
+        self._set_modes(modes64)
+        self._opd = torch.zeros((2, self.n_envs, R, R), dtype=torch.float32, device=self.device)   # ping-pong
+        self._slot = 0
+        self._multi = None            # [k, R, R] surfaces of a [nValidAct, k] command matrix (calibration)
+        self._coefs = torch.zeros((self.n_envs, self._Kp), dtype=torch.float32, device=self.device)
+        self._coefs_matrix = None
+        self.current_coefs = None
+
+    # ---- geometry helpers (DeformableMirror.py:480-492) -------------------------------------------------
+    @staticmethod
+    def rotateDM(x, y, angle):
+        return x * np.cos(angle) - y * np.sin(angle), y * np.cos(angle) + x * np.sin(angle)
+
+    @staticmethod
+    def anamorphosis(x, y, angle, mRad, mNorm):
+        mRad, mNorm = mRad + 1, mNorm + 1
+        xo = x * (mRad * np.cos(angle) ** 2 + mNorm * np.sin(angle) ** 2) + y * (mNorm * np.sin(2 * angle) / 2 - mRad * np.sin(2 * angle) / 2)
+        yo = y * (mRad * np.sin(angle) ** 2 + mNorm * np.cos(angle) ** 2) + x * (mNorm * np.sin(2 * angle) / 2 - mRad * np.sin(2 * angle) / 2)
+        return xo, yo
+
+    def _gaussian_modes(self):
+        """DeformableMirror.py:494-514: anisotropic Gaussian IFs on the grid linspace(0,1,R)*R, float64 on device."""
+        R, mr, dev = self.resolution, self.misReg, self.device
+        u0x = torch.as_tensor(R / 2 + self.xIF * R / self.D, dtype=torch.float64, device=dev)
+        u0y = torch.as_tensor(R / 2 + self.yIF * R / self.D, dtype=torch.float64, device=dev)
+        base = (R / self.nActAlongDiameter) / math.sqrt(2 * math.log(1.0 / self.mechCoupling))
+        cx, cy = (1 + mr.radialScaling) * base, (1 + mr.tangentialScaling) * base
+        th = mr.anamorphosisAngle * math.pi / 180
+        a = math.cos(th) ** 2 / (2 * cx ** 2) + math.sin(th) ** 2 / (2 * cy ** 2)
+        b = -math.sin(2 * th) / (4 * cx ** 2) + math.sin(2 * th) / (4 * cy ** 2)
+        c = math.sin(th) ** 2 / (2 * cx ** 2) + math.cos(th) ** 2 / (2 * cy ** 2)
+        g = torch.linspace(0, 1, R, dtype=torch.float64, device=dev) * R
+        out = torch.empty((R * R, self.nValidAct), dtype=torch.float64, device=dev)
+        chunk = max(1, (1 << 27) // (R * R))
+        for s in range(0, self.nValidAct, chunk):
+            dx = g[None, None, :] - u0x[s:s + chunk, None, None]          # X varies along columns
+            dy = g[None, :, None] - u0y[s:s + chunk, None, None]          # Y varies along rows
+            G = torch.exp(-(a * dx ** 2 + 2 * b * dx * dy + c * dy ** 2))
+            out[:, s:s + chunk] = G.reshape(G.shape[0], R * R).T
+        return out
+
+    def _set_modes(self, modes64):
+        self._modes64 = modes64                      # kept until the calibration is done (free_float64())
+        self._Kp = (self.nValidAct + 15) // 16 * 16
+        self._modes = torch.zeros((modes64.shape[0], self._Kp), dtype=torch.float32, device=self.device)
+        self._modes[:, :self.nValidAct] = modes64.to(torch.float32)
+
+    def free_float64(self):
+        self._modes64 = None
+
+    @property
+    def modes(self):
+        return self._modes64 if self._modes64 is not None else self._modes[:, :self.nValidAct]
+
+    @modes.setter
+    def modes(self, val):
+        m = torch.as_tensor(np.asarray(val) if not torch.is_tensor(val) else val, dtype=torch.float64, device=self.device)
+        self.nValidAct = m.shape[1]
+        self._set_modes(m)
+
+    # ---- surfaces ----------------------------------------------------------------------------------------
+    def _surface(self, coefs_padded, out):
+        """out[f] = modes @ coefs[f] for every frame f (OPD = modes @ coefs, DeformableMirror.py:534-570)."""
+        F = coefs_padded.shape[0]
+        P = self.resolution ** 2
+        o2 = out.reshape(F, P)
+        _lib.check(_lib.load().aoenv_gemm_tn(_lib.ptr(coefs_padded), coefs_padded.stride(0), _lib.ptr(self._modes),
+                                             self._modes.stride(0), _lib.ptr(o2), o2.stride(0), F, P, self._Kp, 1.0,
+                                             _lib.stream_ptr(self.device)), "gemm_tn(dm)")
+
+    def _set_coefs_batch(self, coefs_padded):
+        """Fast path of env.step: per-environment commands [B, Kp]; writes the *next* surface slot and makes it
+        current.  The previous slot keeps the surface the WFS has just seen (tel.OPD stays reproducible)."""
+        self._coefs = coefs_padded
+        self._multi = None
+        self._coefs_matrix = None
+        self._slot ^= 1
+        self._surface(coefs_padded, self._opd[self._slot])
+
+    def _previous_surface(self):
+        return self._opd[self._slot ^ 1]
+
+    @property
+    def coefs(self):
+        if self._coefs_matrix is not None:
+            return self._coefs_matrix
+        c = self._coefs[:, :self.nValidAct]
+        return c[0] if self.n_envs == 1 else c
+
+    @coefs.setter
+    def coefs(self, val):
+        """Reference semantics (DeformableMirror.py:534-570): scalar 0 resets; a vector of length nValidAct commands
+        the mirror (here: every environment); a [nValidAct, k] matrix produces k surfaces at once (calibration).
+        Extension: a [n_envs, nValidAct] tensor commands each environment separately."""
+        nA, B = self.nValidAct, self.n_envs
+        if np.isscalar(val):
+            if val != 0:
+                print("Error: wrong value for the coefficients")
+                return
+            c = torch.zeros((B, self._Kp), dtype=torch.float32, device=self.device)
+            self._set_coefs_batch(c)
+            return
+        t = torch.as_tensor(val, dtype=torch.float32, device=self.device)
+        if t.ndim == 1 and t.shape[0] == nA:
+            c = torch.zeros((B, self._Kp), dtype=torch.float32, device=self.device)
+            c[:, :nA] = t
+            self._set_coefs_batch(c)
+        elif t.ndim == 2 and t.shape[0] == nA and not (t.shape[0] == B and t.shape[1] == nA and B != nA):
+            k = t.shape[1]
+            c = torch.zeros((k, self._Kp), dtype=torch.float32, device=self.device)
+            c[:, :nA] = t.T
+            self._multi = torch.empty((k, self.resolution, self.resolution), dtype=torch.float32, device=self.device)
+            self._surface(c, self._multi)
+            self._coefs_matrix = t
+        elif t.ndim == 2 and t.shape == (B, nA):
+            c = torch.zeros((B, self._Kp), dtype=torch.float32, device=self.device)
+            c[:, :nA] = t
+            self._set_coefs_batch(c)
+        else:
+            print("Error: wrong value for the coefficients")
+            sys.exit(0)                                                     # DeformableMirror.py:567-569
+        self.current_coefs = self.coefs
+
+    @property
+    def OPD(self):
+        if self._multi is not None:
+            return self._multi
+        o = self._opd[self._slot]
+        return o[0] if self.n_envs == 1 else o
+
+    def dm_propagation(self, telescope, OPD_in=None, i_source=None):
+        """DeformableMirror.py:452-478: OPD_no_pupil leaving the mirror (a new tensor)."""
+        dm_opd = self._multi if self._multi is not None else self._opd[self._slot]
+        if telescope.isPaired:
+            base = telescope._materialise() if OPD_in is None else OPD_in
+            if dm_opd.shape[0] != base.shape[0]:
+                base = base[:1].expand(dm_opd.shape[0], -1, -1)
+            return base + dm_opd
+        return dm_opd.clone()

@@ -1,0 +1,307 @@
+"""Gym-style closed-loop AO environment — mirror of MAIN_CODE/OOPAOEnv/OOPAOEnvRazor.py `class OOPAO`
+(Shack-Hartmann branch; twin of OOPAOEnv.py), stepping `n_envs` independent environments in lock-step on one GPU.
+
+    env = OOPAO(); env.set_params_file(param_file, oopao_path); env.set_params(args, "shackhartmann", n_envs=1024)
+    obs = env.reset_soft()
+    obs, reward, strehl, done, info = env.step(i, action)
+
+`step` follows OOPAOEnvRazor.py:474-514 line by line but never leaves the device: seven kernel launches per
+step plus one GEMM-triple per integer-pixel wind shift.  Arrays carry a leading n_envs
+dimension (squeezed when n_envs == 1); rewards / Strehl ratios are tensors of shape [n_envs].
+"""
+import ctypes
+import importlib
+import math
+import types
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..Atmosphere import Atmosphere
+from ..DeformableMirror import DeformableMirror
+from ..MisRegistration import MisRegistration
+from ..ShackHartmann import ShackHartmann
+from ..Source import Source
+from ..Telescope import Telescope
+from ..Zernike import Zernike
+from ..calibration.CalibrationVault import CalibrationVault
+from ..calibration.InteractionMatrix import InteractionMatrix
+
+
+class OOPAO:
+    metadata = {"render.modes": ["rgb_array"]}
+
+    def __init__(self):
+        self.gainCL = None
+        self.atm = self.wfs = self.dm = self.misReg = self.tel = self.source = None
+        self.M2C_CL = self.calib_CL = self.reconstructor = None
+        self.SR = self.total = self.residual = self.wfsSignal = self.OPD = None
+        self.action_buffer = []
+        self.done = False
+        self.param_file = ""
+        self.oopao_path = ""
+        self.delay = 1
+        self.F = 1
+        self.name = "OOPAO"
+        self.dm_mask = self.nActuator = self.xvalid = self.yvalid = None
+        self.leak = 0.99
+        self.n_envs = 1
+        self.device = None
+        self.psf_reward = None        # (zeroPaddingFactor, window) -> Strehl from the PSF peak each step
+
+    # ---- configuration ------------------------------------------------------------------------------------
+    def set_params_file(self, param_file, oopao_path):
+        self.param_file = param_file
+        self.oopao_path = oopao_path
+
+    def _load_param(self, args):
+        if isinstance(self.param_file, dict):
+            return dict(self.param_file)
+        name = self.param_file or "rlao_b200.Conf.parameter_file_synthetic_SHWFS"
+        try:
+            config = importlib.import_module(name)
+        except ModuleNotFoundError:
+            config = importlib.import_module("rlao_b200." + name)
+        return config.initializeParameterFile(args)
+
+    def set_params(self, args=None, wfs_type="shackhartmann", modal_basis="zernike", gainCL=0.5, n_envs=1, device=None,
+                   rng="philox", seed=0, env_offset=0, warp_kernel="lagrange018"):
+        """OOPAOEnvRazor.py:91-339 (SH branch)."""
+        if wfs_type != "shackhartmann":
+            raise NotImplementedError("only the Shack-Hartmann WFS is implemented (Pyramid: SURVEY.md section 8 f-3)")
+        args = args if args is not None else types.SimpleNamespace()
+        self.gainCL = gainCL
+        self.n_envs = int(n_envs)
+        self.env_offset = int(env_offset)
+        param = self._load_param(args)
+        self.param = param
+        self.tel = Telescope(resolution=param["resolution"], diameter=param["diameter"], samplingTime=param["samplingTime"],
+                             centralObstruction=param["centralObstruction"], n_envs=n_envs, device=device)
+        self.device = self.tel.device
+        self.source = Source(optBand=param["opticalBand"], magnitude=param["magnitude"])
+        self.source * self.tel
+        self.atm = Atmosphere(telescope=self.tel, r0=param["r0"], L0=param["L0"], windSpeed=param["windSpeed"],
+                              fractionalR0=param["fractionalR0"], windDirection=param["windDirection"],
+                              altitude=param["altitude"], rng=rng, seed=seed, env_offset=env_offset,
+                              warp_kernel=warp_kernel)
+        self.atm.initializeAtmosphere(self.tel)
+        self.atm.update()
+        self.tel + self.atm
+        # deformable mirror
+        nAct = param["nActuator"]
+        self.nActuator = nAct
+        if param.get("dm_geometry", "razor") == "cartesian":
+            self.dm = DeformableMirror(telescope=self.tel, nSubap=param["nSubaperture"], mechCoupling=param["mechanicalCoupling"],
+                                       misReg=MisRegistration(param))
+            self.dm_mask = np.reshape(self.dm.validAct, (nAct, nAct)).astype(int)
+        else:
+            # OOPAOEnvRazor.py:167-193: explicit coordinates from the actuator mask, DeformableMirror(nSubap=nActuator)
+            x = np.linspace(-self.tel.D / 2, self.tel.D / 2, nAct)
+            X, Y = np.meshgrid(x, x)
+            keep = np.asarray(param["boolActMask"]).astype(bool).reshape(-1)
+            coords = np.stack([X.reshape(-1)[keep], Y.reshape(-1)[keep]], axis=1)
+            self.dm = DeformableMirror(telescope=self.tel, nSubap=nAct, mechCoupling=param["mechanicalCoupling"],
+                                       M4_param=param, coordinates=coords)
+            self.dm_mask = np.asarray(param["boolActMask"]).astype(int)
+        self.xvalid, self.yvalid = np.nonzero(self.dm_mask)
+        self.tel - self.atm
+        self.wfs = ShackHartmann(telescope=self.tel, nSubap=param["nSubaperture"], lightRatio=param.get("lightRatio", 0.5),
+                                 threshold_cog=param.get("threshold_cog", 0.01), is_geometric=False,
+                                 shannon_sampling=param.get("shannon_sampling", True))
+        cam = self.wfs.cam
+        cam.sensor = param.get("cam_sensor", cam.sensor)
+        cam.FWC = param.get("cam_FWC", cam.FWC)
+        cam.bits = param.get("cam_bits", cam.bits)
+        cam.QE = param.get("cam_QE", cam.QE)
+        cam.darkCurrent = param.get("cam_darkCurrent", cam.darkCurrent)
+        cam.integrationTime = param["samplingTime"]
+        cam.seed = seed
+        self.tel * self.wfs
+        # modal basis and calibration
+        nZ = param.get("nZernike", 50)
+        if nZ and nZ > 0:
+            Z = Zernike(self.tel, nZ)
+            Z.computeZernike(self.tel)
+            M2C = torch.linalg.pinv(self.dm.modes[self.tel._pupil_idx, :].double()) @ Z.modes       # :261
+        else:
+            M2C = torch.eye(self.dm.nValidAct, dtype=torch.float64, device=self.device)
+        calib_zonal = InteractionMatrix(ngs=self.source, atm=self.atm, tel=self.tel, dm=self.dm, wfs=self.wfs,
+                                        M2C=torch.eye(self.dm.nValidAct, dtype=torch.float64, device=self.device),
+                                        stroke=1e-9, nMeasurements=param.get("nMeasurements", 25), noise="off")
+        self.calib_zonal = calib_zonal
+        calib = CalibrationVault(calib_zonal.D @ M2C)                                                # :290
+        self.tel.resetOPD()
+        self.dm.coefs = 0
+        self._dm_prev = torch.zeros((self.n_envs, self.dm._Kp), dtype=torch.float32, device=self.device)
+        self._coefs_buf = torch.zeros((2, self.n_envs, self.dm._Kp), dtype=torch.float32, device=self.device)
+        self._coefs_slot = 0
+        self.source * self.tel * self.dm * self.wfs
+        self.tel + self.atm
+        self.calib_CL = calib
+        self.M2C_CL = M2C
+        nLoop = param.get("nLoop", None)
+        self.SR = []
+        self._nLoop = nLoop
+        self.total = torch.zeros((nLoop, self.n_envs), dtype=torch.float32, device=self.device) if nLoop else None
+        self.residual = torch.zeros((nLoop, self.n_envs), dtype=torch.float32, device=self.device) if nLoop else None
+        cam.photonNoise = param.get("cam_photonNoise", True)                                         # :332-333
+        cam.readoutNoise = param.get("cam_readoutNoise", 14)
+        self.set_reconstructor(M2C @ calib.M)                                                        # :336
+        self.F = M2C @ torch.linalg.pinv(M2C)                                                        # :337
+        self._F32 = self.F.to(torch.float32)
+        self.dm.free_float64()
+        # device-side index tables and outputs
+        B, nA = self.n_envs, self.dm.nValidAct
+        self._act_idx = torch.as_tensor((self.xvalid * nAct + self.yvalid).astype(np.int32), device=self.device)
+        self._rec = torch.zeros((B, (nA + 3) // 4 * 4), dtype=torch.float32, device=self.device)
+        self._obs = torch.zeros((B, nAct, nAct), dtype=torch.float32, device=self.device)
+        self._reward = torch.zeros((B,), dtype=torch.float32, device=self.device)
+        self._strehl = torch.zeros((B,), dtype=torch.float32, device=self.device)
+        self._total_now = torch.zeros((B,), dtype=torch.float32, device=self.device)
+        self._residual_now = torch.zeros((B,), dtype=torch.float32, device=self.device)
+        self._phase_scale = 2 * math.pi / self.source.wavelength
+        self._noise_gen = torch.Generator(device=self.device)
+        self._noise_gen.manual_seed(seed * 7919 + env_offset + 5)
+
+    def set_reconstructor(self, R):
+        """reconstructor [nValidAct, nSignal] (float64 kept for inspection, padded float32 copy for the step GEMM)."""
+        self.reconstructor = torch.as_tensor(R, dtype=torch.float64, device=self.device)
+        nA, nSig = self.reconstructor.shape
+        self._Rm = torch.zeros((nA, self.wfs._lds), dtype=torch.float32, device=self.device)
+        self._Rm[:, :nSig] = self.reconstructor.to(torch.float32)
+
+    @property
+    def dm_prev(self):
+        d = self._dm_prev[:, :self.dm.nValidAct]
+        return d[0] if self.n_envs == 1 else d
+
+    @dm_prev.setter
+    def dm_prev(self, val):
+        t = torch.as_tensor(val, dtype=torch.float32, device=self.device)
+        self._dm_prev.zero_()
+        self._dm_prev[:, :self.dm.nValidAct] = t
+
+    # ---- helpers ------------------------------------------------------------------------------------------
+    def _sq(self, t):
+        return t[0] if self.n_envs == 1 else t
+
+    def _observe(self, with_stats):
+        """obs = vec_to_img(-reconstructor @ signal) * 1e6 (+ reward, Strehl, rms diagnostics)."""
+        lib, st, B, nA = _lib.load(), _lib.stream_ptr(self.device), self.n_envs, self.dm.nValidAct
+        sig = self.wfs._signal
+        _lib.check(lib.aoenv_gemm_tn(_lib.ptr(sig), sig.stride(0), _lib.ptr(self._Rm), self._Rm.stride(0), _lib.ptr(self._rec),
+                                     self._rec.stride(0), B, nA, self.wfs._lds, 1.0, st), "gemm_tn(reconstruct)")
+        _lib.check(lib.aoenv_observe(_lib.ptr(self._rec), self._rec.stride(0), _lib.ptr(self._act_idx), B, nA,
+                                     self.nActuator ** 2, _lib.ptr(self.wfs._stats) if with_stats else None,
+                                     float(self.tel.pixelArea), self._phase_scale, _lib.ptr(self._obs), _lib.ptr(self._reward),
+                                     _lib.ptr(self._strehl), _lib.ptr(self._total_now), _lib.ptr(self._residual_now), st),
+                   "observe")
+
+    def _action_tensor(self, action):
+        a = torch.as_tensor(action, dtype=torch.float32, device=self.device)
+        nAct = self.nActuator
+        if a.ndim == 2:
+            a = a.unsqueeze(0).expand(self.n_envs, -1, -1)
+        return a.reshape(self.n_envs, nAct * nAct).contiguous()
+
+    # ---- gym-style API --------------------------------------------------------------------------------------
+    def reset_soft(self):
+        """OOPAOEnvRazor.py:74-79."""
+        self.action_buffer = []
+        self._observe(False)
+        return self._sq(self._obs).clone()
+
+    def reset(self):
+        raise NotImplementedError("reset() rebuilds the whole simulation in the reference (set_params without arguments, "
+                                  "OOPAOEnvRazor.py:66-71, which raises there too); use set_params(...) then reset_soft()")
+
+    def reset_soft_wfs(self):
+        self.action_buffer = []
+        return self._sq(self.wfs._frame).clone()
+
+    def step(self, i, action):
+        """OOPAOEnvRazor.py:474-514."""
+        lib, st, B = _lib.load(), _lib.stream_ptr(self.device), self.n_envs
+        action = self._action_tensor(action)                               # :479 (img_to_vec * 1e-6 is in the kernel)
+        self.atm.update()                                                  # :482 -> tel.OPD = atm.OPD (lazy)
+        dm_surface = self.dm._opd[self.dm._slot]                           # surface commanded at the previous step
+        self.tel._set_lazy(self.atm._opd, dm_surface)                      # :488 tel*dm
+        self.wfs._measure_terms(self.atm._opd, dm_surface, self.env_offset)  # :488 *wfs  (+ stats for :484,502,506)
+        coefs = self._coefs_buf[self._coefs_slot]                         # zero-padded tails, never written
+        self._coefs_slot ^= 1
+        _lib.check(lib.aoenv_command_update(_lib.ptr(action), _lib.ptr(self._act_idx), B, self.dm.nValidAct,
+                                            self.nActuator ** 2, ctypes.c_float(self.leak), _lib.ptr(coefs), _lib.ptr(self._dm_prev),
+                                            coefs.stride(0), st), "command_update")          # :492-493
+        self.dm._set_coefs_batch(coefs)                                    # coefs setter side effect: next surface
+        self._observe(True)                                                # :496-506
+        if self.total is not None and i is not None and 0 <= i < self._nLoop:
+            self.total[i] = self._total_now
+            self.residual[i] = self._residual_now
+        strehl = self._sq(self._strehl).clone()
+        if self.psf_reward is not None:
+            strehl = self.psf_strehl(*self.psf_reward)
+        self.SR.append(strehl)
+        self.wfsSignal = self.wfs.signal
+        return self._sq(self._obs).clone(), self._sq(self._reward).clone(), strehl, False, {"strehl": strehl}
+
+    def calculate_strehl_AVG(self):
+        """OOPAOEnvRazor.py:589-596 (mean over the episode; here also over environments and, when
+        torch.distributed is initialised, over ranks)."""
+        if len(self.SR) == 0:
+            return float("nan")
+        s = torch.stack([x.reshape(-1) for x in self.SR]).double()
+        tot = torch.stack([s.sum(), torch.tensor(float(s.numel()), dtype=torch.float64, device=s.device)])
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.all_reduce(tot)
+        self.SR = []
+        return float(tot[0] / tot[1])
+
+    def integrator(self):
+        return -self.gainCL * self.vec_to_img(self.wfs.signal.double() @ self.reconstructor.T)
+
+    def get_slopes(self):
+        return self.wfs.signal
+
+    def get_strehl(self):
+        """OOPAOEnvRazor.py:604-605."""
+        ph = self.tel._materialise() * self.tel._pupil_f * self._phase_scale
+        v = ph.reshape(ph.shape[0], -1)[:, self.tel._pupil_idx].double().var(dim=1, unbiased=False)
+        return self._sq(torch.exp(-v).float())
+
+    def sample_noise(self, sigma, use_torch=True):
+        """OOPAOEnvRazor.py:616-619: F @ (sigma * N(0, I)), as an actuator image per environment."""
+        z = torch.randn((self.n_envs, self.dm.nValidAct), generator=self._noise_gen, device=self.device) * sigma
+        return self.vec_to_img(z @ self._F32.T)
+
+    def vec_to_img(self, action_vec, use_torch=True):
+        """OOPAOEnvRazor.py:621-630."""
+        v = torch.as_tensor(action_vec, device=self.device)
+        lead = v.shape[:-1]
+        img = torch.zeros(lead + (self.nActuator, self.nActuator), dtype=v.dtype, device=self.device)
+        img[..., torch.as_tensor(self.xvalid, device=self.device), torch.as_tensor(self.yvalid, device=self.device)] = v
+        return img
+
+    def img_to_vec(self, action):
+        """OOPAOEnvRazor.py:634-641."""
+        a = torch.as_tensor(action, device=self.device)
+        return a[..., torch.as_tensor(self.xvalid, device=self.device), torch.as_tensor(self.yvalid, device=self.device)]
+
+    def change_mag(self, mag):
+        """OOPAOEnvRazor.py:644-647."""
+        self.source.nPhoton = self.source.zeroPoint * 10 ** (-0.4 * mag)
+        self.source.magnitude = mag
+        self.source * self.tel * self.wfs
+
+    def psf_strehl(self, zeroPaddingFactor=4, window=32):
+        """Strehl from the science PSF peak (tel.computePSF(zp); PSF.max()/psf_model_max, caller pattern
+        MAIN_CODE/closedLoopPlayground.py:25-30), evaluated with the pruned-DFT kernel on the central window."""
+        from ..psf import psf_peak
+        if not hasattr(self, "_psf_model_max") or self._psf_model_key != (zeroPaddingFactor, window):
+            zero = torch.zeros((1, self.tel.resolution, self.tel.resolution), dtype=torch.float32, device=self.device)
+            self._psf_model_max = psf_peak(self.tel, zero, None, zeroPaddingFactor, window)[0]
+            self._psf_model_key = (zeroPaddingFactor, window)
+        a, b = self.tel._terms()
+        return self._sq(psf_peak(self.tel, a, b, zeroPaddingFactor, window) / self._psf_model_max)
+

@@ -1,0 +1,156 @@
+"""Mirror of MAIN_CODE/PO4AO/util_simple.py for the environment boundary: TorchWrapper, TimeDelayEnv and the
+GPU-resident EfficientExperienceReplay (sample_contiguous semantics of :103-111)."""
+import torch
+
+
+class _Wrapper:
+    """Attribute-forwarding wrapper (the role gym.Wrapper plays in the reference)."""
+
+    def __init__(self, env):
+        self.env = env
+        self._env = env
+
+    def __getattr__(self, name):
+        return getattr(self.__dict__["env"], name)
+
+
+class TimeDelayEnv(_Wrapper):
+    """util_simple.py:25-52: FIFO of `delay` zero actions in front of env.step."""
+
+    def __init__(self, env, delay):
+        super().__init__(env)
+        self.d = delay
+        self._zero()
+
+    def _zero(self):
+        e = self._env
+        shape = (e.nActuator, e.nActuator) if e.n_envs == 1 else (e.n_envs, e.nActuator, e.nActuator)
+        self.action_buffer = [torch.zeros(shape, dtype=torch.float32, device=e.device) for _ in range(self.d)]
+
+    def reset_soft(self):
+        obs = self._env.reset_soft()
+        self._zero()
+        return obs
+
+    def step(self, i, action):
+        self.action_buffer.append(torch.as_tensor(action, dtype=torch.float32, device=self._env.device))
+        out = self._env.step(i, self.action_buffer[0])
+        del self.action_buffer[0]
+        return out
+
+
+class TorchWrapper(_Wrapper):
+    """util_simple.py:201-221.  The reference converts torch -> numpy -> torch around a host simulation and hands
+    back CPU float32 tensors; this wrapper keeps that contract with pinned staging buffers and asynchronous copies
+    (`host_io=True`, default), or keeps everything on the device (`host_io=False`) for on-GPU policies."""
+
+    def __init__(self, env, host_io=True):
+        super().__init__(env)
+        self.host_io = host_io
+        self._pinned = None
+
+    def _to_host(self, *tensors):
+        if self._pinned is None or any(p.shape != t.shape for p, t in zip(self._pinned, tensors)):
+            self._pinned = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors]
+        for p, t in zip(self._pinned, tensors):
+            p.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self._env.device).synchronize()
+        return [p.clone() for p in self._pinned]
+
+    def step(self, i, action):
+        dev = self._env.device
+        a = torch.as_tensor(action)
+        if a.device != dev:
+            a = a.to(dev, dtype=torch.float32, non_blocking=True)
+        obs, reward, strehl, done, info = self._env.step(i, a)
+        if not self.host_io:
+            return obs, reward, strehl, done, [(k, v) for k, v in info.items()]
+        obs_h, reward_h, strehl_h = self._to_host(obs, reward, strehl)
+        if self._env.n_envs == 1:
+            reward_h, strehl_h = float(reward_h), float(strehl_h)
+        return obs_h, reward_h, strehl_h, done, [("strehl", torch.as_tensor(strehl_h, dtype=torch.float32))]
+
+    def reset_soft(self):
+        obs = self._env.reset_soft()
+        return self._to_host(obs)[0] if self.host_io else obs
+
+
+class ReplaySample:
+    def __init__(self, states, actions, rewards, next_states):
+        self._s, self._a, self._r, self._n = states, actions, rewards, next_states
+
+    def state(self):
+        return self._s
+
+    def action(self):
+        return self._a
+
+    def reward(self):
+        return self._r
+
+    def next_state(self):
+        return self._n
+
+    def __len__(self):
+        return self._s.shape[0]
+
+
+class EfficientExperienceReplay:
+    """util_simple.py:55-128 with the storage on `device` and a batch axis: transitions of all environments of a
+    step are appended together, environment-major within an episode so that `sample_contiguous` still draws
+    windows that stay inside one (environment, episode) trajectory."""
+
+    def __init__(self, state_shape, action_shape, max_size=100000, device="cpu"):
+        self.max_size = max_size
+        self.device = torch.device(device)
+        self.states = torch.empty((max_size, *state_shape), device=self.device)
+        self.next_states = torch.empty((max_size, *state_shape), device=self.device)
+        self.actions = torch.empty((max_size, *action_shape), device=self.device)
+        self.rewards = torch.empty((max_size, 1), device=self.device)
+        self.len = 0
+
+    def append(self, obs, action, reward, next_obs, done=False):
+        if not torch.is_tensor(obs):
+            raise TypeError("should be torch")
+        i = self.len
+        self.states[i], self.next_states[i], self.actions[i] = obs, next_obs, action
+        self.rewards[i] = reward
+        self.len += 1
+
+    def append_episode(self, obs, action, reward, next_obs):
+        """Batched variant: tensors [T, B, ...] of one episode of B environments -> B trajectories of length T."""
+        T, B = obs.shape[0], obs.shape[1]
+        n = T * B
+        sl = slice(self.len, self.len + n)
+        tr = lambda x: x.transpose(0, 1).reshape(n, *x.shape[2:])
+        self.states[sl], self.next_states[sl], self.actions[sl] = tr(obs), tr(next_obs), tr(action)
+        self.rewards[sl] = tr(reward.reshape(T, B, 1))
+        self.len += n
+
+    def sample_contiguous(self, horizon, max_ts, batch_size=32):
+        inds = torch.randint(0, max_ts - (horizon + 1), size=(batch_size,))
+        inds += torch.randint(0, len(self) // max_ts, size=(batch_size,)) * max_ts
+        indices = (inds[:, None] + torch.arange(horizon + 1)[None, :]).reshape(-1).to(self.device)
+        return ReplaySample(self.states[indices], self.actions[indices], self.rewards[indices], self.next_states[indices])
+
+    def sample(self, size=512):
+        inds = torch.randperm(self.len, device=self.device)[:size]
+        return ReplaySample(self.states[inds], self.actions[inds], self.rewards[inds], self.next_states[inds])
+
+    def state(self):
+        return self.states[:self.len]
+
+    def next_state(self):
+        return self.next_states[:self.len]
+
+    def action(self):
+        return self.actions[:self.len]
+
+    def reward(self):
+        return self.rewards[:self.len]
+
+    def __len__(self):
+        return self.len
+
+    def clear(self):
+        self.len = 0

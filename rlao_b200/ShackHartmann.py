@@ -1,0 +1,244 @@
+"""ShackHartmann — mirror of OOPAO/ShackHartmann.py (diffractive, NGS, binning 1), batched over environments.
+
+`tel*wfs` / `wfs.wfs_measure()` run two kernels (include/aoenv.h): aoenv_shwfs_frame (lenslet fields ->
+spots -> detector -> camera frame + per-environment maximum) and aoenv_shwfs_slopes (thresholded centre of
+gravity -> slopes).  Results: `wfs.signal` ([nSignal], or [n_envs, nSignal]; [nSignal, k] after a k-frame
+calibration push as in ShackHartmann.py:674), `wfs.signal_2D`, `wfs.cam.frame`.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .Detector import Detector
+
+_SUPPORTED_N = (4, 6, 8)
+
+
+class ShackHartmann:
+    def __init__(self, nSubap, telescope, lightRatio, threshold_cog=0.01, is_geometric=False, binning_factor=1,
+                 padding_extension_factor=1, threshold_convolution=0.05, shannon_sampling=False, unit_P2V=False):
+        self.tag = "shackHartmann"
+        self.telescope = telescope
+        if telescope.src is None:
+            raise AttributeError("The telescope was not coupled to any source object! Make sure to couple it with an src object using src*tel")
+        if is_geometric:
+            raise NotImplementedError("geometric SH-WFS is out of scope (diffractive path only)")
+        if binning_factor != 1 or padding_extension_factor > 2:
+            raise NotImplementedError("binning_factor != 1 / extended field of view are out of scope")
+        if getattr(telescope.src, "type", "NGS") == "LGS":
+            raise NotImplementedError("LGS spot elongation is out of scope")
+        self.device = telescope.device
+        self.n_envs = telescope.n_envs
+        self._is_geometric = False
+        self.nSubap = int(nSubap)
+        self._lightRatio = lightRatio
+        self.binning_factor = 1
+        self.zero_padding = 2
+        self.padding_extension_factor = padding_extension_factor
+        self.threshold_convolution = threshold_convolution
+        self.threshold_cog = threshold_cog
+        self.shannon_sampling = shannon_sampling
+        self.unit_P2V = unit_P2V
+        R = telescope.resolution
+        if R % self.nSubap != 0:
+            raise ValueError("telescope.resolution must be a multiple of nSubap")
+        self.n_pix_subap = R // self.nSubap
+        if self.n_pix_subap not in _SUPPORTED_N:
+            raise NotImplementedError(f"{self.n_pix_subap} pixels per subaperture: compiled sizes are {_SUPPORTED_N}")
+        self.n_pix_subap_init = self.n_pix_subap
+        self.n_pix_lenslet_init = self.n_pix_subap * self.zero_padding
+        self.n_pix_lenslet = self.n_pix_lenslet_init
+        self.is_extended = False
+        self.is_LGS = False
+        self.cam = Detector(round(self.nSubap * self.n_pix_subap))
+        self.cam.photonNoise = 0
+        self.cam.readoutNoise = 0
+        src = telescope.src
+        self.fov_lenslet_arcsec = (self.n_pix_subap * 206265 * self.binning_factor / self.padding_extension_factor
+                                   * src.wavelength / (telescope.D / self.nSubap)) / (1 + self.shannon_sampling)
+        self.fov_pixel_arcsec = self.fov_lenslet_arcsec / self.n_pix_subap
+        self.fov_pixel_binned_arcsec = self.fov_lenslet_arcsec / self.n_pix_subap_init
+        self.get_camera_frame_multi = False
+        ii, jj = np.meshgrid(np.arange(self.nSubap), np.arange(self.nSubap), indexing="ij")
+        self.index_x, self.index_y = ii.reshape(-1), jj.reshape(-1)
+        self.initialize_flux()
+        self._select_valid()
+        B = self.n_envs
+        self._frame = torch.zeros((B, R, R), dtype=torch.float32, device=self.device)
+        self._envmax = torch.zeros((B,), dtype=torch.int32, device=self.device)
+        self._stats = torch.zeros((B, 4), dtype=torch.float64, device=self.device)
+        self._signal = torch.zeros((B, self._lds), dtype=torch.float32, device=self.device)
+        self._signal_is_multi = False
+        self._ones = torch.ones((R, R), dtype=torch.float32, device=self.device)
+        self.initialize_wfs()
+
+    # ---- flux / valid subapertures (ShackHartmann.py:215-240,327-338) -------------------------------------
+    def initialize_flux(self, input_flux_map=None):
+        src, nS, n = self.telescope.src, self.nSubap, self.n_pix_subap
+        flux = np.asarray(src.fluxMap if input_flux_map is None else input_flux_map.T, dtype=np.float64)
+        self.photon_per_subaperture = flux.reshape(nS, n, nS, n).sum(axis=(1, 3)).reshape(-1)
+        self.photon_per_subaperture_2D = self.photon_per_subaperture.reshape(nS, nS)
+        self._amp = torch.as_tensor(np.sqrt(flux), dtype=torch.float32, device=self.device).contiguous()
+        self.current_nPhoton = src.nPhoton
+        self._flux_version = getattr(src, "_flux_version", 0)
+
+    def _select_valid(self):
+        nS = self.nSubap
+        pps = self.photon_per_subaperture
+        self.valid_subapertures = (pps >= self._lightRatio * pps.max()).reshape(nS, nS)
+        self.valid_subapertures_1D = self.valid_subapertures.reshape(-1)
+        self.validLenslets_x, self.validLenslets_y = np.where(self.valid_subapertures)
+        self.valid_slopes_maps = np.concatenate((self.valid_subapertures, self.valid_subapertures))
+        self.nValidSubaperture = int(self.valid_subapertures.sum())
+        self.nSignal = 2 * self.nValidSubaperture
+        self._lds = (self.nSignal + 15) // 16 * 16
+        dev = self.device
+        self._valid_u8 = torch.as_tensor(self.valid_subapertures_1D.astype(np.uint8), device=dev).contiguous()
+        self._valid_idx = torch.as_tensor(np.nonzero(self.valid_subapertures_1D)[0].astype(np.int32), device=dev).contiguous()
+
+    @property
+    def lightRatio(self):
+        return self._lightRatio
+
+    @lightRatio.setter
+    def lightRatio(self, val):
+        """ShackHartmann.py:737-764."""
+        self._lightRatio = val
+        self._select_valid()
+        self._signal = torch.zeros((self.n_envs, self._lds), dtype=torch.float32, device=self.device)
+        self.initialize_wfs()
+
+    @property
+    def is_geometric(self):
+        return self._is_geometric
+
+    @is_geometric.setter
+    def is_geometric(self, val):
+        if val:
+            raise NotImplementedError("geometric SH-WFS is out of scope")
+
+    # ---- kernels ------------------------------------------------------------------------------------------
+    def _run(self, opd_a, opd_b, pupil, scale, shared_max, det, frame, envmax, stats, slopes, ref_xy, inv_units):
+        lib, st = _lib.load(), _lib.stream_ptr(self.device)
+        F = opd_a.shape[0]
+        _lib.check(lib.aoenv_shwfs_frame(_lib.ptr(opd_a), _lib.ptr(opd_b), _lib.ptr(pupil), _lib.ptr(self._amp),
+                                         _lib.ptr(self._valid_u8), F, self.nSubap, self.n_pix_subap, C.c_float(scale),
+                                         C.byref(det) if det is not None else None, int(shared_max), _lib.ptr(frame),
+                                         _lib.ptr(envmax), _lib.ptr(stats), st), "shwfs_frame")
+        _lib.check(lib.aoenv_shwfs_slopes(_lib.ptr(frame), _lib.ptr(envmax), int(shared_max), _lib.ptr(self._valid_idx),
+                                          self.nValidSubaperture, _lib.ptr(ref_xy), C.c_float(inv_units),
+                                          C.c_float(self.threshold_cog), F, self.nSubap, self.n_pix_subap,
+                                          _lib.ptr(slopes), slopes.stride(0), st), "shwfs_slopes")
+
+    def _measure_terms(self, opd_a, opd_b, env_offset=0):
+        """Per-environment measurement (single-frame branch, ShackHartmann.py:522-601) on OPD = opd_a + opd_b."""
+        if self._flux_version != getattr(self.telescope.src, "_flux_version", 0) or self.current_nPhoton != self.telescope.src.nPhoton:
+            self.initialize_flux()                                       # ShackHartmann.py:515-517,534
+        tel = self.telescope
+        det = self.cam.as_struct(env_offset)
+        self._run(opd_a, opd_b, tel._pupil_f, 2 * math.pi / tel.src.wavelength, False, det, self._frame, self._envmax,
+                  self._stats, self._signal, self._ref_xy, 1.0 / self.slopes_units)
+        self._signal_is_multi = False
+        self.cam.frame = self._frame[0] if self.n_envs == 1 else self._frame
+
+    def measure_frames(self, opd):
+        """Multi-frame branch (ShackHartmann.py:605-674): k wavefronts [k, R, R] (OPD_no_pupil, metres), no
+        detector, ONE centroiding threshold for the whole batch.  Returns signal [k, nSignal]."""
+        if self.cam.photonNoise or self.cam.readoutNoise:
+            raise NotImplementedError("noisy multi-frame measurements are not supported (calibrate with noise='off')")
+        k, R = opd.shape[0], self.telescope.resolution
+        frame = torch.empty((k, R, R), dtype=torch.float32, device=self.device)
+        envmax = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        slopes = torch.zeros((k, self._lds), dtype=torch.float32, device=self.device)
+        tel = self.telescope
+        self._run(opd.contiguous(), None, tel._pupil_f, 2 * math.pi / tel.src.wavelength, True, None, frame, envmax, None,
+                  slopes, self._ref_xy, 1.0 / self.slopes_units)
+        return slopes[:, :self.nSignal]
+
+    def wfs_measure(self, phase_in=None):
+        """ShackHartmann.py:511-695."""
+        tel = self.telescope
+        if phase_in is not None:
+            ph = torch.as_tensor(phase_in, dtype=torch.float32, device=self.device)
+            ph = ph.unsqueeze(0) if ph.ndim == 2 else ph
+            lam = tel.src.wavelength
+            tel.OPD = ph * (lam / (2 * math.pi))
+        a, b = tel._terms()
+        if a.shape[0] == self.n_envs:
+            self._measure_terms(a, b)
+        else:
+            opd = a if b is None else a + b
+            self._multi_signal = self.measure_frames(opd)
+            self._signal_is_multi = True
+
+    def sh_measure(self, phase_in):
+        self.wfs_measure(phase_in=phase_in)
+
+    # ---- results ------------------------------------------------------------------------------------------
+    @property
+    def signal(self):
+        if self._signal_is_multi:
+            return self._multi_signal.T                                   # [nSignal, k] as ShackHartmann.py:674
+        s = self._signal[:, :self.nSignal]
+        return s[0] if self.n_envs == 1 else s
+
+    @property
+    def signal_2D(self):
+        s = self._signal[:, :self.nSignal]
+        nS, nV = self.nSubap, self.nValidSubaperture
+        out = torch.zeros((s.shape[0], 2 * nS, nS), dtype=torch.float32, device=self.device)
+        vx = torch.as_tensor(self.validLenslets_x, device=self.device)
+        vy = torch.as_tensor(self.validLenslets_y, device=self.device)
+        out[:, vx, vy] = s[:, :nV]
+        out[:, vx + nS, vy] = s[:, nV:]
+        return out[0] if self.n_envs == 1 else out
+
+    # ---- initialisation (ShackHartmann.py:254-312) ----------------------------------------------------------
+    def initialize_wfs(self):
+        self.isInitialized = False
+        tel, dev = self.telescope, self.device
+        R, nV, nS = tel.resolution, self.nValidSubaperture, self.nSubap
+        lam = tel.src.wavelength
+        zero_ref = torch.zeros((2, nV), dtype=torch.float32, device=dev)
+        frame = torch.empty((1, R, R), dtype=torch.float32, device=dev)
+        envmax = torch.zeros((1,), dtype=torch.int32, device=dev)
+        raw = torch.zeros((1, self._lds), dtype=torch.float32, device=dev)
+
+        def centroids(opd):
+            self._run(opd.reshape(1, R, R).contiguous(), None, tel._pupil_f, 2 * math.pi / lam, False, None, frame, envmax,
+                      None, raw, zero_ref, 1.0)
+            return raw[0, :2 * nV].clone()
+
+        flat = centroids(torch.zeros((R, R), dtype=torch.float32, device=dev))
+        self._ref_xy = flat.reshape(2, nV).contiguous()
+        ref2d = np.zeros((2 * nS, nS))
+        f = flat.double().cpu().numpy()
+        ref2d[self.validLenslets_x, self.validLenslets_y] = f[:nV]
+        ref2d[self.validLenslets_x + nS, self.validLenslets_y] = f[nV:]
+        self.reference_slopes_maps = ref2d
+        # slope units from five tip ramps.  Quirk kept (ShackHartmann.py:288-290): tel.pupil is an int array, so
+        # `Tip[tel.pupil]` fancy-indexes rows 0/1 and the ramp is normalised by the std of the FULL ramp.
+        ramp = np.linspace(0, np.pi, R, endpoint=False)
+        tip = np.tile(ramp[None, :], (R, 1))
+        if not self.unit_P2V:
+            tip = tip / np.std(tip[np.asarray(tel.pupil).astype(int)])
+        amp = 10e-9
+        mean_slope = np.zeros(5)
+        tip_dev = torch.as_tensor(tip, dtype=torch.float64, device=dev)
+        for i in range(5):
+            opd = (tip_dev * ((i - 2) * amp)).to(torch.float32)
+            c = centroids(opd)
+            mean_slope[i] = float((c[:nV].double() - self._ref_xy[0].double()).mean())
+        self.p = np.polyfit(np.linspace(-2, 2, 5) * amp, mean_slope, deg=1)
+        self.slopes_units = float(np.abs(self.p[0]) * (lam / 2 / np.pi))
+        self.isInitialized = True
+        tel.resetOPD()
+
+    def __mul__(self, obj):
+        """wfs*cam (ShackHartmann.py:769-782): the detector already ran inside the frame kernel."""
+        if getattr(obj, "tag", None) != "detector":
+            print("Error light propagated to the wrong type of object")
+        return -1

@@ -1,0 +1,93 @@
+"""ctypes binding of libaoenv_b200.so (include/aoenv.h).
+
+There is no CPU fallback: if the shared library is missing the import of any compute path raises
+`AOEnvLibraryError` telling the user how to build it (`python -c "import __graft_entry__ as g; g.build()"`
+or `bash rlao_b200/csrc/build.sh`).
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libaoenv_b200.so")
+
+
+class AOEnvLibraryError(RuntimeError):
+    pass
+
+
+class DetectorStruct(C.Structure):
+    """aoenv_detector_t (include/aoenv.h)."""
+    _fields_ = [
+        ("photon_noise", C.c_int32), ("sensor_emccd", C.c_int32), ("has_fwc", C.c_int32), ("bits", C.c_int32),
+        ("qe", C.c_float), ("dark_electrons", C.c_float), ("fwc", C.c_float), ("gain", C.c_float),
+        ("readout_noise", C.c_float), ("reserved", C.c_uint32), ("seed", C.c_uint64), ("frame_counter", C.c_uint64),
+    ]
+
+
+_vp, _i, _f, _u64, _d = C.c_void_p, C.c_int, C.c_float, C.c_uint64, C.c_double
+
+# name -> argtypes, exactly the prototypes of include/aoenv.h
+PROTOTYPES = {
+    "aoenv_atm_gather": [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _u64, _u64, _vp, _i, _vp],
+    "aoenv_atm_scatter": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp],
+    "aoenv_map_minmax": [_vp, _i, _i, _i, _vp, _vp],
+    "aoenv_atm_phase": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp],
+    "aoenv_gemm_tn": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _f, _vp],
+    "aoenv_shwfs_frame": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i, _vp, _vp, _vp, _vp],
+    "aoenv_shwfs_slopes": [_vp, _vp, _i, _vp, _i, _vp, _f, _f, _i, _i, _i, _vp, _i, _vp],
+    "aoenv_command_update": [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _i, _vp],
+    "aoenv_observe": [_vp, _i, _vp, _i, _i, _i, _vp, _d, _f, _vp, _vp, _vp, _vp, _vp, _vp],
+    "aoenv_psf_peak": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp],
+}
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (once) and declares every prototype."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AOEnvLibraryError(
+            f"{LIB_PATH} not found: the CUDA extension has not been built. Build it with "
+            "`bash rlao_b200/csrc/build.sh` (needs nvcc with sm_100a support). rlao_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.aoenv_abi_version.restype = C.c_int
+    lib.aoenv_last_error.restype = C.c_char_p
+    lib.aoenv_launch_count.restype = C.c_uint64
+    for name, args in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise RuntimeError(f"libaoenv_b200 {what} failed ({rc}): {load().aoenv_last_error().decode()}")
+
+
+def ptr(t):
+    """Device (or host) address of a tensor, or NULL."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def launch_count():
+    return int(load().aoenv_launch_count())
+
+
+def require_cuda(device):
+    if not torch.cuda.is_available():
+        raise AOEnvLibraryError("rlao_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    dev = torch.device(device if device is not None else "cuda:0")
+    if dev.type != "cuda":
+        raise AOEnvLibraryError(f"rlao_b200 objects live on CUDA devices, got {dev}")
+    return dev

@@ -1,0 +1,27 @@
+// Error plumbing, ABI version and launch accounting for libaoenv_b200.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace aoenv {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+}  // namespace aoenv
+
+extern "C" {
+
+int aoenv_abi_version(void) { return AOENV_ABI_VERSION; }
+const char* aoenv_last_error(void) { return aoenv::g_err; }
+uint64_t aoenv_launch_count(void) { return aoenv::g_launches.load(); }
+
+}  // extern "C"

@@ -1,0 +1,13 @@
+#!/usr/bin/env bash
+# Builds libaoenv_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU).
+set -euo pipefail
+cd "$(dirname "$0")"
+OUT=../libaoenv_b200.so
+SRCS="api.cu atm.cu gemm.cu wfs.cu ctrl.cu"
+[ -f psf.cu ] && SRCS="$SRCS psf.cu"
+[ -f gemm_tc.cu ] && SRCS="$SRCS gemm_tc.cu"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+$NVCC -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
+      -Xcompiler -fPIC,-O2,-Wall -Xptxas -v --shared -o "$OUT" $SRCS 2>&1 | tee build.log | grep -E "error|warning|spill|Used" || true
+test -f "$OUT"
+echo "built $OUT"

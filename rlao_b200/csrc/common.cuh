@@ -1,0 +1,95 @@
+// Shared device/host helpers for libaoenv_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/aoenv.h"
+
+namespace aoenv {
+
+extern thread_local char g_err[512];
+extern std::atomic<uint64_t> g_launches;
+
+int fail(int code, const char* fmt, ...);
+
+#define AOENV_CHECK_ARG(cond, ...)                         \
+  do {                                                     \
+    if (!(cond)) return ::aoenv::fail(-2, __VA_ARGS__);    \
+  } while (0)
+
+#define AOENV_LAUNCH_CHECK(name)                                                        \
+  do {                                                                                  \
+    ::aoenv::g_launches.fetch_add(1, std::memory_order_relaxed);                        \
+    cudaError_t e__ = cudaGetLastError();                                               \
+    if (e__ != cudaSuccess) return ::aoenv::fail(-3, "%s: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+// ---- monotone float <-> int encoding so atomicMax/atomicMin on int32 order floats ----------------------
+__device__ __forceinline__ int32_t float_to_ordered(float f) {
+  int32_t i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int32_t i) {
+  return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- Philox4x32-10 counter-based generator (Salmon et al. 2011) ------------------------------------------
+struct Philox {
+  uint32_t key[2];
+  __device__ __forceinline__ Philox(uint64_t seed) {
+    key[0] = (uint32_t)seed;
+    key[1] = (uint32_t)(seed >> 32);
+  }
+  __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+    uint32_t k0 = key[0], k1 = key[1];
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+      c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+
+// uniform in (0, 1]
+__device__ __forceinline__ float u32_to_unit(uint32_t x) { return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f); }
+
+// two standard normals from two 32-bit words (Box-Muller)
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  const float u1 = u32_to_unit(a);
+  const float u2 = u32_to_unit(b);
+  const float r = sqrtf(-2.0f * logf(u1));
+  float s, c;
+  sincospif(2.0f * u2, &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+}  // namespace aoenv

@@ -1,0 +1,317 @@
+// Shack-Hartmann wavefront sensor + detector (OOPAO/ShackHartmann.py:511-601, OOPAO/Detector.py:190-301),
+// batched over environments.  One thread owns one lenslet: its n x n field lives in registers, the zero-padded
+// 2n-point DFTs are done as two passes of constant-twiddle complex FMAs (only the n non-zero inputs are
+// visited), intensities are binned 2x2 on the fly and pushed through the detector chain before the single
+// store of the camera frame.
+#include <mutex>
+
+#include "common.cuh"
+
+namespace aoenv {
+
+constexpr int kMaxN = 8;                 // pixels per lenslet side
+// c_tw[u * n + a] = exp(-i pi (a + n/2) (2u + N + 1) / N),  N = 2n: the N-point DFT kernel restricted to the n
+// non-zero inputs (which sit at padded positions n/2 .. n/2+n-1, ShackHartmann.py:344), times the half-pixel
+// phasor exp(-i pi (N+1)/N x) of ShackHartmann.py:208-209.
+__constant__ float2 c_tw[2 * kMaxN * kMaxN];
+static int g_tw_n[64] = {0};             // per device: n for which c_tw is currently valid
+static std::mutex g_tw_mutex;
+
+static int ensure_twiddles(int n, cudaStream_t stream) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_tw_mutex);
+  if (dev < 64 && g_tw_n[dev] == n) return 0;
+  const int N = 2 * n;
+  float2 h[2 * kMaxN * kMaxN];
+  for (int u = 0; u < N; ++u)
+    for (int a = 0; a < n; ++a) {
+      const long m = ((long)(a + n / 2) * (2 * u + N + 1)) % (2L * N);
+      const double ang = -M_PI * (double)m / (double)N;
+      h[u * n + a] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+  // synchronous on purpose: `h` is a stack buffer; happens once per (device, n)
+  cudaError_t e = cudaMemcpyToSymbol(c_tw, h, sizeof(float2) * N * n);
+  if (e != cudaSuccess) return fail(-3, "twiddle upload: %s", cudaGetErrorString(e));
+  if (dev < 64) g_tw_n[dev] = n;
+  (void)stream;
+  return 0;
+}
+
+// ---- per-pixel random stream: Philox counter = (pixel, env, frame_lo, frame_hi16 | draw) ---------------------
+struct PixelRng {
+  Philox ph;
+  uint32_t c0, c1, c2, c3hi, sub, have;
+  uint4 buf;
+  __device__ __forceinline__ PixelRng(uint64_t seed, uint32_t pixel, uint32_t env, uint64_t frame)
+      : ph(seed), c0(pixel), c1(env), c2((uint32_t)frame), c3hi(((uint32_t)(frame >> 32)) << 16), sub(0), have(0) {}
+  __device__ __forceinline__ uint32_t next() {
+    if (have == 0) {
+      buf = ph(c0, c1, c2, c3hi | (sub & 0xffffu));
+      ++sub;
+      have = 4;
+    }
+    const uint32_t r = have == 4 ? buf.x : have == 3 ? buf.y : have == 2 ? buf.z : buf.w;
+    --have;
+    return r;
+  }
+  __device__ __forceinline__ float uniform() { return u32_to_unit(next()); }
+  __device__ __forceinline__ float normal() {
+    const uint32_t a = next(), b = next();
+    return box_muller(a, b).x;
+  }
+};
+
+// Poisson(lambda): inversion by sequential search below 12, Hormann's PTRS transformed rejection above
+// (the algorithm numpy's legacy generator also uses for lambda >= 10).
+__device__ float poisson_draw(float lam, PixelRng& rng) {
+  if (!(lam > 0.f)) return 0.f;
+  if (lam < 12.f) {
+    float p = __expf(-lam), F = p;
+    const float u = rng.uniform() * 0.99999994f;
+    int k = 0;
+    while (u > F && k < 200) {
+      ++k;
+      p *= lam / (float)k;
+      F += p;
+    }
+    return (float)k;
+  }
+  const float slam = sqrtf(lam), loglam = logf(lam);
+  const float bb = 0.931f + 2.53f * slam;
+  const float a = -0.059f + 0.02483f * bb;
+  const float invalpha = 1.1239f + 1.1328f / (bb - 3.4f);
+  const float vr = 0.9277f - 3.6224f / (bb - 2.f);
+  for (int it = 0; it < 64; ++it) {
+    const float U = rng.uniform() - 0.5f;
+    const float V = rng.uniform();
+    const float us = 0.5f - fabsf(U);
+    const float k = floorf((2.f * a / us + bb) * U + lam + 0.43f);
+    if (us >= 0.07f && V <= vr) return k;
+    if (k < 0.f || (us < 0.013f && V > us)) continue;
+    if (logf(V) + logf(invalpha) - logf(a / (us * us) + bb) <= -lam + k * loglam - lgammaf(k + 1.f)) return k;
+  }
+  return rintf(lam);
+}
+
+struct DetParams {
+  aoenv_detector_t d;
+  int enabled;
+};
+
+// OOPAO/Detector.py:279-301 (integrate) then :232-276 (readout), one pixel.
+__device__ __forceinline__ float detector_pixel(float x, const DetParams& dp, uint32_t pixel, uint32_t env) {
+  if (!dp.enabled) return x;
+  const aoenv_detector_t& d = dp.d;
+  PixelRng rng(d.seed, pixel, env, d.frame_counter);
+  if (d.photon_noise) x = poisson_draw(x, rng);
+  x *= d.qe;
+  if (d.dark_electrons > 0.f) x += poisson_draw(d.dark_electrons, rng);
+  if (d.has_fwc) x = fminf(fmaxf(x, 0.f), d.fwc);
+  if (d.sensor_emccd) x *= d.gain;
+  if (d.readout_noise != 0.f) x += rintf(rng.normal() * d.readout_noise);
+  if (!d.sensor_emccd) x *= d.gain;
+  if (d.bits > 0) {
+    const float full = (float)((1u << d.bits) - 1u);
+    x = truncf(x / d.fwc * full);
+    x = fminf(x, full);
+  }
+  return x;
+}
+
+template <int n>
+__global__ void __launch_bounds__(128)
+shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ opd_b, const float* __restrict__ pupil,
+                   const float* __restrict__ amp, const uint8_t* __restrict__ valid, int nS, float phase_scale,
+                   const __grid_constant__ DetParams det, int shared_max, float* __restrict__ frame,
+                   int32_t* __restrict__ envmax, double* __restrict__ stats) {
+  constexpr int N = 2 * n;
+  const int R = nS * n;
+  const int b = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = k < nS * nS;
+  const int li = active ? k / nS : 0, lj = active ? k % nS : 0;
+  const bool lit = active && valid[k] != 0;
+
+  float er[n][n], ei[n][n];   // field E[a][b] = tile^T (ShackHartmann.py:341-345 tiles phase.T)
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (active) {
+    const size_t tile = (size_t)(li * n) * R + lj * n;
+    const float* __restrict__ pa = opd_a + (size_t)b * R * R + tile;
+    const float* __restrict__ pb = opd_b ? opd_b + (size_t)b * R * R + tile : nullptr;
+#pragma unroll
+    for (int bb = 0; bb < n; ++bb) {
+#pragma unroll
+      for (int aa = 0; aa < n; ++aa) {
+        const int o = bb * R + aa;
+        const float a = __ldg(pa + o);
+        const float t = pb ? a + __ldg(pb + o) : a;
+        const float pu = __ldg(pupil + tile + o);
+        if (pu > 0.f) {
+          s0 += (double)a;
+          s1 += (double)a * (double)a;
+          s2 += (double)t;
+          s3 += (double)t * (double)t;
+        }
+        float sn, cs;
+        sincosf(t * pu * phase_scale, &sn, &cs);
+        const float am = lit ? __ldg(amp + tile + o) : 0.f;
+        er[aa][bb] = am * cs;
+        ei[aa][bb] = am * sn;
+      }
+    }
+  }
+
+  if (stats != nullptr) {
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+    __shared__ double sh[4][4];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sh[w][0] = s0; sh[w][1] = s1; sh[w][2] = s2; sh[w][3] = s3; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      double t = 0.0;
+      const int nw = blockDim.x >> 5;
+      for (int q = 0; q < nw; ++q) t += sh[q][threadIdx.x];
+      atomicAdd(&stats[(size_t)b * 4 + threadIdx.x], t);
+    }
+  }
+
+  float vmax = -INFINITY;
+  if (active) {
+    float* __restrict__ fout = frame + (size_t)b * R * R + (size_t)(li * n) * R + lj * n;
+    const uint32_t pix0 = (uint32_t)((li * n) * R + lj * n);
+    const float norm = 1.0f / (float)(N * N);
+    for (int p = 0; p < n; ++p) {       // output (binned) row of the spot
+      float acc[n];
+#pragma unroll
+      for (int q = 0; q < n; ++q) acc[q] = 0.f;
+      if (lit) {
+#pragma unroll
+        for (int du = 0; du < 2; ++du) {
+          const int u = 2 * p + du;
+          float yr[n], yi[n];
+#pragma unroll
+          for (int bb = 0; bb < n; ++bb) { yr[bb] = 0.f; yi[bb] = 0.f; }
+#pragma unroll
+          for (int aa = 0; aa < n; ++aa) {
+            const float2 g = c_tw[u * n + aa];
+#pragma unroll
+            for (int bb = 0; bb < n; ++bb) {
+              yr[bb] = fmaf(g.x, er[aa][bb], fmaf(-g.y, ei[aa][bb], yr[bb]));
+              yi[bb] = fmaf(g.x, ei[aa][bb], fmaf(g.y, er[aa][bb], yi[bb]));
+            }
+          }
+#pragma unroll
+          for (int v = 0; v < N; ++v) {
+            float fr = 0.f, fi = 0.f;
+#pragma unroll
+            for (int bb = 0; bb < n; ++bb) {
+              const float2 g = c_tw[v * n + bb];
+              fr = fmaf(yr[bb], g.x, fmaf(-yi[bb], g.y, fr));
+              fi = fmaf(yr[bb], g.y, fmaf(yi[bb], g.x, fi));
+            }
+            acc[v >> 1] = fmaf(fr, fr, fmaf(fi, fi, acc[v >> 1]));
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < n; ++q) {
+        const float val = detector_pixel(acc[q] * norm, det, pix0 + (uint32_t)(p * R + q), (uint32_t)b);
+        fout[(size_t)p * R + q] = val;
+        if (lit) vmax = fmaxf(vmax, val);
+      }
+    }
+  }
+  vmax = warp_max(vmax);
+  if ((threadIdx.x & 31) == 0 && vmax > -INFINITY) atomicMax(&envmax[shared_max ? 0 : b], float_to_ordered(vmax));
+}
+
+// centroid + slopes: one thread per (valid lenslet, environment)
+__global__ void __launch_bounds__(128)
+shwfs_slopes_kernel(const float* __restrict__ frame, const int32_t* __restrict__ envmax, int shared_max,
+                    const int32_t* __restrict__ valid_idx, int nV, const float* __restrict__ ref_xy, float inv_units,
+                    float threshold_cog, int nS, int n, float* __restrict__ slopes, int lds) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nV) return;
+  const int R = nS * n;
+  const int k = __ldg(&valid_idx[t]);
+  const int li = k / nS, lj = k % nS;
+  const float thr = threshold_cog * ordered_to_float(__ldg(&envmax[shared_max ? 0 : b]));
+  const float* __restrict__ f = frame + (size_t)b * R * R + (size_t)(li * n) * R + lj * n;
+  float s = 0.f, sx = 0.f, sy = 0.f;
+  for (int p = 0; p < n; ++p)
+    for (int q = 0; q < n; ++q) {
+      float v = __ldg(f + (size_t)p * R + q);
+      v = v < thr ? 0.f : v;
+      s += v;
+      sx = fmaf(v, (float)p, sx);   // axis 1 of maps_intensity -> centroid[:,0] -> SX (ShackHartmann.py:321,596)
+      sy = fmaf(v, (float)q, sy);   // axis 2 -> centroid[:,1] -> SY
+    }
+  float cx = sx / s, cy = sy / s;
+  if (!isfinite(cx)) cx = 0.f;      // ShackHartmann.py:583-593
+  if (!isfinite(cy)) cy = 0.f;
+  slopes[(size_t)b * lds + t] = (cx - __ldg(&ref_xy[t])) * inv_units;
+  slopes[(size_t)b * lds + nV + t] = (cy - __ldg(&ref_xy[nV + t])) * inv_units;
+}
+
+__global__ void envmax_init_kernel(int32_t* __restrict__ envmax, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) envmax[i] = float_to_ordered(-INFINITY);
+}
+
+}  // namespace aoenv
+
+using namespace aoenv;
+
+extern "C" {
+
+int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil, const float* amp,
+                      const uint8_t* valid, int B, int nS, int n, float phase_scale, const aoenv_detector_t* det,
+                      int shared_max, float* frame, int32_t* envmax, double* stats, void* stream) {
+  AOENV_CHECK_ARG(B > 0 && B <= 65535 && nS > 0, "shwfs_frame: bad shape B=%d nS=%d", B, nS);
+  AOENV_CHECK_ARG(n == 4 || n == 6 || n == 8, "shwfs_frame: %d pixels per lenslet is not a compiled size (4, 6, 8)", n);
+  cudaStream_t s = (cudaStream_t)stream;
+  DetParams dp;
+  dp.enabled = det != nullptr;
+  if (det) {
+    dp.d = *det;
+    AOENV_CHECK_ARG(!(det->bits > 0 && !det->has_fwc), "shwfs_frame: ADC without a full-well capacity is not supported");
+    AOENV_CHECK_ARG(det->bits >= 0 && det->bits < 31, "shwfs_frame: bits=%d", det->bits);
+  }
+  int rc = ensure_twiddles(n, s);
+  if (rc) return rc;
+  envmax_init_kernel<<<(B + 255) / 256, 256, 0, s>>>(envmax, shared_max ? 1 : B);
+  AOENV_LAUNCH_CHECK("envmax_init");
+  if (stats) {
+    cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 4 * (size_t)B, s);
+    if (e != cudaSuccess) return fail(-3, "shwfs_frame memset: %s", cudaGetErrorString(e));
+  }
+  dim3 grid((nS * nS + 127) / 128, B);
+#define AOENV_WFS_CASE(NN)                                                                                   \
+  case NN:                                                                                                   \
+    shwfs_frame_kernel<NN><<<grid, 128, 0, s>>>(opd_a, opd_b, pupil, amp, valid, nS, phase_scale, dp, shared_max, \
+                                                frame, envmax, stats);                                       \
+    break;
+  switch (n) {
+    AOENV_WFS_CASE(4)
+    AOENV_WFS_CASE(6)
+    AOENV_WFS_CASE(8)
+  }
+#undef AOENV_WFS_CASE
+  AOENV_LAUNCH_CHECK("shwfs_frame");
+  return 0;
+}
+
+int aoenv_shwfs_slopes(const float* frame, const int32_t* envmax, int shared_max, const int32_t* valid_idx, int nV,
+                       const float* ref_xy, float inv_units, float threshold_cog, int B, int nS, int n, float* slopes,
+                       int lds, void* stream) {
+  AOENV_CHECK_ARG(B > 0 && B <= 65535 && nV > 0 && lds >= 2 * nV, "shwfs_slopes: bad shape B=%d nV=%d lds=%d", B, nV, lds);
+  dim3 grid((nV + 127) / 128, B);
+  shwfs_slopes_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(frame, envmax, shared_max, valid_idx, nV, ref_xy,
+                                                              inv_units, threshold_cog, nS, n, slopes, lds);
+  AOENV_LAUNCH_CHECK("shwfs_slopes");
+  return 0;
+}
+
+}  // extern "C"

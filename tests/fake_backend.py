@@ -1,0 +1,225 @@
+"""CPU stand-in for libaoenv_b200.so used ONLY by the `-m "not gpu"` tests to exercise the Python host layer
+(object protocol, step sequencing, buffer bookkeeping) without a GPU.  It implements the C ABI of
+include/aoenv.h on raw host addresses with numpy, following the oracle's arithmetic.  It is test
+infrastructure: the product never imports it and has no CPU path."""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from oracle.ao_oracle import ShackHartmannOracle
+
+
+def _arr(ptr, shape, dtype=np.float32):
+    if ptr is None:
+        return None
+    addr = ptr.value if isinstance(ptr, C.c_void_p) else int(ptr)
+    if addr is None or addr == 0:
+        return None
+    n = int(np.prod(shape))
+    ct = {np.float32: C.c_float, np.int32: C.c_int32, np.uint8: C.c_uint8, np.float64: C.c_double}[dtype]
+    return np.ctypeslib.as_array((ct * n).from_address(addr)).reshape(shape)
+
+
+def _val(x):
+    return x.value if hasattr(x, "value") else x
+
+
+def _f2o(f):
+    i = np.float32(f).view(np.int32)
+    return i if i >= 0 else np.int32(i ^ np.int32(0x7fffffff))
+
+
+def _o2f(i):
+    i = np.int32(i)
+    return (i if i >= 0 else np.int32(i ^ np.int32(0x7fffffff))).view(np.float32)
+
+
+class FakeLib:
+    def __init__(self):
+        self.launches = 0
+        self.rs = np.random.RandomState(123)
+
+    def aoenv_abi_version(self):
+        return 1
+
+    def aoenv_last_error(self):
+        return b""
+
+    def aoenv_launch_count(self):
+        return self.launches
+
+    # ---- atmosphere ------------------------------------------------------------------------------------
+    def aoenv_atm_gather(self, map_, B, M, pitch, sx, sy, inner_rc, nI, nO, xi, seed, stream_id, zx, ldz, stream):
+        self.launches += 1
+        m = _arr(map_, (B, M, pitch))
+        rc = _arr(inner_rc, (nI, 2), np.int32)
+        z = _arr(zx, (B, ldz))
+        z[:] = 0
+        z[:, :nI] = m[:, rc[:, 0] - sy, rc[:, 1] - sx]
+        x = _arr(xi, (B, nO))
+        z[:, nI:nI + nO] = x if x is not None else self.rs.normal(size=(B, nO))
+        return 0
+
+    def aoenv_atm_scatter(self, map_in, map_out, B, M, pitch, sx, sy, nO, X, ldx, minmax, stream):
+        self.launches += 2
+        mi, mo = _arr(map_in, (B, M, pitch)), _arr(map_out, (B, M, pitch))
+        x = _arr(X, (B, ldx))
+        mm = _arr(minmax, (B, 2), np.int32)
+        outer = np.ones((M, M), dtype=bool)
+        outer[1:-1, 1:-1] = False
+        for b in range(B):
+            new = np.zeros((M, M), dtype=np.float32)
+            new[1:-1, 1:-1] = mi[b, 1 - sy:M - 1 - sy, 1 - sx:M - 1 - sx]
+            new[outer] = x[b, :nO]
+            mo[b, :, :M] = new
+            mm[b, 0], mm[b, 1] = _f2o(new.min()), _f2o(new.max())
+        return 0
+
+    def aoenv_map_minmax(self, map_, B, M, pitch, minmax, stream):
+        self.launches += 2
+        m = _arr(map_, (B, M, pitch))
+        mm = _arr(minmax, (B, 2), np.int32)
+        for b in range(B):
+            mm[b, 0], mm[b, 1] = _f2o(m[b, :, :M].min()), _f2o(m[b, :, :M].max())
+        return 0
+
+    def aoenv_atm_phase(self, h_map, h_minmax, L, B, R, M, pitch, fp_off, roff, coff, wr, wc, wt, opd_scale, opd_out, stream):
+        self.launches += 1
+        out = _arr(opd_out, (B, R, R))
+        acc = np.zeros((B, R, R), dtype=np.float32)
+        for l in range(L):
+            m = _arr(h_map[l], (B, M, pitch))
+            mm = _arr(h_minmax[l], (B, 2), np.int32)
+            for b in range(B):
+                v = np.zeros((R, R), dtype=np.float32)
+                for pr in range(4):
+                    h = np.zeros((R, R), dtype=np.float32)
+                    r0 = fp_off + roff[l] + pr
+                    for pc in range(4):
+                        c0 = fp_off + coff[l] + pc
+                        h += np.float32(wc[4 * l + pc]) * m[b, r0:r0 + R, c0:c0 + R]
+                    v += np.float32(wr[4 * l + pr]) * h
+                v = np.clip(v, _o2f(mm[b, 0]), _o2f(mm[b, 1]))
+                acc[b] += np.float32(wt[l]) * v
+        out[:] = acc * np.float32(_val(opd_scale))
+        return 0
+
+    # ---- gemm ------------------------------------------------------------------------------------------
+    def aoenv_gemm_tn(self, X, ldx, W, ldw, D, ldd, M, N, K, alpha, stream):
+        self.launches += 1
+        assert K % 16 == 0
+        x, w, d = _arr(X, (M, ldx)), _arr(W, (N, ldw)), _arr(D, (M, ldd))
+        d[:, :N] = (np.float32(_val(alpha)) * (x[:, :K].astype(np.float64) @ w[:, :K].astype(np.float64).T)).astype(np.float32)
+        return 0
+
+    # ---- WFS -------------------------------------------------------------------------------------------
+    def aoenv_shwfs_frame(self, opd_a, opd_b, pupil, amp, valid, B, nS, n, phase_scale, det, shared_max, frame, envmax,
+                          stats, stream):
+        self.launches += 2
+        R = nS * n
+        a, b_ = _arr(opd_a, (B, R, R)), _arr(opd_b, (B, R, R))
+        pu, am = _arr(pupil, (R, R)), _arr(amp, (R, R))
+        va = _arr(valid, (nS * nS,), np.uint8).astype(bool)
+        fr = _arr(frame, (B, R, R))
+        em = _arr(envmax, (1 if shared_max else B,), np.int32)
+        st = _arr(stats, (B, 4), np.float64)
+        scale = np.float32(_val(phase_scale))
+        N = 2 * n
+        k = np.arange(N)
+        xx, yy = np.meshgrid(k, k)
+        phasor = np.exp(-(1j * np.pi * (N + 1) / N) * (xx + yy))
+        tiles = lambda img: img.reshape(nS, n, nS, n).transpose(0, 2, 3, 1).reshape(nS * nS, n, n)
+        lo = N // 2 - n // 2
+        maxes = []
+        for e in range(B):
+            t = a[e] + (b_[e] if b_ is not None else 0)
+            if st is not None:
+                m = pu > 0
+                st[e] = [a[e][m].astype(np.float64).sum(), (a[e][m].astype(np.float64) ** 2).sum(),
+                         t[m].astype(np.float64).sum(), (t[m].astype(np.float64) ** 2).sum()]
+            ph = (t * pu * scale).astype(np.float64)
+            field = np.zeros((nS * nS, N, N), dtype=complex)
+            field[:, lo:lo + n, lo:lo + n] = np.exp(1j * tiles(ph)) * tiles(am.astype(np.float64))
+            I = np.abs(np.fft.fft2(field * phasor, axes=(1, 2)) / N) ** 2
+            spots = I.reshape(-1, n, 2, n, 2).sum(axis=(2, 4))
+            spots[~va] = 0
+            f = spots.reshape(nS, nS, n, n).transpose(0, 2, 1, 3).reshape(R, R)
+            assert det is None or _val(det) is None or not det, "fake backend: detector chain not modelled"
+            fr[e] = f.astype(np.float32)
+            maxes.append(fr[e].reshape(nS, n, nS, n).transpose(0, 2, 1, 3).reshape(nS * nS, n, n)[va].max())
+        if shared_max:
+            em[0] = _f2o(max(maxes))
+        else:
+            for e in range(B):
+                em[e] = _f2o(maxes[e])
+        return 0
+
+    def aoenv_shwfs_slopes(self, frame, envmax, shared_max, valid_idx, nV, ref_xy, inv_units, thr, B, nS, n, slopes, lds, stream):
+        self.launches += 1
+        R = nS * n
+        fr = _arr(frame, (B, R, R))
+        em = _arr(envmax, (1 if shared_max else B,), np.int32)
+        vi = _arr(valid_idx, (nV,), np.int32)
+        ref = _arr(ref_xy, (2, nV))
+        sl = _arr(slopes, (B, lds))
+        for e in range(B):
+            maps = fr[e].reshape(nS, n, nS, n).transpose(0, 2, 1, 3).reshape(nS * nS, n, n)[vi].astype(np.float64)
+            mx = _o2f(em[0 if shared_max else e])
+            # ShackHartmannOracle.centroid thresholds at threshold * maps.max(); feed the kernel's max explicitly
+            im = maps.copy()
+            im[im < np.float32(_val(thr)) * mx] = 0
+            with np.errstate(invalid="ignore", divide="ignore"):
+                s = im.sum(axis=(1, 2))
+                cx = (im * np.arange(n)[None, :, None]).sum(axis=(1, 2)) / s
+                cy = (im * np.arange(n)[None, None, :]).sum(axis=(1, 2)) / s
+            cx[~np.isfinite(cx)] = 0
+            cy[~np.isfinite(cy)] = 0
+            sl[e, :nV] = (cx - ref[0]) * np.float32(_val(inv_units))
+            sl[e, nV:2 * nV] = (cy - ref[1]) * np.float32(_val(inv_units))
+        return 0
+
+    # ---- control ---------------------------------------------------------------------------------------
+    def aoenv_command_update(self, action, act_idx, B, nA, nAct2, leak, coefs, dm_prev, ldc, stream):
+        self.launches += 1
+        a = _arr(action, (B, nAct2))
+        idx = _arr(act_idx, (nA,), np.int32)
+        c, p = _arr(coefs, (B, ldc)), _arr(dm_prev, (B, ldc))
+        new = p[:, :nA] * np.float32(_val(leak)) + a[:, idx] * np.float32(1e-6)
+        c[:, :nA] = new
+        p[:, :nA] = new
+        return 0
+
+    def aoenv_observe(self, rec, ldr, act_idx, B, nA, nAct2, stats, n_pupil, phase_scale, obs, reward, strehl, total,
+                      residual, stream):
+        self.launches += 1
+        r = _arr(rec, (B, ldr))
+        idx = _arr(act_idx, (nA,), np.int32)
+        o = _arr(obs, (B, nAct2))
+        st = _arr(stats, (B, 4), np.float64)
+        o[:] = 0
+        o[:, idx] = -r[:, :nA] * np.float32(1e6)
+        _arr(reward, (B,))[:] = -np.sqrt((o.astype(np.float64) ** 2).sum(axis=1))
+        if st is not None:
+            n = _val(n_pupil)
+            va = np.maximum(st[:, 1] / n - (st[:, 0] / n) ** 2, 0)
+            vt = np.maximum(st[:, 3] / n - (st[:, 2] / n) ** 2, 0)
+            _arr(total, (B,))[:] = np.sqrt(va) * 1e9
+            _arr(residual, (B,))[:] = np.sqrt(vt) * 1e9
+            _arr(strehl, (B,))[:] = np.exp(-vt * float(_val(phase_scale)) ** 2)
+        return 0
+
+    def aoenv_psf_peak(self, *a):
+        raise NotImplementedError("fake backend: psf_peak")
+
+
+def install(monkeypatch):
+    """Routes rlao_b200._lib to the fake backend and lets objects live on the CPU."""
+    from rlao_b200 import _lib
+    fake = FakeLib()
+    monkeypatch.setattr(_lib, "load", lambda: fake)
+    monkeypatch.setattr(_lib, "require_cuda", lambda device: torch.device("cpu"))
+    monkeypatch.setattr(_lib, "stream_ptr", lambda device=None: None)
+    monkeypatch.setattr(_lib, "launch_count", lambda: fake.launches)
+    return fake

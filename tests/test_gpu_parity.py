@@ -1,0 +1,361 @@
+"""Parity of the CUDA path (through the C ABI, via the rlao_b200 host layer) against the CPU oracle and the
+golden fixtures recorded from the unmodified reference.  Tolerances (north_star): noise-free slopes and DM
+surfaces rel. 1e-4 (of the array's max), Strehl rel. 1e-3, on identical inputs; noisy runs: statistics."""
+import ctypes
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.ao_oracle import (AOConfig, AtmosphereOracle, DetectorConfig, EnvOracle, ShackHartmannOracle, compute_psf,
+                              dm_geometry, dm_modes, flux_map, source_properties, telescope_pupil)
+from oracle.golden_configs import CONFIGS, EPISODE_SEED, STEPS
+from oracle.warp018 import warp_translate
+from parity_util import build_env, new_episode, rel_err
+
+pytestmark = pytest.mark.gpu
+
+SLOPE_TOL = 1e-4
+SURFACE_TOL = 1e-4
+STREHL_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _np(t):
+    return t.detach().double().cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_extension_is_the_code_that_runs(dev):
+    from rlao_b200 import _lib
+    lib = _lib.load()
+    n0 = _lib.launch_count()
+    x = torch.randn(8, 16, device=dev)
+    w = torch.randn(5, 16, device=dev)
+    d = torch.zeros(8, 8, device=dev)
+    _lib.check(lib.aoenv_gemm_tn(_lib.ptr(x), 16, _lib.ptr(w), 16, _lib.ptr(d), 8, 8, 5, 16, 1.0, _lib.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    assert _lib.launch_count() == n0 + 1
+    assert rel_err(_np(d[:, :5]), _np(x) @ _np(w).T) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 1, 16), (37, 131, 48), (300, 257, 1360), (128, 128, 16), (1024, 980, 2928)])
+def test_gemm_tn_vs_float64(dev, M, N, K):
+    from rlao_b200 import _lib
+    g = torch.Generator(device=dev).manual_seed(M * 7 + N)
+    x = torch.randn(M, K, device=dev, generator=g)
+    w = torch.randn(N, K, device=dev, generator=g)
+    ldd = (N + 3) // 4 * 4
+    d = torch.full((M, ldd), float("nan"), device=dev)
+    _lib.check(_lib.load().aoenv_gemm_tn(_lib.ptr(x), K, _lib.ptr(w), K, _lib.ptr(d), ldd, M, N, K, 0.5, _lib.stream_ptr(dev)))
+    ref = 0.5 * (_np(x) @ _np(w).T)
+    assert rel_err(_np(d[:, :N]), ref) < 2e-6
+    assert torch.isnan(d[:, N:]).all()          # padding columns are never written
+
+
+def test_gemm_rejects_bad_arguments(dev):
+    from rlao_b200 import _lib
+    x = torch.zeros(4, 20, device=dev)
+    rc = _lib.load().aoenv_gemm_tn(_lib.ptr(x), 20, _lib.ptr(x), 20, _lib.ptr(x), 20, 4, 4, 20, 1.0, _lib.stream_ptr(dev))
+    assert rc != 0 and b"multiple of 16" in _lib.load().aoenv_last_error()
+
+
+# ---------------------------------------------------------------------------------------------------------
+def _tiny_objects(dev, n_envs=1, cfg=None):
+    from rlao_b200.Atmosphere import Atmosphere
+    from rlao_b200.Source import Source
+    from rlao_b200.Telescope import Telescope
+    cfg = cfg or CONFIGS["tiny"]()
+    tel = Telescope(cfg.resolution, cfg.diameter, cfg.samplingTime, cfg.centralObstruction, n_envs=n_envs, device=dev)
+    src = Source(cfg.opticalBand, cfg.magnitude)
+    src * tel
+    atm = Atmosphere(tel, cfg.r0, cfg.L0, cfg.windSpeed, cfg.fractionalR0, cfg.windDirection, cfg.altitude, rng="reference")
+    return cfg, tel, src, atm
+
+
+def test_atmosphere_operators_and_screens_vs_oracle(dev):
+    cfg, tel, src, atm = _tiny_objects(dev)
+    atm.initializeAtmosphere(tel)
+    pupil = telescope_pupil(cfg.resolution)
+    assert np.array_equal(tel.pupil.astype(bool), pupil)
+    orc = AtmosphereOracle(cfg, pupil)
+    assert rel_err(_np(atm._ops.A), orc.A) < 1e-8
+    assert rel_err(_np(atm._ops.B), orc.B) < 1e-8
+    M = atm._M
+    for i, lo in enumerate(orc.layers):
+        assert rel_err(_np(atm._maps[i, atm._cur[i], 0, :, :M]), lo.map) < 2e-6, f"layer {i} map after init"
+    assert rel_err(_np(atm.OPD_no_pupil), orc.OPD_no_pupil) < 2e-6
+    for k in range(40):                     # crosses several integer-pixel boundaries on both layers
+        atm.update()
+        orc.update()
+    for i, (ly, lo) in enumerate(zip(atm._layers, orc.layers)):
+        assert np.allclose(ly.buff, lo.buff, atol=1e-12)
+        assert rel_err(_np(atm._maps[i, atm._cur[i], 0, :, :M]), lo.map) < 5e-6, f"layer {i} map after 40 updates"
+    assert rel_err(_np(atm.OPD_no_pupil), orc.OPD_no_pupil) < 5e-6
+    assert rel_err(_np(atm.OPD), orc.OPD) < 5e-6
+
+
+def test_atmosphere_injected_innovations(dev):
+    """xi-override hook: the oracle's recorded draws, fed back through xi_queue, reproduce its screens."""
+    cfg, tel, src, atm = _tiny_objects(dev)
+    atm.initializeAtmosphere(tel)
+    orc = AtmosphereOracle(cfg, telescope_pupil(cfg.resolution))
+    orc.xi_log.clear()
+    for _ in range(25):
+        orc.update()
+    atm.xi_queue = iter([x[None, :] for x in orc.xi_log])
+    for _ in range(25):
+        atm.update()
+    assert rel_err(_np(atm.OPD_no_pupil), orc.OPD_no_pupil) < 5e-6
+    with pytest.raises(StopIteration):
+        for _ in range(200):
+            atm.update()
+
+
+@pytest.mark.parametrize("kernel", ["lagrange018", "catmull_rom"])
+def test_subpixel_shift_vs_warp_restatement(dev, kernel):
+    cfg, tel, src, atm = _tiny_objects(dev)
+    atm.warp_kernel = kernel
+    atm.initializeAtmosphere(tel)
+    M = atm._M
+    ly = atm._layers[0]
+    for buff in ([0.3, -0.6], [-0.999, 0.001], [0.0, 0.5], [0.75, 0.75]):
+        for l2 in atm._layers:
+            l2.buff = np.array(buff)
+        atm._publish()
+        want = 0
+        for i in range(atm.nLayer):
+            m = _np(atm._maps[i, atm._cur[i], 0, :, :M])
+            sh = warp_translate(m, buff[0], buff[1], kernel=kernel)[1:-1, 1:-1]
+            c = sh.shape[0] // 2
+            want = want + sh[c - cfg.resolution // 2:c + cfg.resolution // 2, c - cfg.resolution // 2:c + cfg.resolution // 2] * math.sqrt(cfg.fractionalR0[i])
+        want = want * 500e-9 / 2 / np.pi
+        assert rel_err(_np(atm.OPD_no_pupil), want) < 2e-6, buff
+
+
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nS,n", [(8, 6), (5, 4), (4, 8), (20, 6)])
+def test_shack_hartmann_vs_oracle(dev, nS, n):
+    from rlao_b200.ShackHartmann import ShackHartmann
+    from rlao_b200.Source import Source
+    from rlao_b200.Telescope import Telescope
+    cfg = AOConfig(nSubap=nS, nPixPerSubap=n)
+    R = cfg.resolution
+    tel = Telescope(R, cfg.diameter, cfg.samplingTime, n_envs=3, device=dev)
+    src = Source(cfg.opticalBand, cfg.magnitude)
+    src * tel
+    wfs = ShackHartmann(nS, tel, cfg.lightRatio)
+    pupil = telescope_pupil(R)
+    wl, nph = source_properties(cfg.opticalBand, cfg.magnitude)
+    orc = ShackHartmannOracle(cfg, pupil, flux_map(pupil, nph, cfg.samplingTime, cfg.diameter), wl)
+    assert np.array_equal(wfs.valid_subapertures, orc.valid)
+    assert rel_err(wfs.reference_slopes_maps, orc.reference_slopes_maps) < 1e-6
+    assert rel_err(wfs.slopes_units, orc.slopes_units) < 2e-5
+    wfs.slopes_units = orc.slopes_units          # identical inputs for the comparison below
+    rs = np.random.RandomState(5)
+    yy, xx = np.mgrid[:R, :R] / R
+    opds = []
+    for e in range(3):
+        c = rs.normal(size=6)
+        opd = 0.4e-6 * (c[0] * xx + c[1] * yy + c[2] * np.sin(7 * xx + 3 * yy) + c[3] * np.cos(11 * yy) * xx
+                        + 0.3 * c[4] * np.sin(23 * xx * yy)) + 0.05e-6 * rs.normal(size=(R, R))
+        opds.append(opd)
+    tel.OPD_no_pupil = torch.as_tensor(np.stack(opds), dtype=torch.float32, device=dev)
+    tel * wfs
+    got_sig, got_frame = _np(wfs.signal), _np(wfs.cam.frame)
+    opd32 = _np(tel.OPD_no_pupil)
+    for e in range(3):
+        want = orc.measure(opd32[e] * pupil * 2 * np.pi / wl)
+        assert rel_err(got_frame[e], orc.frame) < 2e-5, (e, "frame")
+        assert rel_err(got_sig[e], want) < SLOPE_TOL, (e, "slopes")
+    s2d = _np(wfs.signal_2D)
+    assert rel_err(s2d[2], orc.signal_2D) < SLOPE_TOL
+
+
+def test_shack_hartmann_flat_wavefront_gives_zero_signal_at_full_size(dev):
+    from rlao_b200.ShackHartmann import ShackHartmann
+    from rlao_b200.Source import Source
+    from rlao_b200.Telescope import Telescope
+    tel = Telescope(240, 8, 1 / 500, n_envs=5, device=dev)
+    src = Source("I", 8)
+    src * tel
+    wfs = ShackHartmann(40, tel, 0.5)
+    assert wfs.nValidSubaperture == 1264 and wfs.nSignal == 2528       # SURVEY.md section 8 size table
+    tel.resetOPD()
+    tel * wfs
+    assert float(wfs.signal.abs().max()) < 1e-5
+    # piston invariance: a constant OPD changes nothing
+    tel.OPD_no_pupil = torch.full((5, 240, 240), 3e-7, device=dev)
+    tel * wfs
+    assert float(wfs.signal.abs().max()) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_dm_surface_vs_oracle_and_linearity(dev):
+    from rlao_b200.DeformableMirror import DeformableMirror
+    from rlao_b200.Source import Source
+    from rlao_b200.Telescope import Telescope
+    cfg = CONFIGS["cfg1"]()
+    tel = Telescope(cfg.resolution, cfg.diameter, cfg.samplingTime, n_envs=4, device=dev)
+    Source("I", 8) * tel
+    dm = DeformableMirror(tel, cfg.nSubap, cfg.mechCoupling)
+    xIF, yIF, mask, sigma = dm_geometry(cfg)
+    modes, _, _ = dm_modes(cfg, xIF, yIF, sigma)
+    assert dm.nValidAct == 357 == modes.shape[1]                         # pinned by manual_m2c.npy
+    assert np.array_equal(dm.validAct.reshape(21, 21), mask)
+    assert rel_err(_np(dm.modes), modes) < 1e-12
+    rs = np.random.RandomState(1)
+    c = rs.normal(size=(4, 357)) * 1e-7
+    dm.coefs = torch.as_tensor(c, dtype=torch.float32, device=dev)
+    want = (modes @ _np(dm.coefs).T).T.reshape(4, cfg.resolution, cfg.resolution)
+    assert rel_err(_np(dm.OPD), want) < SURFACE_TOL
+    a = _np(dm.OPD).copy()
+    dm.coefs = torch.as_tensor(2 * c, dtype=torch.float32, device=dev)
+    assert rel_err(_np(dm.OPD), 2 * a) < 1e-6                            # linearity
+    dm.coefs = 0
+    assert float(dm.OPD.abs().max()) == 0.0
+    # reference [nValidAct, k] matrix mode (calibration pushes)
+    dm.coefs = torch.eye(357, dtype=torch.float32, device=dev)[:, :7] * 1e-9
+    assert dm.OPD.shape == (7, cfg.resolution, cfg.resolution)
+    assert rel_err(_np(dm.OPD[3]).reshape(-1), modes[:, 3] * 1e-9) < SURFACE_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------
+def _trace(name, dev, steps=None):
+    cfg = CONFIGS[name]()
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    env = build_env(cfg, n_envs=1, rng="reference", device=dev)
+    orc = EnvOracle(cfg)
+    return cfg, gold, env, orc
+
+
+@pytest.mark.parametrize("name", ["tiny", "cfg1"])
+def test_closed_loop_trace_vs_reference_golden(dev, name):
+    cfg, gold, env, orc = _trace(name, dev)
+    # init-time quantities
+    assert np.array_equal(env.wfs.valid_subapertures, gold["valid_subapertures"])
+    assert np.array_equal(env.dm_mask.astype(bool), gold["validAct"].astype(bool))
+    assert rel_err(env.wfs.slopes_units, gold["slopes_units"]) < 2e-5
+    assert rel_err(env.wfs.reference_slopes_maps, gold["reference_slopes_maps"]) < 1e-6
+    # our GPU-calibrated reconstructor (float32 centroids of 1 nm pokes) vs the reference's float64 one
+    assert rel_err(_np(env.reconstructor), orc.reconstructor) < 5e-3
+    # identical inputs from here on: the reference's reconstructor and slope units
+    env.set_reconstructor(orc.reconstructor)
+    env.wfs.slopes_units = float(gold["slopes_units"])
+    n = STEPS[name]
+    obs = new_episode(env, EPISODE_SEED)
+    assert rel_err(_np(obs), gold["obs0"]) < 2e-4
+    assert rel_err(_np(env.wfs.signal), gold["signal0"]) < SLOPE_TOL
+    snap = set(int(s) for s in gold["snap_steps"])
+    for i in range(n):
+        obs, reward, strehl, done, info = env.step(i, cfg.gainCL * obs)
+        assert rel_err(_np(env.wfs.signal), gold["trace_signal"][i]) < 2 * SLOPE_TOL, (i, "slopes")
+        assert rel_err(_np(obs), gold["trace_obs"][i]) < 2e-4, (i, "obs")
+        assert abs(float(strehl) - gold["trace_strehl"][i]) <= STREHL_TOL * gold["trace_strehl"][i] + 1e-30, (i, "strehl")
+        assert abs(float(reward) - gold["trace_reward"][i]) <= 2e-4 * abs(gold["trace_reward"][i]), (i, "reward")
+        assert rel_err(_np(env.dm.coefs), gold["trace_coefs"][i]) < 2e-4, (i, "coefs")
+        if i in snap:
+            assert rel_err(_np(env.atm.OPD), gold[f"atm_OPD_{i}"]) < 1e-5
+            assert rel_err(_np(env.tel.OPD), gold[f"tel_OPD_{i}"]) < SURFACE_TOL
+            assert rel_err(_np(env.wfs.cam.frame), gold[f"frame_{i}"]) < 5e-5
+    assert rel_err(_np(env.total[:n, 0]), gold["trace_total"]) < 1e-4
+    assert rel_err(_np(env.residual[:n, 0]), gold["trace_residual"]) < 1e-3
+    assert done is False and "strehl" in info
+
+
+def test_interaction_matrix_vs_oracle(dev):
+    cfg, gold, env, orc = _trace("tiny", dev)
+    D = _np(env.calib_zonal.D)
+    assert D.shape == orc.D_zonal.shape
+    assert rel_err(D, orc.D_zonal) < 2e-3
+    # SVD bookkeeping of CalibrationVault
+    c = env.calib_CL
+    assert rel_err(_np(c.M @ c.D), np.eye(c.D.shape[1])) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_psf_peak_vs_oracle(dev):
+    from rlao_b200.psf import psf_peak
+    cfg, tel, src, atm = _tiny_objects(dev, n_envs=2)
+    atm.initializeAtmosphere(tel)
+    tel + atm
+    pupil = telescope_pupil(cfg.resolution)
+    wl, nph = source_properties(cfg.opticalBand, cfg.magnitude)
+    fm = flux_map(pupil, nph, cfg.samplingTime, cfg.diameter)
+    # well-corrected wavefront: scale the turbulence down so that the peak sits in the core
+    opd = atm._opd * 0.05
+    peak, win = psf_peak(tel, opd.contiguous(), None, 4, 16, return_window=True)
+    for e in range(2):
+        psf = compute_psf(pupil, fm, _np(opd[e]) * pupil * 2 * np.pi / wl, 4)
+        c = psf.shape[0] // 2
+        assert rel_err(_np(win[e]), psf[c - 8:c + 8, c - 8:c + 8]) < 2e-5
+        assert abs(float(peak[e]) - psf.max()) < 2e-5 * psf.max()
+    # against the full-image torch.fft path of Telescope.computePSF and the golden reference value
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "tiny.npz"))
+    ph = torch.as_tensor(gold["psf_atm_phase"], dtype=torch.float32, device=dev)
+    tel.OPD_no_pupil = (ph * (wl / 2 / np.pi)).unsqueeze(0).expand(2, -1, -1)
+    tel.computePSF(4)
+    cc = tel.PSF.shape[-1] // 2
+    assert rel_err(_np(tel.PSF[0, cc - 8:cc + 8, cc - 8:cc + 8]), gold["psf_atm_crop"]) < 1e-4
+    assert abs(float(tel.PSF[0].max()) - gold["psf_atm_max"]) < 1e-4 * gold["psf_atm_max"]
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_detector_noise_statistics(dev):
+    """Noisy WFS frames: Poisson photon noise (variance = mean), rounded Gaussian read noise, dark current, QE,
+    full-well clipping and ADC quantisation follow OOPAO/Detector.py:190-301 statistically; streams are independent
+    across environments and steps (Philox counters)."""
+    from rlao_b200.ShackHartmann import ShackHartmann
+    from rlao_b200.Source import Source
+    from rlao_b200.Telescope import Telescope
+    B = 256
+    tel = Telescope(48, 8, 1 / 500, n_envs=B, device=dev)
+    src = Source("I", 10)
+    src * tel
+    wfs = ShackHartmann(8, tel, 0.5)
+    tel.resetOPD()
+    tel * wfs
+    ideal = _np(wfs.cam.frame[0])
+    lit = ideal > 0.02 * ideal.max()
+    # (1) photon noise only
+    wfs.cam.photonNoise = True
+    tel * wfs
+    f1 = _np(wfs.cam.frame)
+    tel * wfs
+    f2 = _np(wfs.cam.frame)
+    assert np.all(f1 == np.round(f1)) and f1.min() >= 0
+    mean, var = f1.mean(axis=0), f1.var(axis=0)
+    assert abs(mean[lit].mean() / ideal[lit].mean() - 1) < 0.01
+    assert abs((var[lit] / mean[lit]).mean() - 1) < 0.05              # index of dispersion 1
+    d01 = (f1[0] - ideal)[lit], (f1[1] - ideal)[lit]
+    assert abs(np.corrcoef(*d01)[0, 1]) < 0.1                         # independent across environments
+    dt = (f1 - ideal)[:, lit].reshape(-1), (f2 - ideal)[:, lit].reshape(-1)
+    assert abs(np.corrcoef(*dt)[0, 1]) < 0.02                         # independent across steps
+    # (2) read noise only: round(N(0,1)*RON)
+    wfs.cam.photonNoise = False
+    wfs.cam.readoutNoise = 14
+    tel * wfs
+    r = _np(wfs.cam.frame) - ideal
+    dark_px = ~lit
+    assert abs(r[:, dark_px].std() - 14) < 0.3 and abs(r[:, dark_px].mean()) < 0.2
+    resid = _np(wfs.cam.frame)[:, dark_px] - ideal[dark_px]
+    assert np.abs(resid - np.round(resid)).max() < 1e-3
+    # (3) Razor-like camera: QE, dark current, full well, 10-bit ADC
+    wfs.cam.photonNoise, wfs.cam.readoutNoise = True, 0
+    wfs.cam.QE, wfs.cam.FWC, wfs.cam.bits, wfs.cam.darkCurrent, wfs.cam.sensor = 0.56, 10000, 10, 5000.0, "CMOS"
+    wfs.cam.integrationTime = 1 / 500
+    tel * wfs
+    q = _np(wfs.cam.frame)
+    assert np.all(q == np.round(q)) and q.min() >= 0 and q.max() <= 1023
+    expect = np.clip(ideal * 0.56 + 10.0, 0, 10000) / 10000 * 1023
+    unsat = lit & (ideal * 0.56 < 8000)
+    assert abs((q.mean(axis=0)[unsat] + 0.5).mean() / expect[unsat].mean() - 1) < 0.02
+    assert abs(q[:, dark_px].mean() - (10.0 / 10000 * 1023 - 0.5)) < 0.15
