@@ -255,11 +255,15 @@ def run_gpu_arm(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall0 = time.time()
+    if os.environ.get("AOENV_PROFILE_REGION"):      # lets `ncu --profile-from-start off` see only the timed region
+        torch.cuda.profiler.start()
     e0.record()
     for i in range(args.steps):
         obs, reward, strehl, _, _ = env.step(None, gain * obs)
     e1.record()
     barrier()
+    if os.environ.get("AOENV_PROFILE_REGION"):
+        torch.cuda.profiler.stop()
     t_wall1 = time.time()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - l0

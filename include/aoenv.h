@@ -123,6 +123,16 @@ int aoenv_shwfs_slopes(const float* frame, const int32_t* envmax, int shared_max
                        int nV, const float* ref_xy, float inv_units, float threshold_cog, int B, int nS, int n,
                        float* slopes, int lds, void* stream);
 
+/* Calibration-grade measurement (init only): the two steps above in float64 with the ideal detector, for the
+ * reference slopes / slope units (ShackHartmann.py:254-312) and the interaction matrix pushes
+ * (calibration/InteractionMatrix.py:79-84), whose 1 nm pokes move the spots by ~1e-3 pixel.  opd [F][R][R]
+ * float32 (OPD_no_pupil, metres); frame [F][R][R], slopes [F][lds], ref_xy [2][nV] float64; envmax [F] (or [1]
+ * when shared_max) scratch.  */
+int aoenv_shwfs_measure_f64(const float* opd, const float* pupil, const float* amp, const uint8_t* valid,
+                            const int32_t* valid_idx, int nV, const double* ref_xy, double inv_units, double threshold_cog,
+                            int F, int nS, int n, double phase_scale, int shared_max, double* frame, uint64_t* envmax,
+                            double* slopes, int lds, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Command update and observation — MAIN/OOPAOEnv/OOPAOEnvRazor.py:479,492-500,514,621-641
  * ------------------------------------------------------------------------------------------------------- */

@@ -47,15 +47,17 @@ class TorchWrapper(_Wrapper):
     def __init__(self, env, host_io=True):
         super().__init__(env)
         self.host_io = host_io
-        self._pinned = None
+        self._pinned = {}
 
     def _to_host(self, *tensors):
-        if self._pinned is None or any(p.shape != t.shape for p, t in zip(self._pinned, tensors)):
-            self._pinned = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors]
-        for p, t in zip(self._pinned, tensors):
+        key = tuple((tuple(t.shape), t.dtype) for t in tensors)
+        if key not in self._pinned:
+            self._pinned[key] = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors]
+        bufs = self._pinned[key]
+        for p, t in zip(bufs, tensors):
             p.copy_(t, non_blocking=True)
         torch.cuda.current_stream(self._env.device).synchronize()
-        return [p.clone() for p in self._pinned]
+        return [p.clone() for p in bufs]
 
     def step(self, i, action):
         dev = self._env.device

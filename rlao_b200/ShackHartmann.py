@@ -144,19 +144,30 @@ class ShackHartmann:
         self._signal_is_multi = False
         self.cam.frame = self._frame[0] if self.n_envs == 1 else self._frame
 
+    def _measure_f64(self, opd, shared_max, ref_xy64, inv_units):
+        """Calibration-grade float64 measurement of F wavefronts [F, R, R] with the ideal detector
+        (aoenv_shwfs_measure_f64).  Returns slopes [F, 2*nValid] float64."""
+        F, R, dev = opd.shape[0], self.telescope.resolution, self.device
+        tel = self.telescope
+        frame = torch.empty((F, R, R), dtype=torch.float64, device=dev)
+        envmax = torch.zeros((1 if shared_max else F,), dtype=torch.int64, device=dev)
+        lds = 2 * self.nValidSubaperture
+        slopes = torch.zeros((F, lds), dtype=torch.float64, device=dev)
+        opd = opd.to(torch.float32).contiguous()
+        _lib.check(_lib.load().aoenv_shwfs_measure_f64(
+            _lib.ptr(opd), _lib.ptr(tel._pupil_f), _lib.ptr(self._amp), _lib.ptr(self._valid_u8), _lib.ptr(self._valid_idx),
+            self.nValidSubaperture, _lib.ptr(ref_xy64), float(inv_units), float(self.threshold_cog), F, self.nSubap,
+            self.n_pix_subap, 2 * math.pi / tel.src.wavelength, int(shared_max), _lib.ptr(frame), _lib.ptr(envmax),
+            _lib.ptr(slopes), lds, _lib.stream_ptr(dev)), "shwfs_measure_f64")
+        return slopes
+
     def measure_frames(self, opd):
         """Multi-frame branch (ShackHartmann.py:605-674): k wavefronts [k, R, R] (OPD_no_pupil, metres), no
-        detector, ONE centroiding threshold for the whole batch.  Returns signal [k, nSignal]."""
+        detector, ONE centroiding threshold for the whole batch.  Returns signal [k, nSignal] (float64: this is
+        the calibration path)."""
         if self.cam.photonNoise or self.cam.readoutNoise:
             raise NotImplementedError("noisy multi-frame measurements are not supported (calibrate with noise='off')")
-        k, R = opd.shape[0], self.telescope.resolution
-        frame = torch.empty((k, R, R), dtype=torch.float32, device=self.device)
-        envmax = torch.zeros((1,), dtype=torch.int32, device=self.device)
-        slopes = torch.zeros((k, self._lds), dtype=torch.float32, device=self.device)
-        tel = self.telescope
-        self._run(opd.contiguous(), None, tel._pupil_f, 2 * math.pi / tel.src.wavelength, True, None, frame, envmax, None,
-                  slopes, self._ref_xy, 1.0 / self.slopes_units)
-        return slopes[:, :self.nSignal]
+        return self._measure_f64(opd, True, self._ref_xy64, 1.0 / self.slopes_units)
 
     def wfs_measure(self, phase_in=None):
         """ShackHartmann.py:511-695."""
@@ -202,20 +213,23 @@ class ShackHartmann:
         tel, dev = self.telescope, self.device
         R, nV, nS = tel.resolution, self.nValidSubaperture, self.nSubap
         lam = tel.src.wavelength
-        zero_ref = torch.zeros((2, nV), dtype=torch.float32, device=dev)
-        frame = torch.empty((1, R, R), dtype=torch.float32, device=dev)
-        envmax = torch.zeros((1,), dtype=torch.int32, device=dev)
-        raw = torch.zeros((1, self._lds), dtype=torch.float32, device=dev)
+        zero_ref = torch.zeros((2, nV), dtype=torch.float64, device=dev)
 
         def centroids(opd):
-            self._run(opd.reshape(1, R, R).contiguous(), None, tel._pupil_f, 2 * math.pi / lam, False, None, frame, envmax,
-                      None, raw, zero_ref, 1.0)
-            return raw[0, :2 * nV].clone()
+            return self._measure_f64(opd.reshape(1, R, R), False, zero_ref, 1.0)[0]
 
         flat = centroids(torch.zeros((R, R), dtype=torch.float32, device=dev))
-        self._ref_xy = flat.reshape(2, nV).contiguous()
+        self._ref_xy64 = flat.reshape(2, nV).contiguous()
+        # the float32 step kernels subtract a reference measured by themselves, so that a flat wavefront gives
+        # exactly zero signal as in the reference (same code path for both measurements there)
+        f32 = dict(dtype=torch.float32, device=dev)
+        fr32, em32 = torch.empty((1, R, R), **f32), torch.zeros((1,), dtype=torch.int32, device=dev)
+        raw32 = torch.zeros((1, self._lds), **f32)
+        self._run(torch.zeros((1, R, R), **f32), None, tel._pupil_f, 2 * math.pi / lam, False, None, fr32, em32, None,
+                  raw32, torch.zeros((2, nV), **f32), 1.0)
+        self._ref_xy = raw32[0, :2 * nV].reshape(2, nV).contiguous()
         ref2d = np.zeros((2 * nS, nS))
-        f = flat.double().cpu().numpy()
+        f = flat.cpu().numpy()
         ref2d[self.validLenslets_x, self.validLenslets_y] = f[:nV]
         ref2d[self.validLenslets_x + nS, self.validLenslets_y] = f[nV:]
         self.reference_slopes_maps = ref2d
@@ -231,7 +245,7 @@ class ShackHartmann:
         for i in range(5):
             opd = (tip_dev * ((i - 2) * amp)).to(torch.float32)
             c = centroids(opd)
-            mean_slope[i] = float((c[:nV].double() - self._ref_xy[0].double()).mean())
+            mean_slope[i] = float((c[:nV] - self._ref_xy64[0]).mean())
         self.p = np.polyfit(np.linspace(-2, 2, 5) * amp, mean_slope, deg=1)
         self.slopes_units = float(np.abs(self.p[0]) * (lam / 2 / np.pi))
         self.isInitialized = True

@@ -14,7 +14,8 @@ constexpr int kMaxN = 8;                 // pixels per lenslet side
 // non-zero inputs (which sit at padded positions n/2 .. n/2+n-1, ShackHartmann.py:344), times the half-pixel
 // phasor exp(-i pi (N+1)/N x) of ShackHartmann.py:208-209.
 __constant__ float2 c_tw[2 * kMaxN * kMaxN];
-static int g_tw_n[64] = {0};             // per device: n for which c_tw is currently valid
+__constant__ double2 c_twd[2 * kMaxN * kMaxN];   // float64 copy for the calibration-grade kernels
+static int g_tw_n[64] = {0};             // per device: n for which c_tw / c_twd are currently valid
 static std::mutex g_tw_mutex;
 
 static int ensure_twiddles(int n, cudaStream_t stream) {
@@ -24,14 +25,17 @@ static int ensure_twiddles(int n, cudaStream_t stream) {
   if (dev < 64 && g_tw_n[dev] == n) return 0;
   const int N = 2 * n;
   float2 h[2 * kMaxN * kMaxN];
+  double2 hd[2 * kMaxN * kMaxN];
   for (int u = 0; u < N; ++u)
     for (int a = 0; a < n; ++a) {
       const long m = ((long)(a + n / 2) * (2 * u + N + 1)) % (2L * N);
       const double ang = -M_PI * (double)m / (double)N;
+      hd[u * n + a] = make_double2(cos(ang), sin(ang));
       h[u * n + a] = make_float2((float)cos(ang), (float)sin(ang));
     }
   // synchronous on purpose: `h` is a stack buffer; happens once per (device, n)
   cudaError_t e = cudaMemcpyToSymbol(c_tw, h, sizeof(float2) * N * n);
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_twd, hd, sizeof(double2) * N * n);
   if (e != cudaSuccess) return fail(-3, "twiddle upload: %s", cudaGetErrorString(e));
   if (dev < 64) g_tw_n[dev] = n;
   (void)stream;
@@ -255,6 +259,114 @@ shwfs_slopes_kernel(const float* __restrict__ frame, const int32_t* __restrict__
   slopes[(size_t)b * lds + nV + t] = (cy - __ldg(&ref_xy[nV + t])) * inv_units;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Calibration-grade (float64) variant: ideal detector, used at init for the reference slopes, the slope units
+// (ShackHartmann.py:254-312) and the interaction matrix (calibration/InteractionMatrix.py), whose 1 nm pokes move
+// the spots by ~1e-3 pixel — below what float32 centroids resolve to 1e-4.  Intensities are >= 0, so the bit
+// pattern of a double orders like the value and atomicMax on unsigned long long gives the frame maximum.
+// ---------------------------------------------------------------------------------------------------------
+template <int n>
+__global__ void __launch_bounds__(64)
+shwfs_frame_f64_kernel(const float* __restrict__ opd, const float* __restrict__ pupil, const float* __restrict__ amp,
+                       const uint8_t* __restrict__ valid, int nS, double phase_scale, int shared_max,
+                       double* __restrict__ frame, unsigned long long* __restrict__ envmax) {
+  constexpr int N = 2 * n;
+  const int R = nS * n;
+  const int b = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nS * nS) return;
+  const int li = k / nS, lj = k % nS;
+  const bool lit = valid[k] != 0;
+  const size_t tile = (size_t)(li * n) * R + lj * n;
+  double* __restrict__ fout = frame + (size_t)b * R * R + tile;
+  if (!lit) {
+    for (int p = 0; p < n; ++p)
+      for (int q = 0; q < n; ++q) fout[(size_t)p * R + q] = 0.0;
+    return;
+  }
+  double er[n][n], ei[n][n];
+  const float* __restrict__ pa = opd + (size_t)b * R * R + tile;
+#pragma unroll
+  for (int bb = 0; bb < n; ++bb)
+#pragma unroll
+    for (int aa = 0; aa < n; ++aa) {
+      const int o = bb * R + aa;
+      double sn, cs;
+      sincos((double)__ldg(pa + o) * (double)__ldg(pupil + tile + o) * phase_scale, &sn, &cs);
+      const double am = (double)__ldg(amp + tile + o);
+      er[aa][bb] = am * cs;
+      ei[aa][bb] = am * sn;
+    }
+  double vmax = 0.0;
+  const double norm = 1.0 / (double)(N * N);
+  for (int p = 0; p < n; ++p) {
+    double acc[n];
+#pragma unroll
+    for (int q = 0; q < n; ++q) acc[q] = 0.0;
+    for (int du = 0; du < 2; ++du) {
+      const int u = 2 * p + du;
+      double yr[n], yi[n];
+#pragma unroll
+      for (int bb = 0; bb < n; ++bb) { yr[bb] = 0.0; yi[bb] = 0.0; }
+#pragma unroll
+      for (int aa = 0; aa < n; ++aa) {
+        const double2 g = c_twd[u * n + aa];
+#pragma unroll
+        for (int bb = 0; bb < n; ++bb) {
+          yr[bb] += g.x * er[aa][bb] - g.y * ei[aa][bb];
+          yi[bb] += g.x * ei[aa][bb] + g.y * er[aa][bb];
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < N; ++v) {
+        double fr = 0.0, fi = 0.0;
+#pragma unroll
+        for (int bb = 0; bb < n; ++bb) {
+          const double2 g = c_twd[v * n + bb];
+          fr += yr[bb] * g.x - yi[bb] * g.y;
+          fi += yr[bb] * g.y + yi[bb] * g.x;
+        }
+        acc[v >> 1] += fr * fr + fi * fi;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < n; ++q) {
+      const double val = acc[q] * norm;
+      fout[(size_t)p * R + q] = val;
+      vmax = fmax(vmax, val);
+    }
+  }
+  atomicMax(&envmax[shared_max ? 0 : b], (unsigned long long)__double_as_longlong(vmax));
+}
+
+__global__ void __launch_bounds__(128)
+shwfs_slopes_f64_kernel(const double* __restrict__ frame, const unsigned long long* __restrict__ envmax, int shared_max,
+                        const int32_t* __restrict__ valid_idx, int nV, const double* __restrict__ ref_xy,
+                        double inv_units, double threshold_cog, int nS, int n, double* __restrict__ slopes, int lds) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nV) return;
+  const int R = nS * n;
+  const int k = __ldg(&valid_idx[t]);
+  const int li = k / nS, lj = k % nS;
+  const double thr = threshold_cog * __longlong_as_double((long long)envmax[shared_max ? 0 : b]);
+  const double* __restrict__ f = frame + (size_t)b * R * R + (size_t)(li * n) * R + lj * n;
+  double s = 0.0, sx = 0.0, sy = 0.0;
+  for (int p = 0; p < n; ++p)
+    for (int q = 0; q < n; ++q) {
+      double v = f[(size_t)p * R + q];
+      v = v < thr ? 0.0 : v;
+      s += v;
+      sx += v * (double)p;
+      sy += v * (double)q;
+    }
+  double cx = sx / s, cy = sy / s;
+  if (!isfinite(cx)) cx = 0.0;
+  if (!isfinite(cy)) cy = 0.0;
+  slopes[(size_t)b * lds + t] = (cx - ref_xy[t]) * inv_units;
+  slopes[(size_t)b * lds + nV + t] = (cy - ref_xy[nV + t]) * inv_units;
+}
+
 __global__ void envmax_init_kernel(int32_t* __restrict__ envmax, int count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) envmax[i] = float_to_ordered(-INFINITY);
@@ -311,6 +423,32 @@ int aoenv_shwfs_slopes(const float* frame, const int32_t* envmax, int shared_max
   shwfs_slopes_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(frame, envmax, shared_max, valid_idx, nV, ref_xy,
                                                               inv_units, threshold_cog, nS, n, slopes, lds);
   AOENV_LAUNCH_CHECK("shwfs_slopes");
+  return 0;
+}
+
+int aoenv_shwfs_measure_f64(const float* opd, const float* pupil, const float* amp, const uint8_t* valid,
+                            const int32_t* valid_idx, int nV, const double* ref_xy, double inv_units, double threshold_cog,
+                            int F, int nS, int n, double phase_scale, int shared_max, double* frame, uint64_t* envmax,
+                            double* slopes, int lds, void* stream) {
+  AOENV_CHECK_ARG(F > 0 && F <= 65535 && nS > 0 && nV > 0 && lds >= 2 * nV, "shwfs_measure_f64: bad shape");
+  AOENV_CHECK_ARG(n == 4 || n == 6 || n == 8, "shwfs_measure_f64: %d pixels per lenslet is not a compiled size (4, 6, 8)", n);
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = ensure_twiddles(n, s);
+  if (rc) return rc;
+  cudaError_t e = cudaMemsetAsync(envmax, 0, sizeof(uint64_t) * (shared_max ? 1 : (size_t)F), s);
+  if (e != cudaSuccess) return fail(-3, "shwfs_measure_f64 memset: %s", cudaGetErrorString(e));
+  dim3 grid((nS * nS + 63) / 64, F);
+  unsigned long long* em = reinterpret_cast<unsigned long long*>(envmax);
+  switch (n) {
+    case 4: shwfs_frame_f64_kernel<4><<<grid, 64, 0, s>>>(opd, pupil, amp, valid, nS, phase_scale, shared_max, frame, em); break;
+    case 6: shwfs_frame_f64_kernel<6><<<grid, 64, 0, s>>>(opd, pupil, amp, valid, nS, phase_scale, shared_max, frame, em); break;
+    case 8: shwfs_frame_f64_kernel<8><<<grid, 64, 0, s>>>(opd, pupil, amp, valid, nS, phase_scale, shared_max, frame, em); break;
+  }
+  AOENV_LAUNCH_CHECK("shwfs_frame_f64");
+  dim3 g2((nV + 127) / 128, F);
+  shwfs_slopes_f64_kernel<<<g2, 128, 0, s>>>(frame, em, shared_max, valid_idx, nV, ref_xy, inv_units, threshold_cog, nS, n,
+                                             slopes, lds);
+  AOENV_LAUNCH_CHECK("shwfs_slopes_f64");
   return 0;
 }
 

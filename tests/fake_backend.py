@@ -180,6 +180,47 @@ class FakeLib:
             sl[e, nV:2 * nV] = (cy - ref[1]) * np.float32(_val(inv_units))
         return 0
 
+    def aoenv_shwfs_measure_f64(self, opd, pupil, amp, valid, valid_idx, nV, ref_xy, inv_units, thr, F, nS, n, phase_scale,
+                                shared_max, frame, envmax, slopes, lds, stream):
+        self.launches += 2
+        R = nS * n
+        a = _arr(opd, (F, R, R))
+        pu, am = _arr(pupil, (R, R)), _arr(amp, (R, R))
+        va = _arr(valid, (nS * nS,), np.uint8).astype(bool)
+        vi = _arr(valid_idx, (nV,), np.int32)
+        ref = _arr(ref_xy, (2, nV), np.float64)
+        fr = _arr(frame, (F, R, R), np.float64)
+        sl = _arr(slopes, (F, lds), np.float64)
+        N = 2 * n
+        k = np.arange(N)
+        xx, yy = np.meshgrid(k, k)
+        phasor = np.exp(-(1j * np.pi * (N + 1) / N) * (xx + yy))
+        tiles = lambda img: img.reshape(nS, n, nS, n).transpose(0, 2, 3, 1).reshape(nS * nS, n, n)
+        lo = N // 2 - n // 2
+        maps = []
+        for e in range(F):
+            ph = a[e].astype(np.float64) * pu * float(_val(phase_scale))
+            field = np.zeros((nS * nS, N, N), dtype=complex)
+            field[:, lo:lo + n, lo:lo + n] = np.exp(1j * tiles(ph)) * tiles(am.astype(np.float64))
+            I = np.abs(np.fft.fft2(field * phasor, axes=(1, 2)) / N) ** 2
+            spots = I.reshape(-1, n, 2, n, 2).sum(axis=(2, 4))
+            spots[~va] = 0
+            fr[e] = spots.reshape(nS, nS, n, n).transpose(0, 2, 1, 3).reshape(R, R)
+            maps.append(spots[vi])
+        gmax = max(m.max() for m in maps)
+        for e in range(F):
+            im = maps[e].copy()
+            im[im < float(_val(thr)) * (gmax if shared_max else im.max())] = 0
+            with np.errstate(invalid="ignore", divide="ignore"):
+                s_ = im.sum(axis=(1, 2))
+                cx = (im * np.arange(n)[None, :, None]).sum(axis=(1, 2)) / s_
+                cy = (im * np.arange(n)[None, None, :]).sum(axis=(1, 2)) / s_
+            cx[~np.isfinite(cx)] = 0
+            cy[~np.isfinite(cy)] = 0
+            sl[e, :nV] = (cx - ref[0]) * float(_val(inv_units))
+            sl[e, nV:2 * nV] = (cy - ref[1]) * float(_val(inv_units))
+        return 0
+
     # ---- control ---------------------------------------------------------------------------------------
     def aoenv_command_update(self, action, act_idx, B, nA, nAct2, leak, coefs, dm_prev, ldc, stream):
         self.launches += 1

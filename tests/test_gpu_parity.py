@@ -57,7 +57,7 @@ def test_gemm_tn_vs_float64(dev, M, N, K):
     d = torch.full((M, ldd), float("nan"), device=dev)
     _lib.check(_lib.load().aoenv_gemm_tn(_lib.ptr(x), K, _lib.ptr(w), K, _lib.ptr(d), ldd, M, N, K, 0.5, _lib.stream_ptr(dev)))
     ref = 0.5 * (_np(x) @ _np(w).T)
-    assert rel_err(_np(d[:, :N]), ref) < 2e-6
+    assert rel_err(_np(d[:, :N]), ref) < 1e-5
     assert torch.isnan(d[:, N:]).all()          # padding columns are never written
 
 
@@ -158,7 +158,7 @@ def test_shack_hartmann_vs_oracle(dev, nS, n):
     orc = ShackHartmannOracle(cfg, pupil, flux_map(pupil, nph, cfg.samplingTime, cfg.diameter), wl)
     assert np.array_equal(wfs.valid_subapertures, orc.valid)
     assert rel_err(wfs.reference_slopes_maps, orc.reference_slopes_maps) < 1e-6
-    assert rel_err(wfs.slopes_units, orc.slopes_units) < 2e-5
+    assert rel_err(wfs.slopes_units, orc.slopes_units) < 2e-6
     wfs.slopes_units = orc.slopes_units          # identical inputs for the comparison below
     rs = np.random.RandomState(5)
     yy, xx = np.mgrid[:R, :R] / R
@@ -243,10 +243,10 @@ def test_closed_loop_trace_vs_reference_golden(dev, name):
     # init-time quantities
     assert np.array_equal(env.wfs.valid_subapertures, gold["valid_subapertures"])
     assert np.array_equal(env.dm_mask.astype(bool), gold["validAct"].astype(bool))
-    assert rel_err(env.wfs.slopes_units, gold["slopes_units"]) < 2e-5
+    assert rel_err(env.wfs.slopes_units, gold["slopes_units"]) < 2e-6
     assert rel_err(env.wfs.reference_slopes_maps, gold["reference_slopes_maps"]) < 1e-6
-    # our GPU-calibrated reconstructor (float32 centroids of 1 nm pokes) vs the reference's float64 one
-    assert rel_err(_np(env.reconstructor), orc.reconstructor) < 5e-3
+    # our GPU-calibrated reconstructor (float64 WFS kernels on float32 DM surfaces) vs the reference's
+    assert rel_err(_np(env.reconstructor), orc.reconstructor) < 2e-4
     # identical inputs from here on: the reference's reconstructor and slope units
     env.set_reconstructor(orc.reconstructor)
     env.wfs.slopes_units = float(gold["slopes_units"])
@@ -275,7 +275,7 @@ def test_interaction_matrix_vs_oracle(dev):
     cfg, gold, env, orc = _trace("tiny", dev)
     D = _np(env.calib_zonal.D)
     assert D.shape == orc.D_zonal.shape
-    assert rel_err(D, orc.D_zonal) < 2e-3
+    assert rel_err(D, orc.D_zonal) < 1e-5
     # SVD bookkeeping of CalibrationVault
     c = env.calib_CL
     assert rel_err(_np(c.M @ c.D), np.eye(c.D.shape[1])) < 1e-6
