@@ -81,6 +81,15 @@ int aoenv_atm_phase(const float* const* h_map, const int32_t* const* h_minmax, i
 int aoenv_gemm_tn(const float* X, int ldx, const float* W, int ldw, float* D, int ldd,
                   int M, int N, int K, float alpha, void* stream);
 
+/* Tensor-core variant (tcgen05.mma with TMEM accumulators, TMA-fed, sm_100a) of the same contraction with FP32-grade
+ * accuracy: both operands are given as `parts` (2 or 3) stacked bf16 planes x = x_0 + x_1 (+ x_2) produced by
+ * aoenv_split_bf16 — Xs [parts][MX][ldk], Ws [parts][NW][ldk], ldk % 8 == 0, zero padded beyond K.  parts = 2 keeps the
+ * three leading cross products (relative error ~2^-17), parts = 3 the six leading ones (~2^-24).
+ * D[x][w] = alpha * sum_k X[x][k] W[w][k], D row-major with ldd floats per row. */
+int aoenv_split_bf16(const float* src, int lds, int rows, int K, int parts, void* dst, int ldk, void* stream);
+int aoenv_gemm_tn_tc(const void* Xs, const void* Ws, int ldk, int parts, float* D, int ldd, int MX, int NW, int K,
+                     float alpha, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Shack-Hartmann WFS + detector — OOPAO/ShackHartmann.py:511-601 (and :605-674), OOPAO/Detector.py:190-301
  * ------------------------------------------------------------------------------------------------------- */

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 from numpy.random import RandomState
 
-from . import _lib
+from . import _lib, gemm
 from .tools import vonkarman as vk
 
 
@@ -112,6 +112,7 @@ class Atmosphere:
             self._ldx = (self._nO + 3) // 4 * 4
             self._W = torch.zeros((self._nO, self._K), dtype=torch.float32, device=dev)
             self._W[:, :self._nI] = ops.A.to(torch.float32)
+            self._W_op = gemm.Operator(self._W, parts=3)       # the extruded ring is advected across the pupil: 2^-24
             self._upload_B()
             self._inner_rc = torch.as_tensor(ops.inner_rc, dtype=torch.int32, device=dev).contiguous()
             self._maps = torch.zeros((self.nLayer, 2, B, self._M, self._pitch), dtype=torch.float32, device=dev)
@@ -135,6 +136,7 @@ class Atmosphere:
 
     def _upload_B(self):
         self._W[:, self._nI:self._nI + self._nO] = self._ops.B.to(torch.float32)
+        self._W_op.invalidate()
 
     # ---- random streams -----------------------------------------------------------------------------
     def _host_xi(self, layer_index):
@@ -183,14 +185,10 @@ class Atmosphere:
         _lib.check(lib.aoenv_atm_gather(_lib.ptr(src), B, M, pitch, int(sx), int(sy), _lib.ptr(self._inner_rc), self._nI,
                                         self._nO, _lib.ptr(xi), C.c_uint64(seed), C.c_uint64(stream_id),
                                         _lib.ptr(self._zx), self._K, st), "atm_gather")
-        self._gemm(self._zx, self._W, self._X, B, self._nO, self._K)
+        gemm.gemm_tn(self._zx, self._W_op, self._X, B, self._nO)
         _lib.check(lib.aoenv_atm_scatter(_lib.ptr(src), _lib.ptr(dst), B, M, pitch, int(sx), int(sy), self._nO,
                                          _lib.ptr(self._X), self._ldx, _lib.ptr(self._minmax[i]), st), "atm_scatter")
         self._cur[i] = 1 - cur
-
-    def _gemm(self, X, W, D, M, N, K):
-        _lib.check(_lib.load().aoenv_gemm_tn(_lib.ptr(X), X.stride(0), _lib.ptr(W), W.stride(0), _lib.ptr(D), D.stride(0),
-                                             M, N, K, 1.0, _lib.stream_ptr(self.device)), "gemm_tn")
 
     def _update_layer(self, i):
         """Integer part of updateLayer (Atmosphere.py:350-404); returns nothing, leaves ly.buff ready."""

@@ -11,7 +11,7 @@ import sys
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, gemm
 from .MisRegistration import MisRegistration
 
 
@@ -118,6 +118,7 @@ class DeformableMirror:
         self._Kp = (self.nValidAct + 15) // 16 * 16
         self._modes = torch.zeros((modes64.shape[0], self._Kp), dtype=torch.float32, device=self.device)
         self._modes[:, :self.nValidAct] = modes64.to(torch.float32)
+        self._modes_op = gemm.Operator(self._modes, parts=2)
 
     def free_float64(self):
         self._modes64 = None
@@ -133,14 +134,12 @@ class DeformableMirror:
         self._set_modes(m)
 
     # ---- surfaces ----------------------------------------------------------------------------------------
-    def _surface(self, coefs_padded, out):
+    def _surface(self, coefs_padded, out, backend=None):
         """out[f] = modes @ coefs[f] for every frame f (OPD = modes @ coefs, DeformableMirror.py:534-570)."""
         F = coefs_padded.shape[0]
         P = self.resolution ** 2
         o2 = out.reshape(F, P)
-        _lib.check(_lib.load().aoenv_gemm_tn(_lib.ptr(coefs_padded), coefs_padded.stride(0), _lib.ptr(self._modes),
-                                             self._modes.stride(0), _lib.ptr(o2), o2.stride(0), F, P, self._Kp, 1.0,
-                                             _lib.stream_ptr(self.device)), "gemm_tn(dm)")
+        gemm.gemm_tn(coefs_padded, self._modes_op, o2, F, P, backend=backend)
 
     def _set_coefs_batch(self, coefs_padded):
         """Fast path of env.step: per-environment commands [B, Kp]; writes the *next* surface slot and makes it
@@ -184,7 +183,7 @@ class DeformableMirror:
             c = torch.zeros((k, self._Kp), dtype=torch.float32, device=self.device)
             c[:, :nA] = t.T
             self._multi = torch.empty((k, self.resolution, self.resolution), dtype=torch.float32, device=self.device)
-            self._surface(c, self._multi)
+            self._surface(c, self._multi, backend="simt")     # calibration pushes: exact FP32 (init only)
             self._coefs_matrix = t
         elif t.ndim == 2 and t.shape == (B, nA):
             c = torch.zeros((B, self._Kp), dtype=torch.float32, device=self.device)

@@ -17,7 +17,7 @@ import types
 import numpy as np
 import torch
 
-from .. import _lib
+from .. import _lib, gemm
 from ..Atmosphere import Atmosphere
 from ..DeformableMirror import DeformableMirror
 from ..MisRegistration import MisRegistration
@@ -170,6 +170,7 @@ class OOPAO:
         nA, nSig = self.reconstructor.shape
         self._Rm = torch.zeros((nA, self.wfs._lds), dtype=torch.float32, device=self.device)
         self._Rm[:, :nSig] = self.reconstructor.to(torch.float32)
+        self._Rm_op = gemm.Operator(self._Rm, parts=2)
 
     @property
     def dm_prev(self):
@@ -190,8 +191,7 @@ class OOPAO:
         """obs = vec_to_img(-reconstructor @ signal) * 1e6 (+ reward, Strehl, rms diagnostics)."""
         lib, st, B, nA = _lib.load(), _lib.stream_ptr(self.device), self.n_envs, self.dm.nValidAct
         sig = self.wfs._signal
-        _lib.check(lib.aoenv_gemm_tn(_lib.ptr(sig), sig.stride(0), _lib.ptr(self._Rm), self._Rm.stride(0), _lib.ptr(self._rec),
-                                     self._rec.stride(0), B, nA, self.wfs._lds, 1.0, st), "gemm_tn(reconstruct)")
+        gemm.gemm_tn(sig, self._Rm_op, self._rec, B, nA)
         _lib.check(lib.aoenv_observe(_lib.ptr(self._rec), self._rec.stride(0), _lib.ptr(self._act_idx), B, nA,
                                      self.nActuator ** 2, _lib.ptr(self.wfs._stats) if with_stats else None,
                                      float(self.tel.pixelArea), self._phase_scale, _lib.ptr(self._obs), _lib.ptr(self._reward),

@@ -122,7 +122,11 @@ struct Cfg {
   static constexpr int kXBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kParts * (kWBytes + kXBytes);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int kTmemCols = 2 * BLOCK_N;   // two accumulator buffers
+  // parts == 3 keeps the leading product x_0 w_0 and the five cross terms in separate accumulators (summed in FP32 by
+  // the epilogue): the tensor core adds into the running sum with truncation, so the error grows with the number of
+  // MMAs that touch a LARGE accumulator — this keeps it to K/16 instead of 6K/16.
+  static constexpr int kAccPerBuf = (kParts == 3) ? 2 : 1;
+  static constexpr int kTmemCols = 2 * kAccPerBuf * BLOCK_N;   // two accumulator buffers
   static_assert(kTmemCols == 256 || kTmemCols == 512, "TMEM allocation must be a power of two");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
@@ -205,12 +209,13 @@ gemm_tc_kernel(const __grid_constant__ TensorMaps maps, float* __restrict__ D, i
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        const uint32_t tmem_d = tmem_base + acc * C::kAccPerBuf * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t st = smem_u32(smem + stage * C::kStageBytes);
-          uint32_t first = (kb == 0) ? 1u : 0u;
+          uint32_t first = (kb == 0) ? 1u : 0u;        // first MMA into the main accumulator
+          uint32_t first_x = (kb == 0) ? 1u : 0u;      // first MMA into the cross-term accumulator
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // cross terms in increasing order of magnitude last: (pw, px) with pw + px < kParts
@@ -221,8 +226,13 @@ gemm_tc_kernel(const __grid_constant__ TensorMaps maps, float* __restrict__ D, i
                 if (pw + px >= kParts) continue;
                 const uint64_t da = smem_desc_sw128(st + pw * C::kWBytes + k * UMMA_K * 2);
                 const uint64_t db = smem_desc_sw128(st + kParts * C::kWBytes + px * C::kXBytes + k * UMMA_K * 2);
-                umma_bf16(tmem_d, da, db, idesc, first ? 0u : 1u);
-                first = 0;
+                if (C::kAccPerBuf == 2 && (pw + px) > 0) {
+                  umma_bf16(tmem_d + BLOCK_N, da, db, idesc, first_x ? 0u : 1u);
+                  first_x = 0;
+                } else {
+                  umma_bf16(tmem_d, da, db, idesc, first ? 0u : 1u);
+                  first = 0;
+                }
               }
             }
           }
@@ -247,8 +257,17 @@ gemm_tc_kernel(const __grid_constant__ TensorMaps maps, float* __restrict__ D, i
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::kAccPerBuf * BLOCK_N + c0);
+        tmem_ld32(taddr, v);
+        if (C::kAccPerBuf == 2) {
+          uint32_t u[32];
+          tmem_ld32(taddr + BLOCK_N, u);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+        } else {
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
         const int x0 = n_blk * BLOCK_N + c0;
         if (w_ok) {
 #pragma unroll

@@ -1,0 +1,59 @@
+"""Dense contractions of the step: D[x][w] = alpha * sum_k X[x][k] W[w][k] (include/aoenv.h).
+
+Two hand-written CUDA back ends, both FP32-accurate:
+  "tc"   tcgen05 tensor cores on split-bf16 operands (aoenv_gemm_tn_tc) — the production path;
+  "simt" FP32 FMA kernel (aoenv_gemm_tn) — kept as the on-device cross-check of the tensor-core path.
+Select with rlao_b200.gemm.BACKEND or the AOENV_GEMM environment variable."""
+import os
+
+import torch
+
+from . import _lib
+
+BACKEND = os.environ.get("AOENV_GEMM", "tc")
+
+
+class Operator:
+    """Static operand W [N, Kp] (float32, zero padded to Kp % 16 == 0) plus its lazily built bf16 planes."""
+
+    def __init__(self, W, parts=2):
+        assert W.dtype == torch.float32 and W.stride(1) == 1 and W.stride(0) % 16 == 0
+        self.W, self.parts, self._planes = W, parts, None
+
+    def invalidate(self):
+        self._planes = None
+
+    def planes(self):
+        if self._planes is None:
+            N, Kp = self.W.shape[0], self.W.stride(0)
+            self._planes = torch.empty((self.parts, N, Kp), dtype=torch.bfloat16, device=self.W.device)
+            _lib.check(_lib.load().aoenv_split_bf16(_lib.ptr(self.W), Kp, N, Kp, self.parts, _lib.ptr(self._planes), Kp,
+                                                    _lib.stream_ptr(self.W.device)), "split_bf16(W)")
+        return self._planes
+
+
+_workspaces = {}
+
+
+def _x_planes(X, parts):
+    key = (X.device, X.shape[0], X.stride(0), parts)      # one workspace per shape: calls are stream-ordered
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = torch.empty((parts, X.shape[0], X.stride(0)), dtype=torch.bfloat16, device=X.device)
+        _workspaces[key] = ws
+    return ws
+
+
+def gemm_tn(X, op, D, M, N, alpha=1.0, backend=None):
+    """X [M, Kp] float32, op: Operator over W [N, Kp]; D [M, >=N] float32 (row stride D.stride(0))."""
+    backend = backend or BACKEND
+    lib, st = _lib.load(), _lib.stream_ptr(X.device)
+    Kp = op.W.stride(0)
+    assert X.stride(0) == Kp, "operands must share the padded K"
+    if backend == "simt":
+        _lib.check(lib.aoenv_gemm_tn(_lib.ptr(X), Kp, _lib.ptr(op.W), Kp, _lib.ptr(D), D.stride(0), M, N, Kp, alpha, st), "gemm_tn")
+        return
+    xs = _x_planes(X, op.parts)
+    _lib.check(lib.aoenv_split_bf16(_lib.ptr(X), Kp, M, Kp, op.parts, _lib.ptr(xs), Kp, st), "split_bf16(X)")
+    _lib.check(lib.aoenv_gemm_tn_tc(_lib.ptr(xs), _lib.ptr(op.planes()), Kp, op.parts, _lib.ptr(D), D.stride(0), M, N, Kp,
+                                    alpha, st), "gemm_tn_tc")

@@ -257,8 +257,9 @@ class FakeLib:
 
 def install(monkeypatch):
     """Routes rlao_b200._lib to the fake backend and lets objects live on the CPU."""
-    from rlao_b200 import _lib
+    from rlao_b200 import _lib, gemm
     fake = FakeLib()
+    monkeypatch.setattr(gemm, "BACKEND", "simt")
     monkeypatch.setattr(_lib, "load", lambda: fake)
     monkeypatch.setattr(_lib, "require_cuda", lambda device: torch.device("cpu"))
     monkeypatch.setattr(_lib, "stream_ptr", lambda device=None: None)
