@@ -136,6 +136,7 @@ shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ op
   const bool active = k < nS * nS;
   const int li = active ? k / nS : 0, lj = active ? k % nS : 0;
   const bool lit = active && valid[k] != 0;
+  const float phase_turns = phase_scale * 0.15915494309189535f;      // radians -> turns
 
   float er[n][n], ei[n][n];   // field E[a][b] = tile^T (ShackHartmann.py:341-345 tiles phase.T)
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -157,8 +158,10 @@ shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ op
           s2 += (double)t;
           s3 += (double)t * (double)t;
         }
-        float sn, cs;
-        sincosf(t * pu * phase_scale, &sn, &cs);
+        // phase / 2pi reduced to [-1/2, 1/2] exactly, then the SFU sine/cosine (abs. error ~4e-7 on [-pi, pi])
+        const float turns = t * pu * phase_turns;
+        const float ang = (turns - rintf(turns)) * 6.283185307179586f;
+        const float sn = __sinf(ang), cs = __cosf(ang);
         const float am = lit ? __ldg(amp + tile + o) : 0.f;
         er[aa][bb] = am * cs;
         ei[aa][bb] = am * sn;
@@ -185,44 +188,86 @@ shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ op
     float* __restrict__ fout = frame + (size_t)b * R * R + (size_t)(li * n) * R + lj * n;
     const uint32_t pix0 = (uint32_t)((li * n) * R + lj * n);
     const float norm = 1.0f / (float)(N * N);
-    for (int p = 0; p < n; ++p) {       // output (binned) row of the spot
-      float acc[n];
+    // Radix-2 split of both DFT passes: G[u + n][a] = (-1)^(a + n/2) G[u][a] (the half-pixel phasor keeps the
+    // symmetry), so output rows u and u + n share their even-/odd-class partial sums P, Q:  Y_u = P + Q,
+    // Y_{u+n} = P - Q, and likewise for the columns.  Binned row pp collects u = 2pp, 2pp+1; row pp + n/2 collects
+    // u + n.
+    constexpr int h = n / 2;
+    for (int pp = 0; pp < h; ++pp) {
+      float acc_lo[n], acc_hi[n];
 #pragma unroll
-      for (int q = 0; q < n; ++q) acc[q] = 0.f;
+      for (int q = 0; q < n; ++q) { acc_lo[q] = 0.f; acc_hi[q] = 0.f; }
       if (lit) {
 #pragma unroll
         for (int du = 0; du < 2; ++du) {
-          const int u = 2 * p + du;
-          float yr[n], yi[n];
+          const int u = 2 * pp + du;
+          float pr[n], pi[n], qr[n], qi[n];
 #pragma unroll
-          for (int bb = 0; bb < n; ++bb) { yr[bb] = 0.f; yi[bb] = 0.f; }
+          for (int bb = 0; bb < n; ++bb) { pr[bb] = 0.f; pi[bb] = 0.f; qr[bb] = 0.f; qi[bb] = 0.f; }
 #pragma unroll
           for (int aa = 0; aa < n; ++aa) {
             const float2 g = c_tw[u * n + aa];
+            if (((aa + h) & 1) == 0) {
 #pragma unroll
-            for (int bb = 0; bb < n; ++bb) {
-              yr[bb] = fmaf(g.x, er[aa][bb], fmaf(-g.y, ei[aa][bb], yr[bb]));
-              yi[bb] = fmaf(g.x, ei[aa][bb], fmaf(g.y, er[aa][bb], yi[bb]));
+              for (int bb = 0; bb < n; ++bb) {
+                pr[bb] = fmaf(g.x, er[aa][bb], fmaf(-g.y, ei[aa][bb], pr[bb]));
+                pi[bb] = fmaf(g.x, ei[aa][bb], fmaf(g.y, er[aa][bb], pi[bb]));
+              }
+            } else {
+#pragma unroll
+              for (int bb = 0; bb < n; ++bb) {
+                qr[bb] = fmaf(g.x, er[aa][bb], fmaf(-g.y, ei[aa][bb], qr[bb]));
+                qi[bb] = fmaf(g.x, ei[aa][bb], fmaf(g.y, er[aa][bb], qi[bb]));
+              }
             }
           }
 #pragma unroll
-          for (int v = 0; v < N; ++v) {
-            float fr = 0.f, fi = 0.f;
+          for (int half = 0; half < 2; ++half) {       // half 0: row u (Y = P + Q); half 1: row u + n (Y = P - Q)
+            float yr[n], yi[n];
 #pragma unroll
             for (int bb = 0; bb < n; ++bb) {
-              const float2 g = c_tw[v * n + bb];
-              fr = fmaf(yr[bb], g.x, fmaf(-yi[bb], g.y, fr));
-              fi = fmaf(yr[bb], g.y, fmaf(yi[bb], g.x, fi));
+              yr[bb] = half == 0 ? pr[bb] + qr[bb] : pr[bb] - qr[bb];
+              yi[bb] = half == 0 ? pi[bb] + qi[bb] : pi[bb] - qi[bb];
             }
-            acc[v >> 1] = fmaf(fr, fr, fmaf(fi, fi, acc[v >> 1]));
+#pragma unroll
+            for (int v = 0; v < n; ++v) {
+              float er_ = 0.f, ei_ = 0.f, or_ = 0.f, oi_ = 0.f;
+#pragma unroll
+              for (int bb = 0; bb < n; ++bb) {
+                const float2 g = c_tw[v * n + bb];
+                if (((bb + h) & 1) == 0) {
+                  er_ = fmaf(yr[bb], g.x, fmaf(-yi[bb], g.y, er_));
+                  ei_ = fmaf(yr[bb], g.y, fmaf(yi[bb], g.x, ei_));
+                } else {
+                  or_ = fmaf(yr[bb], g.x, fmaf(-yi[bb], g.y, or_));
+                  oi_ = fmaf(yr[bb], g.y, fmaf(yi[bb], g.x, oi_));
+                }
+              }
+              const float f0r = er_ + or_, f0i = ei_ + oi_;     // F[row][v]
+              const float f1r = er_ - or_, f1i = ei_ - oi_;     // F[row][v + n]
+              const float i0 = fmaf(f0r, f0r, f0i * f0i);
+              const float i1 = fmaf(f1r, f1r, f1i * f1i);
+              if (half == 0) {
+                acc_lo[v >> 1] += i0;
+                acc_lo[(v >> 1) + h] += i1;
+              } else {
+                acc_hi[v >> 1] += i0;
+                acc_hi[(v >> 1) + h] += i1;
+              }
+            }
           }
         }
       }
 #pragma unroll
-      for (int q = 0; q < n; ++q) {
-        const float val = detector_pixel(acc[q] * norm, det, pix0 + (uint32_t)(p * R + q), (uint32_t)b);
-        fout[(size_t)p * R + q] = val;
-        if (lit) vmax = fmaxf(vmax, val);
+      for (int r2 = 0; r2 < 2; ++r2) {
+        const int p = pp + r2 * h;
+#pragma unroll
+        for (int q = 0; q < n; ++q) {
+          const float raw = (r2 == 0 ? acc_lo[q] : acc_hi[q]) * norm;
+          const float val = detector_pixel(raw, det, pix0 + (uint32_t)(p * R + q), (uint32_t)b);
+          fout[(size_t)p * R + q] = val;
+          if (lit) vmax = fmaxf(vmax, val);
+        }
       }
     }
   }
