@@ -26,6 +26,7 @@ WORKLOADS = {
     # name: (nSubap, nLayers, envs per GPU, description)
     "cfg3": (40, 3, 1024, "8m 40x40 SH-WFS, 41x41 DM (1353 act), 3-layer VK atmosphere, integrator, noise off"),
     "cfg2": (20, 1, 1024, "8m 20x20 SH-WFS, 21x21 DM (357 act), 1-layer VK atmosphere, integrator, noise off"),
+    "cfg5": (80, 5, 256, "8m 80x80 SH-WFS, 81x81 DM (5209 act), 5-layer VK atmosphere, integrator, noise off"),
     "cfg1": (20, 1, 1, "8m 20x20 SH-WFS, 21x21 DM, 1 layer, single env"),
     "tiny": (8, 2, 64, "8m 8x8 SH-WFS test system"),
 }

@@ -116,8 +116,9 @@ typedef struct {
  * amp [R][R] = sqrt(fluxMap).  envmax [B] receives max over the environment's valid-lenslet pixels (float bits
  * in a monotone int32 encoding, initialised by this call); shared_max != 0 -> one max for the whole batch in
  * envmax[0] (the interaction-matrix branch, ShackHartmann.py:659).
- * stats [B][4] (float64): sums over pupil pixels of {opd_a, opd_a^2, opd, opd^2} in metres, for
- * env.total / env.residual / get_strehl (MAIN/OOPAOEnv/OOPAOEnvRazor.py:484,502,604-605). May be NULL.
+ * stats [B][4] (float64): sums over pupil pixels of {a, a^2, t, t^2}, a = opd_a - opd_a[centre], t = opd - opd[centre]
+ * in metres (centred on the pupil-centre pixel: only variances are derived from them), for env.total /
+ * env.residual / get_strehl (MAIN/OOPAOEnv/OOPAOEnvRazor.py:484,502,604-605). May be NULL.
  * n (pixels per lenslet) must be one of the compiled sizes (4, 6, 8). */
 int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil, const float* amp,
                       const uint8_t* valid, int B, int nS, int n, float phase_scale,

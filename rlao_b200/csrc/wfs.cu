@@ -104,8 +104,8 @@ struct DetParams {
 };
 
 // OOPAO/Detector.py:279-301 (integrate) then :232-276 (readout), one pixel.
-__device__ __forceinline__ float detector_pixel(float x, const DetParams& dp, uint32_t pixel, uint32_t env) {
-  if (!dp.enabled) return x;
+// Kept out of line: inlined at the 36 call sites it inflates the frame kernel past the instruction cache.
+__device__ __noinline__ float detector_pixel(float x, const DetParams& dp, uint32_t pixel, uint32_t env) {
   const aoenv_detector_t& d = dp.d;
   PixelRng rng(d.seed, pixel, env, d.frame_counter);
   if (d.photon_noise) x = poisson_draw(x, rng);
@@ -139,11 +139,17 @@ shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ op
   const float phase_turns = phase_scale * 0.15915494309189535f;      // radians -> turns
 
   float er[n][n], ei[n][n];   // field E[a][b] = tile^T (ShackHartmann.py:341-345 tiles phase.T)
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  // Pupil statistics for std(OPD) / var(phase): variance is shift invariant, so each thread accumulates its n*n
+  // pixels in float32 relative to the value at the pupil centre (removes the piston that would otherwise dominate
+  // sum x^2), and only the per-thread partial sums are promoted to float64 for the reduction.
+  float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
   if (active) {
     const size_t tile = (size_t)(li * n) * R + lj * n;
     const float* __restrict__ pa = opd_a + (size_t)b * R * R + tile;
     const float* __restrict__ pb = opd_b ? opd_b + (size_t)b * R * R + tile : nullptr;
+    const size_t centre = (size_t)b * R * R + (size_t)(R / 2) * R + R / 2;
+    const float ka = stats ? __ldg(opd_a + centre) : 0.f;
+    const float kt = stats ? (opd_b ? ka + __ldg(opd_b + centre) : ka) : 0.f;
 #pragma unroll
     for (int bb = 0; bb < n; ++bb) {
 #pragma unroll
@@ -152,12 +158,9 @@ shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ op
         const float a = __ldg(pa + o);
         const float t = pb ? a + __ldg(pb + o) : a;
         const float pu = __ldg(pupil + tile + o);
-        if (pu > 0.f) {
-          s0 += (double)a;
-          s1 += (double)a * (double)a;
-          s2 += (double)t;
-          s3 += (double)t * (double)t;
-        }
+        const float in_pupil = pu > 0.f ? 1.f : 0.f;
+        const float da = (a - ka) * in_pupil, dt = (t - kt) * in_pupil;
+        f0 += da; f1 = fmaf(da, da, f1); f2 += dt; f3 = fmaf(dt, dt, f3);
         // phase / 2pi reduced to [-1/2, 1/2] exactly, then the SFU sine/cosine (abs. error ~4e-7 on [-pi, pi])
         const float turns = t * pu * phase_turns;
         const float ang = (turns - rintf(turns)) * 6.283185307179586f;
@@ -168,6 +171,7 @@ shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ op
       }
     }
   }
+  double s0 = (double)f0, s1 = (double)f1, s2 = (double)f2, s3 = (double)f3;
 
   if (stats != nullptr) {
     s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
@@ -193,6 +197,7 @@ shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ op
     // Y_{u+n} = P - Q, and likewise for the columns.  Binned row pp collects u = 2pp, 2pp+1; row pp + n/2 collects
     // u + n.
     constexpr int h = n / 2;
+#pragma unroll 1
     for (int pp = 0; pp < h; ++pp) {
       float acc_lo[n], acc_hi[n];
 #pragma unroll
@@ -264,7 +269,7 @@ shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ op
 #pragma unroll
         for (int q = 0; q < n; ++q) {
           const float raw = (r2 == 0 ? acc_lo[q] : acc_hi[q]) * norm;
-          const float val = detector_pixel(raw, det, pix0 + (uint32_t)(p * R + q), (uint32_t)b);
+          const float val = det.enabled ? detector_pixel(raw, det, pix0 + (uint32_t)(p * R + q), (uint32_t)b) : raw;
           fout[(size_t)p * R + q] = val;
           if (lit) vmax = fmaxf(vmax, val);
         }

@@ -137,8 +137,9 @@ class FakeLib:
             t = a[e] + (b_[e] if b_ is not None else 0)
             if st is not None:
                 m = pu > 0
-                st[e] = [a[e][m].astype(np.float64).sum(), (a[e][m].astype(np.float64) ** 2).sum(),
-                         t[m].astype(np.float64).sum(), (t[m].astype(np.float64) ** 2).sum()]
+                da = (a[e] - a[e][R // 2, R // 2])[m].astype(np.float64)
+                dt = (t - t[R // 2, R // 2])[m].astype(np.float64)
+                st[e] = [da.sum(), (da ** 2).sum(), dt.sum(), (dt ** 2).sum()]
             ph = (t * pu * scale).astype(np.float64)
             field = np.zeros((nS * nS, N, N), dtype=complex)
             field[:, lo:lo + n, lo:lo + n] = np.exp(1j * tiles(ph)) * tiles(am.astype(np.float64))
