@@ -378,7 +378,8 @@ def dominant_roofline(kernels, env, B):
         "aoenv_atm_phase": L * M * M * 4 + P * 4,
         "aoenv_shwfs_frame": 3 * P * 4,
         "aoenv_shwfs_slopes": P * 4 + nSig * 4,
-        "aoenv_atm_scatter": 2 * M * M * 4,
+        "aoenv_atm_ring": 2 * (4 * M - 4) * 4,
+        "aoenv_atm_compact": 2 * M * M * 4,
         "aoenv_atm_gather": 2 * (env.atm._nI + env.atm._nO) * 4,
         "aoenv_command_update": 3 * nA * 4 + env.nActuator ** 2 * 4,
         "aoenv_observe": nA * 4 + env.nActuator ** 2 * 4,

@@ -35,41 +35,47 @@ uint64_t aoenv_launch_count(void);
 /* ---------------------------------------------------------------------------------------------------------
  * Atmosphere — OOPAO/Atmosphere.py
  *
- * State per layer l: `map` [B][M][pitch] (M = R + 6 = layer.mapShift side, pitch >= M floats per row) and the
- * per-environment extrema `minmax` [B][2] of that map (the clip range of skimage.warp, tools.py:215-217).
+ * State per layer: a canvas [B][Mc][pitch] holding the reference's layer.mapShift (side M = R + 6) as a WINDOW at a
+ * movable origin.  The reference shifts the whole map by one pixel at every add_row (Atmosphere.py:301-311); here the
+ * window origin moves by -step instead and only the 4M-4 ring pixels are written.  A window is passed as a pointer
+ * to its origin pixel plus `pitch` (floats per canvas row) and `env_stride` (floats per environment canvas).
+ * `ext` [B][2] (uint64) tracks the window's minimum / maximum WITH position — (monotone key of the float) << 32 |
+ * element index in the canvas — which is the clip range of skimage.warp (tools/tools.py:215-217).
  * ------------------------------------------------------------------------------------------------------- */
 
 /* add_row, step 1 (Atmosphere.py:303-307): gathers, for every environment, the two inner rings Z of the map
  * shifted by (sx, sy) in {-1,0,1}^2 pixels (tx = sx along columns, ty = sy along rows) into zx[b][0..nI), and
  * the innovation xi ~ N(0,1) into zx[b][nI..nI+nO): injected from `xi` [B][nO] when non-null, else Philox
- * (seed, stream_id, b).  zx rows have `ldz` floats (ldz >= nI+nO; the tail is zero-filled).
- * inner_rc [nI][2] holds (row, col) of the inner-ring pixels in MAP coordinates, in the reference's boolean-
- * mask (row-major) order. */
-int aoenv_atm_gather(const float* map, int B, int M, int pitch, int sx, int sy,
+ * (seed, stream_id, b).  zx rows have `ldz` floats (ldz >= nI+nO; the tail is zero-filled).  `win` is the window
+ * BEFORE the shift.  inner_rc [nI][2] holds (row, col) of the inner-ring pixels in window coordinates, in the
+ * reference's boolean-mask (row-major) order. */
+int aoenv_atm_gather(const float* win, int B, int M, int pitch, int64_t env_stride, int sx, int sy,
                      const int32_t* inner_rc, int nI, int nO, const float* xi,
                      uint64_t seed, uint64_t stream_id, float* zx, int ldz, void* stream);
 
-/* add_row, step 3 (Atmosphere.py:309-310): map_out interior <- map_in shifted by (sx, sy); map_out outer ring
- * <- X [B][ldx] (X = A Z + B xi, computed by aoenv_gemm_tn on zx and the stacked operator [A | B]), ring pixels
- * taken in the order of numpy's boolean mask `outerMask` (row 0, then the (r,0),(r,M-1) pairs, then row M-1;
- * nO must equal 4M-4).  Also refreshes minmax[b] = {min, max} of map_out, stored as monotone int32 encodings
- * of the float values (see aoenv_map_minmax). */
-int aoenv_atm_scatter(const float* map_in, float* map_out, int B, int M, int pitch, int sx, int sy, int nO,
-                      const float* X, int ldx, int32_t* minmax, void* stream);
+/* add_row, step 3 (Atmosphere.py:309-310): writes the freshly extruded outer ring X [B][ldx] (X = A Z + B xi, from
+ * the GEMM on zx and the stacked operator [A | B]) on the border of `win`, the window AFTER the shift, ring pixels in
+ * the order of numpy's boolean mask `outerMask` (row 0, then the (r,0),(r,M-1) pairs, then row M-1; nO = 4M-4).
+ * win_offset = element index of the window origin inside the canvas.  Updates ext: extrema whose pixel is still
+ * in the window interior are kept and merged with the ring's; otherwise (or when force_rescan) the environment is
+ * flagged in flag [B] and its window is rescanned exactly. */
+int aoenv_atm_ring(float* win, int B, int M, int pitch, int64_t env_stride, int64_t win_offset, int nO, const float* X,
+                   int ldx, uint64_t* ext, int32_t* flag, int force_rescan, void* stream);
 
-/* minmax[b] = {min, max} over map[b] (used after (re)initialising the screens).  Encoding: the float's bit
- * pattern i, or i ^ 0x7fffffff when i < 0, so that integer order equals float order. */
-int aoenv_map_minmax(const float* map, int B, int M, int pitch, int32_t* minmax, void* stream);
+/* Canvas re-centring: copies the window from src_win to dst_win (another canvas buffer, origin 16-byte aligned) and
+ * adds pos_delta to the positions stored in ext. */
+int aoenv_atm_compact(const float* src_win, float* dst_win, int B, int M, int pitch, int64_t env_stride, uint64_t* ext,
+                      int64_t pos_delta, void* stream);
 
 /* updateLayer tail + fill_phase_support + set_OPD (Atmosphere.py:406-407,439-450,474-478): for each layer the
  * bicubic (4x4 tap) sub-pixel shift of the map, clipped to the map's [min,max], cropped to the R x R pupil
  * footprint, weighted by sqrt(fractionalR0) and summed; opd_out [B][R][R] = sum * opd_scale (lambda/2pi).
- * h_map / h_minmax: host arrays of nLayer device pointers.  h_row_off / h_col_off: first tap offset relative
- * to the output pixel's own map row / column (so tap k reads row i + fp_off + h_row_off[l] + k).
+ * h_win / h_ext: host arrays of nLayer device pointers (window origins, extrema).  h_row_off / h_col_off: first tap
+ * offset relative to the output pixel's own window row / column (tap k reads row i + fp_off + h_row_off[l] + k).
  * h_wrow / h_wcol [nLayer][4]: tap weights (computed by the host in float64 from layer.buff).
- * h_weight [nLayer] = sqrt(fractionalR0).  fp_off = map index of footprint pixel 0 (3 for fov = 0). */
-int aoenv_atm_phase(const float* const* h_map, const int32_t* const* h_minmax, int nLayer, int B, int R, int M,
-                    int pitch, int fp_off, const int32_t* h_row_off, const int32_t* h_col_off,
+ * h_weight [nLayer] = sqrt(fractionalR0).  fp_off = window index of footprint pixel 0 (3 for fov = 0). */
+int aoenv_atm_phase(const float* const* h_win, const uint64_t* const* h_ext, int nLayer, int B, int R, int M, int pitch,
+                    int64_t env_stride, int fp_off, const int32_t* h_row_off, const int32_t* h_col_off,
                     const float* h_wrow, const float* h_wcol, const float* h_weight, float opd_scale,
                     float* opd_out, void* stream);
 

@@ -5,8 +5,10 @@ r0, L0 and the Cn2 profile belong to the Atmosphere object and are therefore sha
 the integer-pixel extrusions (`add_row`) fire on the same step for the whole batch and become one GEMM
 X[B, nO] = [Z | xi][B, nI+nO] @ [A | B]^T.
 
-HBM layout: maps[layer][2][B][M][pitch] float32 (M = R + 6, ping-pong pair per layer), minmax[layer][B][2]
-(monotone-int encoded extrema for the interpolation clip), opd[B][R][R] (OPD_no_pupil in metres).
+HBM layout: canvases[layer][2][B][Mc][pitch] float32 — the reference's (R+6)^2 map is a WINDOW at a movable origin
+inside a canvas of side Mc = M + slack: add_row moves the origin by -step and writes only the 4M-4 ring pixels
+(the reference copies the whole map); the window is re-centred into the other canvas once every `slack` events.
+ext[layer][B][2] uint64 (window extrema with position, for the interpolation clip), opd[B][R][R] (OPD_no_pupil, m).
 """
 import ctypes as C
 import math
@@ -41,7 +43,8 @@ class _LayerView:
     @property
     def mapShift(self):
         a = self._atm
-        m = a._maps[self._i, a._cur[self._i], :, :, :a._M]
+        oy, ox = a._org[self._i]
+        m = a._maps[self._i, a._cur[self._i], :, oy:oy + a._M, ox:ox + a._M]
         return m[0] if a.n_envs == 1 else m
 
     @property
@@ -55,7 +58,7 @@ class _LayerView:
 
 class Atmosphere:
     def __init__(self, telescope, r0, L0, windSpeed, fractionalR0, windDirection, altitude, mode=2, param=None,
-                 asterism=None, rng="philox", seed=0, warp_kernel="lagrange018", env_offset=0):
+                 asterism=None, rng="philox", seed=0, warp_kernel="lagrange018", env_offset=0, canvas_slack=32):
         """`rng`: 'philox' — device counter-based streams (production); 'reference' — the reference's MT19937
         streams for environment 0 (RandomState(42 + 1000*layer) etc., Atmosphere.py:201,579), offset by
         104729*env for the others: host-generated, for parity runs and small batches.
@@ -90,6 +93,7 @@ class Atmosphere:
         self.seed = int(seed)
         self.env_offset = int(env_offset)
         self.warp_kernel = warp_kernel
+        self.canvas_slack = max(1, int(canvas_slack))   # add_row events between two re-centrings of a layer's canvas
         self.xi_queue = None        # optional iterator of [B, nO] tensors: injected innovations (parity runs)
         self.xi_log = None          # set to [] to record every innovation block used
 
@@ -106,7 +110,10 @@ class Atmosphere:
             self._ops = vk.VKOperators(R, tel.D, self._L0, self._r0, self.r0_def, dev)
             ops = self._ops
             self._M = ops.layer_res + self.nExtra
-            self._pitch = (self._M + 3) // 4 * 4
+            self._S = (self.canvas_slack + 3) // 4 * 4        # multiple of 4: re-centred windows stay 16-byte aligned
+            self._Mc = self._M + self._S
+            self._pitch = (self._Mc + 3) // 4 * 4
+            self._env_stride = self._Mc * self._pitch
             self._nO, self._nI = ops.outer_rc.shape[0], ops.inner_rc.shape[0]
             self._K = (self._nI + self._nO + 15) // 16 * 16
             self._ldx = (self._nO + 3) // 4 * 4
@@ -115,9 +122,11 @@ class Atmosphere:
             self._W_op = gemm.Operator(self._W, parts=3)       # the extruded ring is advected across the pupil: 2^-24
             self._upload_B()
             self._inner_rc = torch.as_tensor(ops.inner_rc, dtype=torch.int32, device=dev).contiguous()
-            self._maps = torch.zeros((self.nLayer, 2, B, self._M, self._pitch), dtype=torch.float32, device=dev)
+            self._maps = torch.zeros((self.nLayer, 2, B, self._Mc, self._pitch), dtype=torch.float32, device=dev)
             self._cur = [0] * self.nLayer
-            self._minmax = torch.zeros((self.nLayer, B, 2), dtype=torch.int32, device=dev)
+            self._org = [[0, 0] for _ in range(self.nLayer)]          # window origin (row, col) inside the canvas
+            self._ext = torch.zeros((self.nLayer, B, 2), dtype=torch.int64, device=dev)
+            self._flag = torch.zeros((B,), dtype=torch.int32, device=dev)
             self._zx = torch.zeros((B, self._K), dtype=torch.float32, device=dev)
             self._X = torch.zeros((B, self._ldx), dtype=torch.float32, device=dev)
             self._opd = torch.zeros((B, R, R), dtype=torch.float32, device=dev)
@@ -159,18 +168,50 @@ class Atmosphere:
                 phase = vk.screens_device_rng(self._r0, self._L0, N, delta, B, g, dev)
                 ly.philox_seed = (self.seed * 1000003 + ring_seed(i)) & 0xFFFFFFFFFFFFFFFF
                 ly.events = 0
-            cur = self._cur[i]
-            self._maps[i, cur, :, 1:-1, 1:self._M - 1] = phase
-            self._extrude(i, 0, 0)
+            self._cur[i] = 0
+            self._org[i] = self._fresh_origin(i)
+            oy, ox = self._org[i]
+            self._maps[i, 0, :, oy + 1:oy + self._M - 1, ox + 1:ox + self._M - 1] = phase
+            self._extrude(i, 0, 0, force_rescan=True)
             ly.notDoneOnce = True
 
     # ---- device steps -------------------------------------------------------------------------------
-    def _extrude(self, i, sx, sy):
+    def _fresh_origin(self, i):
+        """Origin with the most head-room for the layer's drift: the origin moves by -sign(v) per event."""
+        ly, S = self._layers[i], self._S
+
+        def pick(v, align):
+            o = S if v > 0 else (0 if v < 0 else S // 2)
+            return o // align * align
+        return [pick(ly.vY, 1), pick(ly.vX, 4)]
+
+    def _win_ptr(self, i, buf=None, org=None):
+        buf = self._cur[i] if buf is None else buf
+        oy, ox = self._org[i] if org is None else org
+        return C.c_void_p(self._maps[i, buf].data_ptr() + 4 * (oy * self._pitch + ox))
+
+    def _compact(self, i):
+        """Re-centres layer i's window into the other canvas buffer."""
+        oy, ox = self._org[i]
+        foy, fox = self._fresh_origin(i)
+        cur = self._cur[i]
+        _lib.check(_lib.load().aoenv_atm_compact(self._win_ptr(i, cur, (oy, ox)), self._win_ptr(i, 1 - cur, (foy, fox)),
+                                                 self.n_envs, self._M, self._pitch, self._env_stride, _lib.ptr(self._ext[i]),
+                                                 (foy - oy) * self._pitch + (fox - ox), _lib.stream_ptr(self.device)),
+                   "atm_compact")
+        self._cur[i], self._org[i] = 1 - cur, [foy, fox]
+
+    def _extrude(self, i, sx, sy, force_rescan=False):
         """add_row (Atmosphere.py:301-311) for layer i and every environment."""
         lib, ly = _lib.load(), self._layers[i]
-        B, M, pitch = self.n_envs, self._M, self._pitch
-        cur = self._cur[i]
-        src, dst = self._maps[i, cur], self._maps[i, 1 - cur]
+        B, M, pitch, S = self.n_envs, self._M, self._pitch, self._S
+        sx, sy = int(sx), int(sy)
+        oy, ox = self._org[i]
+        if not (0 <= oy - sy <= S and 0 <= ox - sx <= S):
+            self._compact(i)
+            oy, ox = self._org[i]
+            if not (0 <= oy - sy <= S and 0 <= ox - sx <= S):
+                raise RuntimeError("canvas_slack too small for this wind direction change")
         st = _lib.stream_ptr(self.device)
         xi = None
         if self.xi_queue is not None:
@@ -182,13 +223,15 @@ class Atmosphere:
         seed = getattr(ly, "philox_seed", 0)
         stream_id = ((ly.events << 8) | i) + (self.env_offset << 40)
         ly.events += 1
-        _lib.check(lib.aoenv_atm_gather(_lib.ptr(src), B, M, pitch, int(sx), int(sy), _lib.ptr(self._inner_rc), self._nI,
-                                        self._nO, _lib.ptr(xi), C.c_uint64(seed), C.c_uint64(stream_id),
+        _lib.check(lib.aoenv_atm_gather(self._win_ptr(i), B, M, pitch, self._env_stride, sx, sy, _lib.ptr(self._inner_rc),
+                                        self._nI, self._nO, _lib.ptr(xi), C.c_uint64(seed), C.c_uint64(stream_id),
                                         _lib.ptr(self._zx), self._K, st), "atm_gather")
         gemm.gemm_tn(self._zx, self._W_op, self._X, B, self._nO)
-        _lib.check(lib.aoenv_atm_scatter(_lib.ptr(src), _lib.ptr(dst), B, M, pitch, int(sx), int(sy), self._nO,
-                                         _lib.ptr(self._X), self._ldx, _lib.ptr(self._minmax[i]), st), "atm_scatter")
-        self._cur[i] = 1 - cur
+        self._org[i] = [oy - sy, ox - sx]
+        noy, nox = self._org[i]
+        _lib.check(lib.aoenv_atm_ring(self._win_ptr(i), B, M, pitch, self._env_stride, noy * pitch + nox, self._nO,
+                                      _lib.ptr(self._X), self._ldx, _lib.ptr(self._ext[i]), _lib.ptr(self._flag),
+                                      int(force_rescan), st), "atm_ring")
 
     def _update_layer(self, i):
         """Integer part of updateLayer (Atmosphere.py:350-404); returns nothing, leaves ly.buff ready."""
@@ -221,8 +264,8 @@ class Atmosphere:
     def _publish(self):
         """Sub-pixel shift of every layer + Cn2-weighted sum -> OPD_no_pupil (Atmosphere.py:406-407,439-478)."""
         L = self.nLayer
-        maps = (C.c_void_p * L)(*[self._maps[i, self._cur[i]].data_ptr() for i in range(L)])
-        mms = (C.c_void_p * L)(*[self._minmax[i].data_ptr() for i in range(L)])
+        maps = (C.c_void_p * L)(*[self._win_ptr(i).value for i in range(L)])
+        mms = (C.c_void_p * L)(*[self._ext[i].data_ptr() for i in range(L)])
         roff, coff = (C.c_int32 * L)(), (C.c_int32 * L)()
         wr, wc, wt = (C.c_float * (4 * L))(), (C.c_float * (4 * L))(), (C.c_float * L)()
         for i, ly in enumerate(self._layers):
@@ -233,7 +276,7 @@ class Atmosphere:
                 wr[4 * i + k], wc[4 * i + k] = wrow[k], wcol[k]
             wt[i] = math.sqrt(self.fractionalR0[i])
         _lib.check(_lib.load().aoenv_atm_phase(maps, mms, L, self.n_envs, self.telescope.resolution, self._M, self._pitch,
-                                               self._fp_off, roff, coff, wr, wc, wt,
+                                               self._env_stride, self._fp_off, roff, coff, wr, wc, wt,
                                                C.c_float(self.wavelength / 2 / math.pi), _lib.ptr(self._opd),
                                                _lib.stream_ptr(self.device)), "atm_phase")
 

@@ -66,7 +66,7 @@ class OOPAO:
         return config.initializeParameterFile(args)
 
     def set_params(self, args=None, wfs_type="shackhartmann", modal_basis="zernike", gainCL=0.5, n_envs=1, device=None,
-                   rng="philox", seed=0, env_offset=0, warp_kernel="lagrange018"):
+                   rng="philox", seed=0, env_offset=0, warp_kernel="lagrange018", canvas_slack=32):
         """OOPAOEnvRazor.py:91-339 (SH branch)."""
         if wfs_type != "shackhartmann":
             raise NotImplementedError("only the Shack-Hartmann WFS is implemented (Pyramid: SURVEY.md section 8 f-3)")
@@ -84,7 +84,7 @@ class OOPAO:
         self.atm = Atmosphere(telescope=self.tel, r0=param["r0"], L0=param["L0"], windSpeed=param["windSpeed"],
                               fractionalR0=param["fractionalR0"], windDirection=param["windDirection"],
                               altitude=param["altitude"], rng=rng, seed=seed, env_offset=env_offset,
-                              warp_kernel=warp_kernel)
+                              warp_kernel=warp_kernel, canvas_slack=canvas_slack)
         self.atm.initializeAtmosphere(self.tel)
         self.atm.update()
         self.tel + self.atm

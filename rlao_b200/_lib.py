@@ -26,14 +26,14 @@ class DetectorStruct(C.Structure):
     ]
 
 
-_vp, _i, _f, _u64, _d = C.c_void_p, C.c_int, C.c_float, C.c_uint64, C.c_double
+_vp, _i, _f, _u64, _d, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_uint64, C.c_double, C.c_int64
 
 # name -> argtypes, exactly the prototypes of include/aoenv.h
 PROTOTYPES = {
-    "aoenv_atm_gather": [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _u64, _u64, _vp, _i, _vp],
-    "aoenv_atm_scatter": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp],
-    "aoenv_map_minmax": [_vp, _i, _i, _i, _vp, _vp],
-    "aoenv_atm_phase": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp],
+    "aoenv_atm_gather": [_vp, _i, _i, _i, _i64, _i, _i, _vp, _i, _i, _vp, _u64, _u64, _vp, _i, _vp],
+    "aoenv_atm_ring": [_vp, _i, _i, _i, _i64, _i64, _i, _vp, _i, _vp, _vp, _i, _vp],
+    "aoenv_atm_compact": [_vp, _vp, _i, _i, _i, _i64, _vp, _i64, _vp],
+    "aoenv_atm_phase": [_vp, _vp, _i, _i, _i, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp],
     "aoenv_gemm_tn": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _f, _vp],
     "aoenv_split_bf16": [_vp, _i, _i, _i, _i, _vp, _i, _vp],
     "aoenv_gemm_tn_tc": [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _f, _vp],

@@ -1,6 +1,11 @@
 // Atmosphere kernels: von Karman infinite phase screens (Assemat et al. 2006) as OOPAO/Atmosphere.py runs them,
 // batched over environments.  All are HBM-bound streaming kernels; the dense part of add_row (X = A Z + B xi)
-// is a GEMM in gemm.cu.
+// is a GEMM (gemm_tc.cu / gemm.cu).
+//
+// Sliding window: the reference shifts the whole (R+6)^2 map by one pixel at every add_row.  Here each layer map
+// lives in a larger canvas and only the WINDOW ORIGIN moves (by -step); add_row then writes just the 4M-4 ring
+// pixels of the new window border.  The canvas is re-centred ("compacted") once every S events.  A "window" is
+// addressed as (pointer to its origin, pitch = canvas pitch, env_stride = canvas size).
 #include "common.cuh"
 
 namespace aoenv {
@@ -10,7 +15,7 @@ namespace aoenv {
 // (OOPAO/Atmosphere.py:303-308).  One thread per entry of zx[b][:].
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-atm_gather_kernel(const float* __restrict__ map, int M, int pitch, int sx, int sy,
+atm_gather_kernel(const float* __restrict__ map, int M, int pitch, size_t env_stride, int sx, int sy,
                   const int2* __restrict__ inner_rc, int nI, int nO, const float* __restrict__ xi,
                   uint64_t seed, uint64_t stream_id, float* __restrict__ zx, int ldz) {
   const int b = blockIdx.y;
@@ -19,7 +24,7 @@ atm_gather_kernel(const float* __restrict__ map, int M, int pitch, int sx, int s
   float v = 0.f;
   if (k < nI) {
     const int2 rc = __ldg(&inner_rc[k]);
-    v = __ldg(&map[((size_t)b * M + (rc.x - sy)) * pitch + (rc.y - sx)]);
+    v = __ldg(&map[(size_t)b * env_stride + (size_t)(rc.x - sy) * pitch + (rc.y - sx)]);
   } else if (k < nI + nO) {
     const int j = k - nI;
     if (xi != nullptr) {
@@ -34,115 +39,143 @@ atm_gather_kernel(const float* __restrict__ map, int M, int pitch, int sx, int s
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// add_row step 3: write the shifted interior and the freshly extruded outer ring into the other map buffer
-// (OOPAO/Atmosphere.py:309-310) and reduce the new map's extrema.  The ring index follows numpy boolean-mask
-// order of `outerMask` (:263-264): row 0, then (r,0),(r,M-1) pairs, then row M-1.
+// Map extrema (the clip range of skimage.warp, tools/tools.py:215-217) are tracked WITH their position:
+// ext[b][0] = packed minimum, ext[b][1] = packed maximum, packed = (monotone 32-bit key of the value) << 32 | pos,
+// pos = element index inside the environment's canvas.  After an add_row the extremum survives iff its pixel is
+// still in the interior of the new window; then new = best(old, ring).  Otherwise that environment is flagged
+// and atm_rescan_kernel recomputes the window extrema exactly.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void minmax_init_kernel(int32_t* __restrict__ minmax, int B) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) {
-    minmax[2 * b + 0] = float_to_ordered(INFINITY);
-    minmax[2 * b + 1] = float_to_ordered(-INFINITY);
-  }
+__device__ __forceinline__ uint32_t key_of(float f) { return (uint32_t)float_to_ordered(f) ^ 0x80000000u; }
+__device__ __forceinline__ float value_of(unsigned long long packed) {
+  return ordered_to_float((int32_t)((uint32_t)(packed >> 32) ^ 0x80000000u));
 }
+__device__ __forceinline__ unsigned long long pack(float f, uint32_t pos) { return ((unsigned long long)key_of(f) << 32) | pos; }
 
-__device__ __forceinline__ void block_minmax_commit(float lo, float hi, int32_t* __restrict__ mm) {
-  __shared__ float s_lo[32], s_hi[32];
-  lo = warp_min(lo);
-  hi = warp_max(hi);
+__device__ __forceinline__ void block_reduce_ext(unsigned long long& lo, unsigned long long& hi) {
+  __shared__ unsigned long long s_lo[32], s_hi[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+    lo = l2 < lo ? l2 : lo;
+    hi = h2 > hi ? h2 : hi;
+  }
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   if (l == 0) { s_lo[w] = lo; s_hi[w] = hi; }
   __syncthreads();
   if (w == 0) {
     const int nw = (blockDim.x + 31) >> 5;
-    lo = l < nw ? s_lo[l] : INFINITY;
-    hi = l < nw ? s_hi[l] : -INFINITY;
-    lo = warp_min(lo);
-    hi = warp_max(hi);
-    if (l == 0) {
-      atomicMin(&mm[0], float_to_ordered(lo));
-      atomicMax(&mm[1], float_to_ordered(hi));
-    }
-  }
-}
-
-// One thread produces 4 consecutive columns of one row (one aligned 128-bit store; pitch % 4 == 0); the shifted
-// source row is read with 4 scalar loads that coalesce across the warp whatever the shift.
-__global__ void __launch_bounds__(256)
-atm_scatter_kernel(const float* __restrict__ map_in, float* __restrict__ map_out, int M, int pitch, int sx, int sy,
-                   const float* __restrict__ X, int ldx, int32_t* __restrict__ minmax, int rows_per_block) {
-  const int b = blockIdx.y;
-  const size_t base = (size_t)b * M * pitch;
-  const float* __restrict__ xb = X + (size_t)b * ldx;
-  const int r_begin = blockIdx.x * rows_per_block;
-  const int r_end = min(M, r_begin + rows_per_block);
-  const int nvec = pitch >> 2;
-  const int rows_in_flight = blockDim.x / 64;          // 64 threads (256 columns) per row
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
-  float lo = INFINITY, hi = -INFINITY;
-  const int last_vec = (M - 1) >> 2;                   // vector holding column M-1
-  auto slow_vec = [&](int r, int v4) {                 // vectors that touch the ring or the padding
-    const int c = v4 << 2;
-    const bool ring_row = (r == 0) || (r == M - 1);
-    const float* __restrict__ src = map_in + base + (size_t)(r - sy) * pitch - sx;
-    float v[4];
+    lo = l < nw ? s_lo[l] : ~0ull;
+    hi = l < nw ? s_hi[l] : 0ull;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int cc = c + k;
-      float x = 0.f;
-      if (cc < M) {
-        if (ring_row) x = __ldg(&xb[(r == 0 ? 0 : M + 2 * (M - 2)) + cc]);
-        else if (cc == 0) x = __ldg(&xb[M + 2 * (r - 1)]);
-        else if (cc == M - 1) x = __ldg(&xb[M + 2 * (r - 1) + 1]);
-        else x = __ldg(&src[cc]);
-        lo = fminf(lo, x);
-        hi = fmaxf(hi, x);
-      }
-      v[k] = x;
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+      lo = l2 < lo ? l2 : lo;
+      hi = h2 > hi ? h2 : hi;
     }
-    *reinterpret_cast<float4*>(map_out + base + (size_t)r * pitch + c) = make_float4(v[0], v[1], v[2], v[3]);
-  };
-  for (int r = r_begin + ty; r < r_end; r += 2 * rows_in_flight) {
-    const int r2 = r + rows_in_flight;
-    const bool two = r2 < r_end;
-    const bool fast1 = r > 0 && r < M - 1;
-    const bool fast2 = two && r2 > 0 && r2 < M - 1;
+  }
+}
+
+// add_row step 3 (OOPAO/Atmosphere.py:309): one CTA per environment writes the ring of the NEW window (ring index in
+// numpy boolean-mask order of `outerMask`, :263-264: row 0, then the (r,0),(r,M-1) pairs, then row M-1), reduces the
+// ring extrema and decides whether the tracked extrema survive.
+__global__ void __launch_bounds__(256)
+atm_ring_kernel(float* __restrict__ win, int M, int pitch, size_t env_stride, uint32_t win_offset,
+                const float* __restrict__ X, int ldx, unsigned long long* __restrict__ ext, int32_t* __restrict__ flag,
+                int force_rescan) {
+  const int b = blockIdx.x;
+  float* __restrict__ w = win + (size_t)b * env_stride;
+  const float* __restrict__ xb = X + (size_t)b * ldx;
+  const int nO = 4 * M - 4;
+  unsigned long long lo = ~0ull, hi = 0ull;
+  for (int k = threadIdx.x; k < nO; k += blockDim.x) {
+    int r, c;
+    if (k < M) { r = 0; c = k; }
+    else if (k >= M + 2 * (M - 2)) { r = M - 1; c = k - (M + 2 * (M - 2)); }
+    else { const int t = k - M; r = 1 + (t >> 1); c = (t & 1) ? M - 1 : 0; }
+    const float v = __ldg(&xb[k]);
+    const uint32_t rel = (uint32_t)(r * pitch + c);
+    w[rel] = v;
+    const unsigned long long pk = pack(v, win_offset + rel);
+    lo = pk < lo ? pk : lo;
+    hi = pk > hi ? pk : hi;
+  }
+  block_reduce_ext(lo, hi);
+  if (threadIdx.x == 0) {
+    const unsigned long long old_lo = ext[2 * b], old_hi = ext[2 * b + 1];
+    const int oy = win_offset / pitch, ox = win_offset % pitch;
+    auto retained = [&](unsigned long long pk) {
+      const uint32_t pos = (uint32_t)pk;
+      const int r = (int)(pos / pitch) - oy, c = (int)(pos % pitch) - ox;
+      return r >= 1 && r <= M - 2 && c >= 1 && c <= M - 2;
+    };
+    const bool ok = !force_rescan && retained(old_lo) && retained(old_hi);
+    ext[2 * b] = ok && old_lo < lo ? old_lo : lo;
+    ext[2 * b + 1] = ok && old_hi > hi ? old_hi : hi;
+    flag[b] = ok ? 0 : 1;
+  }
+}
+
+// Exact extrema of the window interior for the flagged environments, merged into ext (which already holds the ring's).
+__global__ void __launch_bounds__(256)
+atm_rescan_kernel(const float* __restrict__ win, int M, int pitch, size_t env_stride, uint32_t win_offset,
+                  unsigned long long* __restrict__ ext, const int32_t* __restrict__ flag, int rows_per_block) {
+  const int b = blockIdx.y;
+  if (__ldg(&flag[b]) == 0) return;
+  const float* __restrict__ w = win + (size_t)b * env_stride;
+  const int r_begin = 1 + blockIdx.x * rows_per_block;
+  const int r_end = min(M - 1, r_begin + rows_per_block);
+  unsigned long long lo = ~0ull, hi = 0ull;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;       // 64 threads x 4 columns per row, 4 rows in flight
+  for (int r = r_begin + ty; r < r_end; r += 4) {
+    const float* __restrict__ row = w + (size_t)r * pitch;
+    for (int c = 1 + 4 * tx; c < M - 1; c += 256) {
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = (c + k < M - 1) ? __ldg(row + c + k) : 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (c + k < M - 1) {
+          const unsigned long long pk = pack(v[k], win_offset + (uint32_t)(r * pitch + c + k));
+          lo = pk < lo ? pk : lo;
+          hi = pk > hi ? pk : hi;
+        }
+    }
+  }
+  block_reduce_ext(lo, hi);
+  if (threadIdx.x == 0 && r_begin < r_end) {
+    atomicMin(&ext[2 * b], lo);
+    atomicMax(&ext[2 * b + 1], hi);
+  }
+}
+
+// Canvas compaction: copies the window to its new origin in the other canvas buffer (dst origin column is a multiple
+// of 4, so the stores are aligned 128-bit) and moves the tracked extremum positions along.
+__global__ void __launch_bounds__(256)
+atm_compact_kernel(const float* __restrict__ src, float* __restrict__ dst, int M, int pitch, size_t env_stride,
+                   unsigned long long* __restrict__ ext, int pos_delta, int rows_per_block) {
+  const int b = blockIdx.y;
+  const float* __restrict__ s = src + (size_t)b * env_stride;
+  float* __restrict__ d = dst + (size_t)b * env_stride;
+  const int r_begin = blockIdx.x * rows_per_block;
+  const int r_end = min(M, r_begin + rows_per_block);
+  const int nvec = (M + 3) >> 2;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  for (int r = r_begin + ty; r < r_end; r += 4) {
+    const float* __restrict__ sr = s + (size_t)r * pitch;
+    float* __restrict__ dr = d + (size_t)r * pitch;
     for (int v4 = tx; v4 < nvec; v4 += 64) {
-      const bool interior_vec = v4 > 0 && v4 < last_vec;
-      if (interior_vec && fast1 && fast2) {
-        // both rows: plain shifted copy, 8 independent loads in flight
-        const int c = v4 << 2;
-        const float* __restrict__ s1 = map_in + base + (size_t)(r - sy) * pitch - sx + c;
-        const float* __restrict__ s2 = map_in + base + (size_t)(r2 - sy) * pitch - sx + c;
-        const float a0 = __ldg(s1), a1 = __ldg(s1 + 1), a2 = __ldg(s1 + 2), a3 = __ldg(s1 + 3);
-        const float b0 = __ldg(s2), b1 = __ldg(s2 + 1), b2 = __ldg(s2 + 2), b3 = __ldg(s2 + 3);
-        *reinterpret_cast<float4*>(map_out + base + (size_t)r * pitch + c) = make_float4(a0, a1, a2, a3);
-        *reinterpret_cast<float4*>(map_out + base + (size_t)r2 * pitch + c) = make_float4(b0, b1, b2, b3);
-        lo = fminf(fminf(fminf(lo, a0), fminf(a1, a2)), fminf(fminf(a3, b0), fminf(b1, fminf(b2, b3))));
-        hi = fmaxf(fmaxf(fmaxf(hi, a0), fmaxf(a1, a2)), fmaxf(fmaxf(a3, b0), fmaxf(b1, fmaxf(b2, b3))));
+      const int c = v4 << 2;
+      if (c + 3 < M) {
+        *reinterpret_cast<float4*>(dr + c) = make_float4(__ldg(sr + c), __ldg(sr + c + 1), __ldg(sr + c + 2), __ldg(sr + c + 3));
       } else {
-        slow_vec(r, v4);
-        if (two) slow_vec(r2, v4);
+        for (int k = 0; c + k < M; ++k) dr[c + k] = __ldg(sr + c + k);
       }
     }
   }
-  block_minmax_commit(lo, hi, &minmax[2 * b]);
-}
-
-__global__ void __launch_bounds__(256)
-map_minmax_kernel(const float* __restrict__ map, int M, int pitch, int32_t* __restrict__ minmax, int rows_per_block) {
-  const int b = blockIdx.y;
-  const size_t base = (size_t)b * M * pitch;
-  const int r_begin = blockIdx.x * rows_per_block;
-  const int r_end = min(M, r_begin + rows_per_block);
-  float lo = INFINITY, hi = -INFINITY;
-  for (int r = r_begin; r < r_end; ++r)
-    for (int c = threadIdx.x; c < M; c += blockDim.x) {
-      const float v = __ldg(&map[base + (size_t)r * pitch + c]);
-      lo = fminf(lo, v);
-      hi = fmaxf(hi, v);
-    }
-  block_minmax_commit(lo, hi, &minmax[2 * b]);
+  if (blockIdx.x == 0 && threadIdx.x < 2) {
+    const unsigned long long e = ext[2 * b + threadIdx.x];
+    ext[2 * b + threadIdx.x] = (e & 0xffffffff00000000ull) | (uint32_t)((int)(uint32_t)e + pos_delta);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -152,7 +185,7 @@ map_minmax_kernel(const float* __restrict__ map, int M, int pitch, int32_t* __re
 // ---------------------------------------------------------------------------------------------------------
 struct AtmPhaseParams {
   const float* map[AOENV_MAX_LAYERS];
-  const int32_t* minmax[AOENV_MAX_LAYERS];
+  const unsigned long long* ext[AOENV_MAX_LAYERS];
   int row_off[AOENV_MAX_LAYERS];
   int col_off[AOENV_MAX_LAYERS];
   float wrow[AOENV_MAX_LAYERS][4];
@@ -169,7 +202,7 @@ constexpr int kPhTileW = 128, kPhTileH = 32, kPhThreadsX = 32, kPhThreadsY = 4, 
 constexpr int kPhSmemW = kPhTileW + 8;    // 3 extra taps, padded to a multiple of 4
 
 __global__ void __launch_bounds__(kPhThreadsX * kPhThreadsY)
-atm_phase_kernel(const __grid_constant__ AtmPhaseParams p, int R, int M, int pitch, int fp_off, float opd_scale,
+atm_phase_kernel(const __grid_constant__ AtmPhaseParams p, int R, int M, int pitch, size_t env_stride, int fp_off, float opd_scale,
                  float* __restrict__ opd_out) {
   __shared__ __align__(16) float tile[kPhTileH + 3][kPhSmemW];
   const int b = blockIdx.z;
@@ -183,7 +216,7 @@ atm_phase_kernel(const __grid_constant__ AtmPhaseParams p, int R, int M, int pit
     for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
 
   for (int l = 0; l < p.nLayer; ++l) {
-    const float* __restrict__ m = p.map[l] + (size_t)b * M * pitch;
+    const float* __restrict__ m = p.map[l] + (size_t)b * env_stride;
     const int cbase = j0 + fp_off + p.col_off[l];
     const int rbase = i0 + fp_off + p.row_off[l];
     __syncthreads();
@@ -198,8 +231,8 @@ atm_phase_kernel(const __grid_constant__ AtmPhaseParams p, int R, int M, int pit
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    const float lo = ordered_to_float(__ldg(&p.minmax[l][2 * b + 0]));
-    const float hi = ordered_to_float(__ldg(&p.minmax[l][2 * b + 1]));
+    const float lo = value_of(__ldg(&p.ext[l][2 * b + 0]));
+    const float hi = value_of(__ldg(&p.ext[l][2 * b + 1]));
     const float wc0 = p.wcol[l][0], wc1 = p.wcol[l][1], wc2 = p.wcol[l][2], wc3 = p.wcol[l][3];
     const float wr0 = p.wrow[l][0], wr1 = p.wrow[l][1], wr2 = p.wrow[l][2], wr3 = p.wrow[l][3];
     const float w = p.weight[l];
@@ -243,20 +276,6 @@ atm_phase_kernel(const __grid_constant__ AtmPhaseParams p, int R, int M, int pit
 
 using namespace aoenv;
 
-extern "C" {
-
-int aoenv_atm_gather(const float* map, int B, int M, int pitch, int sx, int sy, const int32_t* inner_rc, int nI,
-                     int nO, const float* xi, uint64_t seed, uint64_t stream_id, float* zx, int ldz, void* stream) {
-  AOENV_CHECK_ARG(B > 0 && M > 6 && pitch >= M, "atm_gather: bad shape B=%d M=%d pitch=%d", B, M, pitch);
-  AOENV_CHECK_ARG(sx >= -1 && sx <= 1 && sy >= -1 && sy <= 1, "atm_gather: shift must be in {-1,0,1}");
-  AOENV_CHECK_ARG(ldz >= nI + nO, "atm_gather: ldz=%d < nI+nO=%d", ldz, nI + nO);
-  dim3 grid((ldz + 255) / 256, B);
-  atm_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(map, M, pitch, sx, sy, (const int2*)inner_rc, nI, nO, xi,
-                                                            seed, stream_id, zx, ldz);
-  AOENV_LAUNCH_CHECK("atm_gather");
-  return 0;
-}
-
 static int rows_per_block_for(int B, int M) {
   // enough blocks to fill 148 SMs a few times over even for a handful of environments
   int chunks = (4 * kNumSMs + B - 1) / B;
@@ -265,43 +284,60 @@ static int rows_per_block_for(int B, int M) {
   return (M + chunks - 1) / chunks;
 }
 
-int aoenv_atm_scatter(const float* map_in, float* map_out, int B, int M, int pitch, int sx, int sy, int nO,
-                      const float* X, int ldx, int32_t* minmax, void* stream) {
-  AOENV_CHECK_ARG(B > 0 && M > 6 && pitch >= M && pitch % 4 == 0, "atm_scatter: bad shape (pitch must be a multiple of 4)");
-  AOENV_CHECK_ARG(nO == 4 * M - 4 && ldx >= nO, "atm_scatter: ring has %d pixels, got nO=%d ldx=%d", 4 * M - 4, nO, ldx);
-  AOENV_CHECK_ARG(map_in != map_out, "atm_scatter: in-place shift is not supported");
-  cudaStream_t s = (cudaStream_t)stream;
-  minmax_init_kernel<<<(B + 255) / 256, 256, 0, s>>>(minmax, B);
-  AOENV_LAUNCH_CHECK("minmax_init");
-  const int rpb = rows_per_block_for(B, M);
-  dim3 grid((M + rpb - 1) / rpb, B);
-  atm_scatter_kernel<<<grid, 256, 0, s>>>(map_in, map_out, M, pitch, sx, sy, X, ldx, minmax, rpb);
-  AOENV_LAUNCH_CHECK("atm_scatter");
+extern "C" {
+
+int aoenv_atm_gather(const float* win, int B, int M, int pitch, int64_t env_stride, int sx, int sy,
+                     const int32_t* inner_rc, int nI, int nO, const float* xi, uint64_t seed, uint64_t stream_id,
+                     float* zx, int ldz, void* stream) {
+  AOENV_CHECK_ARG(B > 0 && B <= 65535 && M > 6 && pitch >= M && env_stride >= (int64_t)M * pitch, "atm_gather: bad shape B=%d M=%d pitch=%d", B, M, pitch);
+  AOENV_CHECK_ARG(sx >= -1 && sx <= 1 && sy >= -1 && sy <= 1, "atm_gather: shift must be in {-1,0,1}");
+  AOENV_CHECK_ARG(ldz >= nI + nO, "atm_gather: ldz=%d < nI+nO=%d", ldz, nI + nO);
+  dim3 grid((ldz + 255) / 256, B);
+  atm_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(win, M, pitch, (size_t)env_stride, sx, sy, (const int2*)inner_rc,
+                                                            nI, nO, xi, seed, stream_id, zx, ldz);
+  AOENV_LAUNCH_CHECK("atm_gather");
   return 0;
 }
 
-int aoenv_map_minmax(const float* map, int B, int M, int pitch, int32_t* minmax, void* stream) {
-  AOENV_CHECK_ARG(B > 0 && M > 0 && pitch >= M, "map_minmax: bad shape");
+int aoenv_atm_ring(float* win, int B, int M, int pitch, int64_t env_stride, int64_t win_offset, int nO, const float* X,
+                   int ldx, uint64_t* ext, int32_t* flag, int force_rescan, void* stream) {
+  AOENV_CHECK_ARG(B > 0 && B <= 65535 && M > 6 && pitch >= M, "atm_ring: bad shape");
+  AOENV_CHECK_ARG(nO == 4 * M - 4 && ldx >= nO, "atm_ring: ring has %d pixels, got nO=%d ldx=%d", 4 * M - 4, nO, ldx);
+  AOENV_CHECK_ARG(win_offset >= 0 && win_offset + (int64_t)M * pitch <= env_stride + pitch && env_stride < (1ll << 32), "atm_ring: window leaves the canvas");
   cudaStream_t s = (cudaStream_t)stream;
-  minmax_init_kernel<<<(B + 255) / 256, 256, 0, s>>>(minmax, B);
-  AOENV_LAUNCH_CHECK("minmax_init");
-  const int rpb = rows_per_block_for(B, M);
-  dim3 grid((M + rpb - 1) / rpb, B);
-  map_minmax_kernel<<<grid, 256, 0, s>>>(map, M, pitch, minmax, rpb);
-  AOENV_LAUNCH_CHECK("map_minmax");
+  atm_ring_kernel<<<B, 256, 0, s>>>(win, M, pitch, (size_t)env_stride, (uint32_t)win_offset, X, ldx,
+                                    reinterpret_cast<unsigned long long*>(ext), flag, force_rescan);
+  AOENV_LAUNCH_CHECK("atm_ring");
+  const int rpb = 32;                          // >= 8 CTAs per flagged environment; unflagged ones exit at once
+  dim3 grid((M - 2 + rpb - 1) / rpb, B);
+  atm_rescan_kernel<<<grid, 256, 0, s>>>(win, M, pitch, (size_t)env_stride, (uint32_t)win_offset,
+                                         reinterpret_cast<unsigned long long*>(ext), flag, rpb);
+  AOENV_LAUNCH_CHECK("atm_rescan");
   return 0;
 }
 
-int aoenv_atm_phase(const float* const* h_map, const int32_t* const* h_minmax, int nLayer, int B, int R, int M,
-                    int pitch, int fp_off, const int32_t* h_row_off, const int32_t* h_col_off, const float* h_wrow,
+int aoenv_atm_compact(const float* src_win, float* dst_win, int B, int M, int pitch, int64_t env_stride, uint64_t* ext,
+                      int64_t pos_delta, void* stream) {
+  AOENV_CHECK_ARG(B > 0 && B <= 65535 && M > 6 && pitch >= M && pitch % 4 == 0, "atm_compact: bad shape");
+  AOENV_CHECK_ARG((reinterpret_cast<uintptr_t>(dst_win) & 15) == 0, "atm_compact: destination window must be 16-byte aligned");
+  const int rpb = rows_per_block_for(B, M);
+  dim3 grid((M + rpb - 1) / rpb, B);
+  atm_compact_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src_win, dst_win, M, pitch, (size_t)env_stride,
+                                                             reinterpret_cast<unsigned long long*>(ext), (int)pos_delta, rpb);
+  AOENV_LAUNCH_CHECK("atm_compact");
+  return 0;
+}
+
+int aoenv_atm_phase(const float* const* h_win, const uint64_t* const* h_ext, int nLayer, int B, int R, int M, int pitch,
+                    int64_t env_stride, int fp_off, const int32_t* h_row_off, const int32_t* h_col_off, const float* h_wrow,
                     const float* h_wcol, const float* h_weight, float opd_scale, float* opd_out, void* stream) {
   AOENV_CHECK_ARG(nLayer >= 1 && nLayer <= AOENV_MAX_LAYERS, "atm_phase: nLayer=%d out of range", nLayer);
   AOENV_CHECK_ARG(B > 0 && B <= 65535, "atm_phase: B=%d out of range (1..65535)", B);
   AtmPhaseParams p;
   p.nLayer = nLayer;
   for (int l = 0; l < nLayer; ++l) {
-    p.map[l] = h_map[l];
-    p.minmax[l] = h_minmax[l];
+    p.map[l] = h_win[l];
+    p.ext[l] = reinterpret_cast<const unsigned long long*>(h_ext[l]);
     p.row_off[l] = h_row_off[l];
     p.col_off[l] = h_col_off[l];
     for (int k = 0; k < 4; ++k) {
@@ -309,14 +345,14 @@ int aoenv_atm_phase(const float* const* h_map, const int32_t* const* h_minmax, i
       p.wcol[l][k] = h_wcol[4 * l + k];
     }
     p.weight[l] = h_weight[l];
-    // every tap of every footprint pixel must lie inside the map
+    // every tap of every footprint pixel must lie inside the window
     const int lo_r = fp_off + h_row_off[l], hi_r = fp_off + R - 1 + h_row_off[l] + 3;
     const int lo_c = fp_off + h_col_off[l], hi_c = fp_off + R - 1 + h_col_off[l] + 3;
     AOENV_CHECK_ARG(lo_r >= 0 && lo_c >= 0 && hi_r < M && hi_c < M, "atm_phase: taps of layer %d leave the map", l);
   }
   dim3 block(kPhThreadsX, kPhThreadsY);
   dim3 grid((R + kPhTileW - 1) / kPhTileW, (R + kPhTileH - 1) / kPhTileH, B);
-  atm_phase_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(p, R, M, pitch, fp_off, opd_scale, opd_out);
+  atm_phase_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(p, R, M, pitch, (size_t)env_stride, fp_off, opd_scale, opd_out);
   AOENV_LAUNCH_CHECK("atm_phase");
   return 0;
 }

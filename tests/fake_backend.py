@@ -18,7 +18,7 @@ def _arr(ptr, shape, dtype=np.float32):
     if addr is None or addr == 0:
         return None
     n = int(np.prod(shape))
-    ct = {np.float32: C.c_float, np.int32: C.c_int32, np.uint8: C.c_uint8, np.float64: C.c_double}[dtype]
+    ct = {np.float32: C.c_float, np.int32: C.c_int32, np.uint8: C.c_uint8, np.float64: C.c_double, np.int64: C.c_int64}[dtype]
     return np.ctypeslib.as_array((ct * n).from_address(addr)).reshape(shape)
 
 
@@ -50,48 +50,72 @@ class FakeLib:
     def aoenv_launch_count(self):
         return self.launches
 
-    # ---- atmosphere ------------------------------------------------------------------------------------
-    def aoenv_atm_gather(self, map_, B, M, pitch, sx, sy, inner_rc, nI, nO, xi, seed, stream_id, zx, ldz, stream):
+    # ---- atmosphere (sliding-window canvas) ---------------------------------------------------------------
+    @staticmethod
+    def _window(ptr, B, M, pitch, env_stride):
+        """[B, M, M] strided view of a window given the address of its origin pixel."""
+        addr = ptr.value if isinstance(ptr, C.c_void_p) else int(ptr)
+        n = (B - 1) * env_stride + (M - 1) * pitch + M
+        flat = np.ctypeslib.as_array((C.c_float * n).from_address(addr))
+        return np.lib.stride_tricks.as_strided(flat, shape=(B, M, M), strides=(4 * env_stride, 4 * pitch, 4))
+
+    @staticmethod
+    def _key(v):
+        i = np.asarray(v, dtype=np.float32).view(np.int32).astype(np.int64)
+        o = np.where(i >= 0, i, i ^ 0x7fffffff)
+        return (o & 0xffffffff) ^ 0x80000000
+
+    @staticmethod
+    def _unkey(packed):
+        k = ((int(packed) >> 32) & 0xffffffff) ^ 0x80000000
+        k = k - (1 << 32) if k >= (1 << 31) else k
+        i = np.int32(k)
+        return (i if i >= 0 else np.int32(i ^ np.int32(0x7fffffff))).view(np.float32)
+
+    def aoenv_atm_gather(self, win, B, M, pitch, env_stride, sx, sy, inner_rc, nI, nO, xi, seed, stream_id, zx, ldz, stream):
         self.launches += 1
-        m = _arr(map_, (B, M, pitch))
+        addr = (win.value if isinstance(win, C.c_void_p) else int(win)) - 4 * (sy * pitch + sx)
+        m = self._window(addr, B, M, pitch, env_stride)       # window after the shift (old content)
         rc = _arr(inner_rc, (nI, 2), np.int32)
         z = _arr(zx, (B, ldz))
         z[:] = 0
-        z[:, :nI] = m[:, rc[:, 0] - sy, rc[:, 1] - sx]
+        z[:, :nI] = m[:, rc[:, 0], rc[:, 1]]
         x = _arr(xi, (B, nO))
         z[:, nI:nI + nO] = x if x is not None else self.rs.normal(size=(B, nO))
         return 0
 
-    def aoenv_atm_scatter(self, map_in, map_out, B, M, pitch, sx, sy, nO, X, ldx, minmax, stream):
+    def aoenv_atm_ring(self, win, B, M, pitch, env_stride, win_offset, nO, X, ldx, ext, flag, force_rescan, stream):
         self.launches += 2
-        mi, mo = _arr(map_in, (B, M, pitch)), _arr(map_out, (B, M, pitch))
+        m = self._window(win, B, M, pitch, env_stride)
         x = _arr(X, (B, ldx))
-        mm = _arr(minmax, (B, 2), np.int32)
+        e = _arr(ext, (B, 2), np.int64)
         outer = np.ones((M, M), dtype=bool)
         outer[1:-1, 1:-1] = False
         for b in range(B):
-            new = np.zeros((M, M), dtype=np.float32)
-            new[1:-1, 1:-1] = mi[b, 1 - sy:M - 1 - sy, 1 - sx:M - 1 - sx]
-            new[outer] = x[b, :nO]
-            mo[b, :, :M] = new
-            mm[b, 0], mm[b, 1] = _f2o(new.min()), _f2o(new.max())
+            m[b][outer] = x[b, :nO]
+            flatpos = win_offset + np.arange(M)[:, None] * pitch + np.arange(M)[None, :]
+            keys = (self._key(m[b]).astype(np.uint64) << np.uint64(32)) | flatpos.astype(np.uint64)
+            e[b, 0] = np.int64(np.uint64(keys.min()).astype(np.int64))
+            e[b, 1] = np.int64(np.uint64(keys.max()).astype(np.int64))
         return 0
 
-    def aoenv_map_minmax(self, map_, B, M, pitch, minmax, stream):
-        self.launches += 2
-        m = _arr(map_, (B, M, pitch))
-        mm = _arr(minmax, (B, 2), np.int32)
-        for b in range(B):
-            mm[b, 0], mm[b, 1] = _f2o(m[b, :, :M].min()), _f2o(m[b, :, :M].max())
+    def aoenv_atm_compact(self, src, dst, B, M, pitch, env_stride, ext, pos_delta, stream):
+        self.launches += 1
+        s_, d_ = self._window(src, B, M, pitch, env_stride), self._window(dst, B, M, pitch, env_stride)
+        d_[:] = s_
+        e = _arr(ext, (B, 2), np.int64)
+        u = e.view(np.uint64)
+        u[:] = (u & np.uint64(0xffffffff00000000)) | ((u & np.uint64(0xffffffff)) + np.uint64(pos_delta % (1 << 32))) & np.uint64(0xffffffff)
         return 0
 
-    def aoenv_atm_phase(self, h_map, h_minmax, L, B, R, M, pitch, fp_off, roff, coff, wr, wc, wt, opd_scale, opd_out, stream):
+    def aoenv_atm_phase(self, h_map, h_ext, L, B, R, M, pitch, env_stride, fp_off, roff, coff, wr, wc, wt, opd_scale,
+                        opd_out, stream):
         self.launches += 1
         out = _arr(opd_out, (B, R, R))
         acc = np.zeros((B, R, R), dtype=np.float32)
         for l in range(L):
-            m = _arr(h_map[l], (B, M, pitch))
-            mm = _arr(h_minmax[l], (B, 2), np.int32)
+            m = self._window(h_map[l], B, M, pitch, env_stride)
+            e = _arr(h_ext[l], (B, 2), np.int64).view(np.uint64)
             for b in range(B):
                 v = np.zeros((R, R), dtype=np.float32)
                 for pr in range(4):
@@ -101,7 +125,7 @@ class FakeLib:
                         c0 = fp_off + coff[l] + pc
                         h += np.float32(wc[4 * l + pc]) * m[b, r0:r0 + R, c0:c0 + R]
                     v += np.float32(wr[4 * l + pr]) * h
-                v = np.clip(v, _o2f(mm[b, 0]), _o2f(mm[b, 1]))
+                v = np.clip(v, self._unkey(e[b, 0]), self._unkey(e[b, 1]))
                 acc[b] += np.float32(wt[l]) * v
         out[:] = acc * np.float32(_val(opd_scale))
         return 0

@@ -22,12 +22,12 @@ def param_from_config(cfg):
     return p
 
 
-def build_env(cfg, n_envs=1, rng="reference", seed=0, device=None, env_offset=0):
+def build_env(cfg, n_envs=1, rng="reference", seed=0, device=None, env_offset=0, canvas_slack=32):
     from rlao_b200.OOPAOEnv.OOPAOEnvRazor import OOPAO
     env = OOPAO()
     env.set_params_file(param_from_config(cfg), "")
     env.set_params(types.SimpleNamespace(), "shackhartmann", gainCL=cfg.gainCL, n_envs=n_envs, rng=rng, seed=seed,
-                   device=device, env_offset=env_offset)
+                   device=device, env_offset=env_offset, canvas_slack=canvas_slack)
     env.leak = cfg.leak
     return env
 

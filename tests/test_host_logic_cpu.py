@@ -87,3 +87,22 @@ def test_batched_envs_are_independent_and_lockstep(fake):
     assert r.shape == (3,) and s.shape == (3,)
     avg = env.calculate_strehl_AVG()
     assert 0 <= avg <= 1 and env.SR == []
+
+
+def test_canvas_compaction_is_transparent(fake):
+    """A tiny canvas slack forces the sliding window to be re-centred every other add_row; results must not change."""
+    cfg = CONFIGS["tiny"]()
+    cfg.windSpeed = [30.0, 36.0]                 # ~0.9 and ~1.1 pixels per step: events on every step
+    env_a = build_env(cfg, n_envs=1, rng="reference", canvas_slack=2)
+    env_b = build_env(cfg, n_envs=1, rng="reference", canvas_slack=64)
+    orc = EnvOracle(cfg)
+    oa, ob, oo = new_episode(env_a, 5), new_episode(env_b, 5), orc.new_episode(5)
+    for i in range(10):
+        oa, *_ = env_a.step(i, cfg.gainCL * oa)
+        ob, *_ = env_b.step(i, cfg.gainCL * ob)
+        oo, *_ = orc.step(i, cfg.gainCL * oo)
+    assert env_a.atm._cur != env_b.atm._cur or env_a.atm._org != env_b.atm._org
+    assert rel_err(oa.numpy(), ob.numpy()) < 1e-6
+    assert rel_err(oa.numpy(), oo) < 2e-3
+    for ly, lo in zip(env_a.atm._layers, orc.atm.layers):
+        assert rel_err(ly.mapShift.numpy(), lo.map) < 1e-5
