@@ -96,6 +96,15 @@ int aoenv_split_bf16(const float* src, int lds, int rows, int K, int parts, void
 int aoenv_gemm_tn_tc(const void* Xs, const void* Ws, int ldk, int parts, float* D, int ldd, int MX, int NW, int K,
                      float alpha, void* stream);
 
+/* DM surface for the reference's default geometry (DeformableMirror.py:286-305,494-514: Cartesian actuator grid,
+ * axis-aligned Gaussian influence functions): modes @ coefs factorises as OPD = gy^T (C gx) with C the nAct x nAct
+ * command image.  coefs [B][ldc] (valid actuators only), act_pos [nA] = row*nAct + col of each valid actuator,
+ * gx / gy [nAct][R] = exp(-a (g - u0)^2) per actuator column / row, band_x / band_y [R][2] = first and last actuator
+ * index kept for each pixel column / row (the rest is below float32 resolution).  opd [B][R][R] metres. */
+int aoenv_dm_surface_separable(const float* coefs, int ldc, const int32_t* act_pos, int nA, int nAct, const float* gx,
+                               const float* gy, const int32_t* band_x, const int32_t* band_y, int B, int R, float* opd,
+                               void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Shack-Hartmann WFS + detector — OOPAO/ShackHartmann.py:511-601 (and :605-674), OOPAO/Detector.py:190-301
  * ------------------------------------------------------------------------------------------------------- */

@@ -3,7 +3,12 @@ batched over environments.  `dm.coefs = c` has the reference's side effect: dm.O
 [n_frames, nValidAct] x [R*R, nValidAct]^T contraction on the GPU (include/aoenv.h: aoenv_gemm_tn).
 
 HBM layout: modes[R*R][Kp] float32, Kp = nValidAct rounded up to 16 with zero padding, K-contiguous, so the
-DM surface of every environment is one "TN" GEMM  OPD[B][R*R] = coefs[B][Kp] . modes[R*R][Kp]^T.
+DM surface of every environment is one "TN" GEMM  OPD[B][R*R] = coefs[B][Kp] . modes[R*R][Kp]^T (tcgen05).
+
+`surface_backend`: "gemm" = that dense contraction (any modes: custom, rotated, anamorphic); "separable" = for the
+default Cartesian grid of axis-aligned Gaussians the product factorises into two small banded products
+(aoenv_dm_surface_separable), ~30x fewer flops and exact to float32 rounding; "auto" (default) picks separable
+when the geometry allows it.
 """
 import math
 import sys
@@ -73,6 +78,8 @@ class DeformableMirror:
             modes64 = torch.as_tensor(np.asarray(modes), dtype=torch.float64, device=self.device)
             self.nValidAct = modes64.shape[1]
         self._set_modes(modes64)
+        self.surface_backend = "auto"
+        self._sep = self._separable_tables() if (modes is None and coordinates is None) else None
         self._opd = torch.zeros((2, self.n_envs, R, R), dtype=torch.float32, device=self.device)   # ping-pong
         self._slot = 0
         self._multi = None            # [k, R, R] surfaces of a [nValidAct, k] command matrix (calibration)
@@ -113,6 +120,39 @@ class DeformableMirror:
             out[:, s:s + chunk] = G.reshape(G.shape[0], R * R).T
         return out
 
+    def _separable_tables(self):
+        """Per-column / per-row Gaussian factors and their bands when modes[:, k] = gy_i(y) gx_j(x) on a regular grid."""
+        mr, R, dev = self.misReg, self.resolution, self.device
+        if mr.rotationAngle != 0 or mr.anamorphosisAngle != 0:
+            return None
+        n = self.nAct
+        x = np.linspace(-self.D / 2, self.D / 2, n)
+        X, Y = np.meshgrid(x, x)
+        x3, y3 = self.anamorphosis(X.reshape(-1), Y.reshape(-1), 0.0, mr.tangentialScaling, mr.radialScaling)
+        xg = (x3 - mr.shiftX).reshape(n, n)
+        yg = (y3 - mr.shiftY).reshape(n, n)
+        if np.abs(xg - xg[:1, :]).max() > 1e-12 or np.abs(yg - yg[:, :1]).max() > 1e-12:
+            return None
+        u0x = R / 2 + xg[0, :] * R / self.D                  # per actuator column
+        u0y = R / 2 + yg[:, 0] * R / self.D                  # per actuator row
+        base = (R / self.nActAlongDiameter) / math.sqrt(2 * math.log(1.0 / self.mechCoupling))
+        a = 1.0 / (2 * ((1 + mr.radialScaling) * base) ** 2)
+        c = 1.0 / (2 * ((1 + mr.tangentialScaling) * base) ** 2)
+        g = np.linspace(0, 1, R) * R
+        ex = a * (g[None, :] - u0x[:, None]) ** 2             # [nAct, R]
+        ey = c * (g[None, :] - u0y[:, None]) ** 2
+        CUT = 21.0                                            # exp(-21) = 2^-30.3: below float32 resolution of the sum
+
+        def bands(e):
+            keep = e <= CUT
+            lo = np.where(keep.any(axis=0), keep.argmax(axis=0), 0)
+            hi = np.where(keep.any(axis=0), e.shape[0] - 1 - keep[::-1].argmax(axis=0), -1)
+            return np.stack([lo, hi], axis=1).astype(np.int32)
+        rows, cols = np.nonzero(np.reshape(self.validAct, (n, n)))
+        t = lambda arr, dt: torch.as_tensor(np.ascontiguousarray(arr), dtype=dt, device=dev)
+        return dict(gx=t(np.exp(-ex), torch.float32), gy=t(np.exp(-ey), torch.float32), band_x=t(bands(ex), torch.int32),
+                    band_y=t(bands(ey), torch.int32), act_pos=t((rows * n + cols).astype(np.int32), torch.int32))
+
     def _set_modes(self, modes64):
         self._modes64 = modes64                      # kept until the calibration is done (free_float64())
         self._Kp = (self.nValidAct + 15) // 16 * 16
@@ -132,14 +172,26 @@ class DeformableMirror:
         m = torch.as_tensor(np.asarray(val) if not torch.is_tensor(val) else val, dtype=torch.float64, device=self.device)
         self.nValidAct = m.shape[1]
         self._set_modes(m)
+        self._sep = None                 # user-supplied modes: dense contraction only
 
     # ---- surfaces ----------------------------------------------------------------------------------------
     def _surface(self, coefs_padded, out, backend=None):
         """out[f] = modes @ coefs[f] for every frame f (OPD = modes @ coefs, DeformableMirror.py:534-570)."""
         F = coefs_padded.shape[0]
         P = self.resolution ** 2
-        o2 = out.reshape(F, P)
-        gemm.gemm_tn(coefs_padded, self._modes_op, o2, F, P, backend=backend)
+        choice = self.surface_backend
+        if choice not in ("auto", "gemm", "separable"):
+            raise ValueError("surface_backend must be 'auto', 'gemm' or 'separable'")
+        if choice == "separable" and self._sep is None:
+            raise ValueError("this DM geometry is not separable (rotation / anamorphosis / custom modes): use 'gemm'")
+        if self._sep is not None and choice in ("auto", "separable"):
+            t = self._sep
+            _lib.check(_lib.load().aoenv_dm_surface_separable(
+                _lib.ptr(coefs_padded), coefs_padded.stride(0), _lib.ptr(t["act_pos"]), self.nValidAct, self.nAct,
+                _lib.ptr(t["gx"]), _lib.ptr(t["gy"]), _lib.ptr(t["band_x"]), _lib.ptr(t["band_y"]), F, self.resolution,
+                _lib.ptr(out), _lib.stream_ptr(self.device)), "dm_surface_separable")
+            return
+        gemm.gemm_tn(coefs_padded, self._modes_op, out.reshape(F, P), F, P, backend=backend)
 
     def _set_coefs_batch(self, coefs_padded):
         """Fast path of env.step: per-environment commands [B, Kp]; writes the *next* surface slot and makes it

@@ -138,6 +138,22 @@ class FakeLib:
         d[:, :N] = (np.float32(_val(alpha)) * (x[:, :K].astype(np.float64) @ w[:, :K].astype(np.float64).T)).astype(np.float32)
         return 0
 
+    def aoenv_dm_surface_separable(self, coefs, ldc, act_pos, nA, nAct, gx, gy, band_x, band_y, B, R, opd, stream):
+        self.launches += 1
+        c = _arr(coefs, (B, ldc))
+        pos = _arr(act_pos, (nA,), np.int32)
+        gx_, gy_ = _arr(gx, (nAct, R)).astype(np.float64), _arr(gy, (nAct, R)).astype(np.float64)
+        bx, by = _arr(band_x, (R, 2), np.int32), _arr(band_y, (R, 2), np.int32)
+        j = np.arange(nAct)[:, None]
+        mx = (j >= bx[None, :, 0]) & (j <= bx[None, :, 1])
+        my = (j >= by[None, :, 0]) & (j <= by[None, :, 1])
+        out = _arr(opd, (B, R, R))
+        for b in range(B):
+            C_ = np.zeros(nAct * nAct)
+            C_[pos] = c[b, :nA]
+            out[b] = ((gy_ * my).T @ C_.reshape(nAct, nAct) @ (gx_ * mx)).astype(np.float32)
+        return 0
+
     # ---- WFS -------------------------------------------------------------------------------------------
     def aoenv_shwfs_frame(self, opd_a, opd_b, pupil, amp, valid, B, nS, n, phase_scale, det, shared_max, frame, envmax,
                           stats, stream):

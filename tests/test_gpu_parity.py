@@ -247,7 +247,13 @@ def test_dm_surface_vs_oracle_and_linearity(dev):
     c = rs.normal(size=(4, 357)) * 1e-7
     dm.coefs = torch.as_tensor(c, dtype=torch.float32, device=dev)
     want = (modes @ _np(dm.coefs).T).T.reshape(4, cfg.resolution, cfg.resolution)
+    assert dm._sep is not None                                            # default geometry -> separable kernel
+    assert rel_err(_np(dm.OPD), want) < 2e-6
+    dm.surface_backend = "gemm"                                           # dense tcgen05 contraction of the same thing
+    dm.coefs = torch.as_tensor(c, dtype=torch.float32, device=dev)
     assert rel_err(_np(dm.OPD), want) < SURFACE_TOL
+    dm.surface_backend = "auto"
+    dm.coefs = torch.as_tensor(c, dtype=torch.float32, device=dev)
     a = _np(dm.OPD).copy()
     dm.coefs = torch.as_tensor(2 * c, dtype=torch.float32, device=dev)
     assert rel_err(_np(dm.OPD), 2 * a) < 1e-6                            # linearity
@@ -339,6 +345,30 @@ def test_closed_loop_own_policy_tracks_reference(dev):
         assert rel_err(_np(env.wfs.signal), gold["trace_signal"][i]) < 5e-2, i
         assert abs(float(strehl) - gold["trace_strehl"][i]) <= 0.02 * gold["trace_strehl"][i] + 1e-30, i
     assert rel_err(_np(env.residual[:n, 0]), gold["trace_residual"]) < 5e-3
+
+
+def test_dm_with_rotation_uses_the_dense_contraction(dev):
+    from rlao_b200.DeformableMirror import DeformableMirror
+    from rlao_b200.MisRegistration import MisRegistration
+    from rlao_b200.Source import Source
+    from rlao_b200.Telescope import Telescope
+    tel = Telescope(48, 8, 1 / 500, n_envs=2, device=dev)
+    Source("I", 8) * tel
+    mis = MisRegistration()
+    mis.rotationAngle, mis.shiftX = 3.0, 0.05
+    dm = DeformableMirror(tel, 8, 0.35, misReg=mis)
+    assert dm._sep is None
+    c = torch.randn(2, dm.nValidAct, device=dev) * 1e-7
+    dm.coefs = c
+    want = (_np(dm.modes) @ _np(c).T).T.reshape(2, 48, 48)
+    assert rel_err(_np(dm.OPD), want) < SURFACE_TOL
+    shifted = MisRegistration()
+    shifted.shiftX, shifted.shiftY, shifted.radialScaling = 0.07, -0.02, 0.01
+    dm2 = DeformableMirror(tel, 8, 0.35, misReg=shifted)
+    assert dm2._sep is not None                                           # shifts / scalings keep it separable
+    dm2.coefs = c[:, :dm2.nValidAct]
+    want2 = (_np(dm2.modes) @ _np(c[:, :dm2.nValidAct]).T).T.reshape(2, 48, 48)
+    assert rel_err(_np(dm2.OPD), want2) < 2e-6
 
 
 def test_interaction_matrix_vs_oracle(dev):
