@@ -102,8 +102,12 @@ int aoenv_gemm_tn_tc(const void* Xs, const void* Ws, int ldk, int parts, float* 
  * gx / gy [nAct][R] = exp(-a (g - u0)^2) per actuator column / row, band_x / band_y [R][2] = first and last actuator
  * index kept for each pixel column / row (the rest is below float32 resolution).  opd [B][R][R] metres. */
 int aoenv_dm_surface_separable(const float* coefs, int ldc, const int32_t* act_pos, int nA, int nAct, const float* gx,
-                               const float* gy, const int32_t* band_x, const int32_t* band_y, int B, int R, float* opd,
+                               const float* gy, const int32_t* band_x, const int32_t* band_y, const float* wx,
+                               const int32_t* j0x, const float* wyp, const int32_t* i0y, int W, int B, int R, float* opd,
                                void* stream);
+/* Optional banded tables (W = 12 or 16, else pass W = 0 and NULLs): wx [R][W] / j0x [R] = weights and first actuator
+ * column of pixel column x; wyp [R/2][2][W] / i0y [R/2] = weights and first actuator row of the pixel-row pair
+ * (2k, 2k+1).  With them the kernel runs fully unrolled on fixed-width bands. */
 
 /* ---------------------------------------------------------------------------------------------------------
  * Shack-Hartmann WFS + detector — OOPAO/ShackHartmann.py:511-601 (and :605-674), OOPAO/Detector.py:190-301

@@ -150,8 +150,28 @@ class DeformableMirror:
             return np.stack([lo, hi], axis=1).astype(np.int32)
         rows, cols = np.nonzero(np.reshape(self.validAct, (n, n)))
         t = lambda arr, dt: torch.as_tensor(np.ascontiguousarray(arr), dtype=dt, device=dev)
-        return dict(gx=t(np.exp(-ex), torch.float32), gy=t(np.exp(-ey), torch.float32), band_x=t(bands(ex), torch.int32),
-                    band_y=t(bands(ey), torch.int32), act_pos=t((rows * n + cols).astype(np.int32), torch.int32))
+        bx, by, gxv, gyv = bands(ex), bands(ey), np.exp(-ex), np.exp(-ey)
+        out = dict(gx=t(gxv, torch.float32), gy=t(gyv, torch.float32), band_x=t(bx, torch.int32), band_y=t(by, torch.int32),
+                   act_pos=t((rows * n + cols).astype(np.int32), torch.int32), W=0, wx=None, j0x=None, wyp=None, i0y=None)
+        # fixed-width band tables for the unrolled kernel: per pixel column, and per PAIR of pixel rows
+        if R % 2 == 0:
+            pair_lo = np.minimum(by[0::2, 0], by[1::2, 0])
+            pair_hi = np.maximum(by[0::2, 1], by[1::2, 1])
+            need = int(max((bx[:, 1] - bx[:, 0] + 1).max(), (pair_hi - pair_lo + 1).max()))
+            W = 12 if need <= 12 else (16 if need <= 16 else 0)
+            if W:
+                wx = np.zeros((R, W))
+                for x in range(R):
+                    lo, hi = bx[x]
+                    wx[x, :hi - lo + 1] = gxv[lo:hi + 1, x]
+                wyp = np.zeros((R // 2, 2, W))
+                for k in range(R // 2):
+                    for h in range(2):
+                        lo, hi = by[2 * k + h]
+                        wyp[k, h, lo - pair_lo[k]:hi - pair_lo[k] + 1] = gyv[lo:hi + 1, 2 * k + h]
+                out.update(W=W, wx=t(wx, torch.float32), j0x=t(bx[:, 0], torch.int32), wyp=t(wyp, torch.float32),
+                           i0y=t(pair_lo.astype(np.int32), torch.int32))
+        return out
 
     def _set_modes(self, modes64):
         self._modes64 = modes64                      # kept until the calibration is done (free_float64())
@@ -188,7 +208,8 @@ class DeformableMirror:
             t = self._sep
             _lib.check(_lib.load().aoenv_dm_surface_separable(
                 _lib.ptr(coefs_padded), coefs_padded.stride(0), _lib.ptr(t["act_pos"]), self.nValidAct, self.nAct,
-                _lib.ptr(t["gx"]), _lib.ptr(t["gy"]), _lib.ptr(t["band_x"]), _lib.ptr(t["band_y"]), F, self.resolution,
+                _lib.ptr(t["gx"]), _lib.ptr(t["gy"]), _lib.ptr(t["band_x"]), _lib.ptr(t["band_y"]), _lib.ptr(t["wx"]),
+                _lib.ptr(t["j0x"]), _lib.ptr(t["wyp"]), _lib.ptr(t["i0y"]), t["W"], F, self.resolution,
                 _lib.ptr(out), _lib.stream_ptr(self.device)), "dm_surface_separable")
             return
         gemm.gemm_tn(coefs_padded, self._modes_op, out.reshape(F, P), F, P, backend=backend)

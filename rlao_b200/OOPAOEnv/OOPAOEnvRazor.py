@@ -221,7 +221,14 @@ class OOPAO:
         return self._sq(self.wfs._frame).clone()
 
     def step(self, i, action):
-        """OOPAOEnvRazor.py:474-514."""
+        """OOPAOEnvRazor.py:474-514.  Returns fresh tensors (the reference returns fresh arrays)."""
+        obs, reward, strehl, done, info = self._step_views(i, action)
+        strehl = strehl.clone()
+        self.SR[-1] = strehl
+        return obs.clone(), reward.clone(), strehl, done, {"strehl": strehl}
+
+    def _step_views(self, i, action):
+        """The step itself; returns views of the internal output buffers (overwritten by the next step)."""
         lib, st, B = _lib.load(), _lib.stream_ptr(self.device), self.n_envs
         action = self._action_tensor(action)                               # :479 (img_to_vec * 1e-6 is in the kernel)
         self.atm.update()                                                  # :482 -> tel.OPD = atm.OPD (lazy)
@@ -238,12 +245,12 @@ class OOPAO:
         if self.total is not None and i is not None and 0 <= i < self._nLoop:
             self.total[i] = self._total_now
             self.residual[i] = self._residual_now
-        strehl = self._sq(self._strehl).clone()
+        strehl = self._sq(self._strehl)
         if self.psf_reward is not None:
             strehl = self.psf_strehl(*self.psf_reward)
-        self.SR.append(strehl)
+        self.SR.append(strehl if self.psf_reward is not None else strehl.clone())
         self.wfsSignal = self.wfs.signal
-        return self._sq(self._obs).clone(), self._sq(self._reward).clone(), strehl, False, {"strehl": strehl}
+        return self._sq(self._obs), self._sq(self._reward), strehl, False, {"strehl": strehl}
 
     def calculate_strehl_AVG(self):
         """OOPAOEnvRazor.py:589-596 (mean over the episode; here also over environments and, when

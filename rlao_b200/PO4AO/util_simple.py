@@ -48,25 +48,35 @@ class TorchWrapper(_Wrapper):
         super().__init__(env)
         self.host_io = host_io
         self._pinned = {}
+        self._flip = {}
 
     def _to_host(self, *tensors):
+        """Asynchronous device->pinned-host copies of the step results, one stream synchronisation.  Two sets of
+        pinned buffers alternate, so the tensors handed out at step t stay valid until step t+2 (callers that
+        keep observations longer — e.g. a replay buffer — copy them, as they do with the reference's arrays)."""
         key = tuple((tuple(t.shape), t.dtype) for t in tensors)
         if key not in self._pinned:
-            self._pinned[key] = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors]
-        bufs = self._pinned[key]
-        for p, t in zip(bufs, tensors):
-            p.copy_(t, non_blocking=True)
+            self._pinned[key] = [[torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors] for _ in range(2)]
+            self._flip[key] = 0
+        self._flip[key] ^= 1
+        bufs = self._pinned[key][self._flip[key]]
+        for p_, t in zip(bufs, tensors):
+            p_.copy_(t, non_blocking=True)
         torch.cuda.current_stream(self._env.device).synchronize()
-        return [p.clone() for p in bufs]
+        return bufs
 
     def step(self, i, action):
         dev = self._env.device
         a = torch.as_tensor(action)
         if a.device != dev:
             a = a.to(dev, dtype=torch.float32, non_blocking=True)
-        obs, reward, strehl, done, info = self._env.step(i, a)
         if not self.host_io:
+            obs, reward, strehl, done, info = self._env.step(i, a)
             return obs, reward, strehl, done, [(k, v) for k, v in info.items()]
+        # the bare env can hand out views of its output buffers (they are copied to the host right away); an env
+        # wrapped in TimeDelayEnv goes through its own step()
+        fn = self._env._step_views if "_step_views" in type(self._env).__dict__ else self._env.step
+        obs, reward, strehl, done, info = fn(i, a)
         obs_h, reward_h, strehl_h = self._to_host(obs, reward, strehl)
         if self._env.n_envs == 1:
             reward_h, strehl_h = float(reward_h), float(strehl_h)

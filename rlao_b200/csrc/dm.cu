@@ -58,14 +58,93 @@ dm_separable_kernel(const float* __restrict__ coefs, int ldc, const int32_t* __r
   }
 }
 
+// Banded variant: per pixel column x the (at most W) contributing actuator columns start at j0x[x] with weights
+// wx[x][0..W); per pair of pixel rows (2k, 2k+1) the contributing actuator rows start at i0y[k] with weights
+// wyp[k][0..1][0..W).  Fixed trip counts -> fully unrolled, every load independent; each thread produces a 2 x 4
+// block of the surface, so one 128-bit shared-memory load of T feeds 8 FMAs.
+template <int W>
+__global__ void __launch_bounds__(256)
+dm_separable_banded_kernel(const float* __restrict__ coefs, int ldc, const int32_t* __restrict__ act_pos, int nA, int nAct,
+                           const float* __restrict__ wx, const int32_t* __restrict__ j0x, const float* __restrict__ wyp,
+                           const int32_t* __restrict__ i0y, int R, int x0, int xw, float* __restrict__ opd) {
+  extern __shared__ __align__(16) float sm[];
+  float* sC = sm;
+  float* sT = sm + ((nAct * nAct + 3) & ~3);
+  const int b = blockIdx.y;
+  for (int k = threadIdx.x; k < nAct * nAct; k += blockDim.x) sC[k] = 0.f;
+  __syncthreads();
+  for (int k = threadIdx.x; k < nA; k += blockDim.x) sC[__ldg(&act_pos[k])] = __ldg(&coefs[(size_t)b * ldc + k]);
+  __syncthreads();
+  // stage 1: lanes along x (coalesced weight loads), loop over actuator rows i
+  for (int xl = threadIdx.x; xl < xw; xl += blockDim.x) {
+    const int x = x0 + xl;
+    float w[W];
+    int j0 = 0;
+    if (x < R) {
+      j0 = __ldg(&j0x[x]);
+#pragma unroll
+      for (int q = 0; q < W / 4; ++q) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(wx + (size_t)x * W) + q);
+        w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < W; ++q) w[q] = 0.f;
+    }
+    for (int i = 0; i < nAct; ++i) {
+      const float* __restrict__ c = sC + i * nAct;
+      float t = 0.f;
+#pragma unroll
+      for (int q = 0; q < W; ++q) t = fmaf(c[min(j0 + q, nAct - 1)], w[q], t);
+      sT[i * xw + xl] = t;
+    }
+  }
+  __syncthreads();
+  // stage 2
+  const int nq = xw >> 2, npair = R >> 1;
+  float* __restrict__ out = opd + (size_t)b * R * R;
+  for (int idx = threadIdx.x; idx < npair * nq; idx += blockDim.x) {
+    const int k = idx / nq, q = idx - k * nq;
+    const int i0 = __ldg(&i0y[k]);
+    float w0[W], w1[W];
+#pragma unroll
+    for (int t = 0; t < W / 4; ++t) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(wyp + (size_t)k * 2 * W) + t);
+      const float4 c = __ldg(reinterpret_cast<const float4*>(wyp + (size_t)k * 2 * W + W) + t);
+      w0[4 * t] = a.x; w0[4 * t + 1] = a.y; w0[4 * t + 2] = a.z; w0[4 * t + 3] = a.w;
+      w1[4 * t] = c.x; w1[4 * t + 1] = c.y; w1[4 * t + 2] = c.z; w1[4 * t + 3] = c.w;
+    }
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+#pragma unroll
+    for (int t = 0; t < W; ++t) {
+      const float4 v = *reinterpret_cast<const float4*>(&sT[min(i0 + t, nAct - 1) * xw + 4 * q]);
+      r0.x = fmaf(w0[t], v.x, r0.x); r0.y = fmaf(w0[t], v.y, r0.y); r0.z = fmaf(w0[t], v.z, r0.z); r0.w = fmaf(w0[t], v.w, r0.w);
+      r1.x = fmaf(w1[t], v.x, r1.x); r1.y = fmaf(w1[t], v.y, r1.y); r1.z = fmaf(w1[t], v.z, r1.z); r1.w = fmaf(w1[t], v.w, r1.w);
+    }
+    const int x = x0 + 4 * q;
+    float* __restrict__ o0 = out + (size_t)(2 * k) * R + x;
+    float* __restrict__ o1 = o0 + R;
+    if (x + 3 < R && (R & 3) == 0) {
+      *reinterpret_cast<float4*>(o0) = r0;
+      *reinterpret_cast<float4*>(o1) = r1;
+    } else {
+      const float a0[4] = {r0.x, r0.y, r0.z, r0.w}, a1[4] = {r1.x, r1.y, r1.z, r1.w};
+      for (int c = 0; c < 4; ++c)
+        if (x + c < R) { o0[c] = a0[c]; o1[c] = a1[c]; }
+    }
+  }
+}
+
 }  // namespace aoenv
 
 using namespace aoenv;
 
 extern "C" int aoenv_dm_surface_separable(const float* coefs, int ldc, const int32_t* act_pos, int nA, int nAct,
                                           const float* gx, const float* gy, const int32_t* band_x, const int32_t* band_y,
+                                          const float* wx, const int32_t* j0x, const float* wyp, const int32_t* i0y, int W,
                                           int B, int R, float* opd, void* stream) {
   AOENV_CHECK_ARG(B > 0 && B <= 65535 && R > 0 && nAct > 0 && nA > 0 && nA <= nAct * nAct && ldc >= nA, "dm_surface_separable: bad shape");
+  const bool banded = (W == 12 || W == 16) && (R % 2 == 0) && wx && j0x && wyp && i0y;
   // split the columns across CTAs so that C and T fit in shared memory (and small batches still fill the GPU)
   int parts = 1;
   auto smem_for = [&](int p) {
@@ -76,16 +155,25 @@ extern "C" int aoenv_dm_surface_separable(const float* coefs, int ldc, const int
   const int xw = (((R + parts - 1) / parts) + 3) / 4 * 4;
   const size_t smem = smem_for(parts);
   AOENV_CHECK_ARG(smem <= 200 * 1024, "dm_surface_separable: %d actuators across do not fit in shared memory", nAct);
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(dm_separable_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t attr[3] = {0, 0, 0};
+  const int which = !banded ? 0 : (W == 12 ? 1 : 2);
+  if (smem > 48 * 1024 && smem > attr[which]) {
+    cudaError_t e = which == 0 ? cudaFuncSetAttribute(dm_separable_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                  : which == 1 ? cudaFuncSetAttribute(dm_separable_banded_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                               : cudaFuncSetAttribute(dm_separable_banded_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(-3, "dm_surface_separable smem attribute: %s", cudaGetErrorString(e));
-    attr = smem;
+    attr[which] = smem;
   }
+  cudaStream_t s = (cudaStream_t)stream;
   for (int p = 0; p < parts; ++p) {
-    dm_separable_kernel<<<dim3(1, B), 256, smem, (cudaStream_t)stream>>>(coefs, ldc, act_pos, nA, nAct, gx, gy,
-                                                                         (const int2*)band_x, (const int2*)band_y, R, p * xw,
-                                                                         xw, opd);
+    const dim3 grid(1, B);
+    if (which == 1)
+      dm_separable_banded_kernel<12><<<grid, 256, smem, s>>>(coefs, ldc, act_pos, nA, nAct, wx, j0x, wyp, i0y, R, p * xw, xw, opd);
+    else if (which == 2)
+      dm_separable_banded_kernel<16><<<grid, 256, smem, s>>>(coefs, ldc, act_pos, nA, nAct, wx, j0x, wyp, i0y, R, p * xw, xw, opd);
+    else
+      dm_separable_kernel<<<grid, 256, smem, s>>>(coefs, ldc, act_pos, nA, nAct, gx, gy, (const int2*)band_x,
+                                                  (const int2*)band_y, R, p * xw, xw, opd);
     AOENV_LAUNCH_CHECK("dm_separable");
   }
   return 0;

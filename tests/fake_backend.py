@@ -138,7 +138,8 @@ class FakeLib:
         d[:, :N] = (np.float32(_val(alpha)) * (x[:, :K].astype(np.float64) @ w[:, :K].astype(np.float64).T)).astype(np.float32)
         return 0
 
-    def aoenv_dm_surface_separable(self, coefs, ldc, act_pos, nA, nAct, gx, gy, band_x, band_y, B, R, opd, stream):
+    def aoenv_dm_surface_separable(self, coefs, ldc, act_pos, nA, nAct, gx, gy, band_x, band_y, wx, j0x, wyp, i0y, W, B, R,
+                                   opd, stream):
         self.launches += 1
         c = _arr(coefs, (B, ldc))
         pos = _arr(act_pos, (nA,), np.int32)
