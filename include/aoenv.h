@@ -70,14 +70,15 @@ int aoenv_atm_compact(const float* src_win, float* dst_win, int B, int M, int pi
 /* updateLayer tail + fill_phase_support + set_OPD (Atmosphere.py:406-407,439-450,474-478): for each layer the
  * bicubic (4x4 tap) sub-pixel shift of the map, clipped to the map's [min,max], cropped to the R x R pupil
  * footprint, weighted by sqrt(fractionalR0) and summed; opd_out [B][R][R] = sum * opd_scale (lambda/2pi).
- * h_win / h_ext: host arrays of nLayer device pointers (window origins, extrema).  h_row_off / h_col_off: first tap
- * offset relative to the output pixel's own window row / column (tap k reads row i + fp_off + h_row_off[l] + k).
- * h_wrow / h_wcol [nLayer][4]: tap weights (computed by the host in float64 from layer.buff).
- * h_weight [nLayer] = sqrt(fractionalR0).  fp_off = window index of footprint pixel 0 (3 for fov = 0). */
-int aoenv_atm_phase(const float* const* h_win, const uint64_t* const* h_ext, int nLayer, int B, int R, int M, int pitch,
-                    int64_t env_stride, int fp_off, const int32_t* h_row_off, const int32_t* h_col_off,
-                    const float* h_wrow, const float* h_wcol, const float* h_weight, float opd_scale,
-                    float* opd_out, void* stream);
+ * h_canvas / h_ext: host arrays of nLayer device pointers (canvas base [B][Mc][pitch], extrema); h_org [nLayer][2] =
+ * window origin (row, col) in each canvas.  h_row_off / h_col_off: first tap offset relative to the output pixel's own
+ * window row / column (tap k reads window row i + fp_off + h_row_off[l] + k).  h_wrow / h_wcol [nLayer][4]: tap
+ * weights (computed by the host in float64 from layer.buff).  h_weight [nLayer] = sqrt(fractionalR0).
+ * fp_off = window index of footprint pixel 0 (3 for fov = 0).  The input windows are staged with TMA box loads. */
+int aoenv_atm_phase(const float* const* h_canvas, const uint64_t* const* h_ext, const int32_t* h_org, int nLayer, int B,
+                    int R, int M, int Mc, int pitch, int fp_off, const int32_t* h_row_off, const int32_t* h_col_off,
+                    const float* h_wrow, const float* h_wcol, const float* h_weight, float opd_scale, float* opd_out,
+                    void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Dense contractions — DeformableMirror.coefs setter (OOPAO/DeformableMirror.py:534-570: OPD = modes @ coefs),

@@ -264,8 +264,9 @@ class Atmosphere:
     def _publish(self):
         """Sub-pixel shift of every layer + Cn2-weighted sum -> OPD_no_pupil (Atmosphere.py:406-407,439-478)."""
         L = self.nLayer
-        maps = (C.c_void_p * L)(*[self._win_ptr(i).value for i in range(L)])
-        mms = (C.c_void_p * L)(*[self._ext[i].data_ptr() for i in range(L)])
+        maps = (C.c_void_p * L)(*[self._maps[i, self._cur[i]].data_ptr() for i in range(L)])
+        exts = (C.c_void_p * L)(*[self._ext[i].data_ptr() for i in range(L)])
+        org = (C.c_int32 * (2 * L))(*[v for i in range(L) for v in self._org[i]])
         roff, coff = (C.c_int32 * L)(), (C.c_int32 * L)()
         wr, wc, wt = (C.c_float * (4 * L))(), (C.c_float * (4 * L))(), (C.c_float * L)()
         for i, ly in enumerate(self._layers):
@@ -275,8 +276,8 @@ class Atmosphere:
             for k in range(4):
                 wr[4 * i + k], wc[4 * i + k] = wrow[k], wcol[k]
             wt[i] = math.sqrt(self.fractionalR0[i])
-        _lib.check(_lib.load().aoenv_atm_phase(maps, mms, L, self.n_envs, self.telescope.resolution, self._M, self._pitch,
-                                               self._env_stride, self._fp_off, roff, coff, wr, wc, wt,
+        _lib.check(_lib.load().aoenv_atm_phase(maps, exts, org, L, self.n_envs, self.telescope.resolution, self._M, self._Mc,
+                                               self._pitch, self._fp_off, roff, coff, wr, wc, wt,
                                                C.c_float(self.wavelength / 2 / math.pi), _lib.ptr(self._opd),
                                                _lib.stream_ptr(self.device)), "atm_phase")
 

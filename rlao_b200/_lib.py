@@ -33,7 +33,7 @@ PROTOTYPES = {
     "aoenv_atm_gather": [_vp, _i, _i, _i, _i64, _i, _i, _vp, _i, _i, _vp, _u64, _u64, _vp, _i, _vp],
     "aoenv_atm_ring": [_vp, _i, _i, _i, _i64, _i64, _i, _vp, _i, _vp, _vp, _i, _vp],
     "aoenv_atm_compact": [_vp, _vp, _i, _i, _i, _i64, _vp, _i64, _vp],
-    "aoenv_atm_phase": [_vp, _vp, _i, _i, _i, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp],
+    "aoenv_atm_phase": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp],
     "aoenv_gemm_tn": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _f, _vp],
     "aoenv_split_bf16": [_vp, _i, _i, _i, _i, _vp, _i, _vp],
     "aoenv_gemm_tn_tc": [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _f, _vp],

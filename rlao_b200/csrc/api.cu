@@ -1,7 +1,10 @@
 // Error plumbing, ABI version and launch accounting for libaoenv_b200.
 #include <stdarg.h>
 
+#include <mutex>
+
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace aoenv {
 
@@ -15,6 +18,20 @@ int fail(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+
+namespace tma {
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+}  // namespace tma
 
 }  // namespace aoenv
 

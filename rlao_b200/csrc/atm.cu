@@ -7,6 +7,7 @@
 // pixels of the new window border.  The canvas is re-centred ("compacted") once every S events.  A "window" is
 // addressed as (pointer to its origin, pitch = canvas pitch, env_stride = canvas size).
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace aoenv {
 
@@ -184,10 +185,10 @@ atm_compact_kernel(const float* __restrict__ src, float* __restrict__ dst, int M
 // strip: the horizontal 4-tap pass is done once per input row and reused by the vertical 4-tap pass.
 // ---------------------------------------------------------------------------------------------------------
 struct AtmPhaseParams {
-  const float* map[AOENV_MAX_LAYERS];
+  CUtensorMap map[AOENV_MAX_LAYERS];                 // canvas [B][Mc][pitch] of each layer (3-D tensor map)
   const unsigned long long* ext[AOENV_MAX_LAYERS];
-  int row_off[AOENV_MAX_LAYERS];
-  int col_off[AOENV_MAX_LAYERS];
+  int row0[AOENV_MAX_LAYERS];                        // canvas row / column of the first tap of footprint pixel (0, 0)
+  int col0[AOENV_MAX_LAYERS];
   float wrow[AOENV_MAX_LAYERS][4];
   float wcol[AOENV_MAX_LAYERS][4];
   float weight[AOENV_MAX_LAYERS];
@@ -195,20 +196,65 @@ struct AtmPhaseParams {
 };
 
 // Tile = 128 x 32 output pixels per CTA of 128 threads; each thread owns a 4 (columns) x 8 (rows) register block.
-// Per layer the (32+3) x (128+3) input window is staged in shared memory with coalesced loads (its global alignment
-// depends on the layer's tap offset, the shared-memory copy is 16-byte aligned for every thread), then the separable
-// interpolation runs out of shared memory with two 128-bit loads per input row.
+// Per layer one TMA box load (cp.async.bulk.tensor.3d) brings the (32+3) x (128+8) input window to shared memory with
+// zero fill outside the canvas; two buffers let the load of layer l+1 overlap the interpolation of layer l.  TMA needs
+// the innermost start coordinate 16-byte aligned, so the box starts at the window column rounded down to a multiple
+// of 4 and the remainder `mis` (uniform per CTA and layer) is resolved in registers: three 128-bit shared loads per
+// input row cover the 7 taps of a thread's 4 outputs for any mis in 0..3.
 constexpr int kPhTileW = 128, kPhTileH = 32, kPhThreadsX = 32, kPhThreadsY = 4, kPhRows = 8;
-constexpr int kPhSmemW = kPhTileW + 8;    // 3 extra taps, padded to a multiple of 4
+constexpr int kPhBoxW = kPhTileW + 8, kPhBoxH = kPhTileH + 3;
+constexpr uint32_t kPhBoxBytes = kPhBoxW * kPhBoxH * sizeof(float);
+constexpr int kPhBufFloats = (kPhBoxW * kPhBoxH + 31) / 32 * 32;      // each TMA destination 128-byte aligned
+
+// Tensor maps must be addressed in parameter space: a dynamically indexed `&p.map[l]` would make the compiler copy the
+// parameter block to local memory, which TMA cannot read.  Constant indices keep the generic address in param space.
+__device__ __forceinline__ const CUtensorMap* layer_map(const AtmPhaseParams& p, int l) {
+  switch (l) {
+    case 0: return &p.map[0];
+    case 1: return &p.map[1];
+    case 2: return &p.map[2];
+    case 3: return &p.map[3];
+    case 4: return &p.map[4];
+    case 5: return &p.map[5];
+    case 6: return &p.map[6];
+    default: return &p.map[7];
+  }
+}
+
+template <int MIS>
+__device__ __forceinline__ void phase_rows(const float* __restrict__ tbase, float wc0, float wc1, float wc2, float wc3,
+                                           float (&h)[kPhRows + 3][4]) {
+#pragma unroll
+  for (int t = 0; t < kPhRows + 3; ++t) {
+    const float* __restrict__ trow = tbase + t * kPhBoxW;
+    const float4 a = *reinterpret_cast<const float4*>(trow);
+    const float4 b = *reinterpret_cast<const float4*>(trow + 4);
+    const float4 c = *reinterpret_cast<const float4*>(trow + 8);
+    const float v[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      h[t][k] = wc0 * v[MIS + k] + wc1 * v[MIS + k + 1] + wc2 * v[MIS + k + 2] + wc3 * v[MIS + k + 3];
+  }
+}
 
 __global__ void __launch_bounds__(kPhThreadsX * kPhThreadsY)
-atm_phase_kernel(const __grid_constant__ AtmPhaseParams p, int R, int M, int pitch, size_t env_stride, int fp_off, float opd_scale,
-                 float* __restrict__ opd_out) {
-  __shared__ __align__(16) float tile[kPhTileH + 3][kPhSmemW];
+atm_phase_kernel(const __grid_constant__ AtmPhaseParams p, int R, float opd_scale, float* __restrict__ opd_out) {
+  __shared__ __align__(128) float tile[2][kPhBufFloats];
+  __shared__ __align__(8) uint64_t bar[2];
   const int b = blockIdx.z;
   const int j0 = blockIdx.x * kPhTileW, i0 = blockIdx.y * kPhTileH;
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int tid = ty * kPhThreadsX + tx;
+  const bool leader = (tx == 0 && ty == 0);
+  if (leader) {
+    tma::mbar_init(&bar[0], 1);
+    tma::mbar_init(&bar[1], 1);
+    tma::mbar_fence_init();
+  }
+  __syncthreads();
+  if (leader) {
+    tma::mbar_expect_tx(&bar[0], kPhBoxBytes);
+    tma::load_3d(layer_map(p, 0), &bar[0], &tile[0][0], (p.col0[0] + j0) & ~3, p.row0[0] + i0, b);
+  }
   float acc[kPhRows][4];
 #pragma unroll
   for (int r = 0; r < kPhRows; ++r)
@@ -216,35 +262,24 @@ atm_phase_kernel(const __grid_constant__ AtmPhaseParams p, int R, int M, int pit
     for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
 
   for (int l = 0; l < p.nLayer; ++l) {
-    const float* __restrict__ m = p.map[l] + (size_t)b * env_stride;
-    const int cbase = j0 + fp_off + p.col_off[l];
-    const int rbase = i0 + fp_off + p.row_off[l];
-    __syncthreads();
-    // asynchronous 4-byte copies (LDGSTS): every load of the window is in flight before the first one lands
-    for (int rr = ty; rr < kPhTileH + 3; rr += kPhThreadsY) {           // one warp per input row, lanes along columns
-      const float* __restrict__ grow = m + (size_t)min(rbase + rr, M - 1) * pitch;   // clamps only touch unused outputs
-      const uint32_t srow = (uint32_t)__cvta_generic_to_shared(&tile[rr][0]);
-#pragma unroll
-      for (int cc = tx; cc < kPhTileW + 3; cc += kPhThreadsX)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(srow + 4u * cc), "l"(grow + min(cbase + cc, M - 1)) : "memory");
+    const int buf = l & 1;
+    if (leader && l + 1 < p.nLayer) {     // buffer buf^1 was released by the __syncthreads that ended iteration l-1
+      tma::mbar_expect_tx(&bar[buf ^ 1], kPhBoxBytes);
+      tma::load_3d(layer_map(p, l + 1), &bar[buf ^ 1], &tile[buf ^ 1][0], (p.col0[l + 1] + j0) & ~3, p.row0[l + 1] + i0, b);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
     const float lo = value_of(__ldg(&p.ext[l][2 * b + 0]));
     const float hi = value_of(__ldg(&p.ext[l][2 * b + 1]));
     const float wc0 = p.wcol[l][0], wc1 = p.wcol[l][1], wc2 = p.wcol[l][2], wc3 = p.wcol[l][3];
     const float wr0 = p.wrow[l][0], wr1 = p.wrow[l][1], wr2 = p.wrow[l][2], wr3 = p.wrow[l][3];
     const float w = p.weight[l];
+    tma::mbar_wait(&bar[buf], (l >> 1) & 1);
     float h[kPhRows + 3][4];
-#pragma unroll
-    for (int t = 0; t < kPhRows + 3; ++t) {
-      const float4 a = *reinterpret_cast<const float4*>(&tile[ty * kPhRows + t][tx * 4]);
-      const float4 c = *reinterpret_cast<const float4*>(&tile[ty * kPhRows + t][tx * 4 + 4]);
-      h[t][0] = wc0 * a.x + wc1 * a.y + wc2 * a.z + wc3 * a.w;
-      h[t][1] = wc0 * a.y + wc1 * a.z + wc2 * a.w + wc3 * c.x;
-      h[t][2] = wc0 * a.z + wc1 * a.w + wc2 * c.x + wc3 * c.y;
-      h[t][3] = wc0 * a.w + wc1 * c.x + wc2 * c.y + wc3 * c.z;
+    const float* __restrict__ tbase = &tile[buf][(ty * kPhRows) * kPhBoxW + tx * 4];
+    switch ((p.col0[l] + j0) & 3) {                                     // uniform across the CTA
+      case 0: phase_rows<0>(tbase, wc0, wc1, wc2, wc3, h); break;
+      case 1: phase_rows<1>(tbase, wc0, wc1, wc2, wc3, h); break;
+      case 2: phase_rows<2>(tbase, wc0, wc1, wc2, wc3, h); break;
+      default: phase_rows<3>(tbase, wc0, wc1, wc2, wc3, h); break;
     }
 #pragma unroll
     for (int t = 0; t < kPhRows; ++t)
@@ -254,6 +289,7 @@ atm_phase_kernel(const __grid_constant__ AtmPhaseParams p, int R, int M, int pit
         v = fminf(fmaxf(v, lo), hi);
         acc[t][c] += w * v;
       }
+    __syncthreads();                       // everyone is done with tile[buf] before it is refilled
   }
   float* __restrict__ out = opd_out + (size_t)b * R * R;
   const int jc = j0 + tx * 4;
@@ -328,31 +364,45 @@ int aoenv_atm_compact(const float* src_win, float* dst_win, int B, int M, int pi
   return 0;
 }
 
-int aoenv_atm_phase(const float* const* h_win, const uint64_t* const* h_ext, int nLayer, int B, int R, int M, int pitch,
-                    int64_t env_stride, int fp_off, const int32_t* h_row_off, const int32_t* h_col_off, const float* h_wrow,
-                    const float* h_wcol, const float* h_weight, float opd_scale, float* opd_out, void* stream) {
+int aoenv_atm_phase(const float* const* h_canvas, const uint64_t* const* h_ext, const int32_t* h_org, int nLayer, int B,
+                    int R, int M, int Mc, int pitch, int fp_off, const int32_t* h_row_off, const int32_t* h_col_off,
+                    const float* h_wrow, const float* h_wcol, const float* h_weight, float opd_scale, float* opd_out,
+                    void* stream) {
   AOENV_CHECK_ARG(nLayer >= 1 && nLayer <= AOENV_MAX_LAYERS, "atm_phase: nLayer=%d out of range", nLayer);
   AOENV_CHECK_ARG(B > 0 && B <= 65535, "atm_phase: B=%d out of range (1..65535)", B);
+  AOENV_CHECK_ARG(pitch % 4 == 0 && pitch >= Mc && Mc >= M, "atm_phase: bad canvas Mc=%d pitch=%d", Mc, pitch);
+  tma::EncodeTiledFn enc = tma::get_encode();
+  if (!enc) return fail(-4, "cuTensorMapEncodeTiled is not available from the CUDA driver");
   AtmPhaseParams p;
   p.nLayer = nLayer;
   for (int l = 0; l < nLayer; ++l) {
-    p.map[l] = h_win[l];
+    const int oy = h_org[2 * l], ox = h_org[2 * l + 1];
+    AOENV_CHECK_ARG(oy >= 0 && ox >= 0 && oy + M <= Mc && ox + M <= pitch, "atm_phase: window of layer %d leaves the canvas", l);
+    // every tap of every footprint pixel must lie inside the window
+    const int lo_r = fp_off + h_row_off[l], hi_r = fp_off + R - 1 + h_row_off[l] + 3;
+    const int lo_c = fp_off + h_col_off[l], hi_c = fp_off + R - 1 + h_col_off[l] + 3;
+    AOENV_CHECK_ARG(lo_r >= 0 && lo_c >= 0 && hi_r < M && hi_c < M, "atm_phase: taps of layer %d leave the map", l);
+    AOENV_CHECK_ARG((reinterpret_cast<uintptr_t>(h_canvas[l]) & 15) == 0, "atm_phase: canvas must be 16-byte aligned");
+    cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)Mc, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)Mc * pitch * 4};
+    cuuint32_t box[3] = {(cuuint32_t)kPhBoxW, (cuuint32_t)kPhBoxH, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&p.map[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(h_canvas[l]), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-4, "atm_phase: cuTensorMapEncodeTiled failed (%d)", (int)r);
     p.ext[l] = reinterpret_cast<const unsigned long long*>(h_ext[l]);
-    p.row_off[l] = h_row_off[l];
-    p.col_off[l] = h_col_off[l];
+    p.row0[l] = oy + fp_off + h_row_off[l];
+    p.col0[l] = ox + fp_off + h_col_off[l];
     for (int k = 0; k < 4; ++k) {
       p.wrow[l][k] = h_wrow[4 * l + k];
       p.wcol[l][k] = h_wcol[4 * l + k];
     }
     p.weight[l] = h_weight[l];
-    // every tap of every footprint pixel must lie inside the window
-    const int lo_r = fp_off + h_row_off[l], hi_r = fp_off + R - 1 + h_row_off[l] + 3;
-    const int lo_c = fp_off + h_col_off[l], hi_c = fp_off + R - 1 + h_col_off[l] + 3;
-    AOENV_CHECK_ARG(lo_r >= 0 && lo_c >= 0 && hi_r < M && hi_c < M, "atm_phase: taps of layer %d leave the map", l);
   }
   dim3 block(kPhThreadsX, kPhThreadsY);
   dim3 grid((R + kPhTileW - 1) / kPhTileW, (R + kPhTileH - 1) / kPhTileH, B);
-  atm_phase_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(p, R, M, pitch, (size_t)env_stride, fp_off, opd_scale, opd_out);
+  atm_phase_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(p, R, opd_scale, opd_out);
   AOENV_LAUNCH_CHECK("atm_phase");
   return 0;
 }

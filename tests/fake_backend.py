@@ -108,9 +108,11 @@ class FakeLib:
         u[:] = (u & np.uint64(0xffffffff00000000)) | ((u & np.uint64(0xffffffff)) + np.uint64(pos_delta % (1 << 32))) & np.uint64(0xffffffff)
         return 0
 
-    def aoenv_atm_phase(self, h_map, h_ext, L, B, R, M, pitch, env_stride, fp_off, roff, coff, wr, wc, wt, opd_scale,
+    def aoenv_atm_phase(self, h_canvas, h_ext, h_org, L, B, R, M, Mc, pitch, fp_off, roff, coff, wr, wc, wt, opd_scale,
                         opd_out, stream):
         self.launches += 1
+        env_stride = Mc * pitch
+        h_map = [int(h_canvas[l]) + 4 * (h_org[2 * l] * pitch + h_org[2 * l + 1]) for l in range(L)]
         out = _arr(opd_out, (B, R, R))
         acc = np.zeros((B, R, R), dtype=np.float32)
         for l in range(L):
