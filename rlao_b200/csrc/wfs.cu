@@ -6,6 +6,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "wfs_twiddles.inc"
 
 namespace aoenv {
 
@@ -239,7 +240,8 @@ shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ op
               float er_ = 0.f, ei_ = 0.f, or_ = 0.f, oi_ = 0.f;
 #pragma unroll
               for (int bb = 0; bb < n; ++bb) {
-                const float2 g = c_tw[v * n + bb];
+                // v, bb are compile-time after unrolling: literal twiddles -> immediate-operand FFMAs
+                const float2 g = make_float2(WfsTw<n>::re(v * n + bb), WfsTw<n>::im(v * n + bb));
                 if (((bb + h) & 1) == 0) {
                   er_ = fmaf(yr[bb], g.x, fmaf(-yi[bb], g.y, er_));
                   ei_ = fmaf(yr[bb], g.y, fmaf(yi[bb], g.x, ei_));
