@@ -277,6 +277,9 @@ def run_gpu_arm(args):
     sr_mean = float(strehl.float().mean())
 
     # ---- end-to-end through the host-facing wrapper (pinned host buffers, copies inside the timed region) ----
+    # the host-side "policy" (action = gain * obs on 1.7M floats) may use this rank's share of the host cores
+    # (torchrun pins OMP_NUM_THREADS=1 by default)
+    torch.set_num_threads(max(1, min(16, (os.cpu_count() or 1) // world)))
     wrapped = TorchWrapper(env, host_io=True)
     obs_h = wrapped.reset_soft()
     act_h = torch.empty(obs_h.shape, dtype=torch.float32, pin_memory=True)
