@@ -72,7 +72,6 @@ class ShackHartmann:
         self._stats = torch.zeros((B, 4), dtype=torch.float64, device=self.device)
         self._signal = torch.zeros((B, self._lds), dtype=torch.float32, device=self.device)
         self._signal_is_multi = False
-        self._ones = torch.ones((R, R), dtype=torch.float32, device=self.device)
         self.initialize_wfs()
 
     # ---- flux / valid subapertures (ShackHartmann.py:215-240,327-338) -------------------------------------

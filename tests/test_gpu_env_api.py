@@ -1,0 +1,171 @@
+"""Behaviour of the environment layer on the GPU: wrappers, exploration noise, PSF reward, magnitude change,
+noisy closed loop, determinism and sharding offsets, live atmosphere parameter changes."""
+import math
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.golden_configs import CONFIGS, EPISODE_SEED
+from parity_util import build_env, new_episode, param_from_config, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def test_torch_wrapper_host_io_matches_device_path(dev):
+    """MAIN_CODE/PO4AO/util_simple.py:201-221: host tensors in / out, same numbers as the device-resident loop."""
+    from rlao_b200.PO4AO.util_simple import TorchWrapper
+    cfg = CONFIGS["tiny"]()
+    env_a = build_env(cfg, n_envs=3, rng="philox", seed=4, device=dev)
+    env_b = build_env(cfg, n_envs=3, rng="philox", seed=4, device=dev)
+    wrapped = TorchWrapper(env_b)
+    obs_a = new_episode(env_a, 9)
+    new_episode(env_b, 9)
+    obs_b = wrapped.reset_soft()
+    assert obs_b.device.type == "cpu" and obs_b.dtype == torch.float32
+    for i in range(6):
+        obs_a, r_a, s_a, _, _ = env_a.step(i, cfg.gainCL * obs_a)
+        obs_b, r_b, s_b, done, info = wrapped.step(i, cfg.gainCL * obs_b)
+        assert obs_b.device.type == "cpu" and r_b.device.type == "cpu"
+        assert torch.equal(obs_a.cpu(), obs_b) and torch.equal(r_a.cpu(), r_b) and torch.equal(s_a.cpu(), s_b)
+    assert info[0][0] == "strehl" and done is False
+    single = TorchWrapper(build_env(cfg, n_envs=1, rng="philox", device=dev))
+    o = single.reset_soft()
+    o, r, s, _, _ = single.step(0, 0.5 * o)
+    assert o.shape == (cfg.nSubap + 1, cfg.nSubap + 1) and isinstance(r, float) and isinstance(s, float)
+
+
+def test_time_delay_env_delays_actions(dev):
+    """util_simple.py:25-52: with delay d the env receives the action issued d steps earlier (zeros first)."""
+    from rlao_b200.PO4AO.util_simple import TimeDelayEnv
+    cfg = CONFIGS["tiny"]()
+    env_a = build_env(cfg, n_envs=2, rng="philox", seed=2, device=dev)
+    env_b = TimeDelayEnv(build_env(cfg, n_envs=2, rng="philox", seed=2, device=dev), 1)
+    obs_a = new_episode(env_a, 3)
+    new_episode(env_b._env, 3)
+    obs_b = env_b.reset_soft()
+    prev = torch.zeros_like(obs_a)
+    for i in range(4):
+        act = 0.3 * obs_b
+        obs_b, *_ = env_b.step(i, act)
+        obs_a, *_ = env_a.step(i, prev)        # undelayed env driven with last step's action
+        prev = act
+        assert torch.allclose(obs_a, obs_b, rtol=0, atol=1e-6 * float(obs_a.abs().max()))
+
+
+def test_sample_noise_lives_in_the_controlled_subspace(dev):
+    """OOPAOEnvRazor.py:616-619: F @ (sigma N(0, I)), F = M2C pinv(M2C) is a projector."""
+    cfg = CONFIGS["tiny"]()
+    env = build_env(cfg, n_envs=5, rng="philox", device=dev)
+    z = env.sample_noise(0.05)
+    assert z.shape == (5, cfg.nSubap + 1, cfg.nSubap + 1)
+    v = env.img_to_vec(z).double()
+    assert rel_err((v @ env.F.T).cpu().numpy(), v.cpu().numpy()) < 1e-5
+    assert torch.equal(env.vec_to_img(env.img_to_vec(z)), z)
+    assert 0.0 < float(v.std()) < 0.05
+
+
+def test_psf_strehl_reward(dev):
+    """Science-path Strehl from the PSF peak (Telescope.computePSF(4); PSF.max() / psf_model_max)."""
+    cfg = CONFIGS["tiny"]()
+    env = build_env(cfg, n_envs=2, rng="philox", device=dev)
+    env.tel.resetOPD()
+    assert torch.allclose(env.psf_strehl(4, 16), torch.ones(2, device=dev), atol=1e-5)
+    # aberrated wavefront: same number as the reference definition evaluated by the oracle on the full image
+    from oracle.ao_oracle import compute_psf, flux_map, source_properties, telescope_pupil
+    rs = np.random.RandomState(0)
+    yy, xx = np.mgrid[:cfg.resolution, :cfg.resolution] / cfg.resolution
+    opd = 30e-9 * (np.sin(9 * xx) + np.cos(7 * yy * xx)) + 5e-9 * rs.normal(size=xx.shape)
+    env.tel.OPD_no_pupil = torch.as_tensor(opd, dtype=torch.float32, device=dev)
+    pupil = telescope_pupil(cfg.resolution)
+    wl, nph = source_properties(cfg.opticalBand, cfg.magnitude)
+    fm = flux_map(pupil, nph, cfg.samplingTime, cfg.diameter)
+    opd32 = env.tel.OPD_no_pupil[0].double().cpu().numpy()
+    want = compute_psf(pupil, fm, opd32 * pupil * 2 * np.pi / wl, 4).max() / compute_psf(pupil, fm, 0 * opd32, 4).max()
+    sr_psf = env.psf_strehl(4, 16)
+    assert abs(float(sr_psf[0]) - want) < 1e-4 * want and abs(float(sr_psf[1]) - want) < 1e-4 * want
+    # (PSF.max()/model max can exceed exp(-var) and even 1: the flat-wavefront peak straddles four binned pixels,
+    # Telescope.py:330 half-pixel phasor + 2x2 binning, and a little tilt centres it on one)
+    assert 0.5 < want < 1.05
+    # as the per-step reward
+    obs = new_episode(env, 5)
+    env.psf_reward = (4, 16)
+    obs, reward, strehl, _, info = env.step(0, cfg.gainCL * obs)
+    assert strehl.shape == (2,) and torch.all(strehl > 0) and torch.all(strehl <= 1.0001)
+    assert info["strehl"] is strehl
+
+
+def test_change_mag_rescales_flux_not_slopes(dev):
+    """OOPAOEnvRazor.py:644-647."""
+    cfg = CONFIGS["tiny"]()
+    env = build_env(cfg, n_envs=1, rng="philox", device=dev)
+    new_episode(env, 5)
+    sig0, frame0 = env.wfs.signal.clone(), env.wfs.cam.frame.clone()
+    env.change_mag(cfg.magnitude + 2.5)          # 10x fewer photons
+    assert rel_err(env.wfs.cam.frame.cpu().numpy() * 10.0, frame0.cpu().numpy()) < 1e-5
+    assert rel_err(env.wfs.signal.cpu().numpy(), sig0.cpu().numpy()) < 1e-4
+
+
+def test_noisy_closed_loop_converges(dev):
+    """BASELINE.json configs[3]-style run: Razor-like camera (photon + read noise, QE, FWC, 10-bit ADC)."""
+    cfg = CONFIGS["tiny_noise"]()
+    env = build_env(cfg, n_envs=16, rng="philox", seed=3, device=dev)
+    obs = new_episode(env, 11)
+    s_first = None
+    for i in range(40):
+        obs, reward, strehl, _, _ = env.step(i, cfg.gainCL * obs)
+        if i == 0:
+            s_first = strehl.clone()
+    frame = env.wfs.cam.frame
+    # integer ADU, clipped at 2^bits-1 above; read noise is added after the full-well clip, so small negatives occur
+    assert torch.equal(frame, frame.round()) and float(frame.max()) <= 1023 and float(frame.min()) > -100
+    assert float(env.residual[39].mean()) < 0.6 * float(env.total[39].mean())
+    assert float(strehl.mean()) > 10 * float(s_first.mean())
+    # environments see different noise and turbulence
+    assert float((obs[0] - obs[1]).abs().max()) > 0
+
+
+def test_determinism_and_shard_offsets(dev):
+    cfg = CONFIGS["tiny"]()
+
+    def run(seed, offset):
+        env = build_env(cfg, n_envs=2, rng="philox", seed=seed, device=dev, env_offset=offset)
+        obs = new_episode(env, 21)
+        for i in range(5):
+            obs, *_ = env.step(i, cfg.gainCL * obs)
+        return obs
+    a, b, c, d = run(1, 0), run(1, 0), run(2, 0), run(1, 2)
+    assert torch.equal(a, b)                                   # same seed, same shard: bit-identical
+    assert float((a - c).abs().max()) > 0                      # another seed
+    assert float((a - d).abs().max()) > 0                      # another shard of the same job
+
+
+def test_live_atmosphere_parameter_changes(dev):
+    """OOPAO/Atmosphere.py:792-870: r0 rescales the innovation factor B only; windSpeed / windDirection update the
+    per-step shift (and the canvas follows a reversed drift)."""
+    cfg = CONFIGS["tiny"]()
+    env = build_env(cfg, n_envs=2, rng="philox", device=dev, canvas_slack=4)
+    atm = env.atm
+    A0, B0 = atm._ops.A.clone(), atm._ops.B.clone()
+    atm.r0 = cfg.r0 / 2
+    assert torch.equal(atm._ops.A, A0)
+    assert rel_err(atm._ops.B.cpu().numpy(), (B0 * 2 ** (5 / 6)).cpu().numpy()) < 1e-6
+    assert rel_err(atm._W[:, atm._nI:atm._nI + atm._nO].cpu().numpy(), atm._ops.B.float().cpu().numpy()) < 1e-7
+    atm.windSpeed = [40.0, 30.0]
+    atm.windDirection = [180.0, 300.0]                         # reverse the drift
+    for _ in range(25):
+        atm.update()
+    assert np.allclose(atm.layer_1.ratio, [40 * math.sin(math.pi) * cfg.samplingTime / atm.ps_loop,
+                                           40 * math.cos(math.pi) * cfg.samplingTime / atm.ps_loop], atol=1e-9)
+    assert torch.isfinite(atm.OPD_no_pupil).all() and float(atm.OPD_no_pupil.abs().max()) < 1e-4
+    for i in range(atm.nLayer):
+        oy, ox = atm._org[i]
+        assert 0 <= oy <= atm._S and 0 <= ox <= atm._S
