@@ -110,7 +110,8 @@ struct Cfg {
 
 template <int kParts, int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ TensorMaps maps, float* __restrict__ D, int ldd, int MX, int NW, int K, float alpha) {
+gemm_tc_kernel(const __grid_constant__ TensorMaps maps, float* __restrict__ D, int ldd, int MX, int NW, int K, float alpha,
+               int split_k) {
   using C = Cfg<kParts, BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -124,8 +125,10 @@ gemm_tc_kernel(const __grid_constant__ TensorMaps maps, float* __restrict__ D, i
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (NW + BLOCK_M - 1) / BLOCK_M;
   const int num_n = (MX + BLOCK_N - 1) / BLOCK_N;
-  const int num_tiles = num_m * num_n;
+  const int num_mn = num_m * num_n;
+  const int num_tiles = num_mn * split_k;            // split-K: tile t covers k-blocks [kb0, kb1) of output tile t % num_mn
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const int kb_per = (num_kb + split_k - 1) / split_k;
 
   if (warp == 0 && lane == 0) {
     for (int p = 0; p < kParts; ++p) {
@@ -161,8 +164,10 @@ gemm_tc_kernel(const __grid_constant__ TensorMaps maps, float* __restrict__ D, i
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m_blk = t / num_n, n_blk = t % num_n;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int mn = t % num_mn, ks = t / num_mn;
+        const int m_blk = mn / num_n, n_blk = mn % num_n;
+        const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * C::kStageBytes;
           mbar_expect_tx(&full_bar[stage], C::kStageBytes);
@@ -187,12 +192,14 @@ gemm_tc_kernel(const __grid_constant__ TensorMaps maps, float* __restrict__ D, i
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + acc * C::kAccPerBuf * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int ks = t / num_mn;
+        const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t st = smem_u32(smem + stage * C::kStageBytes);
-          uint32_t first = (kb == 0) ? 1u : 0u;        // first MMA into the main accumulator
-          uint32_t first_x = (kb == 0) ? 1u : 0u;      // first MMA into the cross-term accumulator
+          uint32_t first = (kb == kb0) ? 1u : 0u;      // first MMA into the main accumulator
+          uint32_t first_x = (kb == kb0) ? 1u : 0u;    // first MMA into the cross-term accumulator
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // cross terms in increasing order of magnitude last: (pw, px) with pw + px < kParts
@@ -214,7 +221,7 @@ gemm_tc_kernel(const __grid_constant__ TensorMaps maps, float* __restrict__ D, i
             }
           }
           umma_commit(&empty_bar[stage]);                     // frees the stage when these MMAs retire
-          if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
+          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);     // accumulator complete
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -226,7 +233,8 @@ gemm_tc_kernel(const __grid_constant__ TensorMaps maps, float* __restrict__ D, i
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m_blk = t / num_n, n_blk = t % num_n;
+      const int mn = t % num_mn;
+      const int m_blk = mn / num_n, n_blk = mn % num_n;
       mbar_wait(&tmem_full[acc], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int w_row = m_blk * BLOCK_M + q * 32 + lane;
@@ -249,7 +257,12 @@ gemm_tc_kernel(const __grid_constant__ TensorMaps maps, float* __restrict__ D, i
         if (w_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (x0 + j < MX) D[(size_t)(x0 + j) * ldd + w_row] = alpha * __uint_as_float(v[j]);
+            if (x0 + j < MX) {
+              float* dst = &D[(size_t)(x0 + j) * ldd + w_row];
+              const float val = alpha * __uint_as_float(v[j]);
+              if (split_k > 1) atomicAdd(dst, val);       // D was zeroed; two partials add commutatively -> deterministic
+              else *dst = val;
+            }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -319,9 +332,18 @@ static int launch(const __nv_bfloat16* Xs, const __nv_bfloat16* Ws, int ldk, flo
     if (e != cudaSuccess) return fail(-3, "gemm_tc smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int num_tiles = ((NW + BLOCK_M - 1) / BLOCK_M) * ((MX + BLOCK_N - 1) / BLOCK_N);
+  const int num_mn = ((NW + BLOCK_M - 1) / BLOCK_M) * ((MX + BLOCK_N - 1) / BLOCK_N);
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  // small outputs leave most SMs idle: split K in two (two partial sums added with float atomics commute, so the
+  // result stays bit-reproducible; more than two would not)
+  const int split_k = (2 * num_mn <= kNumSMs && num_kb >= 8) ? 2 : 1;
+  if (split_k > 1) {
+    cudaError_t e = cudaMemset2DAsync(D, sizeof(float) * (size_t)ldd, 0, sizeof(float) * (size_t)NW, (size_t)MX, s);
+    if (e != cudaSuccess) return fail(-3, "gemm_tc memset: %s", cudaGetErrorString(e));
+  }
+  const int num_tiles = num_mn * split_k;
   const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
-  gemm_tc_kernel<kParts, BLOCK_N><<<grid, kThreads, C::kSmemBytes, s>>>(maps, D, ldd, MX, NW, K, alpha);
+  gemm_tc_kernel<kParts, BLOCK_N><<<grid, kThreads, C::kSmemBytes, s>>>(maps, D, ldd, MX, NW, K, alpha, split_k);
   AOENV_LAUNCH_CHECK("gemm_tc");
   return 0;
 }
