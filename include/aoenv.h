@@ -48,10 +48,11 @@ uint64_t aoenv_launch_count(void);
  * the innovation xi ~ N(0,1) into zx[b][nI..nI+nO): injected from `xi` [B][nO] when non-null, else Philox
  * (seed, stream_id, b).  zx rows have `ldz` floats (ldz >= nI+nO; the tail is zero-filled).  `win` is the window
  * BEFORE the shift.  inner_rc [nI][2] holds (row, col) of the inner-ring pixels in window coordinates, in the
- * reference's boolean-mask (row-major) order. */
+ * reference's boolean-mask (row-major) order.  zx_planes (nullable): [parts][B][ldz] bf16, the same vector in the
+ * split-bf16 operand format of aoenv_gemm_tn_tc, written in the same pass. */
 int aoenv_atm_gather(const float* win, int B, int M, int pitch, int64_t env_stride, int sx, int sy,
                      const int32_t* inner_rc, int nI, int nO, const float* xi,
-                     uint64_t seed, uint64_t stream_id, float* zx, int ldz, void* stream);
+                     uint64_t seed, uint64_t stream_id, float* zx, int ldz, void* zx_planes, int parts, void* stream);
 
 /* add_row, step 3 (Atmosphere.py:309-310): writes the freshly extruded outer ring X [B][ldx] (X = A Z + B xi, from
  * the GEMM on zx and the stacked operator [A | B]) on the border of `win`, the window AFTER the shift, ring pixels in
@@ -148,10 +149,11 @@ int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil
 /* centroid + slopes (ShackHartmann.py:314-324,580-601): threshold at thr * max, first moments along the
  * lenslet map's axis 1 -> X and axis 2 -> Y, NaN/Inf -> 0, minus reference, divided by slopes_units.
  * valid_idx [nV]: lenslet numbers k = i*nS + j of the valid lenslets (row-major); ref_xy [2][nV].
- * slopes [B][lds]: first nV entries X, next nV entries Y (= wfs.signal). */
+ * slopes [B][lds]: first nV entries X, next nV entries Y (= wfs.signal).  slope_planes (nullable): [parts][B][lds]
+ * bf16, the same vector as operand planes of aoenv_gemm_tn_tc (the reconstruction), written in the same pass. */
 int aoenv_shwfs_slopes(const float* frame, const int32_t* envmax, int shared_max, const int32_t* valid_idx,
                        int nV, const float* ref_xy, float inv_units, float threshold_cog, int B, int nS, int n,
-                       float* slopes, int lds, void* stream);
+                       float* slopes, int lds, void* slope_planes, int parts, void* stream);
 
 /* Calibration-grade measurement (init only): the two steps above in float64 with the ideal detector, for the
  * reference slopes / slope units (ShackHartmann.py:254-312) and the interaction matrix pushes

@@ -128,6 +128,7 @@ class Atmosphere:
             self._ext = torch.zeros((self.nLayer, B, 2), dtype=torch.int64, device=dev)
             self._flag = torch.zeros((B,), dtype=torch.int32, device=dev)
             self._zx = torch.zeros((B, self._K), dtype=torch.float32, device=dev)
+            self._zx_planes = torch.zeros((self._W_op.parts, B, self._K), dtype=torch.bfloat16, device=dev)
             self._X = torch.zeros((B, self._ldx), dtype=torch.float32, device=dev)
             self._opd = torch.zeros((B, R, R), dtype=torch.float32, device=dev)
             self._fp_off = 1 + (ops.layer_res // 2 - R // 2)         # crop [1:-1] + centred footprint (:231-232)
@@ -213,6 +214,7 @@ class Atmosphere:
             if not (0 <= oy - sy <= S and 0 <= ox - sx <= S):
                 raise RuntimeError("canvas_slack too small for this wind direction change")
         st = _lib.stream_ptr(self.device)
+        tc = gemm.uses_tensor_cores()
         xi = None
         if self.xi_queue is not None:
             xi = torch.as_tensor(next(self.xi_queue), dtype=torch.float32, device=self.device).reshape(B, self._nO).contiguous()
@@ -225,8 +227,9 @@ class Atmosphere:
         ly.events += 1
         _lib.check(lib.aoenv_atm_gather(self._win_ptr(i), B, M, pitch, self._env_stride, sx, sy, _lib.ptr(self._inner_rc),
                                         self._nI, self._nO, _lib.ptr(xi), C.c_uint64(seed), C.c_uint64(stream_id),
-                                        _lib.ptr(self._zx), self._K, st), "atm_gather")
-        gemm.gemm_tn(self._zx, self._W_op, self._X, B, self._nO)
+                                        _lib.ptr(self._zx), self._K, _lib.ptr(self._zx_planes) if tc else None,
+                                        self._W_op.parts, st), "atm_gather")
+        gemm.gemm_tn(self._zx, self._W_op, self._X, B, self._nO, x_planes=self._zx_planes if tc else None)
         self._org[i] = [oy - sy, ox - sx]
         noy, nox = self._org[i]
         _lib.check(lib.aoenv_atm_ring(self._win_ptr(i), B, M, pitch, self._env_stride, noy * pitch + nox, self._nO,

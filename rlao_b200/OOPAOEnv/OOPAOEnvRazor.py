@@ -191,7 +191,8 @@ class OOPAO:
         """obs = vec_to_img(-reconstructor @ signal) * 1e6 (+ reward, Strehl, rms diagnostics)."""
         lib, st, B, nA = _lib.load(), _lib.stream_ptr(self.device), self.n_envs, self.dm.nValidAct
         sig = self.wfs._signal
-        gemm.gemm_tn(sig, self._Rm_op, self._rec, B, nA)
+        gemm.gemm_tn(sig, self._Rm_op, self._rec, B, nA,
+                     x_planes=self.wfs._signal_planes if gemm.uses_tensor_cores() else None)
         _lib.check(lib.aoenv_observe(_lib.ptr(self._rec), self._rec.stride(0), _lib.ptr(self._act_idx), B, nA,
                                      self.nActuator ** 2, _lib.ptr(self.wfs._stats) if with_stats else None,
                                      float(self.tel.pixelArea), self._phase_scale, _lib.ptr(self._obs), _lib.ptr(self._reward),

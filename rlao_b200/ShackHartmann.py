@@ -11,7 +11,7 @@ import math
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, gemm
 from .Detector import Detector
 
 _SUPPORTED_N = (4, 6, 8)
@@ -71,6 +71,7 @@ class ShackHartmann:
         self._envmax = torch.zeros((B,), dtype=torch.int32, device=self.device)
         self._stats = torch.zeros((B, 4), dtype=torch.float64, device=self.device)
         self._signal = torch.zeros((B, self._lds), dtype=torch.float32, device=self.device)
+        self._signal_planes = torch.zeros((2, B, self._lds), dtype=torch.bfloat16, device=self.device)   # GEMM operand form
         self._signal_is_multi = False
         self.initialize_wfs()
 
@@ -108,6 +109,7 @@ class ShackHartmann:
         self._lightRatio = val
         self._select_valid()
         self._signal = torch.zeros((self.n_envs, self._lds), dtype=torch.float32, device=self.device)
+        self._signal_planes = torch.zeros((2, self.n_envs, self._lds), dtype=torch.bfloat16, device=self.device)
         self.initialize_wfs()
 
     @property
@@ -120,7 +122,8 @@ class ShackHartmann:
             raise NotImplementedError("geometric SH-WFS is out of scope")
 
     # ---- kernels ------------------------------------------------------------------------------------------
-    def _run(self, opd_a, opd_b, pupil, scale, shared_max, det, frame, envmax, stats, slopes, ref_xy, inv_units):
+    def _run(self, opd_a, opd_b, pupil, scale, shared_max, det, frame, envmax, stats, slopes, ref_xy, inv_units,
+             slope_planes=None):
         lib, st = _lib.load(), _lib.stream_ptr(self.device)
         F = opd_a.shape[0]
         _lib.check(lib.aoenv_shwfs_frame(_lib.ptr(opd_a), _lib.ptr(opd_b), _lib.ptr(pupil), _lib.ptr(self._amp),
@@ -130,7 +133,7 @@ class ShackHartmann:
         _lib.check(lib.aoenv_shwfs_slopes(_lib.ptr(frame), _lib.ptr(envmax), int(shared_max), _lib.ptr(self._valid_idx),
                                           self.nValidSubaperture, _lib.ptr(ref_xy), C.c_float(inv_units),
                                           C.c_float(self.threshold_cog), F, self.nSubap, self.n_pix_subap,
-                                          _lib.ptr(slopes), slopes.stride(0), st), "shwfs_slopes")
+                                          _lib.ptr(slopes), slopes.stride(0), _lib.ptr(slope_planes), 2, st), "shwfs_slopes")
 
     def _measure_terms(self, opd_a, opd_b, env_offset=0):
         """Per-environment measurement (single-frame branch, ShackHartmann.py:522-601) on OPD = opd_a + opd_b."""
@@ -139,7 +142,8 @@ class ShackHartmann:
         tel = self.telescope
         det = self.cam.as_struct(env_offset)
         self._run(opd_a, opd_b, tel._pupil_f, 2 * math.pi / tel.src.wavelength, False, det, self._frame, self._envmax,
-                  self._stats, self._signal, self._ref_xy, 1.0 / self.slopes_units)
+                  self._stats, self._signal, self._ref_xy, 1.0 / self.slopes_units,
+                  slope_planes=self._signal_planes if gemm.uses_tensor_cores() else None)
         self._signal_is_multi = False
         self.cam.frame = self._frame[0] if self.n_envs == 1 else self._frame
 

@@ -30,7 +30,7 @@ _vp, _i, _f, _u64, _d, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_uint64, C.c_do
 
 # name -> argtypes, exactly the prototypes of include/aoenv.h
 PROTOTYPES = {
-    "aoenv_atm_gather": [_vp, _i, _i, _i, _i64, _i, _i, _vp, _i, _i, _vp, _u64, _u64, _vp, _i, _vp],
+    "aoenv_atm_gather": [_vp, _i, _i, _i, _i64, _i, _i, _vp, _i, _i, _vp, _u64, _u64, _vp, _i, _vp, _i, _vp],
     "aoenv_atm_ring": [_vp, _i, _i, _i, _i64, _i64, _i, _vp, _i, _vp, _vp, _i, _vp],
     "aoenv_atm_compact": [_vp, _vp, _i, _i, _i, _i64, _vp, _i64, _vp],
     "aoenv_atm_phase": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp],
@@ -39,7 +39,7 @@ PROTOTYPES = {
     "aoenv_gemm_tn_tc": [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _f, _vp],
     "aoenv_dm_surface_separable": [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
     "aoenv_shwfs_frame": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i, _vp, _vp, _vp, _vp],
-    "aoenv_shwfs_slopes": [_vp, _vp, _i, _vp, _i, _vp, _f, _f, _i, _i, _i, _vp, _i, _vp],
+    "aoenv_shwfs_slopes": [_vp, _vp, _i, _vp, _i, _vp, _f, _f, _i, _i, _i, _vp, _i, _vp, _i, _vp],
     "aoenv_shwfs_measure_f64": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _d, _d, _i, _i, _i, _d, _i, _vp, _vp, _vp, _i, _vp],
     "aoenv_command_update": [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _i, _vp],
     "aoenv_observe": [_vp, _i, _vp, _i, _i, _i, _vp, _d, _f, _vp, _vp, _vp, _vp, _vp, _vp],

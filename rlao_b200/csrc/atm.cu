@@ -18,7 +18,8 @@ namespace aoenv {
 __global__ void __launch_bounds__(256)
 atm_gather_kernel(const float* __restrict__ map, int M, int pitch, size_t env_stride, int sx, int sy,
                   const int2* __restrict__ inner_rc, int nI, int nO, const float* __restrict__ xi,
-                  uint64_t seed, uint64_t stream_id, float* __restrict__ zx, int ldz) {
+                  uint64_t seed, uint64_t stream_id, float* __restrict__ zx, int ldz,
+                  __nv_bfloat16* __restrict__ planes, int parts) {
   const int b = blockIdx.y;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= ldz) return;
@@ -37,6 +38,7 @@ atm_gather_kernel(const float* __restrict__ map, int M, int pitch, size_t env_st
     }
   }
   zx[(size_t)b * ldz + k] = v;
+  if (planes != nullptr) store_bf16_planes(planes, (size_t)gridDim.y * ldz, (size_t)b * ldz + k, parts, v);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -324,13 +326,15 @@ extern "C" {
 
 int aoenv_atm_gather(const float* win, int B, int M, int pitch, int64_t env_stride, int sx, int sy,
                      const int32_t* inner_rc, int nI, int nO, const float* xi, uint64_t seed, uint64_t stream_id,
-                     float* zx, int ldz, void* stream) {
+                     float* zx, int ldz, void* zx_planes, int parts, void* stream) {
   AOENV_CHECK_ARG(B > 0 && B <= 65535 && M > 6 && pitch >= M && env_stride >= (int64_t)M * pitch, "atm_gather: bad shape B=%d M=%d pitch=%d", B, M, pitch);
   AOENV_CHECK_ARG(sx >= -1 && sx <= 1 && sy >= -1 && sy <= 1, "atm_gather: shift must be in {-1,0,1}");
   AOENV_CHECK_ARG(ldz >= nI + nO, "atm_gather: ldz=%d < nI+nO=%d", ldz, nI + nO);
+  AOENV_CHECK_ARG(zx_planes == nullptr || parts == 2 || parts == 3, "atm_gather: parts must be 2 or 3");
   dim3 grid((ldz + 255) / 256, B);
   atm_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(win, M, pitch, (size_t)env_stride, sx, sy, (const int2*)inner_rc,
-                                                            nI, nO, xi, seed, stream_id, zx, ldz);
+                                                            nI, nO, xi, seed, stream_id, zx, ldz,
+                                                            (__nv_bfloat16*)zx_planes, parts);
   AOENV_LAUNCH_CHECK("atm_gather");
   return 0;
 }

@@ -1,5 +1,6 @@
 // Shared device/host helpers for libaoenv_b200 (sm_100a).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -90,6 +91,17 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
   float s, c;
   sincospif(2.0f * u2, &s, &c);
   return make_float2(r * c, r * s);
+}
+
+// x = x_0 + x_1 (+ x_2), x_0 = bf16(x), x_1 = bf16(x - x_0), ...: the operand format of the split-bf16 tensor-core GEMM
+// (gemm_tc.cu).  Producers of a GEMM operand call this to write the planes next to (or instead of) the float32 value.
+__device__ __forceinline__ void store_bf16_planes(__nv_bfloat16* __restrict__ planes, size_t plane_stride, size_t idx,
+                                                  int parts, float x) {
+  for (int p = 0; p < parts; ++p) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    planes[(size_t)p * plane_stride + idx] = h;
+    x -= __bfloat162float(h);
+  }
 }
 
 }  // namespace aoenv

@@ -286,7 +286,8 @@ shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ op
 __global__ void __launch_bounds__(128)
 shwfs_slopes_kernel(const float* __restrict__ frame, const int32_t* __restrict__ envmax, int shared_max,
                     const int32_t* __restrict__ valid_idx, int nV, const float* __restrict__ ref_xy, float inv_units,
-                    float threshold_cog, int nS, int n, float* __restrict__ slopes, int lds) {
+                    float threshold_cog, int nS, int n, float* __restrict__ slopes, int lds,
+                    __nv_bfloat16* __restrict__ planes, int parts) {
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nV) return;
@@ -307,8 +308,13 @@ shwfs_slopes_kernel(const float* __restrict__ frame, const int32_t* __restrict__
   float cx = sx / s, cy = sy / s;
   if (!isfinite(cx)) cx = 0.f;      // ShackHartmann.py:583-593
   if (!isfinite(cy)) cy = 0.f;
-  slopes[(size_t)b * lds + t] = (cx - __ldg(&ref_xy[t])) * inv_units;
-  slopes[(size_t)b * lds + nV + t] = (cy - __ldg(&ref_xy[nV + t])) * inv_units;
+  const float sx_ = (cx - __ldg(&ref_xy[t])) * inv_units, sy_ = (cy - __ldg(&ref_xy[nV + t])) * inv_units;
+  slopes[(size_t)b * lds + t] = sx_;
+  slopes[(size_t)b * lds + nV + t] = sy_;
+  if (planes != nullptr) {      // operand planes of the reconstruction GEMM (padding columns stay zero from allocation)
+    store_bf16_planes(planes, (size_t)gridDim.y * lds, (size_t)b * lds + t, parts, sx_);
+    store_bf16_planes(planes, (size_t)gridDim.y * lds, (size_t)b * lds + nV + t, parts, sy_);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -469,11 +475,12 @@ int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil
 
 int aoenv_shwfs_slopes(const float* frame, const int32_t* envmax, int shared_max, const int32_t* valid_idx, int nV,
                        const float* ref_xy, float inv_units, float threshold_cog, int B, int nS, int n, float* slopes,
-                       int lds, void* stream) {
+                       int lds, void* slope_planes, int parts, void* stream) {
   AOENV_CHECK_ARG(B > 0 && B <= 65535 && nV > 0 && lds >= 2 * nV, "shwfs_slopes: bad shape B=%d nV=%d lds=%d", B, nV, lds);
   dim3 grid((nV + 127) / 128, B);
   shwfs_slopes_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(frame, envmax, shared_max, valid_idx, nV, ref_xy,
-                                                              inv_units, threshold_cog, nS, n, slopes, lds);
+                                                              inv_units, threshold_cog, nS, n, slopes, lds,
+                                                              (__nv_bfloat16*)slope_planes, parts);
   AOENV_LAUNCH_CHECK("shwfs_slopes");
   return 0;
 }

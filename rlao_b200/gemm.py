@@ -44,8 +44,13 @@ def _x_planes(X, parts):
     return ws
 
 
-def gemm_tn(X, op, D, M, N, alpha=1.0, backend=None):
-    """X [M, Kp] float32, op: Operator over W [N, Kp]; D [M, >=N] float32 (row stride D.stride(0))."""
+def uses_tensor_cores(backend=None):
+    return (backend or BACKEND) == "tc"
+
+
+def gemm_tn(X, op, D, M, N, alpha=1.0, backend=None, x_planes=None):
+    """X [M, Kp] float32, op: Operator over W [N, Kp]; D [M, >=N] float32 (row stride D.stride(0)).
+    x_planes: X already in split-bf16 form [op.parts, M, Kp] (written by the kernel that produced X)."""
     backend = backend or BACKEND
     lib, st = _lib.load(), _lib.stream_ptr(X.device)
     Kp = op.W.stride(0)
@@ -53,7 +58,10 @@ def gemm_tn(X, op, D, M, N, alpha=1.0, backend=None):
     if backend == "simt":
         _lib.check(lib.aoenv_gemm_tn(_lib.ptr(X), Kp, _lib.ptr(op.W), Kp, _lib.ptr(D), D.stride(0), M, N, Kp, alpha, st), "gemm_tn")
         return
-    xs = _x_planes(X, op.parts)
-    _lib.check(lib.aoenv_split_bf16(_lib.ptr(X), Kp, M, Kp, op.parts, _lib.ptr(xs), Kp, st), "split_bf16(X)")
+    if x_planes is not None:
+        xs = x_planes
+    else:
+        xs = _x_planes(X, op.parts)
+        _lib.check(lib.aoenv_split_bf16(_lib.ptr(X), Kp, M, Kp, op.parts, _lib.ptr(xs), Kp, st), "split_bf16(X)")
     _lib.check(lib.aoenv_gemm_tn_tc(_lib.ptr(xs), _lib.ptr(op.planes()), Kp, op.parts, _lib.ptr(D), D.stride(0), M, N, Kp,
                                     alpha, st), "gemm_tn_tc")

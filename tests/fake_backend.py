@@ -72,7 +72,8 @@ class FakeLib:
         i = np.int32(k)
         return (i if i >= 0 else np.int32(i ^ np.int32(0x7fffffff))).view(np.float32)
 
-    def aoenv_atm_gather(self, win, B, M, pitch, env_stride, sx, sy, inner_rc, nI, nO, xi, seed, stream_id, zx, ldz, stream):
+    def aoenv_atm_gather(self, win, B, M, pitch, env_stride, sx, sy, inner_rc, nI, nO, xi, seed, stream_id, zx, ldz,
+                         zx_planes, parts, stream):
         self.launches += 1
         addr = (win.value if isinstance(win, C.c_void_p) else int(win)) - 4 * (sy * pitch + sx)
         m = self._window(addr, B, M, pitch, env_stride)       # window after the shift (old content)
@@ -200,7 +201,8 @@ class FakeLib:
                 em[e] = _f2o(maxes[e])
         return 0
 
-    def aoenv_shwfs_slopes(self, frame, envmax, shared_max, valid_idx, nV, ref_xy, inv_units, thr, B, nS, n, slopes, lds, stream):
+    def aoenv_shwfs_slopes(self, frame, envmax, shared_max, valid_idx, nV, ref_xy, inv_units, thr, B, nS, n, slopes, lds,
+                           slope_planes, parts, stream):
         self.launches += 1
         R = nS * n
         fr = _arr(frame, (B, R, R))
