@@ -193,10 +193,8 @@ class Telescope:
             self._opd_np = dm_opd
             self._lazy = None
         elif tag == "detector":
-            self.computePSF(obj.psf_sampling)
-            obj._integrated_time += self.samplingTime
-            obj.integrate(self.PSF)
-            self.PSF = obj.frame
+            raise NotImplementedError("tel*detector (science camera on the PSF) is out of scope (SURVEY.md section 8 f-4); "
+                                      "use tel.computePSF(zp) / env.psf_strehl(zp, window)")
         else:
             raise AttributeError(f"Telescope cannot be propagated to an object with tag {tag!r}")
         return self

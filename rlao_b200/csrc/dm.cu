@@ -12,7 +12,8 @@ namespace aoenv {
 __global__ void __launch_bounds__(256)
 dm_separable_kernel(const float* __restrict__ coefs, int ldc, const int32_t* __restrict__ act_pos, int nA, int nAct,
                     const float* __restrict__ gx, const float* __restrict__ gy, const int2* __restrict__ band_x,
-                    const int2* __restrict__ band_y, int R, int x0, int xw, float* __restrict__ opd) {
+                    const int2* __restrict__ band_y, int R, int xw, float* __restrict__ opd) {
+  const int x0 = blockIdx.x * xw;                 // column slab of this CTA
   extern __shared__ __align__(16) float sm[];
   float* sC = sm;                       // [nAct][nAct]
   float* sT = sm + ((nAct * nAct + 3) & ~3);   // [nAct][xw]   (xw = columns handled by this CTA, multiple of 4)
@@ -66,7 +67,8 @@ template <int W>
 __global__ void __launch_bounds__(256)
 dm_separable_banded_kernel(const float* __restrict__ coefs, int ldc, const int32_t* __restrict__ act_pos, int nA, int nAct,
                            const float* __restrict__ wx, const int32_t* __restrict__ j0x, const float* __restrict__ wyp,
-                           const int32_t* __restrict__ i0y, int R, int x0, int xw, float* __restrict__ opd) {
+                           const int32_t* __restrict__ i0y, int R, int xw, float* __restrict__ opd) {
+  const int x0 = blockIdx.x * xw;                 // column slab of this CTA
   extern __shared__ __align__(16) float sm[];
   float* sC = sm;
   float* sT = sm + ((nAct * nAct + 3) & ~3);
@@ -165,16 +167,14 @@ extern "C" int aoenv_dm_surface_separable(const float* coefs, int ldc, const int
     attr[which] = smem;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  for (int p = 0; p < parts; ++p) {
-    const dim3 grid(1, B);
-    if (which == 1)
-      dm_separable_banded_kernel<12><<<grid, 256, smem, s>>>(coefs, ldc, act_pos, nA, nAct, wx, j0x, wyp, i0y, R, p * xw, xw, opd);
-    else if (which == 2)
-      dm_separable_banded_kernel<16><<<grid, 256, smem, s>>>(coefs, ldc, act_pos, nA, nAct, wx, j0x, wyp, i0y, R, p * xw, xw, opd);
-    else
-      dm_separable_kernel<<<grid, 256, smem, s>>>(coefs, ldc, act_pos, nA, nAct, gx, gy, (const int2*)band_x,
-                                                  (const int2*)band_y, R, p * xw, xw, opd);
-    AOENV_LAUNCH_CHECK("dm_separable");
-  }
+  const dim3 grid(parts, B);
+  if (which == 1)
+    dm_separable_banded_kernel<12><<<grid, 256, smem, s>>>(coefs, ldc, act_pos, nA, nAct, wx, j0x, wyp, i0y, R, xw, opd);
+  else if (which == 2)
+    dm_separable_banded_kernel<16><<<grid, 256, smem, s>>>(coefs, ldc, act_pos, nA, nAct, wx, j0x, wyp, i0y, R, xw, opd);
+  else
+    dm_separable_kernel<<<grid, 256, smem, s>>>(coefs, ldc, act_pos, nA, nAct, gx, gy, (const int2*)band_x,
+                                                (const int2*)band_y, R, xw, opd);
+  AOENV_LAUNCH_CHECK("dm_separable");
   return 0;
 }

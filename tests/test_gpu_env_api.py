@@ -169,3 +169,36 @@ def test_live_atmosphere_parameter_changes(dev):
     for i in range(atm.nLayer):
         oy, ox = atm._org[i]
         assert 0 <= oy <= atm._S and 0 <= ox <= atm._S
+
+
+def test_gymnasium_signature_history_and_delay(dev):
+    """MAIN_CODE/OOPAOEnv/OOPAOEnv_VPG.py:117-137,553-611: reset(seed) -> (obs, info); step(action) -> 5-tuple with a
+    newest-first observation stack and a FIFO of `delay` frames in front of the DM."""
+    from rlao_b200.OOPAOEnv.gymnasium_api import GymnasiumSH
+    from rlao_b200.PO4AO.util_simple import TimeDelayEnv
+    cfg = CONFIGS["tiny"]()
+    nA = cfg.nSubap + 1
+    g = GymnasiumSH(build_env(cfg, n_envs=2, rng="philox", seed=6, device=dev), n_history=3, delay=1, episode_length=4)
+    assert g.observation_space.shape == (2, 3, nA, nA) and g.action_space.shape == (2, nA, nA)
+    obs, info = g.reset(seed=12)
+    assert obs.shape == (2, 3, nA, nA) and info == {} and float(obs[:, 1:].abs().max()) == 0.0
+    screen_seed = int(np.random.RandomState(12).randint(0, 100000))
+    ref = TimeDelayEnv(build_env(cfg, n_envs=2, rng="philox", seed=6, device=dev), 1)
+    ref._env.dm.coefs = 0
+    ref._env.dm_prev = 0
+    ref._env.atm.generateNewPhaseScreen(seed=screen_seed)
+    ref._env.tel * ref._env.wfs
+    o_ref = ref.reset_soft()
+    assert torch.equal(obs[:, 0], o_ref)
+    hist = [o_ref]
+    for t in range(4):
+        act = cfg.gainCL * obs[:, 0]
+        obs, reward, terminated, truncated, info = g.step(act if t % 2 == 0 else g.img_to_vec(act))
+        o_ref, _, s_ref, _, _ = ref.step(t, cfg.gainCL * o_ref)
+        hist.insert(0, o_ref)
+        assert torch.equal(obs[:, 0], o_ref) and torch.equal(reward, s_ref)
+        assert torch.equal(obs[:, 1], hist[1]) and (t == 0 or torch.equal(obs[:, 2], hist[2]))
+        assert terminated is False and truncated is (t == 3) and info["strehl"] is reward
+    # a second reset with the same seed replays the episode
+    obs2, _ = g.reset(seed=12)
+    assert torch.equal(obs2[:, 0], hist[-1])
