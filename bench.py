@@ -23,26 +23,40 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (nSubap, nLayers, envs per GPU, description)
-    "cfg3": (40, 3, 1024, "8m 40x40 SH-WFS, 41x41 DM (1353 act), 3-layer VK atmosphere, integrator, noise off"),
-    "cfg2": (20, 1, 1024, "8m 20x20 SH-WFS, 21x21 DM (357 act), 1-layer VK atmosphere, integrator, noise off"),
-    "cfg5": (80, 5, 256, "8m 80x80 SH-WFS, 81x81 DM (5209 act), 5-layer VK atmosphere, integrator, noise off"),
-    "cfg1": (20, 1, 1, "8m 20x20 SH-WFS, 21x21 DM, 1 layer, single env"),
-    "tiny": (8, 2, 64, "8m 8x8 SH-WFS test system"),
+    # name: (nSubap, nLayers, envs per GPU, description, options)
+    "cfg3": (40, 3, 1024, "8m 40x40 SH-WFS, 41x41 DM (1353 act), 3-layer VK atmosphere, integrator, noise off", {}),
+    "cfg2": (20, 1, 1024, "8m 20x20 SH-WFS, 21x21 DM (357 act), 1-layer VK atmosphere, integrator, noise off", {}),
+    "cfg4": (20, 1, 4096, "8m 20x20 SH-WFS, 21x21 DM, 1 layer, Razor-like camera: photon noise, RON 14 e-, QE 0.56, dark 5, "
+                          "FWC 1e4, 10-bit ADC", {"noise": True}),
+    "cfg4lowflux": (20, 1, 4096, "cfg4 at magnitude 12", {"noise": True, "magnitude": 12}),
+    "cfg5": (80, 5, 256, "8m 80x80 SH-WFS, 81x81 DM (5209 act), 5-layer VK atmosphere, integrator, noise off", {}),
+    "cfg5psf": (80, 5, 256, "cfg5 with the science-PSF Strehl (zero padding 4, N=1920) as the per-step reward",
+                {"psf": (4, 32)}),
+    "cfg1": (20, 1, 1, "8m 20x20 SH-WFS, 21x21 DM, 1 layer, single env", {}),
+    "tiny": (8, 2, 64, "8m 8x8 SH-WFS test system", {}),
 }
 
 
-def make_args(nSubap, nLayers):
+def make_args(nSubap, nLayers, opts=None):
     from rlao_b200.Conf.parameter_file_synthetic_SHWFS import layer_profile
     prof = layer_profile(nLayers)
-    return types.SimpleNamespace(r0=0.13, L0=25, nSubaperture=nSubap, nLoop=None, gainCL=0.5, **prof)
+    opts = opts or {}
+    extra = {k: opts[k] for k in ("noise", "magnitude") if k in opts}
+    return types.SimpleNamespace(r0=0.13, L0=25, nSubaperture=nSubap, nLoop=None, gainCL=0.5, **prof, **extra)
 
 
-def oracle_config(nSubap, nLayers):
-    from oracle.ao_oracle import AOConfig
+def oracle_config(nSubap, nLayers, opts=None):
+    from oracle.ao_oracle import AOConfig, DetectorConfig
+    from oracle.golden_configs import RAZOR_DETECTOR
     from rlao_b200.Conf.parameter_file_synthetic_SHWFS import layer_profile
     prof = layer_profile(nLayers)
-    return AOConfig(nSubap=nSubap, windSpeed=[float(v) for v in prof["windSpeed"]],
+    opts = opts or {}
+    extra = {}
+    if opts.get("noise"):
+        extra["detector"] = DetectorConfig(**RAZOR_DETECTOR)
+    if "magnitude" in opts:
+        extra["magnitude"] = float(opts["magnitude"])
+    return AOConfig(**extra, nSubap=nSubap, windSpeed=[float(v) for v in prof["windSpeed"]],
                     windDirection=[float(v) for v in prof["windDirection"]], fractionalR0=prof["fractionalR0"],
                     altitude=[0.0] * nLayers, nZernike=50, nLoop=4096)
 
@@ -111,9 +125,9 @@ def _cpu_worker(env, seed, n_steps, q):
         q.put((time.perf_counter() - t0, float(np.abs(obs).max())))
 
 
-def cpu_env(nSubap, nLayers, reconstructor=None):
+def cpu_env(nSubap, nLayers, reconstructor=None, opts=None):
     from oracle.ao_oracle import EnvOracle
-    return EnvOracle(oracle_config(nSubap, nLayers), reconstructor=reconstructor)
+    return EnvOracle(oracle_config(nSubap, nLayers, opts), reconstructor=reconstructor)
 
 
 def time_cpu(env, n_procs, n_steps):
@@ -140,11 +154,11 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    nS, nL, B, desc = WORKLOADS[args.workload]
+    nS, nL, B, desc, opts = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     n_procs = max(1, min(cores, 64))
     t_init = time.perf_counter()
-    env = cpu_env(nS, nL)
+    env = cpu_env(nS, nL, opts=opts)
     t_init = time.perf_counter() - t_init
     per_step = 0.12 if nS >= 40 else 0.02
     n_steps = max(3, int(min(20.0, 8.0 * max(1, args.steps)) / per_step / 4))
@@ -226,18 +240,20 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    nS, nL, B, desc = WORKLOADS[args.workload]
+    nS, nL, B, desc, opts = WORKLOADS[args.workload]
     if args.envs:
         B = args.envs
     env = OOPAO()
     env.set_params_file("rlao_b200.Conf.parameter_file_synthetic_SHWFS", "")
-    env.set_params(make_args(nS, nL), "shackhartmann", gainCL=0.5, n_envs=B, device=dev, rng="philox", seed=1,
+    env.set_params(make_args(nS, nL, opts), "shackhartmann", gainCL=0.5, n_envs=B, device=dev, rng="philox", seed=1,
                    env_offset=rank * B)
     env.atm.generateNewPhaseScreen(17)
     env.dm.coefs = 0
     env.tel * env.dm * env.wfs
     obs = env.reset_soft()
     gain = env.gainCL
+    if opts.get("psf"):
+        env.psf_reward = tuple(opts["psf"])
 
     def barrier():
         if world > 1:
@@ -317,7 +333,7 @@ def run_gpu_arm(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             t0 = time.perf_counter()
-            orc = cpu_env(nS, nL, reconstructor=env.reconstructor.cpu().numpy())
+            orc = cpu_env(nS, nL, reconstructor=env.reconstructor.cpu().numpy(), opts=opts)
             n_cpu = 100 if nS >= 40 else 400
             v, worst, wall = time_cpu(orc, 1, n_cpu)
             cpu_baseline = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
@@ -333,6 +349,7 @@ def run_gpu_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "description": desc, "envs_per_gpu": B, "total_envs": world * B,
                        "policy": "integrator gainCL=0.5, leak=0.99", "rng": "philox",
+                       "reconstructor": "50-mode Zernike modal (the reference's default, OOPAOEnvRazor.py:256-337)",
                        "l2": "per-step working set (layer maps) %.0f MB per GPU exceeds the 126 MB L2" % (
                            env.atm._maps.numel() * 4 / 2 / 1e6),
                        "mean_strehl_last_step": sr_mean},
@@ -408,6 +425,114 @@ def dominant_roofline(kernels, env, B):
     return out
 
 
+def run_po4ao_arm(args):
+    """SURVEY.md section 8(d) cfg 2: policy-driven rollouts (ConvPolicy, n_history = 20, random weights) of all
+    environments in lock-step, telemetry histories and the replay buffer on the device."""
+    import torch
+    import torch.distributed as dist
+    from rlao_b200 import _lib
+    from rlao_b200.PO4AO import mbrl
+    from rlao_b200.PO4AO.conv_models_simple import ConvPolicy, EnsembleDynamics
+    from rlao_b200.PO4AO.util_simple import EfficientExperienceReplay, TorchWrapper
+    from rlao_b200.OOPAOEnv.OOPAOEnvRazor import OOPAO
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nS, nL, B, desc, opts = WORKLOADS[args.workload]
+    if args.envs:
+        B = args.envs
+    n_history = 20
+    base = OOPAO()
+    base.set_params_file("rlao_b200.Conf.parameter_file_synthetic_SHWFS", "")
+    base.set_params(make_args(nS, nL, opts), "shackhartmann", gainCL=0.5, n_envs=B, device=dev, rng="philox", seed=1,
+                    env_offset=rank * B)
+    env = TorchWrapper(base, host_io=False)
+    nA = env.nActuator
+    torch.manual_seed(5)
+    policy = ConvPolicy(env.xvalid, env.yvalid, 0.0, env.F.float(), n_history).to(dev)
+    dynamics = EnsembleDynamics(env.xvalid, env.yvalid, n_history).to(dev)
+    replay = EfficientExperienceReplay((nA, nA), (nA, nA), max_size=(args.steps + args.warmup) * B, device=dev, n_envs=B)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def episode(n, it):
+        return mbrl.run(env, None, None, None, replay, policy, dynamics, n_history, n, warmup_ts=0, sigma=0.0, episode=1,
+                        iteration=it)
+
+    episode(args.warmup, 1)
+    replay.clear()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    base.atm.generateNewPhaseScreen(93234 * 2)
+    base.dm.coefs = 0
+    base.tel * base.dm * base.wfs
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record()
+    sr, reward_sum, *_ = mbrl.run(env, None, None, None, replay, policy, dynamics, n_history, args.steps, warmup_ts=0, sigma=0.0,
+                                  episode=1, iteration=2, new_screen=False)
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t[0])
+
+    # where the time goes: the policy forward alone, and the environment step alone
+    obs = torch.randn((B, 1, nA, nA), device=dev)
+    hist = torch.randn((B, 2 * (n_history - 1), nA, nA), device=dev)
+    with torch.no_grad():
+        for _ in range(3):
+            policy(obs, hist)
+        e0.record()
+        for _ in range(10):
+            policy(obs, hist)
+        e1.record()
+    torch.cuda.synchronize()
+    ms_policy = e0.elapsed_time(e1) / 10
+    act = torch.zeros((B, nA, nA), device=dev)
+    e0.record()
+    for i in range(10):
+        base._step_views(None, act)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_env = e0.elapsed_time(e1) / 10
+    if rank == 0:
+        flops = 2 * 9 * nA * nA * ((2 * n_history - 1) * 64 + 64 * 64 + 64) * B
+        line = {
+            "metric": "closed-loop AO env-steps/sec (batched envs)", "value": world * B * args.steps / (ms_max * 1e-3),
+            "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "description": desc, "envs_per_gpu": B, "total_envs": world * B,
+                       "policy": "PO4AO ConvPolicy n_history=20 (random weights, PyTorch/cuDNN, TF32 convolutions as PyTorch "
+                                 "defaults), histories + replay on the device", "rng": "philox",
+                       "mean_strehl": sr},
+            "clocks": clocks, "e2e": None, "gpu_launches": launches,
+            "breakdown_ms": {"policy_forward": ms_policy, "env_step": ms_env,
+                             "policy_tflops": flops / (ms_policy * 1e-3) / 1e12},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -417,10 +542,14 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0, help="environments per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--policy", default="integrator", choices=["integrator", "po4ao"],
+                    help="po4ao: ConvPolicy (n_history 20) rollouts through rlao_b200.PO4AO.mbrl.run with a GPU replay")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.policy == "po4ao":
+        run_po4ao_arm(args)
     else:
         run_gpu_arm(args)
 

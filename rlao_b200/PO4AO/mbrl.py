@@ -1,0 +1,202 @@
+"""PO4AO rollout and training loops — mirror of MAIN_CODE/PO4AO/mbrl.py (`get_env` :22-31, `run` :33-91,
+`train_dynamics` :94-142, `train_policy` :148-221) and of its Shack-Hartmann twin mbrl_funcsRAZOR.py, for a batch of
+environments that lives on the GPU.
+
+Differences from the reference, none of them in the arithmetic:
+  * `run` steps `env.n_envs` environments in lock-step; observations, telemetry histories, actions and the replay
+    stay on the device and nothing in the loop synchronises with the host (the reference converts
+    torch -> numpy -> torch around every step and rolls its histories with `torch.cat`);
+  * the histories are sliding windows over a double-length buffer: one image is written per step instead of the
+    whole (n_history - 1)-deep stack being re-concatenated;
+  * `train_dynamics` / `train_policy` leave the models on `device` (the reference moves them to the CPU and back
+    every episode) and, when `torch.distributed` is initialised, average the gradients over the ranks so that each
+    GPU trains on the windows of its own shard of environments.
+With one environment and the same torch seed the sampled windows, losses and updated weights are the
+reference's (tests/test_po4ao.py checks them against fixtures generated from the reference's own modules).
+"""
+import torch
+import torch.distributed as dist
+
+from .util_simple import TimeDelayEnv, TorchWrapper
+
+
+def get_env(args, gainCL=0.2, wfs_type="shackhartmann", n_envs=1, device=None, host_io=False, **kw):
+    """mbrl_funcsRAZOR.py:25-34 (`get_env(args)` of mbrl.py:22-31 with the SH defaults)."""
+    from ..OOPAOEnv.OOPAOEnvRazor import OOPAO
+    env = OOPAO()
+    env.set_params_file(getattr(args, "param_file", None), getattr(args, "oopao_path", ""))
+    env.set_params(args, wfs_type, gainCL=gainCL, n_envs=n_envs, device=device, **kw)
+    if getattr(args, "delay", 0) > 0:
+        env = TimeDelayEnv(env, args.delay)
+    return TorchWrapper(env, host_io=host_io)
+
+
+class _History:
+    """Last `depth` images per environment, oldest first, as a view: a buffer of 2*depth slots is written at
+    `p` and `p + depth`, so the window [p+1, p+1+depth) is always contiguous."""
+
+    def __init__(self, init):
+        self.depth = init.shape[1]
+        self.buf = torch.cat([init, init], dim=1).contiguous() if self.depth > 0 else init
+        self.p = self.depth - 1 if self.depth > 0 else 0
+
+    def push(self, img):
+        if self.depth == 0:
+            return
+        self.p = (self.p + 1) % self.depth
+        self.buf[:, self.p] = img
+        self.buf[:, self.p + self.depth] = img
+
+    def window(self):
+        if self.depth == 0:
+            return self.buf
+        return self.buf[:, self.p + 1:self.p + 1 + self.depth]
+
+
+@torch.no_grad()
+def run(env, past_obs, past_act, obs, replay, policy, dynamics, n_history, max_ts, warmup_ts, sigma, writer=None,
+        episode=0, iteration=0, use_recon=False, reconstructor=None, new_screen=True):
+    """One episode of `max_ts` frames (mbrl.py:33-91).
+
+    Returns (env.calculate_strehl_AVG(), reward_sum, past_obs, past_act, obs, rewards, iteration) like the
+    reference; with n_envs > 1 `reward_sum` is a [n_envs] tensor, `rewards` a [max_ts, n_envs] tensor, and the
+    histories are [n_envs, n_history-1, nAct, nAct].
+    """
+    dynamics.eval()
+    policy.eval()
+    B = env.n_envs
+    if new_screen:                                            # mbrl.py:49-52 (the SH twin leaves this to the caller)
+        env.atm.generateNewPhaseScreen(93234 * iteration)
+        env.dm.coefs = 0
+        env.tel * env.dm * env.wfs
+    obs = env.reset_soft()
+    dev = obs.device
+    obs = obs.reshape(B, *obs.shape[-2:])
+    nA = obs.shape[-1]
+    if past_obs is None:
+        past_obs = torch.zeros((B, n_history - 1, nA, nA), dtype=torch.float32, device=dev)
+        past_act = torch.zeros((B, n_history - 1, nA, nA), dtype=torch.float32, device=dev)
+    h_obs = _History(past_obs.reshape(B, n_history - 1, nA, nA).to(dev))
+    h_act = _History(past_act.reshape(B, n_history - 1, nA, nA).to(dev))
+    rewards = torch.empty((max_ts, B), dtype=torch.float32, device=dev)
+    squeeze = (lambda t: t[0]) if B == 1 else (lambda t: t)
+
+    for t in range(max_ts):
+        if episode < warmup_ts:                                # integrator + exploration noise (:67-70)
+            action = env.gainCL * obs + env.sample_noise(sigma).reshape(B, nA, nA).to(dev)
+        else:                                                  # :72-73
+            history = torch.cat([h_obs.window(), h_act.window()], dim=1) if n_history > 1 else None
+            action = policy(obs.unsqueeze(1), history)[:, 0]
+        action = action.to(torch.float32)
+        next_obs, reward, strehl, done, _ = env.step(t, squeeze(action))
+        next_obs = torch.as_tensor(next_obs, device=dev).reshape(B, nA, nA)
+        h_obs.push(obs)                                        # :79-80
+        h_act.push(action)
+        rewards[t] = torch.as_tensor(reward, dtype=torch.float32, device=dev).reshape(B)
+        replay.append(squeeze(obs), squeeze(action), squeeze(rewards[t]), squeeze(next_obs), done)   # :86
+        obs = next_obs
+
+    reward_sum = rewards.sum(dim=0)
+    past_obs, past_act = h_obs.window().clone(), h_act.window().clone()
+    if B == 1:
+        return (env.calculate_strehl_AVG(), float(reward_sum[0]), past_obs, past_act, obs[0],
+                [float(r) for r in rewards[:, 0].cpu()], iteration)
+    return env.calculate_strehl_AVG(), reward_sum, past_obs, past_act, obs, rewards, iteration
+
+
+def _windows(sample, batch_size, n_history, device):
+    """The unfolding both trainers apply to a `sample_contiguous` draw (mbrl.py:113-126, 172-186):
+    (state, action) = frame n_history-1 of each window, history = the n_history-1 frames before it, target = the
+    state of the last frame."""
+    states = sample.state().to(device)
+    actions = sample.action().to(device)
+    states = states.view(batch_size, n_history + 1, *states.shape[1:])
+    actions = actions.view(batch_size, n_history + 1, *actions.shape[1:])
+    past_obs, past_act = states[:, :n_history - 1], actions[:, :n_history - 1]
+    state, action = states[:, n_history - 1:n_history], actions[:, n_history - 1:n_history]
+    return state, action, past_obs, past_act, states[:, -1:]
+
+
+def _average_gradients(params):
+    """Data-parallel step between the ranks that each hold a shard of the environments (SURVEY.md section 8 e)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat)
+    flat /= dist.get_world_size()
+    o = 0
+    for g in grads:
+        g.copy_(flat[o:o + g.numel()].view_as(g))
+        o += g.numel()
+
+
+def train_dynamics(n_history, max_ts, batch_size, dynamics, optimizer, replay, dyn_iters=5, device="cuda:0",
+                   keep_on_device=True):
+    """mbrl.py:94-142: every member of the ensemble regresses the next state on its own bootstrap of windows."""
+    dynamics.train()
+    dynamics.to(device)
+    loss = torch.zeros((), device=device)
+    for _ in range(dyn_iters):
+        optimizer.zero_grad()
+        loss = 0
+        for member in dynamics.models:
+            sample = replay.sample_contiguous(n_history, max_ts, batch_size)
+            state, action, past_obs, past_act, target = _windows(sample, batch_size, n_history, device)
+            pred = member(state, action, torch.cat([past_obs, past_act], dim=1))
+            assert pred.shape == target.shape
+            loss = loss + (target - pred).pow(2).mean()
+        loss.backward()
+        _average_gradients(list(dynamics.parameters()))
+        torch.nn.utils.clip_grad_norm_(dynamics.parameters(), 0.5)
+        optimizer.step()
+    if not keep_on_device:
+        dynamics.to("cpu")
+    return loss.item()
+
+
+def loss_fn(state, action):
+    """mbrl.py:145-146."""
+    return state.pow(2).mean() + 0.001 * action.pow(2).mean()
+
+
+def train_policy(opt, policy, dynamics, replay, device, n_history, max_ts, batch_size, T, pol_iters=5,
+                 keep_on_device=True):
+    """mbrl.py:148-221: back-propagate the T-step model rollout cost through the frozen ensemble."""
+    dynamics.train()
+    policy.train()
+    for p in dynamics.parameters():
+        p.requires_grad_(False)
+    policy.to(device)
+    dynamics.to(device)
+    loss = torch.zeros((), device=device)
+    for _ in range(pol_iters):
+        opt.zero_grad()
+        sample = replay.sample_contiguous(n_history, max_ts, batch_size)
+        state, action, past_obs, past_act, _ = _windows(sample, batch_size, n_history, device)
+        # NB (:188, 204): `losses` is a [batch] vector to which a scalar (batch-mean) stage cost is broadcast
+        cost = torch.zeros((), device=device)
+        for _t in range(T):
+            if n_history > 1:
+                history = torch.cat([past_obs, past_act], dim=1)
+                action = policy(state, history)
+                next_state = dynamics(state, action, history)
+            else:
+                action = policy(state)
+                next_state = dynamics(state, action)
+            cost = cost + loss_fn(next_state[:, 0], action)
+            past_act = torch.cat([past_act[:, 1:], action], dim=1)       # :207-208
+            past_obs = torch.cat([past_obs[:, 1:], state], dim=1)
+            state = next_state.mean(dim=1, keepdim=True)                 # :211-212 ensemble mean
+        loss = cost
+        loss.backward()
+        _average_gradients(list(policy.parameters()))
+        opt.step()
+    for p in dynamics.parameters():
+        p.requires_grad_(True)
+    if not keep_on_device:
+        policy.to("cpu")
+        dynamics.to("cpu")
+    return loss.item()

@@ -88,32 +88,44 @@ class TorchWrapper(_Wrapper):
 
 
 class ReplaySample:
+    """util_simple.py:130-161."""
+
     def __init__(self, states, actions, rewards, next_states):
-        self._s, self._a, self._r, self._n = states, actions, rewards, next_states
+        self.states, self.actions, self.rewards, self.next_states = states, actions, rewards, next_states
 
     def state(self):
-        return self._s
+        return self.states
 
     def action(self):
-        return self._a
+        return self.actions
 
     def reward(self):
-        return self._r
+        return self.rewards
 
     def next_state(self):
-        return self._n
+        return self.next_states
 
     def __len__(self):
-        return self._s.shape[0]
+        return len(self.states)
+
+    def to(self, device):
+        self.states, self.actions = self.states.to(device), self.actions.to(device)
+        self.rewards, self.next_states = self.rewards.to(device), self.next_states.to(device)
+        return self
 
 
 class EfficientExperienceReplay:
-    """util_simple.py:55-128 with the storage on `device` and a batch axis: transitions of all environments of a
-    step are appended together, environment-major within an episode so that `sample_contiguous` still draws
-    windows that stay inside one (environment, episode) trajectory."""
+    """util_simple.py:55-128 with the storage on `device` and `n_envs` environments stepping in lock-step.
 
-    def __init__(self, state_shape, action_shape, max_size=100000, device="cpu"):
+    Rows are appended time-major: one `append` call stores the transitions of all environments of a step in
+    `n_envs` consecutive rows, so an episode of `max_ts` steps is a block of `max_ts * n_envs` rows and the
+    trajectory of environment b inside it has stride `n_envs`.  `sample_contiguous` draws windows that stay inside
+    one (episode, environment) trajectory; with n_envs == 1 the layout, the index arithmetic and the random-number
+    consumption are the reference's (:103-111)."""
+
+    def __init__(self, state_shape, action_shape, max_size=100000, device="cpu", n_envs=1):
         self.max_size = max_size
+        self.n_envs = int(n_envs)
         self.device = torch.device(device)
         self.states = torch.empty((max_size, *state_shape), device=self.device)
         self.next_states = torch.empty((max_size, *state_shape), device=self.device)
@@ -121,28 +133,41 @@ class EfficientExperienceReplay:
         self.rewards = torch.empty((max_size, 1), device=self.device)
         self.len = 0
 
-    def append(self, obs, action, reward, next_obs, done=False):
-        if not torch.is_tensor(obs):
-            raise TypeError("should be torch")
-        i = self.len
-        self.states[i], self.next_states[i], self.actions[i] = obs, next_obs, action
-        self.rewards[i] = reward
-        self.len += 1
-
-    def append_episode(self, obs, action, reward, next_obs):
-        """Batched variant: tensors [T, B, ...] of one episode of B environments -> B trajectories of length T."""
-        T, B = obs.shape[0], obs.shape[1]
-        n = T * B
+    def add(self, replay):
+        """:68-81."""
+        n = len(replay)
         sl = slice(self.len, self.len + n)
-        tr = lambda x: x.transpose(0, 1).reshape(n, *x.shape[2:])
-        self.states[sl], self.next_states[sl], self.actions[sl] = tr(obs), tr(next_obs), tr(action)
-        self.rewards[sl] = tr(reward.reshape(T, B, 1))
+        self.states[sl], self.next_states[sl] = replay.state()[:n], replay.next_state()[:n]
+        self.actions[sl], self.rewards[sl] = replay.action()[:n], replay.reward()[:n]
         self.len += n
 
+    def __add__(self, replay):
+        self.add(replay)
+        return self
+
+    def append(self, obs, action, reward, next_obs, done=False):
+        """:87-99; with n_envs > 1 the arguments carry a leading [n_envs] axis."""
+        if not torch.is_tensor(obs):
+            raise TypeError("should be torch")
+        B = self.n_envs
+        if self.len + B > self.max_size:
+            raise IndexError(f"replay is full ({self.max_size} transitions)")
+        if B == 1:
+            i = self.len
+            self.states[i], self.next_states[i], self.actions[i] = obs, next_obs, action
+            self.rewards[i] = reward
+        else:
+            sl = slice(self.len, self.len + B)
+            self.states[sl], self.next_states[sl], self.actions[sl] = obs, next_obs, action
+            self.rewards[sl] = torch.as_tensor(reward, device=self.device).reshape(B, 1)
+        self.len += B
+
     def sample_contiguous(self, horizon, max_ts, batch_size=32):
-        inds = torch.randint(0, max_ts - (horizon + 1), size=(batch_size,))
-        inds += torch.randint(0, len(self) // max_ts, size=(batch_size,)) * max_ts
-        indices = (inds[:, None] + torch.arange(horizon + 1)[None, :]).reshape(-1).to(self.device)
+        B = self.n_envs
+        start = torch.randint(0, max_ts - (horizon + 1), size=(batch_size,))
+        traj = torch.randint(0, len(self) // max_ts, size=(batch_size,))          # (episode, environment) pairs
+        first = (traj // B) * (max_ts * B) + (traj % B) + start * B
+        indices = (first[:, None] + torch.arange(horizon + 1)[None, :] * B).reshape(-1).to(self.device)
         return ReplaySample(self.states[indices], self.actions[indices], self.rewards[indices], self.next_states[indices])
 
     def sample(self, size=512):
@@ -166,3 +191,8 @@ class EfficientExperienceReplay:
 
     def clear(self):
         self.len = 0
+
+
+def get_n_params(model):
+    """util_simple.py:217-224."""
+    return sum(p.numel() for p in model.parameters())

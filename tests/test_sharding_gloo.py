@@ -31,7 +31,21 @@ def _worker(rank, ws, port, q):
         env = OOPAO()
         env.SR = [torch.full((4,), float(rank + 1)), torch.full((4,), float(rank + 1))]
         avg = env.calculate_strehl_AVG()
-        q.put((rank, n, off, sr, rew, cnt, gs[:, 0, 0].tolist(), ga[:, 0].tolist(), avg))
+        # PO4AO trainers average gradients over ranks: each rank trains on its own (different) replay shard, both
+        # end up with identical weights
+        from rlao_b200.PO4AO import mbrl
+        from rlao_b200.PO4AO.conv_models_simple import EnsembleDynamics
+        from rlao_b200.PO4AO.util_simple import EfficientExperienceReplay
+        torch.manual_seed(0)
+        xv, yv = torch.nonzero(torch.ones(5, 5), as_tuple=True)
+        dyn = EnsembleDynamics(xv, yv, 2, n_models=1)
+        rp = EfficientExperienceReplay((5, 5), (5, 5), max_size=64)
+        gen = torch.Generator().manual_seed(100 + rank)
+        for _ in range(16):
+            rp.append(torch.randn(5, 5, generator=gen), torch.randn(5, 5, generator=gen), 0.0, torch.randn(5, 5, generator=gen))
+        mbrl.train_dynamics(2, 8, 4, dyn, torch.optim.SGD(dyn.parameters(), lr=0.1), rp, dyn_iters=2, device="cpu")
+        wsum = float(sum(p.double().abs().sum() for p in dyn.parameters()))
+        q.put((rank, n, off, sr, rew, cnt, gs[:, 0, 0].tolist(), ga[:, 0].tolist(), avg, wsum))
     finally:
         dist.destroy_process_group()
 
@@ -47,9 +61,10 @@ def test_world_size_two_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, n0, o0, sr0, rew0, c0, gs0, ga0, avg0), (r1, n1, o1, sr1, rew1, c1, gs1, ga1, avg1) = res
+    (r0, n0, o0, sr0, rew0, c0, gs0, ga0, avg0, w0), (r1, n1, o1, sr1, rew1, c1, gs1, ga1, avg1, w1) = res
     assert (n0, o0, n1, o1) == (5, 0, 5, 5)
     assert sr0 == sr1 == 0.5 and rew0 == rew1 == -2.0 and c0 == c1 == 10
     assert gs0 == gs1 == [0.0, 0.0, 0.0, 1.0, 1.0, 1.0]
     assert ga0 == ga1 == [10.0, 10.0, 10.0, 11.0, 11.0, 11.0]
     assert avg0 == avg1 == 1.5
+    assert w0 == w1
