@@ -65,43 +65,79 @@ def oracle_config(nSubap, nLayers, opts=None):
 # clocks
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+    """SM clock and throttle reasons sampled DURING the timed region (the recipe's clocks line).  Uses NVML in a
+    thread of this process (clock + event-reason queries only: `nvidia-smi --query-gpu=...,power.draw -lms` stalls
+    kernel launches for tens of milliseconds per sample, which showed up as a 2x slowdown of launch-heavy loops);
+    falls back to an `nvidia-smi` poller when the NVML binding is missing."""
+    Q = "index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    PERIOD = 0.05
 
     def __init__(self, gpu_index):
-        self.rows, self.gpu, self.proc = [], gpu_index, None
+        self.rows, self.gpu, self.proc, self.nvml, self._stop = [], gpu_index, None, None, threading.Event()
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.gpu < len(ids) and ids[self.gpu].isdigit():
+                return int(ids[self.gpu])
+        return self.gpu
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            threading.Thread(target=self._poll_nvml, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self._physical_index()), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.15] or [r for t, r in self.rows][-3:]
-        sm, mx, reasons = [], None, set()
-        for r in rows:
+    def _poll_nvml(self):
+        nv = self.nvml
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        while not self._stop.is_set():
             try:
-                sm.append(float(r[1]))
-                mx = float(r[2])
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                self.rows.append((time.time(), sm, self.max_sm, [n for n, bit in names if mask & bit]))
             except Exception:
                 pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+            self._stop.wait(self.PERIOD)
+
+    def _read(self):
+        for line in self.proc.stdout:
+            r = [x.strip() for x in line.split(",")]
+            try:
+                reasons = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7])
+                           if v.lower().startswith("active")]
+                self.rows.append((time.time(), float(r[1]), float(r[2]), reasons))
+            except Exception:
+                pass
+
+    def stop(self, t0, t1):
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML binding and no nvidia-smi"]}
+        time.sleep(2 * self.PERIOD)
+        self._stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
+        rows = [r for r in self.rows if t0 <= r[0] <= t1 + 2 * self.PERIOD] or self.rows[-3:]
+        sm = sorted(r[1] for r in rows)
+        reasons = sorted({n for r in rows for n in r[3]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": rows[-1][2] if rows else None, "reasons": reasons,
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -536,8 +572,8 @@ def run_po4ao_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0, help="environments per GPU (default: the workload's)")

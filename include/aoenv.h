@@ -185,13 +185,19 @@ int aoenv_observe(const float* rec, int ldr, const int32_t* act_idx, int B, int 
  * Science-path PSF Strehl — OOPAO/Telescope.py:260-360 (computePSF(zp) -> PropagateField), PSF.max()
  * The reference pads the pupil field to N = os*zp*R (os = 2 for even image sizes), takes |FFT/N|^2 and bins
  * os x os.  This entry point evaluates that PSF on the central `win` x `win` binned pixels only (pruned DFT)
- * and returns their maximum in psf_max [B]; psf_win [B][win][win] may be NULL.
- * tw [2N][2] = (cos, sin)(-pi m / N), m = 0..2N-1 (float32, host-computed in float64);
- * scratch: at least B * os*win * R * 2 floats.
+ * and returns their maximum in psf_max [B]; psf_win [B][win][win] may be NULL.  Three launches: the pupil field
+ * written transposed in split-bf16 form, the row transform as one tcgen05 GEMM (M = B*R, N = 2*Wu, K = 2*R,
+ * Wu = os*win), the column transform + |.|^2 + binning + maximum.
+ * w1_planes: bf16 [2][2*Wu][ldk], the two split-bf16 parts (aoenv_split_bf16) of the real operator
+ *   [[Wr, -Wi], [Wi, Wr]], (Wr + i Wi)[u][y] = exp(-i pi (pad + y)(2 d_u + 1) / N), pad = (N-R)/2,
+ *   d_u = os*((N/os)/2 - win/2) + u - N/2, columns [0,R) multiply Re(field), [R,2R) Im(field), zero padded to ldk;
+ * g2: float2 [R][Wu], g2[x][v] = exp(-i pi (pad + x)(2 d_v + 1) / N);  both host-computed in float64;
+ * field_planes: bf16 workspace [2][B*R][ldk] whose columns [2R, ldk) are zero; ldk % 8 == 0;
+ * scratch: B*R * 2*Wu floats.
  * ------------------------------------------------------------------------------------------------------- */
-int aoenv_psf_peak(const float* opd_a, const float* opd_b, const float* pupil, const float* amp, const float* tw,
-                   int B, int R, int N, int os, int win, float phase_scale, float* scratch, float* psf_win,
-                   float* psf_max, void* stream);
+int aoenv_psf_peak(const float* opd_a, const float* opd_b, const float* pupil, const float* amp,
+                   const void* w1_planes, const float* g2, int B, int R, int N, int os, int win, float phase_scale,
+                   void* field_planes, int ldk, float* scratch, float* psf_win, float* psf_max, void* stream);
 
 #ifdef __cplusplus
 }

@@ -43,7 +43,7 @@ PROTOTYPES = {
     "aoenv_shwfs_measure_f64": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _d, _d, _i, _i, _i, _d, _i, _vp, _vp, _vp, _i, _vp],
     "aoenv_command_update": [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _i, _vp],
     "aoenv_observe": [_vp, _i, _vp, _i, _i, _i, _vp, _d, _f, _vp, _vp, _vp, _vp, _vp, _vp],
-    "aoenv_psf_peak": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp],
+    "aoenv_psf_peak": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _i, _vp, _vp, _vp, _vp],
 }
 
 _lib = None

@@ -1,92 +1,105 @@
 // Science-path PSF peak (OOPAO/Telescope.py:260-360: computePSF -> PropagateField; callers take PSF.max()).
 // The reference zero-pads the R x R pupil field to N x N, multiplies by the half-pixel phasor exp(-i pi (x+y)/N),
 // takes the centred FFT / N, |.|^2 and bins os x os.  Only the neighbourhood of the core is needed for a Strehl
-// ratio, so this is a pruned DFT: stage 1 transforms the R input rows to the Wu = os*win wanted output rows,
-// stage 2 the R input columns to the Wu wanted output columns; twiddles come from one exact table
-// tw[m] = exp(-i pi m / N), m in [0, 2N).  Row/column kernel: exp(-i pi (pad + y)(2 d + 1) / N), d = s - N/2
-// (a factor (-1)^d is dropped: it does not change |F|^2).
+// ratio, so this is a pruned DFT onto the Wu = os*win wanted output rows / columns:
+//
+//   stage 0  psf_field_kernel   E[b][y][x] = amp * exp(i phase) written TRANSPOSED and split in bf16 parts:
+//                               X[p][(b, x)][c*R + y]  (c = 0 real, 1 imaginary)  — the operand layout of gemm_tc.cu
+//   stage 1  tcgen05 GEMM       T[(b, x)][c'*Wu + u] = sum_{c,y} X[(b, x)][c*R + y] * W1[c'*Wu + u][c*R + y]
+//                               with W1 = [[Wr, -Wi], [Wi, Wr]], w(u, y) = exp(-i pi (pad + y)(2 d_u + 1) / N),
+//                               d_u = s0 + u - N/2: the R input rows -> Wu output rows as ONE real GEMM
+//                               (M = B*R, N = 2*Wu, K = 2*R; FP32-grade through the split-bf16 scheme)
+//   stage 2  psf_window_kernel  F[b][u][v] = sum_x T[b][u][x] * w(v, x); |F|^2 / N^2, os x os binning, window max
+//
+// (a factor (-1)^d is dropped from w: it does not change |F|^2).  The twiddle operands come from the host in
+// float64-exact form: w1 as split-bf16 planes, g2[x][v] = w(v, x) as float2.
 #include "common.cuh"
 
 namespace aoenv {
 
-constexpr int kS = 16;   // output rows per thread in stage 1
-
-__global__ void __launch_bounds__(128)
-psf_stage1_kernel(const float* __restrict__ opd_a, const float* __restrict__ opd_b, const float* __restrict__ pupil,
-                  const float* __restrict__ amp, const float2* __restrict__ tw, int R, int N, int pad, int s0, int Wu,
-                  float phase_scale, float2* __restrict__ T) {
+// ---- stage 0 ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+psf_field_kernel(const float* __restrict__ opd_a, const float* __restrict__ opd_b, const float* __restrict__ pupil,
+                 const float* __restrict__ amp, int R, float phase_turns, __nv_bfloat16* __restrict__ planes, int ldk,
+                 size_t plane_stride) {
+  __shared__ float sr[32][33], si[32][33];
   const int b = blockIdx.z;
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int sb = blockIdx.y * kS;
-  const bool ok = x < R;
-  float ar[kS], ai[kS];
-  long mult[kS];
-#pragma unroll
-  for (int k = 0; k < kS; ++k) {
-    ar[k] = 0.f; ai[k] = 0.f;
-    const long d = (long)(s0 + sb + k) - N / 2;
-    mult[k] = (((2 * d + 1) % (2L * N)) + 2L * N) % (2L * N);
-  }
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
   const size_t img = (size_t)b * R * R;
-  for (int y = 0; y < R; ++y) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int y = y0 + ty + 8 * j, x = x0 + tx;
     float er = 0.f, ei = 0.f;
-    if (ok) {
+    if (y < R && x < R) {
       const size_t o = (size_t)y * R + x;
       float t = __ldg(opd_a + img + o);
       if (opd_b) t += __ldg(opd_b + img + o);
-      float sn, cs;
-      sincosf(t * __ldg(pupil + o) * phase_scale, &sn, &cs);
+      const float turns = t * __ldg(pupil + o) * phase_turns;
+      const float ang = (turns - rintf(turns)) * 6.283185307179586f;
       const float am = __ldg(amp + o);
-      er = am * cs; ei = am * sn;
+      er = am * __cosf(ang);
+      ei = am * __sinf(ang);
     }
-    const long py = pad + y;
-#pragma unroll
-    for (int k = 0; k < kS; ++k) {
-      const float2 g = __ldg(&tw[(py * mult[k]) % (2L * N)]);
-      ar[k] = fmaf(er, g.x, fmaf(-ei, g.y, ar[k]));
-      ai[k] = fmaf(er, g.y, fmaf(ei, g.x, ai[k]));
-    }
+    sr[ty + 8 * j][tx] = er;
+    si[ty + 8 * j][tx] = ei;
   }
-  if (ok) {
+  __syncthreads();
+  const int y = y0 + tx;
 #pragma unroll
-    for (int k = 0; k < kS; ++k)
-      if (sb + k < Wu) T[((size_t)b * Wu + sb + k) * R + x] = make_float2(ar[k], ai[k]);
+  for (int j = 0; j < 4; ++j) {
+    const int x = x0 + ty + 8 * j;
+    if (y < R && x < R) {
+      const size_t row = ((size_t)b * R + x) * ldk;
+      float vr = sr[tx][ty + 8 * j], vi = si[tx][ty + 8 * j];
+      const __nv_bfloat16 hr = __float2bfloat16_rn(vr), hi = __float2bfloat16_rn(vi);
+      planes[row + y] = hr;
+      planes[row + R + y] = hi;
+      vr -= __bfloat162float(hr);
+      vi -= __bfloat162float(hi);
+      planes[plane_stride + row + y] = __float2bfloat16_rn(vr);
+      planes[plane_stride + row + R + y] = __float2bfloat16_rn(vi);
+    }
   }
 }
 
-// one block per (binned output row, environment); thread t = un-binned output column
+// ---- stage 2 ----------------------------------------------------------------------------------------------
+constexpr int kRows = 8;     // un-binned output rows per block
+
 __global__ void __launch_bounds__(256)
-psf_stage2_kernel(const float2* __restrict__ T, const float2* __restrict__ tw, int R, int N, int pad, int s0, int Wu,
-                  int os, int win, float* __restrict__ psf_win, int* __restrict__ psf_max_bits) {
-  extern __shared__ float2 sT[];            // [os][R]
-  __shared__ float sI[256];
-  const int b = blockIdx.y, yb = blockIdx.x;
-  for (int i = threadIdx.x; i < os * R; i += blockDim.x)
-    sT[i] = T[((size_t)b * Wu + (size_t)yb * os) * R + i];
-  __syncthreads();
-  const int t = threadIdx.x;
-  float inten = 0.f;
-  if (t < Wu) {
-    const long d = (long)(s0 + t) - N / 2;
-    const long mult = (((2 * d + 1) % (2L * N)) + 2L * N) % (2L * N);
-    for (int r = 0; r < os; ++r) {
-      float fr = 0.f, fi = 0.f;
-      for (int x = 0; x < R; ++x) {
-        const float2 g = __ldg(&tw[((long)(pad + x) * mult) % (2L * N)]);
-        const float2 v = sT[r * R + x];
-        fr = fmaf(v.x, g.x, fmaf(-v.y, g.y, fr));
-        fi = fmaf(v.x, g.y, fmaf(v.y, g.x, fi));
-      }
-      inten += fr * fr + fi * fi;
-    }
-    inten /= (float)N * (float)N;
+psf_window_kernel(const float* __restrict__ T, int ldt, const float2* __restrict__ g2, int R, int Wu, int os, int win,
+                  float inv_n2, float* __restrict__ psf_win, int* __restrict__ psf_max_bits) {
+  extern __shared__ float2 sT[];                 // [kRows][R]
+  __shared__ float sI[kRows * 256];              // [kRows][Wu], Wu <= 256
+  const int b = blockIdx.y, u0 = blockIdx.x * kRows;
+  for (int i = threadIdx.x; i < R * kRows; i += blockDim.x) {
+    const int x = i >> 3, j = i & 7;
+    const float* __restrict__ row = T + ((size_t)b * R + x) * ldt + u0 + j;
+    sT[j * R + x] = make_float2(__ldg(row), __ldg(row + Wu));
   }
-  sI[t] = inten;
   __syncthreads();
-  if (t < win) {
+  for (int o = threadIdx.x; o < kRows * Wu; o += blockDim.x) {
+    const int r = o / Wu, v = o - r * Wu;
+    const float2* __restrict__ t = sT + r * R;
+    float fr = 0.f, fi = 0.f;
+#pragma unroll 4
+    for (int x = 0; x < R; ++x) {
+      const float2 g = __ldg(&g2[(size_t)x * Wu + v]);
+      const float2 e = t[x];
+      fr = fmaf(e.x, g.x, fmaf(-e.y, g.y, fr));
+      fi = fmaf(e.x, g.y, fmaf(e.y, g.x, fi));
+    }
+    sI[o] = (fr * fr + fi * fi) * inv_n2;
+  }
+  __syncthreads();
+  const int rows_b = kRows / os;
+  for (int o = threadIdx.x; o < rows_b * win; o += blockDim.x) {
+    const int rb = o / win, cb = o - rb * win;
     float v = 0.f;
-    for (int r = 0; r < os; ++r) v += sI[t * os + r];
-    if (psf_win) psf_win[((size_t)b * win + yb) * win + t] = v;
+    for (int i = 0; i < os; ++i)
+      for (int j = 0; j < os; ++j) v += sI[(rb * os + i) * Wu + cb * os + j];
+    const int yb = u0 / os + rb;
+    if (psf_win) psf_win[((size_t)b * win + yb) * win + cb] = v;
     atomicMax(&psf_max_bits[b], __float_as_int(v));   // v >= 0: int order == float order
   }
 }
@@ -96,24 +109,33 @@ psf_stage2_kernel(const float2* __restrict__ T, const float2* __restrict__ tw, i
 using namespace aoenv;
 
 extern "C" int aoenv_psf_peak(const float* opd_a, const float* opd_b, const float* pupil, const float* amp,
-                              const float* tw, int B, int R, int N, int os, int win, float phase_scale, float* scratch,
-                              float* psf_win, float* psf_max, void* stream) {
+                              const void* w1_planes, const float* g2, int B, int R, int N, int os, int win,
+                              float phase_scale, void* field_planes, int ldk, float* scratch, float* psf_win,
+                              float* psf_max, void* stream) {
   AOENV_CHECK_ARG(B > 0 && B <= 65535 && R > 0 && N >= R && (N - R) % 2 == 0, "psf_peak: bad shape B=%d R=%d N=%d", B, R, N);
   AOENV_CHECK_ARG((os == 1 || os == 2) && N % os == 0, "psf_peak: oversampling %d unsupported", os);
   const int Wu = os * win;
-  AOENV_CHECK_ARG(win > 0 && Wu <= 256 && Wu <= N && Wu % kS == 0, "psf_peak: window of %d binned pixels unsupported", win);
+  AOENV_CHECK_ARG(win > 0 && Wu <= 256 && Wu <= N && Wu % kRows == 0, "psf_peak: window of %d binned pixels unsupported", win);
+  AOENV_CHECK_ARG(ldk >= 2 * R && ldk % 8 == 0, "psf_peak: ldk=%d must be a multiple of 8 and >= 2R", ldk);
+  AOENV_CHECK_ARG((long long)B * R < (1LL << 31), "psf_peak: B*R too large");
   cudaStream_t s = (cudaStream_t)stream;
-  const int pad = (N - R) / 2;
-  const int s0 = os * ((N / os) / 2 - win / 2);
   cudaError_t e = cudaMemsetAsync(psf_max, 0, sizeof(float) * (size_t)B, s);
   if (e != cudaSuccess) return fail(-3, "psf_peak memset: %s", cudaGetErrorString(e));
-  dim3 g1((R + 127) / 128, Wu / kS, B);
-  psf_stage1_kernel<<<g1, 128, 0, s>>>(opd_a, opd_b, pupil, amp, (const float2*)tw, R, N, pad, s0, Wu, phase_scale,
-                                       (float2*)scratch);
-  AOENV_LAUNCH_CHECK("psf_stage1");
-  dim3 g2(win, B);
-  psf_stage2_kernel<<<g2, 256, sizeof(float2) * os * R, s>>>((const float2*)scratch, (const float2*)tw, R, N, pad, s0, Wu,
-                                                            os, win, psf_win, (int*)psf_max);
-  AOENV_LAUNCH_CHECK("psf_stage2");
+  const int MX = B * R;
+  dim3 g0((R + 31) / 32, (R + 31) / 32, B);
+  psf_field_kernel<<<g0, 256, 0, s>>>(opd_a, opd_b, pupil, amp, R, phase_scale * 0.15915494309189535f,
+                                      (__nv_bfloat16*)field_planes, ldk, (size_t)MX * ldk);
+  AOENV_LAUNCH_CHECK("psf_field");
+  int rc = aoenv_gemm_tn_tc(field_planes, w1_planes, ldk, 2, scratch, 2 * Wu, MX, 2 * Wu, 2 * R, 1.0f, stream);
+  if (rc) return rc;
+  dim3 g2d(Wu / kRows, B);
+  const size_t smem = sizeof(float2) * (size_t)kRows * R;
+  if (smem > 48 * 1024) {      // per device; cheap enough to repeat
+    e = cudaFuncSetAttribute(psf_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(-3, "psf_window smem attribute: %s", cudaGetErrorString(e));
+  }
+  psf_window_kernel<<<g2d, 256, smem, s>>>(scratch, 2 * Wu, (const float2*)g2, R, Wu, os, win,
+                                           1.0f / ((float)N * (float)N), psf_win, (int*)psf_max);
+  AOENV_LAUNCH_CHECK("psf_window");
   return 0;
 }

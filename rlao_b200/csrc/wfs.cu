@@ -43,78 +43,91 @@ static int ensure_twiddles(int n, cudaStream_t stream) {
   return 0;
 }
 
-// ---- per-pixel random stream: Philox counter = (pixel, env, frame_lo, frame_hi16 | draw) ---------------------
+// ---- per-pixel random stream: Philox counter = (pixel, env, frame_lo, frame_hi16 << 16 | block) -------------------
+// Block 0 of a pixel's stream feeds the photon draw (words x, y) and the read-out normal (z, w); block 1 the dark
+// current; blocks 16.. / 32.. the (rare) further attempts of the rejection sampler.  Every lane of a warp therefore
+// calls the generator at the same program points — a lazily refilled buffer would refill at different call sites in
+// different lanes and serialise the ten Philox rounds once per site.
 struct PixelRng {
   Philox ph;
-  uint32_t c0, c1, c2, c3hi, sub, have;
-  uint4 buf;
+  uint32_t c0, c1, c2, c3hi;
   __device__ __forceinline__ PixelRng(uint64_t seed, uint32_t pixel, uint32_t env, uint64_t frame)
-      : ph(seed), c0(pixel), c1(env), c2((uint32_t)frame), c3hi(((uint32_t)(frame >> 32)) << 16), sub(0), have(0) {}
-  __device__ __forceinline__ uint32_t next() {
-    if (have == 0) {
-      buf = ph(c0, c1, c2, c3hi | (sub & 0xffffu));
-      ++sub;
-      have = 4;
-    }
-    const uint32_t r = have == 4 ? buf.x : have == 3 ? buf.y : have == 2 ? buf.z : buf.w;
-    --have;
-    return r;
-  }
-  __device__ __forceinline__ float uniform() { return u32_to_unit(next()); }
-  __device__ __forceinline__ float normal() {
-    const uint32_t a = next(), b = next();
-    return box_muller(a, b).x;
-  }
+      : ph(seed), c0(pixel), c1(env), c2((uint32_t)frame), c3hi(((uint32_t)(frame >> 32)) << 16) {}
+  __device__ __forceinline__ uint4 block(uint32_t i) const { return ph(c0, c1, c2, c3hi | (i & 0xffffu)); }
 };
 
-// Poisson(lambda): inversion by sequential search below 12, Hormann's PTRS transformed rejection above
-// (the algorithm numpy's legacy generator also uses for lambda >= 10).
-__device__ float poisson_draw(float lam, PixelRng& rng) {
+// log(k!) for the PTRS acceptance test: table below 10, Stirling's series above (error < 1e-7 relative there)
+__constant__ float c_logfact[10] = {0.f, 0.f, 0.6931471806f, 1.7917594692f, 3.1780538303f, 4.7874917428f,
+                                    6.5792512120f, 8.5251613611f, 10.6046029027f, 12.8018274801f};
+__device__ __forceinline__ float log_factorial(float k) {
+  if (k < 10.f) return c_logfact[(int)k];
+  const float r = __frcp_rn(k);
+  return (k + 0.5f) * __logf(k) - k + 0.9189385332f + r * (0.0833333333f - 0.00277777778f * r * r);
+}
+
+struct RcpTable { float v[64]; };
+constexpr RcpTable make_rcp() {
+  RcpTable t{};
+  t.v[0] = 0.f;
+  for (int k = 1; k < 64; ++k) t.v[k] = 1.0f / (float)k;
+  return t;
+}
+__constant__ RcpTable c_rcp_table = make_rcp();
+
+// Poisson(lambda) from the uniform words (w0, w1): inversion by sequential search below 12 (one word), Hormann's PTRS
+// transformed rejection above (two words per attempt; the algorithm numpy's legacy generator also uses for
+// lambda >= 10); attempts after the first take their words from block `retry_block + attempt` of the pixel's stream.
+__device__ __forceinline__ float poisson_draw(float lam, uint32_t w0, uint32_t w1, const PixelRng& rng, uint32_t retry_block) {
   if (!(lam > 0.f)) return 0.f;
   if (lam < 12.f) {
     float p = __expf(-lam), F = p;
-    const float u = rng.uniform() * 0.99999994f;
+    const float u = u32_to_unit(w0) * 0.99999994f;
     int k = 0;
-    while (u > F && k < 200) {
+    while (u > F && k < 63) {            // P(k >= 63 | lambda < 12) < 1e-24
       ++k;
-      p *= lam / (float)k;
+      p *= lam * c_rcp_table.v[k];
       F += p;
     }
     return (float)k;
   }
-  const float slam = sqrtf(lam), loglam = logf(lam);
+  const float slam = sqrtf(lam), loglam = __logf(lam);
   const float bb = 0.931f + 2.53f * slam;
   const float a = -0.059f + 0.02483f * bb;
-  const float invalpha = 1.1239f + 1.1328f / (bb - 3.4f);
-  const float vr = 0.9277f - 3.6224f / (bb - 2.f);
-  for (int it = 0; it < 64; ++it) {
-    const float U = rng.uniform() - 0.5f;
-    const float V = rng.uniform();
+  const float invalpha = 1.1239f + __fdividef(1.1328f, bb - 3.4f);
+  const float vr = 0.9277f - __fdividef(3.6224f, bb - 2.f);
+  for (int it = 0; it < 15; ++it) {
+    if (it > 0) {
+      const uint4 r = rng.block(retry_block + (uint32_t)it);
+      w0 = r.x;
+      w1 = r.y;
+    }
+    const float U = u32_to_unit(w0) - 0.5f;
+    const float V = u32_to_unit(w1);
     const float us = 0.5f - fabsf(U);
-    const float k = floorf((2.f * a / us + bb) * U + lam + 0.43f);
+    const float k = floorf((__fdividef(2.f * a, us) + bb) * U + lam + 0.43f);
     if (us >= 0.07f && V <= vr) return k;
     if (k < 0.f || (us < 0.013f && V > us)) continue;
-    if (logf(V) + logf(invalpha) - logf(a / (us * us) + bb) <= -lam + k * loglam - lgammaf(k + 1.f)) return k;
+    if (__logf(V * invalpha * __frcp_rn(__fdividef(a, us * us) + bb)) <= -lam + k * loglam - log_factorial(k)) return k;
   }
   return rintf(lam);
 }
 
-struct DetParams {
-  aoenv_detector_t d;
-  int enabled;
-};
-
 // OOPAO/Detector.py:279-301 (integrate) then :232-276 (readout), one pixel.
-// Kept out of line: inlined at the 36 call sites it inflates the frame kernel past the instruction cache.
-__device__ __noinline__ float detector_pixel(float x, const DetParams& dp, uint32_t pixel, uint32_t env) {
-  const aoenv_detector_t& d = dp.d;
-  PixelRng rng(d.seed, pixel, env, d.frame_counter);
-  if (d.photon_noise) x = poisson_draw(x, rng);
+__device__ __forceinline__ float detector_pixel(float x, const aoenv_detector_t& d, uint32_t pixel, uint32_t env) {
+  const PixelRng rng(d.seed, pixel, env, d.frame_counter);
+  const uint4 r0 = rng.block(0);
+  if (d.photon_noise) x = poisson_draw(x, r0.x, r0.y, rng, 16);
   x *= d.qe;
-  if (d.dark_electrons > 0.f) x += poisson_draw(d.dark_electrons, rng);
+  if (d.dark_electrons > 0.f) {
+    const uint4 r1 = rng.block(1);
+    x += poisson_draw(d.dark_electrons, r1.x, r1.y, rng, 32);
+  }
   if (d.has_fwc) x = fminf(fmaxf(x, 0.f), d.fwc);
   if (d.sensor_emccd) x *= d.gain;
-  if (d.readout_noise != 0.f) x += rintf(rng.normal() * d.readout_noise);
+  if (d.readout_noise != 0.f) {           // Box-Muller with the SFU logarithm / cosine: the draw is rounded to whole electrons
+    const float g = sqrtf(-2.0f * __logf(u32_to_unit(r0.z))) * __cosf(6.283185307179586f * u32_to_unit(r0.w));
+    x += rintf(g * d.readout_noise);
+  }
   if (!d.sensor_emccd) x *= d.gain;
   if (d.bits > 0) {
     const float full = (float)((1u << d.bits) - 1u);
@@ -124,11 +137,50 @@ __device__ __noinline__ float detector_pixel(float x, const DetParams& dp, uint3
   return x;
 }
 
+// The camera as its own pass over the noise-free frame.  One block per (row of lenslets, environment): the n frame
+// rows of that lenslet row are one contiguous run of n*R floats, staged through shared memory, and the work items are
+// ordered pixel-position-major (item w = position-in-lenslet * nS + lenslet), so the lanes of a warp hold the SAME
+// pixel position of neighbouring lenslets.  In closed loop those pixels carry similar flux, so a warp stays in one
+// regime of the Poisson sampler (inversion for the dim rim, PTRS for the core) instead of paying for both, and the
+// rejection loops of its lanes have similar lengths.  The random stream of a pixel depends only on (pixel, env,
+// frame counter), not on this ordering.
+__global__ void __launch_bounds__(256, 6)
+shwfs_detector_kernel(float* __restrict__ frame, const uint8_t* __restrict__ valid, int nS, int n, float inv_nS, float inv_n,
+                      const __grid_constant__ aoenv_detector_t det, int shared_max, int32_t* __restrict__ envmax) {
+  extern __shared__ float tile[];                // [n][R]
+  const int R = nS * n, count = n * R;
+  const int li = blockIdx.x, b = blockIdx.y;
+  const size_t base = (size_t)b * R * R + (size_t)li * count;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) tile[i] = frame[base + i];
+  __syncthreads();
+  float vmax = -INFINITY;
+  for (int w = threadIdx.x; w < count; w += blockDim.x) {
+    const int pos = (int)(((float)w + 0.5f) * inv_nS);       // exact: the fraction is >= 1/(2 nS) away from an integer
+    const int lens = w - pos * nS;
+    const int p = (int)(((float)pos + 0.5f) * inv_n);
+    const int q = pos - p * n;
+    const int local = p * R + lens * n + q;
+    const float val = detector_pixel(tile[local], det, (uint32_t)(li * count + local), (uint32_t)b);
+    tile[local] = val;
+    if (valid[li * nS + lens]) vmax = fmaxf(vmax, val);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < count; i += blockDim.x) frame[base + i] = tile[i];
+  vmax = warp_max(vmax);
+  __shared__ float sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = vmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) vmax = fmaxf(vmax, sm[w]);
+    if (vmax > -INFINITY) atomicMax(&envmax[shared_max ? 0 : b], float_to_ordered(vmax));
+  }
+}
+
 template <int n>
 __global__ void __launch_bounds__(128)
 shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ opd_b, const float* __restrict__ pupil,
                    const float* __restrict__ amp, const uint8_t* __restrict__ valid, int nS, float phase_scale,
-                   const __grid_constant__ DetParams det, int shared_max, float* __restrict__ frame,
+                   int track_max, int shared_max, float* __restrict__ frame,
                    int32_t* __restrict__ envmax, double* __restrict__ stats) {
   constexpr int N = 2 * n;
   const int R = nS * n;
@@ -191,7 +243,6 @@ shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ op
   float vmax = -INFINITY;
   if (active) {
     float* __restrict__ fout = frame + (size_t)b * R * R + (size_t)(li * n) * R + lj * n;
-    const uint32_t pix0 = (uint32_t)((li * n) * R + lj * n);
     const float norm = 1.0f / (float)(N * N);
     // Radix-2 split of both DFT passes: G[u + n][a] = (-1)^(a + n/2) G[u][a] (the half-pixel phasor keeps the
     // symmetry), so output rows u and u + n share their even-/odd-class partial sums P, Q:  Y_u = P + Q,
@@ -270,16 +321,17 @@ shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ op
         const int p = pp + r2 * h;
 #pragma unroll
         for (int q = 0; q < n; ++q) {
-          const float raw = (r2 == 0 ? acc_lo[q] : acc_hi[q]) * norm;
-          const float val = det.enabled ? detector_pixel(raw, det, pix0 + (uint32_t)(p * R + q), (uint32_t)b) : raw;
+          const float val = (r2 == 0 ? acc_lo[q] : acc_hi[q]) * norm;
           fout[(size_t)p * R + q] = val;
           if (lit) vmax = fmaxf(vmax, val);
         }
       }
     }
   }
-  vmax = warp_max(vmax);
-  if ((threadIdx.x & 31) == 0 && vmax > -INFINITY) atomicMax(&envmax[shared_max ? 0 : b], float_to_ordered(vmax));
+  if (track_max) {            // with a camera model the maximum is taken after the detector pass
+    vmax = warp_max(vmax);
+    if ((threadIdx.x & 31) == 0 && vmax > -INFINITY) atomicMax(&envmax[shared_max ? 0 : b], float_to_ordered(vmax));
+  }
 }
 
 // centroid + slopes: one thread per (valid lenslet, environment)
@@ -442,10 +494,7 @@ int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil
   AOENV_CHECK_ARG(B > 0 && B <= 65535 && nS > 0, "shwfs_frame: bad shape B=%d nS=%d", B, nS);
   AOENV_CHECK_ARG(n == 4 || n == 6 || n == 8, "shwfs_frame: %d pixels per lenslet is not a compiled size (4, 6, 8)", n);
   cudaStream_t s = (cudaStream_t)stream;
-  DetParams dp;
-  dp.enabled = det != nullptr;
   if (det) {
-    dp.d = *det;
     AOENV_CHECK_ARG(!(det->bits > 0 && !det->has_fwc), "shwfs_frame: ADC without a full-well capacity is not supported");
     AOENV_CHECK_ARG(det->bits >= 0 && det->bits < 31, "shwfs_frame: bits=%d", det->bits);
   }
@@ -460,8 +509,8 @@ int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil
   dim3 grid((nS * nS + 127) / 128, B);
 #define AOENV_WFS_CASE(NN)                                                                                   \
   case NN:                                                                                                   \
-    shwfs_frame_kernel<NN><<<grid, 128, 0, s>>>(opd_a, opd_b, pupil, amp, valid, nS, phase_scale, dp, shared_max, \
-                                                frame, envmax, stats);                                       \
+    shwfs_frame_kernel<NN><<<grid, 128, 0, s>>>(opd_a, opd_b, pupil, amp, valid, nS, phase_scale, det == nullptr,  \
+                                                shared_max, frame, envmax, stats);                           \
     break;
   switch (n) {
     AOENV_WFS_CASE(4)
@@ -470,6 +519,13 @@ int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil
   }
 #undef AOENV_WFS_CASE
   AOENV_LAUNCH_CHECK("shwfs_frame");
+  if (det) {
+    const int R = nS * n;
+    dim3 gd(nS, B);
+    shwfs_detector_kernel<<<gd, 256, sizeof(float) * (size_t)n * R, s>>>(frame, valid, nS, n, 1.0f / (float)nS, 1.0f / (float)n,
+                                                                       *det, shared_max, envmax);
+    AOENV_LAUNCH_CHECK("shwfs_detector");
+  }
   return 0;
 }
 

@@ -4,18 +4,38 @@ import math
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, gemm
 
-_TW = {}
+_OPS = {}
+_WORK = {}
 
 
-def _twiddles(N, device):
-    key = (N, str(device))
-    if key not in _TW:
-        m = np.arange(2 * N, dtype=np.float64)
-        ang = -math.pi * m / N
-        _TW[key] = torch.as_tensor(np.stack([np.cos(ang), np.sin(ang)], axis=1), dtype=torch.float32, device=device).contiguous()
-    return _TW[key]
+def _operators(R, N, os_, window, device):
+    """Twiddle operands of the pruned DFT (include/aoenv.h), exact integer phase reduction in float64."""
+    key = (R, N, os_, window, str(device))
+    if key not in _OPS:
+        Wu, pad = os_ * window, (N - R) // 2
+        s0 = os_ * ((N // os_) // 2 - window // 2)
+        d = s0 + np.arange(Wu, dtype=np.int64) - N // 2
+        m = ((pad + np.arange(R, dtype=np.int64))[None, :] * (2 * d + 1)[:, None]) % (2 * N)       # [Wu, R]
+        ang = -math.pi * m.astype(np.float64) / N
+        wr, wi = np.cos(ang), np.sin(ang)
+        ldk = (2 * R + 15) // 16 * 16
+        w1 = np.zeros((2 * Wu, ldk), dtype=np.float32)
+        w1[:Wu, :R], w1[:Wu, R:2 * R] = wr, -wi
+        w1[Wu:, :R], w1[Wu:, R:2 * R] = wi, wr
+        op = gemm.Operator(torch.as_tensor(w1, device=device).contiguous(), parts=2)
+        g2 = torch.as_tensor(np.stack([wr.T, wi.T], axis=-1), dtype=torch.float32, device=device).contiguous()   # [R, Wu, 2]
+        _OPS[key] = (op, g2, ldk)
+    return _OPS[key]
+
+
+def _workspace(F, R, ldk, Wu, device):
+    key = (F, R, ldk, Wu, str(device))
+    if key not in _WORK:
+        _WORK[key] = (torch.zeros((2, F * R, ldk), dtype=torch.bfloat16, device=device),
+                      torch.empty((F * R, 2 * Wu), dtype=torch.float32, device=device))
+    return _WORK[key]
 
 
 def psf_peak(tel, opd_a, opd_b, zeroPaddingFactor=4, window=32, return_window=False):
@@ -26,12 +46,13 @@ def psf_peak(tel, opd_a, opd_b, zeroPaddingFactor=4, window=32, return_window=Fa
         raise NotImplementedError("odd PSF sizes use a different phasor (Telescope.py:330)")
     F, R = opd_a.shape[0], tel.resolution
     dev = tel.device
-    tw = _twiddles(N, dev)
-    scratch = torch.empty((F, os_ * window, R, 2), dtype=torch.float32, device=dev)
+    op, g2, ldk = _operators(R, N, os_, window, dev)
+    planes, scratch = _workspace(F, R, ldk, os_ * window, dev)
     out = torch.empty((F,), dtype=torch.float32, device=dev)
     win = torch.empty((F, window, window), dtype=torch.float32, device=dev) if return_window else None
     amp = (tel._pupil_f * torch.as_tensor(tel.pupilReflectivity, dtype=torch.float32, device=dev) * tel.src._amp_dev).contiguous()
     _lib.check(_lib.load().aoenv_psf_peak(_lib.ptr(opd_a), _lib.ptr(opd_b), _lib.ptr(tel._pupil_f), _lib.ptr(amp),
-                                          _lib.ptr(tw), F, R, N, os_, window, 2 * math.pi / tel.src.wavelength,
-                                          _lib.ptr(scratch), _lib.ptr(win), _lib.ptr(out), _lib.stream_ptr(dev)), "psf_peak")
+                                          _lib.ptr(op.planes()), _lib.ptr(g2), F, R, N, os_, window,
+                                          2 * math.pi / tel.src.wavelength, _lib.ptr(planes), ldk, _lib.ptr(scratch),
+                                          _lib.ptr(win), _lib.ptr(out), _lib.stream_ptr(dev)), "psf_peak")
     return (out, win) if return_window else out
