@@ -63,6 +63,18 @@ int aoenv_atm_gather(const float* win, int B, int M, int pitch, int64_t env_stri
 int aoenv_atm_ring(float* win, int B, int M, int pitch, int64_t env_stride, int64_t win_offset, int nO, const float* X,
                    int ldx, uint64_t* ext, int32_t* flag, int force_rescan, void* stream);
 
+/* The same two steps for G <= AOENV_MAX_LAYERS layers at once (the layers of one atmosphere whose add_row falls in the
+ * same round of a step share the operator [A | B], so their Z / X rows stack into ONE GEMM of G*B rows):
+ * wins, sx, sy, seeds, stream_ids, win_offsets, exts are HOST arrays of G per-layer values with the meaning of the
+ * single-layer arguments; zx / zx_planes / X / flag / xi hold G*B rows, layer-major ((g*B + b)). */
+int aoenv_atm_gather_multi(const void* const* wins, const int32_t* sx, const int32_t* sy, const uint64_t* seeds,
+                           const uint64_t* stream_ids, int G, int B, int M, int pitch, int64_t env_stride,
+                           const int32_t* inner_rc, int nI, int nO, const float* xi, float* zx, int ldz,
+                           void* zx_planes, int parts, void* stream);
+int aoenv_atm_ring_multi(void* const* wins, const int64_t* win_offsets, void* const* exts, int G, int B, int M,
+                         int pitch, int64_t env_stride, int nO, const float* X, int ldx, int32_t* flag,
+                         int force_rescan, void* stream);
+
 /* Canvas re-centring: copies the window from src_win to dst_win (another canvas buffer, origin 16-byte aligned) and
  * adds pos_delta to the positions stored in ext. */
 int aoenv_atm_compact(const float* src_win, float* dst_win, int B, int M, int pitch, int64_t env_stride, uint64_t* ext,

@@ -58,7 +58,7 @@ class _LayerView:
 
 class Atmosphere:
     def __init__(self, telescope, r0, L0, windSpeed, fractionalR0, windDirection, altitude, mode=2, param=None,
-                 asterism=None, rng="philox", seed=0, warp_kernel="lagrange018", env_offset=0, canvas_slack=32):
+                 asterism=None, rng="philox", seed=0, warp_kernel="lagrange018", env_offset=0, canvas_slack=96):
         """`rng`: 'philox' — device counter-based streams (production); 'reference' — the reference's MT19937
         streams for environment 0 (RandomState(42 + 1000*layer) etc., Atmosphere.py:201,579), offset by
         104729*env for the others: host-generated, for parity runs and small batches.
@@ -126,10 +126,13 @@ class Atmosphere:
             self._cur = [0] * self.nLayer
             self._org = [[0, 0] for _ in range(self.nLayer)]          # window origin (row, col) inside the canvas
             self._ext = torch.zeros((self.nLayer, B, 2), dtype=torch.int64, device=dev)
-            self._flag = torch.zeros((B,), dtype=torch.int32, device=dev)
-            self._zx = torch.zeros((B, self._K), dtype=torch.float32, device=dev)
-            self._zx_planes = torch.zeros((self._W_op.parts, B, self._K), dtype=torch.bfloat16, device=dev)
-            self._X = torch.zeros((B, self._ldx), dtype=torch.float32, device=dev)
+            # add_row workspaces hold one row per (layer of a group, environment): layers that extrude in the same
+            # round of a step share the operator [A | B] and go through ONE gather / GEMM / ring sequence
+            G = self._group_max = min(self.nLayer, _lib.MAX_LAYERS)
+            self._flag = torch.zeros((G * B,), dtype=torch.int32, device=dev)
+            self._zx = torch.zeros((G * B, self._K), dtype=torch.float32, device=dev)
+            self._zx_planes = torch.zeros((self._W_op.parts * G * B, self._K), dtype=torch.bfloat16, device=dev)
+            self._X = torch.zeros((G * B, self._ldx), dtype=torch.float32, device=dev)
             self._opd = torch.zeros((B, R, R), dtype=torch.float32, device=dev)
             self._fp_off = 1 + (ops.layer_res // 2 - R // 2)         # crop [1:-1] + centred footprint (:231-232)
             self.ps_loop = ops.layer_D / ops.layer_res
@@ -204,43 +207,75 @@ class Atmosphere:
 
     def _extrude(self, i, sx, sy, force_rescan=False):
         """add_row (Atmosphere.py:301-311) for layer i and every environment."""
-        lib, ly = _lib.load(), self._layers[i]
-        B, M, pitch, S = self.n_envs, self._M, self._pitch, self._S
-        sx, sy = int(sx), int(sy)
-        oy, ox = self._org[i]
-        if not (0 <= oy - sy <= S and 0 <= ox - sx <= S):
-            self._compact(i)
-            oy, ox = self._org[i]
-            if not (0 <= oy - sy <= S and 0 <= ox - sx <= S):
-                raise RuntimeError("canvas_slack too small for this wind direction change")
+        self._extrude_group([(i, sx, sy)], force_rescan)
+
+    def _extrude_group(self, group, force_rescan=False):
+        """add_row for the layers of `group` = [(layer, sx, sy), ...] (distinct layers) and every environment."""
+        lib = _lib.load()
+        B, M, pitch, S, G = self.n_envs, self._M, self._pitch, self._S, len(group)
         st = _lib.stream_ptr(self.device)
         tc = gemm.uses_tensor_cores()
         xi = None
-        if self.xi_queue is not None:
-            xi = torch.as_tensor(next(self.xi_queue), dtype=torch.float32, device=self.device).reshape(B, self._nO).contiguous()
-        elif self.rng == "reference":
-            xi = self._host_xi(i)
-        if self.xi_log is not None:
-            self.xi_log.append(None if xi is None else xi.clone())
-        seed = getattr(ly, "philox_seed", 0)
-        stream_id = ((ly.events << 8) | i) + (self.env_offset << 40)
-        ly.events += 1
-        _lib.check(lib.aoenv_atm_gather(self._win_ptr(i), B, M, pitch, self._env_stride, sx, sy, _lib.ptr(self._inner_rc),
-                                        self._nI, self._nO, _lib.ptr(xi), C.c_uint64(seed), C.c_uint64(stream_id),
-                                        _lib.ptr(self._zx), self._K, _lib.ptr(self._zx_planes) if tc else None,
-                                        self._W_op.parts, st), "atm_gather")
-        gemm.gemm_tn(self._zx, self._W_op, self._X, B, self._nO, x_planes=self._zx_planes if tc else None)
-        self._org[i] = [oy - sy, ox - sx]
-        noy, nox = self._org[i]
-        _lib.check(lib.aoenv_atm_ring(self._win_ptr(i), B, M, pitch, self._env_stride, noy * pitch + nox, self._nO,
-                                      _lib.ptr(self._X), self._ldx, _lib.ptr(self._ext[i]), _lib.ptr(self._flag),
-                                      int(force_rescan), st), "atm_ring")
+        wins, sxs, sys_, seeds, ids = [], [], [], [], []
+        for i, sx, sy in group:
+            ly = self._layers[i]
+            sx, sy = int(sx), int(sy)
+            oy, ox = self._org[i]
+            if not (0 <= oy - sy <= S and 0 <= ox - sx <= S):
+                self._compact(i)
+                oy, ox = self._org[i]
+                if not (0 <= oy - sy <= S and 0 <= ox - sx <= S):
+                    raise RuntimeError("canvas_slack too small for this wind direction change")
+            if self.xi_queue is not None or self.rng == "reference":
+                assert G == 1, "injected innovations are consumed in the reference's order, one layer at a time"
+                if self.xi_queue is not None:
+                    xi = torch.as_tensor(next(self.xi_queue), dtype=torch.float32, device=self.device).reshape(B, self._nO).contiguous()
+                else:
+                    xi = self._host_xi(i)
+            if self.xi_log is not None:
+                self.xi_log.append(None if xi is None else xi.clone())
+            wins.append(self._win_ptr(i))
+            sxs.append(sx)
+            sys_.append(sy)
+            seeds.append(getattr(ly, "philox_seed", 0))
+            ids.append(((ly.events << 8) | i) + (self.env_offset << 40))
+            ly.events += 1
+        planes = _lib.ptr(self._zx_planes) if tc else None
+        if G == 1:
+            _lib.check(lib.aoenv_atm_gather(wins[0], B, M, pitch, self._env_stride, sxs[0], sys_[0], _lib.ptr(self._inner_rc),
+                                            self._nI, self._nO, _lib.ptr(xi), C.c_uint64(seeds[0]), C.c_uint64(ids[0]),
+                                            _lib.ptr(self._zx), self._K, planes, self._W_op.parts, st), "atm_gather")
+        else:
+            _lib.check(lib.aoenv_atm_gather_multi((C.c_void_p * G)(*[w.value if hasattr(w, "value") else w for w in wins]),
+                                                  (C.c_int32 * G)(*sxs), (C.c_int32 * G)(*sys_), (C.c_uint64 * G)(*seeds),
+                                                  (C.c_uint64 * G)(*ids), G, B, M, pitch, self._env_stride,
+                                                  _lib.ptr(self._inner_rc), self._nI, self._nO, None, _lib.ptr(self._zx), self._K,
+                                                  planes, self._W_op.parts, st), "atm_gather_multi")
+        gemm.gemm_tn(self._zx, self._W_op, self._X, G * B, self._nO, x_planes=self._zx_planes if tc else None)
+        wins, offs, exts = [], [], []
+        for i, sx, sy in group:
+            oy, ox = self._org[i]
+            self._org[i] = [oy - int(sy), ox - int(sx)]
+            noy, nox = self._org[i]
+            wins.append(self._win_ptr(i))
+            offs.append(noy * pitch + nox)
+            exts.append(self._ext[i].data_ptr())
+        if G == 1:
+            _lib.check(lib.aoenv_atm_ring(wins[0], B, M, pitch, self._env_stride, offs[0], self._nO, _lib.ptr(self._X), self._ldx,
+                                          exts[0], _lib.ptr(self._flag), int(force_rescan), st), "atm_ring")
+        else:
+            _lib.check(lib.aoenv_atm_ring_multi((C.c_void_p * G)(*[w.value if hasattr(w, "value") else w for w in wins]),
+                                                (C.c_int64 * G)(*offs), (C.c_void_p * G)(*exts), G, B, M, pitch, self._env_stride,
+                                                self._nO, _lib.ptr(self._X), self._ldx, _lib.ptr(self._flag), int(force_rescan), st),
+                       "atm_ring_multi")
 
-    def _update_layer(self, i):
-        """Integer part of updateLayer (Atmosphere.py:350-404); returns nothing, leaves ly.buff ready."""
+    def _plan_layer(self, i):
+        """Integer part of updateLayer (Atmosphere.py:350-404): the add_row steps (sx, sy) layer i takes this frame, in
+        order; leaves ly.buff ready for the sub-pixel shift."""
         ly = self._layers[i]
+        steps = []
         if ly.vX == 0 and ly.vY == 0:
-            return
+            return steps
         if ly.notDoneOnce:
             ly.notDoneOnce = False
             ly.ratio = np.array([ly.vX * self.telescope.samplingTime / self.ps_loop,
@@ -252,17 +287,37 @@ class Atmosphere:
         n = n.astype(int)
         sgn = np.sign(ratio)
         for _ in range(n.min()):
-            self._extrude(i, sgn[0], sgn[1])
+            steps.append((sgn[0], sgn[1]))
         for _ in range(n.max() - n.min()):
             step = sgn.copy()
             step[n == n.min()] = 0
-            self._extrude(i, step[0], step[1])
+            steps.append((step[0], step[1]))
         ly.buff = ly.buff + (np.abs(ratio) % 1) * sgn
         if abs(ly.buff[0]) >= 1 or abs(ly.buff[1]) >= 1:
             step = np.sign(ly.buff)
             step[np.abs(ly.buff) < 1] = 0
-            self._extrude(i, step[0], step[1])
+            steps.append((step[0], step[1]))
         ly.buff = (np.abs(ly.buff) % 1) * np.sign(ly.buff)
+        return steps
+
+    def _update_layer(self, i):
+        for sx, sy in self._plan_layer(i):
+            self._extrude(i, sx, sy)
+
+    def _update_layers(self):
+        """All layers of one frame.  Layers are independent, and with the counter-based generator the innovation of
+        an add_row depends only on (layer, event number, environment): the r-th add_row of every layer that has
+        one this frame is done together.  Injected / host-generated innovations keep the reference's layer-by-layer
+        order."""
+        if self.xi_queue is not None or self.rng == "reference" or self.nLayer == 1:
+            for i in range(self.nLayer):
+                self._update_layer(i)
+            return
+        plans = [self._plan_layer(i) for i in range(self.nLayer)]
+        for r in range(max((len(p_) for p_ in plans), default=0)):
+            group = [(i, *plans[i][r]) for i in range(self.nLayer) if len(plans[i]) > r]
+            for k in range(0, len(group), self._group_max):
+                self._extrude_group(group[k:k + self._group_max])
 
     def _publish(self):
         """Sub-pixel shift of every layer + Cn2-weighted sum -> OPD_no_pupil (Atmosphere.py:406-407,439-478)."""
@@ -289,8 +344,7 @@ class Atmosphere:
         """Atmosphere.py:409-428."""
         if OPD is None:
             self.user_defined_opd = False
-            for i in range(self.nLayer):
-                self._update_layer(i)
+            self._update_layers()
             self._publish()
         else:
             self.user_defined_opd = True

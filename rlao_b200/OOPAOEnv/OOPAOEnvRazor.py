@@ -66,7 +66,7 @@ class OOPAO:
         return config.initializeParameterFile(args)
 
     def set_params(self, args=None, wfs_type="shackhartmann", modal_basis="zernike", gainCL=0.5, n_envs=1, device=None,
-                   rng="philox", seed=0, env_offset=0, warp_kernel="lagrange018", canvas_slack=32):
+                   rng="philox", seed=0, env_offset=0, warp_kernel="lagrange018", canvas_slack=96):
         """OOPAOEnvRazor.py:91-339 (SH branch)."""
         if wfs_type != "shackhartmann":
             raise NotImplementedError("only the Shack-Hartmann WFS is implemented (Pyramid: SURVEY.md section 8 f-3)")

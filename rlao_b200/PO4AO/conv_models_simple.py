@@ -88,7 +88,11 @@ class ConvPolicy(_ActuatorGrid):
     def forward(self, state, history=None):
         state = _as_batch(state)
         feats = state if history is None else torch.cat([state, _as_batch(history)], dim=1)
-        out = self.net(feats).clamp(-1, 1)
+        return self.project(self.net(feats))
+
+    def project(self, out):
+        """clamp to [-1, 1], keep the valid actuators, apply F (:94-108); out [B, 1, nAct, nAct]."""
+        out = out.clamp(-1, 1)
         _, flat = self._grid(out)
         B, rows, cols = out.shape[0], out.shape[-2], out.shape[-1]
         vec = out.reshape(B, -1)[:, flat] @ self.F[0].t()            # F @ v for every environment

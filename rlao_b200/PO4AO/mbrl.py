@@ -53,6 +53,60 @@ class _History:
         return self.buf[:, self.p + 1:self.p + 1 + self.depth]
 
 
+class _RolloutPolicy:
+    """ConvPolicy inference inside `run` without moving the telemetry: instead of rolling the (n_history - 1)-deep
+    stacks and concatenating [state, past_obs, past_act] every step (mbrl.py:72, 79-80), the images stay where they
+    were written — two rings inside ONE channels-last input tensor — and the input channels of the first
+    convolution's weight are permuted to follow the rings (a 64 x (2 n_history - 1) x 3 x 3 gather per step).  A
+    convolution sums over its input channels, so permuting channels and weights together leaves the result unchanged
+    up to the order of that sum.
+
+    channels [0, n_h)         observation ring: slot p_o holds the current state, the others the past observations
+    channels [n_h, 2 n_h - 1)  action ring:      slot p_a holds the newest action
+    """
+
+    def __init__(self, policy, past_obs, past_act, n_history):
+        B, d, nA = past_obs.shape[0], n_history - 1, past_obs.shape[-1]
+        dev = past_obs.device
+        self.policy, self.nH, self.d = policy, n_history, d
+        self.inp = torch.zeros((B, 2 * n_history - 1, nA, nA), dtype=torch.float32, device=dev).contiguous(
+            memory_format=torch.channels_last)
+        # age order -> slots: past_obs[j] (0 = oldest) lives in slot j, the next state goes to slot d  (p_o = d)
+        self.inp[:, :d] = past_obs
+        self.inp[:, n_history:] = past_act
+        self.p_o, self.p_a = d - 1, d - 1            # advanced before each write
+        self.net = policy.net
+        self.w0, self.b0 = self.net[0].weight, self.net[0].bias
+        self.rest = self.net[1:]
+        # perm[p_o, p_a][slot] = reference channel whose weights that slot needs
+        po = torch.arange(n_history).view(-1, 1, 1)
+        pa = torch.arange(d).view(1, -1, 1)
+        slot_o = torch.arange(n_history).view(1, 1, -1)
+        slot_a = torch.arange(d).view(1, 1, -1)
+        age_o = (slot_o - po - 1) % n_history                          # 0 .. n_h-2 = past (oldest first), n_h-1 = state
+        ref_o = torch.where(age_o == n_history - 1, torch.zeros_like(age_o), age_o + 1).expand(n_history, d, n_history)
+        ref_a = (n_history + (slot_a - pa - 1) % d).expand(n_history, d, d)
+        self.perm = torch.cat([ref_o, ref_a], dim=2).to(dev)             # [n_h, d, 2 n_h - 1]
+
+    def act(self, obs):
+        """obs [B, nAct, nAct] (the current state) -> action [B, nAct, nAct]."""
+        self.p_o = (self.p_o + 1) % self.nH
+        self.inp[:, self.p_o] = obs
+        w = self.w0.index_select(1, self.perm[self.p_o, self.p_a])
+        out = torch.nn.functional.conv2d(self.inp, w, self.b0, padding=1)
+        return self.policy.project(self.rest(out))[:, 0]
+
+    def record(self, action):
+        self.p_a = (self.p_a + 1) % self.d
+        self.inp[:, self.nH + self.p_a] = action
+
+    def histories(self):
+        """(past_obs, past_act) in the reference's order (oldest first), past_obs including the last state."""
+        o = [(self.p_o + 1 + j + 1) % self.nH for j in range(self.d)]
+        a = [(self.p_a + 1 + j) % self.d + self.nH for j in range(self.d)]
+        return self.inp[:, o].contiguous(), self.inp[:, a].contiguous()
+
+
 @torch.no_grad()
 def run(env, past_obs, past_act, obs, replay, policy, dynamics, n_history, max_ts, warmup_ts, sigma, writer=None,
         episode=0, iteration=0, use_recon=False, reconstructor=None, new_screen=True):
@@ -76,28 +130,39 @@ def run(env, past_obs, past_act, obs, replay, policy, dynamics, n_history, max_t
     if past_obs is None:
         past_obs = torch.zeros((B, n_history - 1, nA, nA), dtype=torch.float32, device=dev)
         past_act = torch.zeros((B, n_history - 1, nA, nA), dtype=torch.float32, device=dev)
-    h_obs = _History(past_obs.reshape(B, n_history - 1, nA, nA).to(dev))
-    h_act = _History(past_act.reshape(B, n_history - 1, nA, nA).to(dev))
+    past_obs = past_obs.reshape(B, n_history - 1, nA, nA).to(dev)
+    past_act = past_act.reshape(B, n_history - 1, nA, nA).to(dev)
+    use_policy = episode >= warmup_ts
+    fast = use_policy and n_history > 1 and hasattr(policy, "project") and hasattr(policy, "net")
+    if fast:
+        roll = _RolloutPolicy(policy, past_obs, past_act, n_history)
+    else:
+        h_obs, h_act = _History(past_obs), _History(past_act)
     rewards = torch.empty((max_ts, B), dtype=torch.float32, device=dev)
     squeeze = (lambda t: t[0]) if B == 1 else (lambda t: t)
 
     for t in range(max_ts):
-        if episode < warmup_ts:                                # integrator + exploration noise (:67-70)
+        if not use_policy:                                     # integrator + exploration noise (:67-70)
             action = env.gainCL * obs + env.sample_noise(sigma).reshape(B, nA, nA).to(dev)
-        else:                                                  # :72-73
+        elif fast:                                             # :72-73 without moving the telemetry
+            action = roll.act(obs)
+        else:
             history = torch.cat([h_obs.window(), h_act.window()], dim=1) if n_history > 1 else None
             action = policy(obs.unsqueeze(1), history)[:, 0]
         action = action.to(torch.float32)
         next_obs, reward, strehl, done, _ = env.step(t, squeeze(action))
         next_obs = torch.as_tensor(next_obs, device=dev).reshape(B, nA, nA)
-        h_obs.push(obs)                                        # :79-80
-        h_act.push(action)
+        if fast:                                               # :79-80 (the state is already in its ring slot)
+            roll.record(action)
+        else:
+            h_obs.push(obs)
+            h_act.push(action)
         rewards[t] = torch.as_tensor(reward, dtype=torch.float32, device=dev).reshape(B)
         replay.append(squeeze(obs), squeeze(action), squeeze(rewards[t]), squeeze(next_obs), done)   # :86
         obs = next_obs
 
     reward_sum = rewards.sum(dim=0)
-    past_obs, past_act = h_obs.window().clone(), h_act.window().clone()
+    past_obs, past_act = roll.histories() if fast else (h_obs.window().clone(), h_act.window().clone())
     if B == 1:
         return (env.calculate_strehl_AVG(), float(reward_sum[0]), past_obs, past_act, obs[0],
                 [float(r) for r in rewards[:, 0].cpu()], iteration)

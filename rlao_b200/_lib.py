@@ -26,12 +26,16 @@ class DetectorStruct(C.Structure):
     ]
 
 
+MAX_LAYERS = 8          # AOENV_MAX_LAYERS (include/aoenv.h)
+
 _vp, _i, _f, _u64, _d, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_uint64, C.c_double, C.c_int64
 
 # name -> argtypes, exactly the prototypes of include/aoenv.h
 PROTOTYPES = {
     "aoenv_atm_gather": [_vp, _i, _i, _i, _i64, _i, _i, _vp, _i, _i, _vp, _u64, _u64, _vp, _i, _vp, _i, _vp],
     "aoenv_atm_ring": [_vp, _i, _i, _i, _i64, _i64, _i, _vp, _i, _vp, _vp, _i, _vp],
+    "aoenv_atm_gather_multi": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _vp],
+    "aoenv_atm_ring_multi": [_vp, _vp, _vp, _i, _i, _i, _i, _i64, _i, _vp, _i, _vp, _i, _vp],
     "aoenv_atm_compact": [_vp, _vp, _i, _i, _i, _i64, _vp, _i64, _vp],
     "aoenv_atm_phase": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp],
     "aoenv_gemm_tn": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _f, _vp],

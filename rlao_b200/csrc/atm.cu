@@ -15,30 +15,42 @@ namespace aoenv {
 // add_row step 1: gather the two inner rings of the one-pixel-shifted map + the innovation vector
 // (OOPAO/Atmosphere.py:303-308).  One thread per entry of zx[b][:].
 // ---------------------------------------------------------------------------------------------------------
+// Several layers whose add_row falls in the same round of a step are processed by one launch: gridDim.z = layers in
+// the group, per-layer arguments in a __grid_constant__ block (indexed loads from the constant bank).
+struct AtmGroup {
+  float* win[AOENV_MAX_LAYERS];                  // window origin (gather: the NEW origin; ring: canvas base)
+  unsigned long long* ext[AOENV_MAX_LAYERS];
+  unsigned long long seed[AOENV_MAX_LAYERS], stream_id[AOENV_MAX_LAYERS];
+  uint32_t win_offset[AOENV_MAX_LAYERS];
+  int sx[AOENV_MAX_LAYERS], sy[AOENV_MAX_LAYERS];
+};
+
 __global__ void __launch_bounds__(256)
-atm_gather_kernel(const float* __restrict__ map, int M, int pitch, size_t env_stride, int sx, int sy,
+atm_gather_kernel(const __grid_constant__ AtmGroup grp, int M, int pitch, size_t env_stride,
                   const int2* __restrict__ inner_rc, int nI, int nO, const float* __restrict__ xi,
-                  uint64_t seed, uint64_t stream_id, float* __restrict__ zx, int ldz,
-                  __nv_bfloat16* __restrict__ planes, int parts) {
-  const int b = blockIdx.y;
+                  float* __restrict__ zx, int ldz, __nv_bfloat16* __restrict__ planes, int parts) {
+  const int b = blockIdx.y, g = blockIdx.z;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= ldz) return;
+  const size_t row = (size_t)g * gridDim.y + b;
   float v = 0.f;
   if (k < nI) {
     const int2 rc = __ldg(&inner_rc[k]);
-    v = __ldg(&map[(size_t)b * env_stride + (size_t)(rc.x - sy) * pitch + (rc.y - sx)]);
+    const float* __restrict__ map = grp.win[g];
+    v = __ldg(&map[(size_t)b * env_stride + (size_t)(rc.x - grp.sy[g]) * pitch + (rc.y - grp.sx[g])]);
   } else if (k < nI + nO) {
     const int j = k - nI;
     if (xi != nullptr) {
-      v = __ldg(&xi[(size_t)b * nO + j]);
+      v = __ldg(&xi[row * nO + j]);
     } else {
-      Philox rng(seed);
+      const unsigned long long stream_id = grp.stream_id[g];
+      Philox rng(grp.seed[g]);
       const uint4 r = rng((uint32_t)j, (uint32_t)b, (uint32_t)stream_id, (uint32_t)(stream_id >> 32));
       v = box_muller(r.x, r.y).x;
     }
   }
-  zx[(size_t)b * ldz + k] = v;
-  if (planes != nullptr) store_bf16_planes(planes, (size_t)gridDim.y * ldz, (size_t)b * ldz + k, parts, v);
+  zx[row * ldz + k] = v;
+  if (planes != nullptr) store_bf16_planes(planes, (size_t)gridDim.z * gridDim.y * ldz, row * ldz + k, parts, v);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -82,12 +94,14 @@ __device__ __forceinline__ void block_reduce_ext(unsigned long long& lo, unsigne
 // numpy boolean-mask order of `outerMask`, :263-264: row 0, then the (r,0),(r,M-1) pairs, then row M-1), reduces the
 // ring extrema and decides whether the tracked extrema survive.
 __global__ void __launch_bounds__(256)
-atm_ring_kernel(float* __restrict__ win, int M, int pitch, size_t env_stride, uint32_t win_offset,
-                const float* __restrict__ X, int ldx, unsigned long long* __restrict__ ext, int32_t* __restrict__ flag,
-                int force_rescan) {
-  const int b = blockIdx.x;
-  float* __restrict__ w = win + (size_t)b * env_stride;
-  const float* __restrict__ xb = X + (size_t)b * ldx;
+atm_ring_kernel(const __grid_constant__ AtmGroup grp, int M, int pitch, size_t env_stride,
+                const float* __restrict__ X, int ldx, int32_t* __restrict__ flag, int force_rescan) {
+  const int b = blockIdx.x, g = blockIdx.y;
+  const size_t row = (size_t)g * gridDim.x + b;
+  const uint32_t win_offset = grp.win_offset[g];
+  unsigned long long* __restrict__ ext = grp.ext[g];
+  float* __restrict__ w = grp.win[g] + (size_t)b * env_stride;
+  const float* __restrict__ xb = X + row * ldx;
   const int nO = 4 * M - 4;
   unsigned long long lo = ~0ull, hi = 0ull;
   for (int k = threadIdx.x; k < nO; k += blockDim.x) {
@@ -114,27 +128,29 @@ atm_ring_kernel(float* __restrict__ win, int M, int pitch, size_t env_stride, ui
     const bool ok = !force_rescan && retained(old_lo) && retained(old_hi);
     ext[2 * b] = ok && old_lo < lo ? old_lo : lo;
     ext[2 * b + 1] = ok && old_hi > hi ? old_hi : hi;
-    flag[b] = ok ? 0 : 1;
+    flag[row] = ok ? 0 : 1;
   }
 }
 
 // Exact extrema of the window interior for the flagged environments, merged into ext (which already holds the ring's).
 __global__ void __launch_bounds__(256)
-atm_rescan_kernel(const float* __restrict__ win, int M, int pitch, size_t env_stride, uint32_t win_offset,
-                  unsigned long long* __restrict__ ext, const int32_t* __restrict__ flag, int rows_per_block) {
-  const int b = blockIdx.y;
-  if (__ldg(&flag[b]) == 0) return;
-  const float* __restrict__ w = win + (size_t)b * env_stride;
+atm_rescan_kernel(const __grid_constant__ AtmGroup grp, int M, int pitch, size_t env_stride,
+                  const int32_t* __restrict__ flag, int rows_per_block) {
+  const int b = blockIdx.y, g = blockIdx.z;
+  if (__ldg(&flag[(size_t)g * gridDim.y + b]) == 0) return;
+  const uint32_t win_offset = grp.win_offset[g];
+  unsigned long long* __restrict__ ext = grp.ext[g];
+  const float* __restrict__ w = grp.win[g] + (size_t)b * env_stride;
   const int r_begin = 1 + blockIdx.x * rows_per_block;
   const int r_end = min(M - 1, r_begin + rows_per_block);
   unsigned long long lo = ~0ull, hi = 0ull;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;       // 64 threads x 4 columns per row, 4 rows in flight
   for (int r = r_begin + ty; r < r_end; r += 4) {
-    const float* __restrict__ row = w + (size_t)r * pitch;
+    const float* __restrict__ rowp = w + (size_t)r * pitch;
     for (int c = 1 + 4 * tx; c < M - 1; c += 256) {
       float v[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] = (c + k < M - 1) ? __ldg(row + c + k) : 0.f;
+      for (int k = 0; k < 4; ++k) v[k] = (c + k < M - 1) ? __ldg(rowp + c + k) : 0.f;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         if (c + k < M - 1) {
@@ -324,36 +340,69 @@ static int rows_per_block_for(int B, int M) {
 
 extern "C" {
 
+int aoenv_atm_gather_multi(const void* const* wins, const int32_t* sx, const int32_t* sy, const uint64_t* seeds,
+                           const uint64_t* stream_ids, int G, int B, int M, int pitch, int64_t env_stride,
+                           const int32_t* inner_rc, int nI, int nO, const float* xi, float* zx, int ldz, void* zx_planes,
+                           int parts, void* stream) {
+  AOENV_CHECK_ARG(G > 0 && G <= AOENV_MAX_LAYERS, "atm_gather: %d layers in one group (max %d)", G, AOENV_MAX_LAYERS);
+  AOENV_CHECK_ARG(B > 0 && B <= 65535 && M > 6 && pitch >= M && env_stride >= (int64_t)M * pitch, "atm_gather: bad shape B=%d M=%d pitch=%d", B, M, pitch);
+  AOENV_CHECK_ARG(ldz >= nI + nO, "atm_gather: ldz=%d < nI+nO=%d", ldz, nI + nO);
+  AOENV_CHECK_ARG(zx_planes == nullptr || parts == 2 || parts == 3, "atm_gather: parts must be 2 or 3");
+  AtmGroup grp{};
+  for (int g = 0; g < G; ++g) {
+    AOENV_CHECK_ARG(sx[g] >= -1 && sx[g] <= 1 && sy[g] >= -1 && sy[g] <= 1, "atm_gather: shift must be in {-1,0,1}");
+    grp.win[g] = (float*)wins[g];
+    grp.sx[g] = sx[g];
+    grp.sy[g] = sy[g];
+    grp.seed[g] = seeds ? seeds[g] : 0;
+    grp.stream_id[g] = stream_ids ? stream_ids[g] : 0;
+  }
+  dim3 grid((ldz + 255) / 256, B, G);
+  atm_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(grp, M, pitch, (size_t)env_stride, (const int2*)inner_rc, nI, nO,
+                                                            xi, zx, ldz, (__nv_bfloat16*)zx_planes, parts);
+  AOENV_LAUNCH_CHECK("atm_gather");
+  return 0;
+}
+
 int aoenv_atm_gather(const float* win, int B, int M, int pitch, int64_t env_stride, int sx, int sy,
                      const int32_t* inner_rc, int nI, int nO, const float* xi, uint64_t seed, uint64_t stream_id,
                      float* zx, int ldz, void* zx_planes, int parts, void* stream) {
-  AOENV_CHECK_ARG(B > 0 && B <= 65535 && M > 6 && pitch >= M && env_stride >= (int64_t)M * pitch, "atm_gather: bad shape B=%d M=%d pitch=%d", B, M, pitch);
-  AOENV_CHECK_ARG(sx >= -1 && sx <= 1 && sy >= -1 && sy <= 1, "atm_gather: shift must be in {-1,0,1}");
-  AOENV_CHECK_ARG(ldz >= nI + nO, "atm_gather: ldz=%d < nI+nO=%d", ldz, nI + nO);
-  AOENV_CHECK_ARG(zx_planes == nullptr || parts == 2 || parts == 3, "atm_gather: parts must be 2 or 3");
-  dim3 grid((ldz + 255) / 256, B);
-  atm_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(win, M, pitch, (size_t)env_stride, sx, sy, (const int2*)inner_rc,
-                                                            nI, nO, xi, seed, stream_id, zx, ldz,
-                                                            (__nv_bfloat16*)zx_planes, parts);
-  AOENV_LAUNCH_CHECK("atm_gather");
+  const void* wins[1] = {win};
+  const int32_t sxs[1] = {sx}, sys[1] = {sy};
+  const uint64_t seeds[1] = {seed}, ids[1] = {stream_id};
+  return aoenv_atm_gather_multi(wins, sxs, sys, seeds, ids, 1, B, M, pitch, env_stride, inner_rc, nI, nO, xi, zx, ldz,
+                                zx_planes, parts, stream);
+}
+
+int aoenv_atm_ring_multi(void* const* wins, const int64_t* win_offsets, void* const* exts, int G, int B, int M, int pitch,
+                         int64_t env_stride, int nO, const float* X, int ldx, int32_t* flag, int force_rescan, void* stream) {
+  AOENV_CHECK_ARG(G > 0 && G <= AOENV_MAX_LAYERS, "atm_ring: %d layers in one group (max %d)", G, AOENV_MAX_LAYERS);
+  AOENV_CHECK_ARG(B > 0 && B <= 65535 && M > 6 && pitch >= M, "atm_ring: bad shape");
+  AOENV_CHECK_ARG(nO == 4 * M - 4 && ldx >= nO, "atm_ring: ring has %d pixels, got nO=%d ldx=%d", 4 * M - 4, nO, ldx);
+  AtmGroup grp{};
+  for (int g = 0; g < G; ++g) {
+    AOENV_CHECK_ARG(win_offsets[g] >= 0 && win_offsets[g] + (int64_t)M * pitch <= env_stride + pitch && env_stride < (1ll << 32),
+                    "atm_ring: window leaves the canvas");
+    grp.win[g] = (float*)wins[g];
+    grp.ext[g] = (unsigned long long*)exts[g];
+    grp.win_offset[g] = (uint32_t)win_offsets[g];
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  atm_ring_kernel<<<dim3(B, G), 256, 0, s>>>(grp, M, pitch, (size_t)env_stride, X, ldx, flag, force_rescan);
+  AOENV_LAUNCH_CHECK("atm_ring");
+  const int rpb = 32;                          // >= 8 CTAs per flagged environment; unflagged ones exit at once
+  dim3 grid((M - 2 + rpb - 1) / rpb, B, G);
+  atm_rescan_kernel<<<grid, 256, 0, s>>>(grp, M, pitch, (size_t)env_stride, flag, rpb);
+  AOENV_LAUNCH_CHECK("atm_rescan");
   return 0;
 }
 
 int aoenv_atm_ring(float* win, int B, int M, int pitch, int64_t env_stride, int64_t win_offset, int nO, const float* X,
                    int ldx, uint64_t* ext, int32_t* flag, int force_rescan, void* stream) {
-  AOENV_CHECK_ARG(B > 0 && B <= 65535 && M > 6 && pitch >= M, "atm_ring: bad shape");
-  AOENV_CHECK_ARG(nO == 4 * M - 4 && ldx >= nO, "atm_ring: ring has %d pixels, got nO=%d ldx=%d", 4 * M - 4, nO, ldx);
-  AOENV_CHECK_ARG(win_offset >= 0 && win_offset + (int64_t)M * pitch <= env_stride + pitch && env_stride < (1ll << 32), "atm_ring: window leaves the canvas");
-  cudaStream_t s = (cudaStream_t)stream;
-  atm_ring_kernel<<<B, 256, 0, s>>>(win, M, pitch, (size_t)env_stride, (uint32_t)win_offset, X, ldx,
-                                    reinterpret_cast<unsigned long long*>(ext), flag, force_rescan);
-  AOENV_LAUNCH_CHECK("atm_ring");
-  const int rpb = 32;                          // >= 8 CTAs per flagged environment; unflagged ones exit at once
-  dim3 grid((M - 2 + rpb - 1) / rpb, B);
-  atm_rescan_kernel<<<grid, 256, 0, s>>>(win, M, pitch, (size_t)env_stride, (uint32_t)win_offset,
-                                         reinterpret_cast<unsigned long long*>(ext), flag, rpb);
-  AOENV_LAUNCH_CHECK("atm_rescan");
-  return 0;
+  void* wins[1] = {win};
+  void* exts[1] = {ext};
+  const int64_t offs[1] = {win_offset};
+  return aoenv_atm_ring_multi(wins, offs, exts, 1, B, M, pitch, env_stride, nO, X, ldx, flag, force_rescan, stream);
 }
 
 int aoenv_atm_compact(const float* src_win, float* dst_win, int B, int M, int pitch, int64_t env_stride, uint64_t* ext,

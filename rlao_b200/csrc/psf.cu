@@ -18,17 +18,18 @@
 namespace aoenv {
 
 // ---- stage 0 ----------------------------------------------------------------------------------------------
+// 64 (y) x 32 (x) tiles through shared memory: coalesced float reads along x, bf16x2 stores along y (128 B per warp).
 __global__ void __launch_bounds__(256)
 psf_field_kernel(const float* __restrict__ opd_a, const float* __restrict__ opd_b, const float* __restrict__ pupil,
                  const float* __restrict__ amp, int R, float phase_turns, __nv_bfloat16* __restrict__ planes, int ldk,
                  size_t plane_stride) {
-  __shared__ float sr[32][33], si[32][33];
+  __shared__ float sr[64][33], si[64][33];
   const int b = blockIdx.z;
-  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 64;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
   const size_t img = (size_t)b * R * R;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < 8; ++j) {
     const int y = y0 + ty + 8 * j, x = x0 + tx;
     float er = 0.f, ei = 0.f;
     if (y < R && x < R) {
@@ -45,20 +46,20 @@ psf_field_kernel(const float* __restrict__ opd_a, const float* __restrict__ opd_
     si[ty + 8 * j][tx] = ei;
   }
   __syncthreads();
-  const int y = y0 + tx;
+  const int yl = 2 * tx, y = y0 + yl;             // this thread's pair of rows (R is even: ldk >= 2R, both multiples of 2)
+  if (y >= R) return;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int x = x0 + ty + 8 * j;
-    if (y < R && x < R) {
+    const int xl = ty + 8 * j, x = x0 + xl;
+    if (x < R) {
       const size_t row = ((size_t)b * R + x) * ldk;
-      float vr = sr[tx][ty + 8 * j], vi = si[tx][ty + 8 * j];
-      const __nv_bfloat16 hr = __float2bfloat16_rn(vr), hi = __float2bfloat16_rn(vi);
-      planes[row + y] = hr;
-      planes[row + R + y] = hi;
-      vr -= __bfloat162float(hr);
-      vi -= __bfloat162float(hi);
-      planes[plane_stride + row + y] = __float2bfloat16_rn(vr);
-      planes[plane_stride + row + R + y] = __float2bfloat16_rn(vi);
+      const float r0 = sr[yl][xl], r1 = sr[yl + 1][xl], i0 = si[yl][xl], i1 = si[yl + 1][xl];
+      const __nv_bfloat162 hr = __floats2bfloat162_rn(r0, r1), hi = __floats2bfloat162_rn(i0, i1);
+      const float2 fr = __bfloat1622float2(hr), fi = __bfloat1622float2(hi);
+      *reinterpret_cast<__nv_bfloat162*>(planes + row + y) = hr;
+      *reinterpret_cast<__nv_bfloat162*>(planes + row + R + y) = hi;
+      *reinterpret_cast<__nv_bfloat162*>(planes + plane_stride + row + y) = __floats2bfloat162_rn(r0 - fr.x, r1 - fr.y);
+      *reinterpret_cast<__nv_bfloat162*>(planes + plane_stride + row + R + y) = __floats2bfloat162_rn(i0 - fi.x, i1 - fi.y);
     }
   }
 }
@@ -66,10 +67,13 @@ psf_field_kernel(const float* __restrict__ opd_a, const float* __restrict__ opd_
 // ---- stage 2 ----------------------------------------------------------------------------------------------
 constexpr int kRows = 8;     // un-binned output rows per block
 
+// One block per (group of kRows output rows, environment).  Thread (v, slice) accumulates all kRows rows of output
+// column v over its slice of the R input columns: one coalesced twiddle load feeds 4*kRows FMAs, the T values are
+// shared-memory broadcasts.  The slices are then summed through shared memory.
 __global__ void __launch_bounds__(256)
 psf_window_kernel(const float* __restrict__ T, int ldt, const float2* __restrict__ g2, int R, int Wu, int os, int win,
-                  float inv_n2, float* __restrict__ psf_win, int* __restrict__ psf_max_bits) {
-  extern __shared__ float2 sT[];                 // [kRows][R]
+                  int slices, float inv_n2, float* __restrict__ psf_win, int* __restrict__ psf_max_bits) {
+  extern __shared__ float2 sT[];                 // [kRows][R], then reused as [slices][kRows][Wu] partial sums
   __shared__ float sI[kRows * 256];              // [kRows][Wu], Wu <= 256
   const int b = blockIdx.y, u0 = blockIdx.x * kRows;
   for (int i = threadIdx.x; i < R * kRows; i += blockDim.x) {
@@ -78,29 +82,49 @@ psf_window_kernel(const float* __restrict__ T, int ldt, const float2* __restrict
     sT[j * R + x] = make_float2(__ldg(row), __ldg(row + Wu));
   }
   __syncthreads();
-  for (int o = threadIdx.x; o < kRows * Wu; o += blockDim.x) {
-    const int r = o / Wu, v = o - r * Wu;
-    const float2* __restrict__ t = sT + r * R;
-    float fr = 0.f, fi = 0.f;
-#pragma unroll 4
-    for (int x = 0; x < R; ++x) {
+  const int v = threadIdx.x % Wu, sl = threadIdx.x / Wu;
+  float fr[kRows], fi[kRows];
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) { fr[r] = 0.f; fi[r] = 0.f; }
+  if (sl < slices) {
+    const int per = (R + slices - 1) / slices;
+    const int x0 = sl * per, x1 = min(R, x0 + per);
+#pragma unroll 2
+    for (int x = x0; x < x1; ++x) {
       const float2 g = __ldg(&g2[(size_t)x * Wu + v]);
-      const float2 e = t[x];
-      fr = fmaf(e.x, g.x, fmaf(-e.y, g.y, fr));
-      fi = fmaf(e.x, g.y, fmaf(e.y, g.x, fi));
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        const float2 e = sT[r * R + x];
+        fr[r] = fmaf(e.x, g.x, fmaf(-e.y, g.y, fr[r]));
+        fi[r] = fmaf(e.x, g.y, fmaf(e.y, g.x, fi[r]));
+      }
     }
-    sI[o] = (fr * fr + fi * fi) * inv_n2;
+  }
+  __syncthreads();                               // everyone is done reading sT
+  if (sl < slices) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) sT[(sl * kRows + r) * Wu + v] = make_float2(fr[r], fi[r]);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < kRows * Wu; o += blockDim.x) {
+    float ar = 0.f, ai = 0.f;
+    for (int q = 0; q < slices; ++q) {
+      const float2 p = sT[q * kRows * Wu + o];
+      ar += p.x;
+      ai += p.y;
+    }
+    sI[o] = (ar * ar + ai * ai) * inv_n2;
   }
   __syncthreads();
   const int rows_b = kRows / os;
   for (int o = threadIdx.x; o < rows_b * win; o += blockDim.x) {
     const int rb = o / win, cb = o - rb * win;
-    float v = 0.f;
+    float val = 0.f;
     for (int i = 0; i < os; ++i)
-      for (int j = 0; j < os; ++j) v += sI[(rb * os + i) * Wu + cb * os + j];
+      for (int j = 0; j < os; ++j) val += sI[(rb * os + i) * Wu + cb * os + j];
     const int yb = u0 / os + rb;
-    if (psf_win) psf_win[((size_t)b * win + yb) * win + cb] = v;
-    atomicMax(&psf_max_bits[b], __float_as_int(v));   // v >= 0: int order == float order
+    if (psf_win) psf_win[((size_t)b * win + yb) * win + cb] = val;
+    atomicMax(&psf_max_bits[b], __float_as_int(val));   // val >= 0: int order == float order
   }
 }
 
@@ -117,24 +141,28 @@ extern "C" int aoenv_psf_peak(const float* opd_a, const float* opd_b, const floa
   const int Wu = os * win;
   AOENV_CHECK_ARG(win > 0 && Wu <= 256 && Wu <= N && Wu % kRows == 0, "psf_peak: window of %d binned pixels unsupported", win);
   AOENV_CHECK_ARG(ldk >= 2 * R && ldk % 8 == 0, "psf_peak: ldk=%d must be a multiple of 8 and >= 2R", ldk);
+  AOENV_CHECK_ARG(R % 2 == 0, "psf_peak: odd pupil size R=%d", R);
   AOENV_CHECK_ARG((long long)B * R < (1LL << 31), "psf_peak: B*R too large");
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(psf_max, 0, sizeof(float) * (size_t)B, s);
   if (e != cudaSuccess) return fail(-3, "psf_peak memset: %s", cudaGetErrorString(e));
   const int MX = B * R;
-  dim3 g0((R + 31) / 32, (R + 31) / 32, B);
+  dim3 g0((R + 31) / 32, (R + 63) / 64, B);
   psf_field_kernel<<<g0, 256, 0, s>>>(opd_a, opd_b, pupil, amp, R, phase_scale * 0.15915494309189535f,
                                       (__nv_bfloat16*)field_planes, ldk, (size_t)MX * ldk);
   AOENV_LAUNCH_CHECK("psf_field");
   int rc = aoenv_gemm_tn_tc(field_planes, w1_planes, ldk, 2, scratch, 2 * Wu, MX, 2 * Wu, 2 * R, 1.0f, stream);
   if (rc) return rc;
   dim3 g2d(Wu / kRows, B);
-  const size_t smem = sizeof(float2) * (size_t)kRows * R;
+  const int slices = 256 / Wu > 0 ? 256 / Wu : 1;
+  size_t smem = sizeof(float2) * (size_t)kRows * R;
+  const size_t partial = sizeof(float2) * (size_t)slices * kRows * Wu;
+  if (partial > smem) smem = partial;
   if (smem > 48 * 1024) {      // per device; cheap enough to repeat
     e = cudaFuncSetAttribute(psf_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(-3, "psf_window smem attribute: %s", cudaGetErrorString(e));
   }
-  psf_window_kernel<<<g2d, 256, smem, s>>>(scratch, 2 * Wu, (const float2*)g2, R, Wu, os, win,
+  psf_window_kernel<<<g2d, 256, smem, s>>>(scratch, 2 * Wu, (const float2*)g2, R, Wu, os, win, slices,
                                            1.0f / ((float)N * (float)N), psf_win, (int*)psf_max);
   AOENV_LAUNCH_CHECK("psf_window");
   return 0;

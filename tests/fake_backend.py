@@ -100,6 +100,23 @@ class FakeLib:
             e[b, 1] = np.int64(np.uint64(keys.max()).astype(np.int64))
         return 0
 
+    def aoenv_atm_gather_multi(self, wins, sx, sy, seeds, stream_ids, G, B, M, pitch, env_stride, inner_rc, nI, nO, xi, zx, ldz,
+                               zx_planes, parts, stream):
+        z0 = zx.value if isinstance(zx, C.c_void_p) else int(zx)
+        for g in range(G):
+            self.aoenv_atm_gather(int(wins[g]), B, M, pitch, env_stride, int(sx[g]), int(sy[g]), inner_rc, nI, nO, None,
+                                  int(seeds[g]), int(stream_ids[g]), z0 + 4 * g * B * ldz, ldz, None, parts, stream)
+        self.launches -= G - 1
+        return 0
+
+    def aoenv_atm_ring_multi(self, wins, win_offsets, exts, G, B, M, pitch, env_stride, nO, X, ldx, flag, force_rescan, stream):
+        x0 = X.value if isinstance(X, C.c_void_p) else int(X)
+        for g in range(G):
+            self.aoenv_atm_ring(int(wins[g]), B, M, pitch, env_stride, int(win_offsets[g]), nO, x0 + 4 * g * B * ldx, ldx,
+                                int(exts[g]), flag, force_rescan, stream)
+        self.launches -= 2 * (G - 1)
+        return 0
+
     def aoenv_atm_compact(self, src, dst, B, M, pitch, env_stride, ext, pos_delta, stream):
         self.launches += 1
         s_, d_ = self._window(src, B, M, pitch, env_stride), self._window(dst, B, M, pitch, env_stride)

@@ -14,6 +14,7 @@ from oracle.ao_oracle import (AOConfig, AtmosphereOracle, DetectorConfig, EnvOra
 from oracle.golden_configs import CONFIGS, EPISODE_SEED, STEPS
 from oracle.warp018 import warp_translate
 from parity_util import build_env, new_episode, rel_err
+from rlao_b200 import _lib
 
 pytestmark = pytest.mark.gpu
 
@@ -149,6 +150,37 @@ def test_sliding_window_canvas_vs_oracle(dev):
             r, c = pos // pitch - oy, pos % pitch - ox
             assert got[r, c] == got.reshape(-1)[want_pos]        # tracked extremum is the window's true extremum
     assert any(c == 1 for c in atm._cur) or True
+
+
+def test_layers_extruded_together_equal_layers_extruded_one_by_one(dev):
+    """Counter-based innovations depend on (layer, event, environment) only: the grouped add_row (one gather / GEMM /
+    ring for all layers of a round) must give bit-identical maps, extrema and OPD to the layer-by-layer sequence."""
+    from rlao_b200.Atmosphere import Atmosphere
+    from rlao_b200.Source import Source
+    from rlao_b200.Telescope import Telescope
+    cfg = CONFIGS["tiny"]()
+    speeds, dirs, frac = [47.0, 21.0, 12.0, 33.0], [10.0, 130.0, 250.0, 300.0], [0.4, 0.3, 0.2, 0.1]
+
+    def build():
+        tel = Telescope(cfg.resolution, cfg.diameter, cfg.samplingTime, n_envs=3, device=dev)
+        Source(cfg.opticalBand, cfg.magnitude) * tel
+        atm = Atmosphere(tel, cfg.r0, cfg.L0, speeds, frac, dirs, [0.0] * 4, rng="philox", seed=5, canvas_slack=6)
+        atm.initializeAtmosphere(tel)
+        return atm
+    a, b = build(), build()
+    b._update_layers = lambda: [b._update_layer(i) for i in range(b.nLayer)]
+    launches = []
+    for k in range(25):
+        l0 = _lib.launch_count()
+        a.update()
+        l1 = _lib.launch_count()
+        b.update()
+        launches.append((l1 - l0, _lib.launch_count() - l1))
+        assert torch.equal(a.OPD_no_pupil, b.OPD_no_pupil), k
+    for i in range(4):
+        assert torch.equal(a._layers[i].mapShift, b._layers[i].mapShift)
+        assert torch.equal(a._ext[i], b._ext[i])
+    assert sum(x for x, _ in launches) < sum(y for _, y in launches)      # fewer launches when grouped
 
 
 @pytest.mark.parametrize("kernel", ["lagrange018", "catmull_rom"])
