@@ -228,20 +228,19 @@ class OOPAO:
         self.SR[-1] = strehl
         return obs.clone(), reward.clone(), strehl, done, {"strehl": strehl}
 
-    def _step_views(self, i, action):
-        """The step itself; returns views of the internal output buffers (overwritten by the next step)."""
+    def _step_views(self, i, action, action_ready=None, after_observe=None):
+        """The step itself; returns views of the internal output buffers (overwritten by the next step).
+
+        The observation of frame i depends on the slopes only, not on the action applied in this call (one frame of
+        DM lag), so it is produced BEFORE the command update: a host-facing caller can start copying it out
+        (`after_observe(obs, reward, strehl)` is called at that point of the stream) while the command update and the
+        next DM surface are still being computed, and can upload the action on another stream (`action_ready`: CUDA
+        event the command update waits for) while the atmosphere and the WFS run."""
         lib, st, B = _lib.load(), _lib.stream_ptr(self.device), self.n_envs
-        action = self._action_tensor(action)                               # :479 (img_to_vec * 1e-6 is in the kernel)
         self.atm.update()                                                  # :482 -> tel.OPD = atm.OPD (lazy)
         dm_surface = self.dm._opd[self.dm._slot]                           # surface commanded at the previous step
         self.tel._set_lazy(self.atm._opd, dm_surface)                      # :488 tel*dm
         self.wfs._measure_terms(self.atm._opd, dm_surface, self.env_offset)  # :488 *wfs  (+ stats for :484,502,506)
-        coefs = self._coefs_buf[self._coefs_slot]                         # zero-padded tails, never written
-        self._coefs_slot ^= 1
-        _lib.check(lib.aoenv_command_update(_lib.ptr(action), _lib.ptr(self._act_idx), B, self.dm.nValidAct,
-                                            self.nActuator ** 2, ctypes.c_float(self.leak), _lib.ptr(coefs), _lib.ptr(self._dm_prev),
-                                            coefs.stride(0), st), "command_update")          # :492-493
-        self.dm._set_coefs_batch(coefs)                                    # coefs setter side effect: next surface
         self._observe(True)                                                # :496-506
         if self.total is not None and i is not None and 0 <= i < self._nLoop:
             self.total[i] = self._total_now
@@ -249,6 +248,17 @@ class OOPAO:
         strehl = self._sq(self._strehl)
         if self.psf_reward is not None:
             strehl = self.psf_strehl(*self.psf_reward)
+        if after_observe is not None:
+            after_observe(self._sq(self._obs), self._sq(self._reward), strehl)
+        if action_ready is not None:
+            torch.cuda.current_stream(self.device).wait_event(action_ready)
+        action = self._action_tensor(action)                               # :479 (img_to_vec * 1e-6 is in the kernel)
+        coefs = self._coefs_buf[self._coefs_slot]                         # zero-padded tails, never written
+        self._coefs_slot ^= 1
+        _lib.check(lib.aoenv_command_update(_lib.ptr(action), _lib.ptr(self._act_idx), B, self.dm.nValidAct,
+                                            self.nActuator ** 2, ctypes.c_float(self.leak), _lib.ptr(coefs), _lib.ptr(self._dm_prev),
+                                            coefs.stride(0), st), "command_update")          # :492-493
+        self.dm._set_coefs_batch(coefs)                                    # coefs setter side effect: next surface
         self.SR.append(strehl if self.psf_reward is not None else strehl.clone())
         self.wfsSignal = self.wfs.signal
         return self._sq(self._obs), self._sq(self._reward), strehl, False, {"strehl": strehl}

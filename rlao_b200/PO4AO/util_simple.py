@@ -49,38 +49,86 @@ class TorchWrapper(_Wrapper):
         self.host_io = host_io
         self._pinned = {}
         self._flip = {}
+        self._copy_stream = None
+        self._act_dev = None
+        self._act_slot = 0
+        self._out_ready = None
 
-    def _to_host(self, *tensors):
-        """Asynchronous device->pinned-host copies of the step results, one stream synchronisation.  Two sets of
-        pinned buffers alternate, so the tensors handed out at step t stay valid until step t+2 (callers that
-        keep observations longer — e.g. a replay buffer — copy them, as they do with the reference's arrays)."""
+    def _host_buffers(self, tensors):
+        """Two sets of pinned buffers alternate, so the tensors handed out at step t stay valid until step t+2
+        (callers that keep observations longer — e.g. a replay buffer — copy them, as they do with the reference's
+        arrays)."""
         key = tuple((tuple(t.shape), t.dtype) for t in tensors)
         if key not in self._pinned:
             self._pinned[key] = [[torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors] for _ in range(2)]
             self._flip[key] = 0
         self._flip[key] ^= 1
-        bufs = self._pinned[key][self._flip[key]]
+        return self._pinned[key][self._flip[key]]
+
+    def _to_host(self, *tensors):
+        """Asynchronous device->pinned-host copies on the current stream, one stream synchronisation."""
+        bufs = self._host_buffers(tensors)
         for p_, t in zip(bufs, tensors):
             p_.copy_(t, non_blocking=True)
         torch.cuda.current_stream(self._env.device).synchronize()
         return bufs
 
+    def _step_pipelined(self, i, action):
+        """Host tensors in / out with the copies off the critical path: the action goes up on a copy stream while
+        the atmosphere and the WFS of this frame run (the command update waits for it), and the observation comes down
+        on the copy stream while the command update and the next DM surface are computed."""
+        env, dev = self._env, self._env.device
+        main = torch.cuda.current_stream(dev)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        a = torch.as_tensor(action)
+        ready = None
+        if a.device.type == "cpu":
+            a = a.to(torch.float32)
+            if self._act_dev is None or self._act_dev[0].shape != a.shape:
+                self._act_dev = [torch.empty(a.shape, dtype=torch.float32, device=dev) for _ in range(2)]
+            self._act_slot ^= 1
+            a_dev = self._act_dev[self._act_slot]          # the other buffer may still be read by the last command update
+            with torch.cuda.stream(self._copy_stream):
+                a_dev.copy_(a, non_blocking=True)
+                ready = self._copy_stream.record_event()
+            a = a_dev
+        out = {}
+
+        def after_observe(obs, reward, strehl):
+            seen = main.record_event()
+            self._copy_stream.wait_event(seen)
+            tensors = (obs, reward, strehl)
+            bufs = self._host_buffers(tensors)
+            with torch.cuda.stream(self._copy_stream):
+                for p_, t in zip(bufs, tensors):
+                    p_.copy_(t, non_blocking=True)
+                out["ready"] = self._copy_stream.record_event()
+            out["bufs"], out["keep"] = bufs, tensors
+
+        env._step_views(i, a, action_ready=ready, after_observe=after_observe)
+        out["ready"].synchronize()
+        return out["bufs"]
+
     def step(self, i, action):
         dev = self._env.device
-        a = torch.as_tensor(action)
-        if a.device != dev:
-            a = a.to(dev, dtype=torch.float32, non_blocking=True)
         if not self.host_io:
+            a = torch.as_tensor(action)
+            if a.device != dev:
+                a = a.to(dev, dtype=torch.float32, non_blocking=True)
             obs, reward, strehl, done, info = self._env.step(i, a)
             return obs, reward, strehl, done, [(k, v) for k, v in info.items()]
-        # the bare env can hand out views of its output buffers (they are copied to the host right away); an env
-        # wrapped in TimeDelayEnv goes through its own step()
-        fn = self._env._step_views if "_step_views" in type(self._env).__dict__ else self._env.step
-        obs, reward, strehl, done, info = fn(i, a)
-        obs_h, reward_h, strehl_h = self._to_host(obs, reward, strehl)
+        if "_step_views" in type(self._env).__dict__:
+            obs_h, reward_h, strehl_h = self._step_pipelined(i, action)
+        else:                                           # e.g. an env wrapped in TimeDelayEnv goes through its own step()
+            a = torch.as_tensor(action)
+            if a.device != dev:
+                a = a.to(dev, dtype=torch.float32, non_blocking=True)
+            obs, reward, strehl, done, info = self._env.step(i, a)
+            obs_h, reward_h, strehl_h = self._to_host(obs, reward, strehl)
         if self._env.n_envs == 1:
             reward_h, strehl_h = float(reward_h), float(strehl_h)
-        return obs_h, reward_h, strehl_h, done, [("strehl", torch.as_tensor(strehl_h, dtype=torch.float32))]
+        return obs_h, reward_h, strehl_h, False, [("strehl", torch.as_tensor(strehl_h, dtype=torch.float32))]
 
     def reset_soft(self):
         obs = self._env.reset_soft()
