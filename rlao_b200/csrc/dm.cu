@@ -64,7 +64,7 @@ dm_separable_kernel(const float* __restrict__ coefs, int ldc, const int32_t* __r
 // wyp[k][0..1][0..W).  Fixed trip counts -> fully unrolled, every load independent; each thread produces a 2 x 4
 // block of the surface, so one 128-bit shared-memory load of T feeds 8 FMAs.
 template <int W>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 dm_separable_banded_kernel(const float* __restrict__ coefs, int ldc, const int32_t* __restrict__ act_pos, int nA, int nAct,
                            const float* __restrict__ wx, const int32_t* __restrict__ j0x, const float* __restrict__ wyp,
                            const int32_t* __restrict__ i0y, int R, int xw, float* __restrict__ opd) {

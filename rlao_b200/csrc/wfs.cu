@@ -191,7 +191,9 @@ shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ op
   const bool lit = active && valid[k] != 0;
   const float phase_turns = phase_scale * 0.15915494309189535f;      // radians -> turns
 
-  float er[n][n], ei[n][n];   // field E[a][b] = tile^T (ShackHartmann.py:341-345 tiles phase.T)
+  // field E[a][b] = tile^T (ShackHartmann.py:341-345 tiles phase.T), kept as pairs along b:
+  // er2[a][k] = (Re E[a][2k], Re E[a][2k+1]) so that the first DFT pass runs on packed FP32 (FFMA2)
+  float2 er2[n][n / 2], ei2[n][n / 2];
   // Pupil statistics for std(OPD) / var(phase): variance is shift invariant, so each thread accumulates its n*n
   // pixels in float32 relative to the value at the pupil centre (removes the piston that would otherwise dominate
   // sum x^2), and only the per-thread partial sums are promoted to float64 for the reduction.
@@ -216,27 +218,23 @@ shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ op
         f0 += da; f1 = fmaf(da, da, f1); f2 += dt; f3 = fmaf(dt, dt, f3);
         // phase / 2pi reduced to [-1/2, 1/2] exactly, then the SFU sine/cosine (abs. error ~4e-7 on [-pi, pi])
         const float turns = t * pu * phase_turns;
-        const float ang = (turns - rintf(turns)) * 6.283185307179586f;
+        // nearest integer by the 1.5 * 2^23 trick (two FADDs; rintf would go through the transcendental pipe, which the
+        // sine and cosine already load): exact for |turns| < 2^22
+        const float ang = (turns - ((turns + 12582912.0f) - 12582912.0f)) * 6.283185307179586f;
         const float sn = __sinf(ang), cs = __cosf(ang);
         const float am = lit ? __ldg(amp + tile + o) : 0.f;
-        er[aa][bb] = am * cs;
-        ei[aa][bb] = am * sn;
+        if ((bb & 1) == 0) { er2[aa][bb >> 1].x = am * cs; ei2[aa][bb >> 1].x = am * sn; }
+        else { er2[aa][bb >> 1].y = am * cs; ei2[aa][bb >> 1].y = am * sn; }
       }
     }
   }
   double s0 = (double)f0, s1 = (double)f1, s2 = (double)f2, s3 = (double)f3;
 
-  if (stats != nullptr) {
+  if (stats != nullptr) {       // one atomic per warp and statistic: no block barrier, warps drift freely between phases
     s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
-    __shared__ double sh[4][4];
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (l == 0) { sh[w][0] = s0; sh[w][1] = s1; sh[w][2] = s2; sh[w][3] = s3; }
-    __syncthreads();
-    if (threadIdx.x < 4) {
-      double t = 0.0;
-      const int nw = blockDim.x >> 5;
-      for (int q = 0; q < nw; ++q) t += sh[q][threadIdx.x];
-      atomicAdd(&stats[(size_t)b * 4 + threadIdx.x], t);
+    if ((threadIdx.x & 31) == 0) {
+      double* __restrict__ st = stats + (size_t)b * 4;
+      atomicAdd(st, s0); atomicAdd(st + 1, s1); atomicAdd(st + 2, s2); atomicAdd(st + 3, s3);
     }
   }
 
@@ -248,71 +246,68 @@ shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ op
     // symmetry), so output rows u and u + n share their even-/odd-class partial sums P, Q:  Y_u = P + Q,
     // Y_{u+n} = P - Q, and likewise for the columns.  Binned row pp collects u = 2pp, 2pp+1; row pp + n/2 collects
     // u + n.
+    // Both passes run on packed pairs: pass 1 on pairs of columns b (twiddle = broadcast scalar from the constant
+    // bank), pass 2 on the pair (row u, row u + n), which share their twiddles (broadcast immediates).  Each
+    // FFMA2 / FADD2 / FMUL2 is two IEEE FP32 operations in one issue slot, in the same order as the scalar formulation.
     constexpr int h = n / 2;
 #pragma unroll 1
     for (int pp = 0; pp < h; ++pp) {
-      float acc_lo[n], acc_hi[n];
+      float2 acc[n];                         // acc[q] = (binned row pp, binned row pp + n/2) at binned column q
 #pragma unroll
-      for (int q = 0; q < n; ++q) { acc_lo[q] = 0.f; acc_hi[q] = 0.f; }
+      for (int q = 0; q < n; ++q) acc[q] = make_float2(0.f, 0.f);
       if (lit) {
 #pragma unroll
         for (int du = 0; du < 2; ++du) {
           const int u = 2 * pp + du;
-          float pr[n], pi[n], qr[n], qi[n];
+          float2 pr[h], pi[h], qr[h], qi[h];
 #pragma unroll
-          for (int bb = 0; bb < n; ++bb) { pr[bb] = 0.f; pi[bb] = 0.f; qr[bb] = 0.f; qi[bb] = 0.f; }
+          for (int k = 0; k < h; ++k) { pr[k] = pi[k] = qr[k] = qi[k] = make_float2(0.f, 0.f); }
 #pragma unroll
           for (int aa = 0; aa < n; ++aa) {
             const float2 g = c_tw[u * n + aa];
+            const float2 gx = dup2(g.x), gy = dup2(g.y), ngy = dup2(-g.y);
             if (((aa + h) & 1) == 0) {
 #pragma unroll
-              for (int bb = 0; bb < n; ++bb) {
-                pr[bb] = fmaf(g.x, er[aa][bb], fmaf(-g.y, ei[aa][bb], pr[bb]));
-                pi[bb] = fmaf(g.x, ei[aa][bb], fmaf(g.y, er[aa][bb], pi[bb]));
+              for (int k = 0; k < h; ++k) {
+                pr[k] = fma2(gx, er2[aa][k], fma2(ngy, ei2[aa][k], pr[k]));
+                pi[k] = fma2(gx, ei2[aa][k], fma2(gy, er2[aa][k], pi[k]));
               }
             } else {
 #pragma unroll
-              for (int bb = 0; bb < n; ++bb) {
-                qr[bb] = fmaf(g.x, er[aa][bb], fmaf(-g.y, ei[aa][bb], qr[bb]));
-                qi[bb] = fmaf(g.x, ei[aa][bb], fmaf(g.y, er[aa][bb], qi[bb]));
+              for (int k = 0; k < h; ++k) {
+                qr[k] = fma2(gx, er2[aa][k], fma2(ngy, ei2[aa][k], qr[k]));
+                qi[k] = fma2(gx, ei2[aa][k], fma2(gy, er2[aa][k], qi[k]));
               }
             }
           }
+          // Y[b] = (row u: P + Q, row u + n: P - Q)
+          float2 yr[n], yi[n];
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {       // half 0: row u (Y = P + Q); half 1: row u + n (Y = P - Q)
-            float yr[n], yi[n];
+          for (int bb = 0; bb < n; ++bb) {
+            const float p_r = (bb & 1) ? pr[bb >> 1].y : pr[bb >> 1].x, q_r = (bb & 1) ? qr[bb >> 1].y : qr[bb >> 1].x;
+            const float p_i = (bb & 1) ? pi[bb >> 1].y : pi[bb >> 1].x, q_i = (bb & 1) ? qi[bb >> 1].y : qi[bb >> 1].x;
+            yr[bb] = make_float2(p_r + q_r, p_r - q_r);
+            yi[bb] = make_float2(p_i + q_i, p_i - q_i);
+          }
+#pragma unroll
+          for (int v = 0; v < n; ++v) {
+            float2 er_ = make_float2(0.f, 0.f), ei_ = er_, or_ = er_, oi_ = er_;
 #pragma unroll
             for (int bb = 0; bb < n; ++bb) {
-              yr[bb] = half == 0 ? pr[bb] + qr[bb] : pr[bb] - qr[bb];
-              yi[bb] = half == 0 ? pi[bb] + qi[bb] : pi[bb] - qi[bb];
-            }
-#pragma unroll
-            for (int v = 0; v < n; ++v) {
-              float er_ = 0.f, ei_ = 0.f, or_ = 0.f, oi_ = 0.f;
-#pragma unroll
-              for (int bb = 0; bb < n; ++bb) {
-                // v, bb are compile-time after unrolling: literal twiddles -> immediate-operand FFMAs
-                const float2 g = make_float2(WfsTw<n>::re(v * n + bb), WfsTw<n>::im(v * n + bb));
-                if (((bb + h) & 1) == 0) {
-                  er_ = fmaf(yr[bb], g.x, fmaf(-yi[bb], g.y, er_));
-                  ei_ = fmaf(yr[bb], g.y, fmaf(yi[bb], g.x, ei_));
-                } else {
-                  or_ = fmaf(yr[bb], g.x, fmaf(-yi[bb], g.y, or_));
-                  oi_ = fmaf(yr[bb], g.y, fmaf(yi[bb], g.x, oi_));
-                }
-              }
-              const float f0r = er_ + or_, f0i = ei_ + oi_;     // F[row][v]
-              const float f1r = er_ - or_, f1i = ei_ - oi_;     // F[row][v + n]
-              const float i0 = fmaf(f0r, f0r, f0i * f0i);
-              const float i1 = fmaf(f1r, f1r, f1i * f1i);
-              if (half == 0) {
-                acc_lo[v >> 1] += i0;
-                acc_lo[(v >> 1) + h] += i1;
+              // v, bb are compile-time after unrolling: literal twiddles -> broadcast-immediate FFMA2s
+              const float gx = WfsTw<n>::re(v * n + bb), gy = WfsTw<n>::im(v * n + bb);
+              if (((bb + h) & 1) == 0) {
+                er_ = fma2(yr[bb], dup2(gx), fma2(yi[bb], dup2(-gy), er_));
+                ei_ = fma2(yr[bb], dup2(gy), fma2(yi[bb], dup2(gx), ei_));
               } else {
-                acc_hi[v >> 1] += i0;
-                acc_hi[(v >> 1) + h] += i1;
+                or_ = fma2(yr[bb], dup2(gx), fma2(yi[bb], dup2(-gy), or_));
+                oi_ = fma2(yr[bb], dup2(gy), fma2(yi[bb], dup2(gx), oi_));
               }
             }
+            const float2 f0r = add2(er_, or_), f0i = add2(ei_, oi_);     // F[row][v]
+            const float2 f1r = sub2(er_, or_), f1i = sub2(ei_, oi_);     // F[row][v + n]
+            acc[v >> 1] = add2(acc[v >> 1], fma2(f0r, f0r, mul2(f0i, f0i)));
+            acc[(v >> 1) + h] = add2(acc[(v >> 1) + h], fma2(f1r, f1r, mul2(f1i, f1i)));
           }
         }
       }
@@ -321,7 +316,7 @@ shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ op
         const int p = pp + r2 * h;
 #pragma unroll
         for (int q = 0; q < n; ++q) {
-          const float val = (r2 == 0 ? acc_lo[q] : acc_hi[q]) * norm;
+          const float val = (r2 == 0 ? acc[q].x : acc[q].y) * norm;
           fout[(size_t)p * R + q] = val;
           if (lit) vmax = fmaxf(vmax, val);
         }
