@@ -116,13 +116,16 @@ dm_separable_banded_kernel(const float* __restrict__ coefs, int ldc, const int32
       w0[4 * t] = a.x; w0[4 * t + 1] = a.y; w0[4 * t + 2] = a.z; w0[4 * t + 3] = a.w;
       w1[4 * t] = c.x; w1[4 * t + 1] = c.y; w1[4 * t + 2] = c.z; w1[4 * t + 3] = c.w;
     }
-    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+    // packed FP32: each FFMA2 updates two neighbouring pixels with the (broadcast) row weight
+    float2 a0 = make_float2(0.f, 0.f), b0 = a0, a1 = a0, b1 = a0;
 #pragma unroll
     for (int t = 0; t < W; ++t) {
       const float4 v = *reinterpret_cast<const float4*>(&sT[min(i0 + t, nAct - 1) * xw + 4 * q]);
-      r0.x = fmaf(w0[t], v.x, r0.x); r0.y = fmaf(w0[t], v.y, r0.y); r0.z = fmaf(w0[t], v.z, r0.z); r0.w = fmaf(w0[t], v.w, r0.w);
-      r1.x = fmaf(w1[t], v.x, r1.x); r1.y = fmaf(w1[t], v.y, r1.y); r1.z = fmaf(w1[t], v.z, r1.z); r1.w = fmaf(w1[t], v.w, r1.w);
+      const float2 lo = make_float2(v.x, v.y), hi = make_float2(v.z, v.w);
+      a0 = fma2(dup2(w0[t]), lo, a0); b0 = fma2(dup2(w0[t]), hi, b0);
+      a1 = fma2(dup2(w1[t]), lo, a1); b1 = fma2(dup2(w1[t]), hi, b1);
     }
+    const float4 r0 = make_float4(a0.x, a0.y, b0.x, b0.y), r1 = make_float4(a1.x, a1.y, b1.x, b1.y);
     const int x = x0 + 4 * q;
     float* __restrict__ o0 = out + (size_t)(2 * k) * R + x;
     float* __restrict__ o1 = o0 + R;
