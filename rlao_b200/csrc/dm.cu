@@ -64,7 +64,7 @@ dm_separable_kernel(const float* __restrict__ coefs, int ldc, const int32_t* __r
 // wyp[k][0..1][0..W).  Fixed trip counts -> fully unrolled, every load independent; each thread produces a 2 x 4
 // block of the surface, so one 128-bit shared-memory load of T feeds 8 FMAs.
 template <int W>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
 dm_separable_banded_kernel(const float* __restrict__ coefs, int ldc, const int32_t* __restrict__ act_pos, int nA, int nAct,
                            const float* __restrict__ wx, const int32_t* __restrict__ j0x, const float* __restrict__ wyp,
                            const int32_t* __restrict__ i0y, int R, int xw, float* __restrict__ opd) {
@@ -72,8 +72,11 @@ dm_separable_banded_kernel(const float* __restrict__ coefs, int ldc, const int32
   extern __shared__ __align__(16) float sm[];
   float* sC = sm;
   float* sT = sm + ((nAct * nAct + 3) & ~3);
+  float* sW = sT + nAct * xw;                     // [R/2][2][W] row weights of stage 2
   const int b = blockIdx.y;
   for (int k = threadIdx.x; k < nAct * nAct; k += blockDim.x) sC[k] = 0.f;
+  for (int k = threadIdx.x; k < (R >> 1) * 2 * W / 4; k += blockDim.x)
+    reinterpret_cast<float4*>(sW)[k] = __ldg(reinterpret_cast<const float4*>(wyp) + k);
   __syncthreads();
   for (int k = threadIdx.x; k < nA; k += blockDim.x) sC[__ldg(&act_pos[k])] = __ldg(&coefs[(size_t)b * ldc + k]);
   __syncthreads();
@@ -102,40 +105,51 @@ dm_separable_banded_kernel(const float* __restrict__ coefs, int ldc, const int32
     }
   }
   __syncthreads();
-  // stage 2
+  // stage 2: thread (q, chunk) owns four neighbouring columns and walks down a chunk of row pairs.  The W rows of T its
+  // band touches stay in registers and are re-read from shared memory only when the band start moves (once per actuator
+  // pitch), not once per output pair.  Lanes of a warp share k, so the weight loads are warp-uniform.  Packed FP32: each FFMA2 updates two neighbouring pixels with the (broadcast) row weight.
   const int nq = xw >> 2, npair = R >> 1;
+  const int chunks = max(1, (int)blockDim.x / nq);
+  const int per = (npair + chunks - 1) / chunks;
   float* __restrict__ out = opd + (size_t)b * R * R;
-  for (int idx = threadIdx.x; idx < npair * nq; idx += blockDim.x) {
-    const int k = idx / nq, q = idx - k * nq;
-    const int i0 = __ldg(&i0y[k]);
-    float w0[W], w1[W];
+  for (int item = threadIdx.x; item < nq * chunks; item += blockDim.x) {
+    const int ch = item / nq, q = item - ch * nq;
+    const int k_end = min(npair, (ch + 1) * per);
+    float4 win[W];
+    int base = -(1 << 20);
+    for (int k = ch * per; k < k_end; ++k) {
+      const int i0 = __ldg(&i0y[k]);
+      if (i0 != base) {                     // the band start moves once per actuator pitch (every few row pairs)
 #pragma unroll
-    for (int t = 0; t < W / 4; ++t) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(wyp + (size_t)k * 2 * W) + t);
-      const float4 c = __ldg(reinterpret_cast<const float4*>(wyp + (size_t)k * 2 * W + W) + t);
-      w0[4 * t] = a.x; w0[4 * t + 1] = a.y; w0[4 * t + 2] = a.z; w0[4 * t + 3] = a.w;
-      w1[4 * t] = c.x; w1[4 * t + 1] = c.y; w1[4 * t + 2] = c.z; w1[4 * t + 3] = c.w;
-    }
-    // packed FP32: each FFMA2 updates two neighbouring pixels with the (broadcast) row weight
-    float2 a0 = make_float2(0.f, 0.f), b0 = a0, a1 = a0, b1 = a0;
+        for (int t = 0; t < W; ++t) win[t] = *reinterpret_cast<const float4*>(&sT[min(i0 + t, nAct - 1) * xw + 4 * q]);
+        base = i0;
+      }
+      float2 a0 = make_float2(0.f, 0.f), b0 = a0, a1 = a0, b1 = a0;
 #pragma unroll
-    for (int t = 0; t < W; ++t) {
-      const float4 v = *reinterpret_cast<const float4*>(&sT[min(i0 + t, nAct - 1) * xw + 4 * q]);
-      const float2 lo = make_float2(v.x, v.y), hi = make_float2(v.z, v.w);
-      a0 = fma2(dup2(w0[t]), lo, a0); b0 = fma2(dup2(w0[t]), hi, b0);
-      a1 = fma2(dup2(w1[t]), lo, a1); b1 = fma2(dup2(w1[t]), hi, b1);
-    }
-    const float4 r0 = make_float4(a0.x, a0.y, b0.x, b0.y), r1 = make_float4(a1.x, a1.y, b1.x, b1.y);
-    const int x = x0 + 4 * q;
-    float* __restrict__ o0 = out + (size_t)(2 * k) * R + x;
-    float* __restrict__ o1 = o0 + R;
-    if (x + 3 < R && (R & 3) == 0) {
-      *reinterpret_cast<float4*>(o0) = r0;
-      *reinterpret_cast<float4*>(o1) = r1;
-    } else {
-      const float a0[4] = {r0.x, r0.y, r0.z, r0.w}, a1[4] = {r1.x, r1.y, r1.z, r1.w};
-      for (int c = 0; c < 4; ++c)
-        if (x + c < R) { o0[c] = a0[c]; o1[c] = a1[c]; }
+      for (int t4 = 0; t4 < W / 4; ++t4) {
+        const float4 u0 = reinterpret_cast<const float4*>(sW + (size_t)k * 2 * W)[t4];
+        const float4 u1 = reinterpret_cast<const float4*>(sW + (size_t)k * 2 * W + W)[t4];
+        const float w0[4] = {u0.x, u0.y, u0.z, u0.w}, w1[4] = {u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 v = win[4 * t4 + j];
+          const float2 lo = make_float2(v.x, v.y), hi = make_float2(v.z, v.w);
+          a0 = fma2(dup2(w0[j]), lo, a0); b0 = fma2(dup2(w0[j]), hi, b0);
+          a1 = fma2(dup2(w1[j]), lo, a1); b1 = fma2(dup2(w1[j]), hi, b1);
+        }
+      }
+      const float4 r0 = make_float4(a0.x, a0.y, b0.x, b0.y), r1 = make_float4(a1.x, a1.y, b1.x, b1.y);
+      const int x = x0 + 4 * q;
+      float* __restrict__ o0 = out + (size_t)(2 * k) * R + x;
+      float* __restrict__ o1 = o0 + R;
+      if (x + 3 < R && (R & 3) == 0) {
+        *reinterpret_cast<float4*>(o0) = r0;
+        *reinterpret_cast<float4*>(o1) = r1;
+      } else {
+        const float c0[4] = {r0.x, r0.y, r0.z, r0.w}, c1[4] = {r1.x, r1.y, r1.z, r1.w};
+        for (int c = 0; c < 4; ++c)
+          if (x + c < R) { o0[c] = c0[c]; o1[c] = c1[c]; }
+      }
     }
   }
 }
@@ -154,7 +168,7 @@ extern "C" int aoenv_dm_surface_separable(const float* coefs, int ldc, const int
   int parts = 1;
   auto smem_for = [&](int p) {
     const int xw = (((R + p - 1) / p) + 3) / 4 * 4;
-    return (size_t)(((nAct * nAct + 3) & ~3) + nAct * xw) * sizeof(float);
+    return (size_t)(((nAct * nAct + 3) & ~3) + nAct * xw + (banded ? (R / 2) * 2 * W : 0)) * sizeof(float);
   };
   while (smem_for(parts) > 96 * 1024 || (B * parts < 2 * kNumSMs && parts < 8)) ++parts;
   const int xw = (((R + parts - 1) / parts) + 3) / 4 * 4;
