@@ -174,14 +174,12 @@ extern "C" int aoenv_dm_surface_separable(const float* coefs, int ldc, const int
   const int xw = (((R + parts - 1) / parts) + 3) / 4 * 4;
   const size_t smem = smem_for(parts);
   AOENV_CHECK_ARG(smem <= 200 * 1024, "dm_surface_separable: %d actuators across do not fit in shared memory", nAct);
-  static size_t attr[3] = {0, 0, 0};
   const int which = !banded ? 0 : (W == 12 ? 1 : 2);
-  if (smem > 48 * 1024 && smem > attr[which]) {
+  if (smem > 48 * 1024) {       // per device and size: cheap enough to repeat at every launch
     cudaError_t e = which == 0 ? cudaFuncSetAttribute(dm_separable_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                   : which == 1 ? cudaFuncSetAttribute(dm_separable_banded_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                                : cudaFuncSetAttribute(dm_separable_banded_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(-3, "dm_surface_separable smem attribute: %s", cudaGetErrorString(e));
-    attr[which] = smem;
   }
   cudaStream_t s = (cudaStream_t)stream;
   const dim3 grid(parts, B);

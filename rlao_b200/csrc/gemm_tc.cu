@@ -326,11 +326,14 @@ static int launch(const __nv_bfloat16* Xs, const __nv_bfloat16* Ws, int ldk, flo
     rc = make_map(&maps.x[p], Xs + (size_t)p * MX * ldk, MX, K, ldk, BLOCK_N);
     if (rc) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  // function attributes are per device: remember which devices have been configured (one process may drive several)
+  static std::atomic<uint64_t> configured{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 64 || !((configured.load(std::memory_order_relaxed) >> dev) & 1)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<kParts, BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return fail(-3, "gemm_tc smem attribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    if (dev < 64) configured.fetch_or(1ull << dev, std::memory_order_relaxed);
   }
   const int num_mn = ((NW + BLOCK_M - 1) / BLOCK_M) * ((MX + BLOCK_N - 1) / BLOCK_N);
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
