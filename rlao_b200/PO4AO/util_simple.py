@@ -118,7 +118,10 @@ class TorchWrapper(_Wrapper):
                 a = a.to(dev, dtype=torch.float32, non_blocking=True)
             obs, reward, strehl, done, info = self._env.step(i, a)
             return obs, reward, strehl, done, [(k, v) for k, v in info.items()]
-        if "_step_views" in type(self._env).__dict__:
+        # small batches are launch-bound: the extra stream / event traffic of the pipelined path costs more than the
+        # copies it hides
+        big = self._env.n_envs * self._env.nActuator ** 2 >= 65536
+        if big and "_step_views" in type(self._env).__dict__:
             obs_h, reward_h, strehl_h = self._step_pipelined(i, action)
         else:                                           # e.g. an env wrapped in TimeDelayEnv goes through its own step()
             a = torch.as_tensor(action)
