@@ -106,3 +106,76 @@ def test_canvas_compaction_is_transparent(fake):
     assert rel_err(oa.numpy(), oo) < 2e-3
     for ly, lo in zip(env_a.atm._layers, orc.atm.layers):
         assert rel_err(ly.mapShift.numpy(), lo.map) < 1e-5
+
+
+def test_gymnasium_adapter_on_cpu(fake):
+    """OOPAOEnv_VPG.py:117-137,553-611 signature: observation stack newest-first, delay FIFO, truncation."""
+    from rlao_b200.OOPAOEnv.gymnasium_api import GymnasiumSH
+    cfg = CONFIGS["tiny"]()
+    nA = cfg.nSubap + 1
+    g = GymnasiumSH(build_env(cfg, n_envs=1, rng="philox"), n_history=3, delay=2, episode_length=3)
+    assert g.observation_space.shape == (3, nA, nA)
+    obs, info = g.reset(seed=3)
+    assert obs.shape == (3, nA, nA) and info == {} and float(obs[1:].abs().max()) == 0.0
+    first = obs[0].clone()
+    seen = []
+    for t in range(3):
+        obs, reward, terminated, truncated, info = g.step(0.3 * obs[0])
+        seen.append(obs[0].clone())
+        assert terminated is False and truncated is (t == 2)
+    assert torch.equal(obs[1], seen[1]) and torch.equal(obs[2], seen[0])
+    # with a two-frame FIFO the DM stays flat for the first two steps: coefs only receive zeros
+    assert float(g.env.dm_prev.abs().max()) > 0.0                       # third step applied the first action
+    obs2, _ = g.reset(seed=3)
+    assert torch.equal(obs2[0], first)
+
+
+def test_layers_extruded_in_rounds_use_the_grouped_entry_points(fake, monkeypatch):
+    """Philox mode with several layers: one gather_multi / ring_multi per round; injected innovations keep the
+    reference's layer-by-layer order through the single-layer entry points."""
+    cfg = CONFIGS["tiny"]()
+    cfg.windSpeed = [60.0, 45.0]                                        # > 1 px per step: several rounds per frame
+    calls = []
+    for name in ("aoenv_atm_gather", "aoenv_atm_gather_multi", "aoenv_atm_ring", "aoenv_atm_ring_multi"):
+        orig = getattr(fake, name)
+        monkeypatch.setattr(fake, name, (lambda o, n: lambda *a: (calls.append(n), o(*a))[1])(orig, name))
+    env = build_env(cfg, n_envs=2, rng="philox")
+    calls.clear()
+    for _ in range(4):
+        env.atm.update()
+    assert "aoenv_atm_gather_multi" in calls and "aoenv_atm_ring_multi" in calls
+    assert calls.count("aoenv_atm_gather_multi") == calls.count("aoenv_atm_ring_multi")
+    env_ref = build_env(cfg, n_envs=2, rng="reference")
+    before = sum(ly.events for ly in env_ref.atm._layers)
+    calls.clear()
+    for _ in range(4):
+        env_ref.atm.update()
+    assert "aoenv_atm_gather_multi" not in calls
+    assert calls.count("aoenv_atm_gather") == sum(ly.events for ly in env_ref.atm._layers) - before
+    assert torch.isfinite(env.atm.OPD_no_pupil).all()
+
+
+def test_po4ao_rollout_host_logic_on_cpu(fake):
+    """mbrl.run on the CPU stand-in: warm-up episode (integrator + noise) then a policy episode through the ring-buffer
+    inference path; replay rows are the consecutive frames of each environment."""
+    from rlao_b200.PO4AO import mbrl
+    from rlao_b200.PO4AO.conv_models_simple import ConvPolicy, EnsembleDynamics
+    from rlao_b200.PO4AO.util_simple import EfficientExperienceReplay, TorchWrapper
+    cfg = CONFIGS["tiny"]()
+    B, nH, max_ts = 2, 3, 6
+    env = TorchWrapper(build_env(cfg, n_envs=B, rng="philox"), host_io=False)
+    nA = env.nActuator
+    torch.manual_seed(0)
+    dynamics = EnsembleDynamics(env.xvalid, env.yvalid, nH, n_models=2)
+    policy = ConvPolicy(env.xvalid, env.yvalid, 0.05, env.F.float(), nH)
+    rp = EfficientExperienceReplay((nA, nA), (nA, nA), max_size=2 * max_ts * B, n_envs=B)
+    past_obs = past_act = obs = None
+    for ep in range(2):
+        sr, rsum, past_obs, past_act, obs, rewards, _ = mbrl.run(env, past_obs, past_act, obs, rp, policy, dynamics, nH, max_ts,
+                                                                 warmup_ts=1, sigma=0.02, episode=ep, iteration=ep)
+        assert rsum.shape == (B,) and rewards.shape == (max_ts, B) and np.isfinite(sr)
+    st, nx = rp.state().reshape(2, max_ts, B, nA, nA), rp.next_state().reshape(2, max_ts, B, nA, nA)
+    assert torch.equal(st[:, 1:], nx[:, :-1])
+    assert torch.equal(past_obs[:, -1], st[1, -1]) and torch.equal(past_act[:, -1], rp.action().reshape(2, max_ts, B, nA, nA)[1, -1])
+    loss = mbrl.train_dynamics(nH, max_ts, 4, dynamics, torch.optim.Adam(dynamics.parameters()), rp, dyn_iters=1, device="cpu")
+    assert np.isfinite(loss)
