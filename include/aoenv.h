@@ -141,6 +141,10 @@ typedef struct {
   uint64_t frame_counter;  /* advances once per call: independent draws per step                            */
 } aoenv_detector_t;
 
+/* Selects the implementation of the n = 6 frame kernel: 0 = term-by-term pruned DFT (default), 1 = factorised
+ * (radix 2 x Good-Thomas 2 x 3).  Same frame to float32 rounding; returns the previous setting. */
+int aoenv_set_wfs6_variant(int factorised);
+
 /* wfs_measure, diffractive branch up to the detector: per lenslet, the transposed n x n tile of
  * phase = (opd_a + opd_b) * pupil * phase_scale is zero-padded to 2n x 2n, multiplied by sqrt(flux) and the
  * half-pixel phasor, Fourier transformed, |.|^2 / (2n)^2, binned 2x2 -> n x n spot, written at tile (i, j) of

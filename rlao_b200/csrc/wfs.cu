@@ -3,6 +3,7 @@
 // 2n-point DFTs are done as two passes of constant-twiddle complex FMAs (only the n non-zero inputs are
 // visited), intensities are binned 2x2 on the fly and pushed through the detector chain before the single
 // store of the camera frame.
+#include <stdlib.h>
 #include <mutex>
 
 #include "common.cuh"
@@ -329,6 +330,186 @@ shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ op
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// n = 6 (the reference's 6 pixels per subaperture, N = 12): the same frame as shwfs_frame_kernel<6>, with the pruned
+// DFTs factorised instead of summed term by term.
+//   * the half-pixel phasor exp(-i pi 13 (a+3)/12) exp(-i pi 13 (b+3)/12) is folded into the angle of the field;
+//     the remaining kernel is W^{(a+3)u} = W^{3u} W^{au}, W = exp(-2 pi i / 12), and the unit factor W^{3u} (W^{3v}) does
+//     not change |F|^2, so each pass is a plain 12-point DFT of 6 inputs at indices 0..5;
+//   * u = 2k + r:  H[2k + r] = DFT6( x[a] W^{r a} )[k]  — two 6-point DFTs, the second on the twiddled sequence;
+//   * DFT6 = Good-Thomas 2 x 3 (no inner twiddles): s[a2] = z[2 a2] +- z[2 a2 + 3], then a 3-point DFT;
+//     output k = (3 k1 + 4 k2) mod 6.
+// Packed FP32 throughout: pass 1 carries (r = 0, r = 1) in the two lanes, pass 2 the row pair (2p, 2p + 1) — exactly
+// the four samples a binned pixel sums.  Rows are produced in two phases (k1 = 0: binned rows 0, 4, 2; k1 = 1: rows
+// 3, 1, 5) so that only half of the intermediate lives in registers; the field waits in shared memory, one column of
+// 72 floats per thread.  2.1 k FP32 pipe slots per lenslet for transform + intensities instead of 3.5 k.
+// ---------------------------------------------------------------------------------------------------------
+struct C2 { float2 r, i; };          // two complex numbers, lane-wise
+__device__ __forceinline__ C2 cadd(const C2& a, const C2& b) { return {add2(a.r, b.r), add2(a.i, b.i)}; }
+__device__ __forceinline__ C2 csub(const C2& a, const C2& b) { return {sub2(a.r, b.r), sub2(a.i, b.i)}; }
+// a * (wr + i wi), constants
+__device__ __forceinline__ C2 cmulc(const C2& a, float wr, float wi) {
+  return {fma2(a.r, dup2(wr), mul2(a.i, dup2(-wi))), fma2(a.r, dup2(wi), mul2(a.i, dup2(wr)))};
+}
+__device__ __forceinline__ void dft3(const C2& z0, const C2& z1, const C2& z2, C2& y0, C2& y1, C2& y2) {
+  constexpr float c = 0.8660254037844386f;
+  const C2 t = cadd(z1, z2), d = csub(z1, z2);
+  y0 = cadd(z0, t);
+  const C2 m = {fma2(dup2(-0.5f), t.r, z0.r), fma2(dup2(-0.5f), t.i, z0.i)};
+  y1 = {fma2(dup2(c), d.i, m.r), fma2(dup2(-c), d.r, m.i)};      // m - i c d
+  y2 = {fma2(dup2(-c), d.i, m.r), fma2(dup2(c), d.r, m.i)};      // m + i c d
+}
+// one half of DFT6 (k1 = 0: outputs k = 0, 4, 2; k1 = 1: outputs k = 3, 1, 5), inputs z[0..5]
+template <int K1>
+__device__ __forceinline__ void dft6_half(const C2 (&z)[6], C2& y0, C2& y1, C2& y2) {
+  const C2 s0 = K1 == 0 ? cadd(z[0], z[3]) : csub(z[0], z[3]);
+  const C2 s1 = K1 == 0 ? cadd(z[2], z[5]) : csub(z[2], z[5]);
+  const C2 s2 = K1 == 0 ? cadd(z[4], z[1]) : csub(z[4], z[1]);
+  dft3(s0, s1, s2, y0, y1, y2);
+}
+// z[a] * W^a, W = exp(-2 pi i / 12)
+__device__ __forceinline__ void twiddle6(const C2 (&z)[6], C2 (&w)[6]) {
+  constexpr float c = 0.8660254037844386f;
+  w[0] = z[0];
+  w[1] = cmulc(z[1], c, -0.5f);
+  w[2] = cmulc(z[2], 0.5f, -c);
+  w[3] = {z[3].i, mul2(z[3].r, dup2(-1.0f))};                    // * (-i)
+  w[4] = cmulc(z[4], -0.5f, -c);
+  w[5] = cmulc(z[5], -c, -0.5f);
+}
+__host__ __device__ constexpr int dft6_row(int k1, int k2) { return (3 * k1 + 4 * k2) % 6; }
+
+// pass 1 of one phase: Hp[k2][b] = (DFT6(x)[k], DFT6(x W^a)[k]) for k = dft6_row(K1, k2)
+template <int K1>
+__device__ __forceinline__ void wfs6_pass1(const float* __restrict__ sF, C2 (&Hp)[3][6]) {
+  constexpr float c = 0.8660254037844386f;
+#pragma unroll
+  for (int b = 0; b < 6; ++b) {
+    C2 z[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      const float xr = sF[(2 * (a * 6 + b)) * 128], xi = sF[(2 * (a * 6 + b) + 1) * 128];
+      float wr, wi;                                              // x * W^a
+      if (a == 0) { wr = xr; wi = xi; }
+      else if (a == 1) { wr = fmaf(xr, c, xi * 0.5f); wi = fmaf(xi, c, xr * -0.5f); }
+      else if (a == 2) { wr = fmaf(xr, 0.5f, xi * c); wi = fmaf(xi, 0.5f, xr * -c); }
+      else if (a == 3) { wr = xi; wi = -xr; }
+      else if (a == 4) { wr = fmaf(xr, -0.5f, xi * c); wi = fmaf(xi, -0.5f, xr * -c); }
+      else { wr = fmaf(xr, -c, xi * 0.5f); wi = fmaf(xi, -c, xr * -0.5f); }
+      z[a] = {make_float2(xr, wr), make_float2(xi, wi)};
+    }
+    dft6_half<K1>(z, Hp[0][b], Hp[1][b], Hp[2][b]);
+  }
+}
+
+// pass 2 of one phase + intensities + binning + store of three binned rows
+template <int K1>
+__device__ __forceinline__ void wfs6_pass2(const C2 (&Hp)[3][6], float norm, float* __restrict__ fout, int R, float& vmax) {
+#pragma unroll
+  for (int k2 = 0; k2 < 3; ++k2) {
+    const int p = dft6_row(K1, k2);                              // lanes = frame rows (2p, 2p + 1) before binning
+    C2 yw[6];
+    twiddle6(Hp[k2], yw);
+    float row[6];
+#pragma unroll
+    for (int q1 = 0; q1 < 2; ++q1) {
+      C2 e[3], o[3];
+      if (q1 == 0) { dft6_half<0>(Hp[k2], e[0], e[1], e[2]); dft6_half<0>(yw, o[0], o[1], o[2]); }
+      else { dft6_half<1>(Hp[k2], e[0], e[1], e[2]); dft6_half<1>(yw, o[0], o[1], o[2]); }
+#pragma unroll
+      for (int q2 = 0; q2 < 3; ++q2) {
+        const float2 i0 = fma2(e[q2].r, e[q2].r, mul2(e[q2].i, e[q2].i));       // v = 2q
+        const float2 i1 = fma2(o[q2].r, o[q2].r, mul2(o[q2].i, o[q2].i));       // v = 2q + 1
+        const float2 t = add2(i0, i1);
+        row[dft6_row(q1, q2)] = (t.x + t.y) * norm;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      fout[(size_t)p * R + q] = row[q];
+      vmax = fmaxf(vmax, row[q]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128, 3)
+shwfs_frame6_kernel(const float* __restrict__ opd_a, const float* __restrict__ opd_b, const float* __restrict__ pupil,
+                    const float* __restrict__ amp, const uint8_t* __restrict__ valid, int nS, float phase_scale,
+                    int track_max, int shared_max, float* __restrict__ frame, int32_t* __restrict__ envmax,
+                    double* __restrict__ stats) {
+  constexpr int n = 6, N = 12;
+  __shared__ float sF_all[2 * n * n * 128];      // field, element-major: thread t owns sF_all[e * 128 + t]
+  float* __restrict__ sF = sF_all + threadIdx.x;
+  const int R = nS * n;
+  const int b = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = k < nS * nS;
+  const int li = active ? k / nS : 0, lj = active ? k % nS : 0;
+  const bool lit = active && valid[k] != 0;
+  const float phase_turns = phase_scale * 0.15915494309189535f;      // radians -> turns
+  float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;                      // pupil statistics, see shwfs_frame_kernel
+  if (active) {
+    const size_t tile = (size_t)(li * n) * R + lj * n;
+    const float* __restrict__ pa = opd_a + (size_t)b * R * R + tile;
+    const float* __restrict__ pb = opd_b ? opd_b + (size_t)b * R * R + tile : nullptr;
+    const size_t centre = (size_t)b * R * R + (size_t)(R / 2) * R + R / 2;
+    const float ka = stats ? __ldg(opd_a + centre) : 0.f;
+    const float kt = stats ? (opd_b ? ka + __ldg(opd_b + centre) : ka) : 0.f;
+#pragma unroll
+    for (int bb = 0; bb < n; ++bb) {
+#pragma unroll
+      for (int aa = 0; aa < n; ++aa) {
+        const int o = bb * R + aa;
+        const float a = __ldg(pa + o);
+        const float t = pb ? a + __ldg(pb + o) : a;
+        const float pu = __ldg(pupil + tile + o);
+        const float in_pupil = pu > 0.f ? 1.f : 0.f;
+        const float da = (a - ka) * in_pupil, dt = (t - kt) * in_pupil;
+        f0 += da; f1 = fmaf(da, da, f1); f2 += dt; f3 = fmaf(dt, dt, f3);
+        if (lit) {
+          // phase / 2pi plus the half-pixel phasor of both axes, -13 (a + b + 6) / 24 turns (compile-time constant)
+          constexpr double kTurn = -13.0 / 24.0;
+          const double cst = kTurn * (double)(aa + bb + n);
+          const float cfrac = (float)(cst - (double)(long long)(cst - 0.5));      // reduced to [-0.5, 0.5]
+          const float turns = fmaf(t * pu, phase_turns, cfrac);
+          const float ang = (turns - ((turns + 12582912.0f) - 12582912.0f)) * 6.283185307179586f;
+          const float am = __ldg(amp + tile + o);
+          sF[(2 * (aa * n + bb)) * 128] = am * __cosf(ang);
+          sF[(2 * (aa * n + bb) + 1) * 128] = am * __sinf(ang);
+        }
+      }
+    }
+  }
+  if (stats != nullptr) {
+    double s0 = warp_sum((double)f0), s1 = warp_sum((double)f1), s2 = warp_sum((double)f2), s3 = warp_sum((double)f3);
+    if ((threadIdx.x & 31) == 0) {
+      double* __restrict__ st = stats + (size_t)b * 4;
+      atomicAdd(st, s0); atomicAdd(st + 1, s1); atomicAdd(st + 2, s2); atomicAdd(st + 3, s3);
+    }
+  }
+  float vmax = -INFINITY;
+  if (active) {
+    float* __restrict__ fout = frame + (size_t)b * R * R + (size_t)(li * n) * R + lj * n;
+    if (lit) {
+      const float norm = 1.0f / (float)(N * N);
+      C2 Hp[3][6];
+      wfs6_pass1<0>(sF, Hp);
+      wfs6_pass2<0>(Hp, norm, fout, R, vmax);
+      wfs6_pass1<1>(sF, Hp);
+      wfs6_pass2<1>(Hp, norm, fout, R, vmax);
+    } else {
+#pragma unroll
+      for (int p = 0; p < n; ++p)
+#pragma unroll
+        for (int q = 0; q < n; ++q) fout[(size_t)p * R + q] = 0.f;
+    }
+  }
+  if (track_max) {
+    vmax = warp_max(vmax);
+    if ((threadIdx.x & 31) == 0 && vmax > -INFINITY) atomicMax(&envmax[shared_max ? 0 : b], float_to_ordered(vmax));
+  }
+}
+
 // centroid + slopes: one thread per (valid lenslet, environment)
 __global__ void __launch_bounds__(128)
 shwfs_slopes_kernel(const float* __restrict__ frame, const int32_t* __restrict__ envmax, int shared_max,
@@ -481,7 +662,19 @@ __global__ void envmax_init_kernel(int32_t* __restrict__ envmax, int count) {
 
 using namespace aoenv;
 
+// n = 6 has two implementations of the same frame: the term-by-term transform (default: faster on B200, where the kernel
+// is bound by the FP32 pipe and dependency chains rather than by instruction count) and the factorised one
+// (shwfs_frame6_kernel).  aoenv_set_wfs6_variant / AOENV_WFS6=factorised selects the latter; the tests run both.
+static std::atomic<int> g_wfs6_factorised{[] {
+  const char* e = getenv("AOENV_WFS6");
+  return (e && e[0] == 'f') ? 1 : 0;
+}()};
+
 extern "C" {
+
+int aoenv_set_wfs6_variant(int factorised) {
+  return g_wfs6_factorised.exchange(factorised ? 1 : 0);
+}
 
 int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil, const float* amp,
                       const uint8_t* valid, int B, int nS, int n, float phase_scale, const aoenv_detector_t* det,
@@ -509,8 +702,15 @@ int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil
     break;
   switch (n) {
     AOENV_WFS_CASE(4)
-    AOENV_WFS_CASE(6)
     AOENV_WFS_CASE(8)
+    case 6:
+      if (g_wfs6_factorised.load(std::memory_order_relaxed))
+        shwfs_frame6_kernel<<<grid, 128, 0, s>>>(opd_a, opd_b, pupil, amp, valid, nS, phase_scale, det == nullptr, shared_max,
+                                                 frame, envmax, stats);
+      else
+        shwfs_frame_kernel<6><<<grid, 128, 0, s>>>(opd_a, opd_b, pupil, amp, valid, nS, phase_scale, det == nullptr, shared_max,
+                                                   frame, envmax, stats);
+      break;
   }
 #undef AOENV_WFS_CASE
   AOENV_LAUNCH_CHECK("shwfs_frame");

@@ -47,6 +47,9 @@ class FakeLib:
     def aoenv_last_error(self):
         return b""
 
+    def aoenv_set_wfs6_variant(self, factorised):
+        return 0
+
     def aoenv_launch_count(self):
         return self.launches
 

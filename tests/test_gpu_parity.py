@@ -241,6 +241,20 @@ def test_shack_hartmann_vs_oracle(dev, nS, n):
         assert rel_err(got_sig[e], want) < SLOPE_TOL, (e, "slopes")
     s2d = _np(wfs.signal_2D)
     assert rel_err(s2d[2], orc.signal_2D) < SLOPE_TOL
+    if n == 6:
+        # the factorised implementation of the n = 6 transform (radix 2 x Good-Thomas 2 x 3) gives the same frame
+        lib = _lib.load()
+        prev = lib.aoenv_set_wfs6_variant(1)
+        try:
+            tel * wfs
+            alt_sig, alt_frame = _np(wfs.signal), _np(wfs.cam.frame)
+        finally:
+            lib.aoenv_set_wfs6_variant(prev)
+        assert rel_err(alt_frame, got_frame) < 5e-6
+        assert rel_err(alt_sig, got_sig) < 2e-5
+        for e in range(3):
+            orc.measure(opd32[e] * pupil * 2 * np.pi / wl)
+            assert rel_err(alt_frame[e], orc.frame) < 2e-5, (e, "frame, factorised")
 
 
 def test_shack_hartmann_flat_wavefront_gives_zero_signal_at_full_size(dev):
