@@ -149,7 +149,7 @@ def test_sliding_window_canvas_vs_oracle(dev):
             pos = int(packed) & 0xffffffff
             r, c = pos // pitch - oy, pos % pitch - ox
             assert got[r, c] == got.reshape(-1)[want_pos]        # tracked extremum is the window's true extremum
-    assert any(c == 1 for c in atm._cur) or True
+    assert sum(ly.events for ly in atm._layers) > 8 * atm._S        # the canvases were re-centred many times
 
 
 def test_layers_extruded_together_equal_layers_extruded_one_by_one(dev):
