@@ -23,6 +23,15 @@ def cfg1():
                     nZernike=50, nLoop=64)
 
 
-CONFIGS = {"tiny": tiny, "tiny_noise": tiny_noise, "cfg1": cfg1}
-STEPS = {"tiny": 30, "tiny_noise": 12, "cfg1": 24}
+def cfg3():
+    """BASELINE.json configs[2], the benchmark configuration: 8 m, 40x40 SH, 41x41 DM, three layers (SURVEY.md section
+    8 d; one environment of the 8192)."""
+    return AOConfig(nSubap=40, windSpeed=[10.0, 12.0, 11.0], windDirection=[0.0, 72.0, 144.0],
+                    fractionalR0=[0.45 / 0.65, 0.1 / 0.65, 0.1 / 0.65], altitude=[0.0, 0.0, 0.0], nZernike=50, nLoop=64)
+
+
+CONFIGS = {"tiny": tiny, "tiny_noise": tiny_noise, "cfg1": cfg1, "cfg3": cfg3}
+STEPS = {"tiny": 30, "tiny_noise": 12, "cfg1": 24, "cfg3": 8}
+# fixtures of the large configuration keep float32 snapshots of the last step only (size)
+COMPACT = {"cfg3"}
 EPISODE_SEED = 17          # MAIN_CODE/integrator_oopao_razor.py:46

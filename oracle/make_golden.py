@@ -16,7 +16,7 @@ import numpy as np
 from numpy.random import RandomState
 
 from . import ref_harness as rh
-from .golden_configs import CONFIGS, STEPS, EPISODE_SEED
+from .golden_configs import COMPACT, CONFIGS, STEPS, EPISODE_SEED
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 DET_SEED = 1234
@@ -84,16 +84,20 @@ def generate(name):
         tr["obs"][i], tr["reward"][i], tr["strehl"][i] = obs, reward, strehl
         tr["signal"][i] = env.wfs.signal
         tr["coefs"][i] = env.dm.coefs
-        if i in (0, n // 2, n - 1):
-            snaps[f"atm_OPD_{i}"] = env.atm.OPD.copy()
-            snaps[f"tel_OPD_{i}"] = env.tel.OPD.copy()
-            snaps[f"frame_{i}"] = np.asarray(env.wfs.cam.frame).copy()
+        if i in ((n - 1,) if name in COMPACT else (0, n // 2, n - 1)):
+            ft = np.float32 if name in COMPACT else np.float64
+            snaps[f"atm_OPD_{i}"] = env.atm.OPD.astype(ft)
+            snaps[f"tel_OPD_{i}"] = env.tel.OPD.astype(ft)
+            snaps[f"frame_{i}"] = np.asarray(env.wfs.cam.frame).astype(ft)
     for k, v in tr.items():
         g["trace_" + k] = v
     g["trace_total"] = env.total[:n].copy()
     g["trace_residual"] = env.residual[:n].copy()
     g.update(snaps)
-    g["snap_steps"] = np.array([0, n // 2, n - 1])
+    g["snap_steps"] = np.array([n - 1] if name in COMPACT else [0, n // 2, n - 1])
+    if name in COMPACT:
+        for k in ("frame0", "trace_signal", "trace_coefs", "psf_atm_phase", "signal_after_build", "signal0", "reference_slopes_maps"):
+            g[k] = np.asarray(g[k]).astype(np.float32)
     for i in range(env.atm.nLayer):
         ly = getattr(env.atm, f"layer_{i + 1}")
         g[f"final_buff_{i}"] = ly.buff.copy()

@@ -4,7 +4,7 @@ import numpy as np
 from numpy.random import RandomState
 
 from .ao_oracle import EnvOracle, compute_psf
-from .golden_configs import CONFIGS, STEPS, EPISODE_SEED
+from .golden_configs import COMPACT, CONFIGS, STEPS, EPISODE_SEED
 from .make_golden import digest, DET_SEED
 
 
@@ -53,7 +53,7 @@ def replay_oracle(name, env=None, steps=None):
         tr["obs"][i], tr["reward"][i], tr["strehl"][i] = obs, reward, strehl
         tr["signal"][i] = env.wfs.signal
         tr["coefs"][i] = env.coefs
-        if i in (0, n // 2, n - 1):
+        if i in ((n - 1,) if name in COMPACT else (0, n // 2, n - 1)):
             g[f"atm_OPD_{i}"] = env.atm.OPD.copy()
             g[f"tel_OPD_{i}"] = env.tel_OPD.copy()
             g[f"frame_{i}"] = np.asarray(env.wfs.frame).copy()
@@ -61,7 +61,7 @@ def replay_oracle(name, env=None, steps=None):
         g["trace_" + k] = v
     g["trace_total"] = env.total[:n].copy()
     g["trace_residual"] = env.residual[:n].copy()
-    g["snap_steps"] = np.array([0, n // 2, n - 1])
+    g["snap_steps"] = np.array([n - 1] if name in COMPACT else [0, n // 2, n - 1])
     for i, ly in enumerate(env.atm.layers):
         g[f"final_buff_{i}"] = ly.buff.copy()
         g[f"final_map_digest_{i}"] = digest(ly.map)
