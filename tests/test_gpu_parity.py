@@ -510,3 +510,48 @@ def test_detector_noise_statistics(dev):
     unsat = lit & (ideal * 0.56 < 8000)
     assert abs((q.mean(axis=0)[unsat] + 0.5).mean() / expect[unsat].mean() - 1) < 0.02
     assert abs(q[:, dark_px].mean() - (10.0 / 10000 * 1023 - 0.5)) < 0.15
+
+
+def test_poisson_sampler_matches_the_poisson_pmf(dev):
+    """Photon-noise draws against scipy's Poisson pmf, pixel by pixel, across the regimes of the sampler (sequential
+    inversion below 12, PTRS transformed rejection above, OOPAO/Detector.py:190-206 -> numpy's legacy poisson)."""
+    from scipy import stats
+    from rlao_b200.ShackHartmann import ShackHartmann
+    from rlao_b200.Source import Source
+    from rlao_b200.Telescope import Telescope
+    B, K = 512, 8
+    checked = []
+    for mag in (5.0, 9.0, 12.5):
+        tel = Telescope(48, 8, 1 / 500, n_envs=B, device=dev)
+        Source("I", mag) * tel
+        wfs = ShackHartmann(8, tel, 0.5)
+        tel.resetOPD()
+        tel * wfs
+        ideal = _np(wfs.cam.frame[0]).astype(np.float64)
+        wfs.cam.photonNoise = True
+        draws = []
+        for _ in range(K):
+            tel * wfs
+            draws.append(_np(wfs.cam.frame))
+        x = np.concatenate(draws, axis=0).astype(np.int64)              # [K*B, R, R]
+        # one pixel per decade of flux present in this frame (+ the two sides of the algorithm switch at 12)
+        targets = [0.3, 3.0, 11.0, 13.0, 15.0, 18.0, 40.0, 400.0, 1500.0, 4000.0, 12000.0, 40000.0]
+        flat = ideal.reshape(-1)
+        for tgt in targets:
+            j = int(np.argmin(np.abs(np.log(np.maximum(flat, 1e-9) / tgt))))
+            lam = flat[j]
+            if not (0.75 * tgt < lam < 1.33 * tgt) or any(abs(lam - c) < 1e-6 * lam for c in checked):
+                continue
+            s = x.reshape(x.shape[0], -1)[:, j]
+            lo, hi = int(stats.poisson.ppf(1e-4, lam)), int(stats.poisson.ppf(1 - 1e-4, lam))
+            edges = np.unique(np.round(np.linspace(lo, hi + 1, 24)).astype(int))
+            cdf = stats.poisson.cdf(edges - 1, lam)
+            p = np.diff(np.concatenate([[0.0], cdf, [1.0]]))                 # (-inf, e0), [e0, e1), ..., [e_last, inf)
+            obs = np.histogram(s, bins=np.concatenate([[-1], edges, [10 ** 9]]))[0]
+            keep = p * s.size >= 5
+            chi2 = (((obs[keep] - p[keep] * s.size) ** 2) / (p[keep] * s.size)).sum()
+            pval = stats.chi2.sf(chi2, int(keep.sum()) - 1)
+            assert pval > 1e-4, (mag, lam, chi2, pval)
+            assert abs(s.mean() - lam) < 5 * np.sqrt(lam / s.size) + 1e-3 * lam, (mag, lam, s.mean())
+            checked.append(lam)
+    assert min(checked) < 1.0 and max(checked) > 1000 and any(8 < c < 12 for c in checked) and any(12 < c < 20 for c in checked)
