@@ -236,8 +236,16 @@ class OOPAO:
         (`after_observe(obs, reward, strehl)` is called at that point of the stream) while the command update and the
         next DM surface are still being computed, and can upload the action on another stream (`action_ready`: CUDA
         event the command update waits for) while the atmosphere and the WFS run."""
-        lib, st, B = _lib.load(), _lib.stream_ptr(self.device), self.n_envs
-        self.atm.update()                                                  # :482 -> tel.OPD = atm.OPD (lazy)
+        out = self._measure_frame(i, after_observe)
+        self._apply_command(action, action_ready)
+        return out
+
+    def _measure_frame(self, i, after_observe=None, atmosphere_done=False):
+        """First half of step (OOPAOEnvRazor.py:482-488, 496-506): atmosphere, WFS on (atmosphere + the DM surface
+        commanded at the previous step), reconstruction, reward, Strehl.  `atmosphere_done`: atm.update() for this
+        frame has already been issued (it depends on nothing the step computes)."""
+        if not atmosphere_done:
+            self.atm.update()                                              # :482 -> tel.OPD = atm.OPD (lazy)
         dm_surface = self.dm._opd[self.dm._slot]                           # surface commanded at the previous step
         self.tel._set_lazy(self.atm._opd, dm_surface)                      # :488 tel*dm
         self.wfs._measure_terms(self.atm._opd, dm_surface, self.env_offset)  # :488 *wfs  (+ stats for :484,502,506)
@@ -250,6 +258,13 @@ class OOPAO:
             strehl = self.psf_strehl(*self.psf_reward)
         if after_observe is not None:
             after_observe(self._sq(self._obs), self._sq(self._reward), strehl)
+        self.SR.append(strehl if self.psf_reward is not None else strehl.clone())
+        self.wfsSignal = self.wfs.signal
+        return self._sq(self._obs), self._sq(self._reward), strehl, False, {"strehl": strehl}
+
+    def _apply_command(self, action, action_ready=None):
+        """Second half of step (OOPAOEnvRazor.py:479, 492-493): dm.coefs = dm_prev * leak + action, next DM surface."""
+        lib, st, B = _lib.load(), _lib.stream_ptr(self.device), self.n_envs
         if action_ready is not None:
             torch.cuda.current_stream(self.device).wait_event(action_ready)
         action = self._action_tensor(action)                               # :479 (img_to_vec * 1e-6 is in the kernel)
@@ -259,9 +274,6 @@ class OOPAO:
                                             self.nActuator ** 2, ctypes.c_float(self.leak), _lib.ptr(coefs), _lib.ptr(self._dm_prev),
                                             coefs.stride(0), st), "command_update")          # :492-493
         self.dm._set_coefs_batch(coefs)                                    # coefs setter side effect: next surface
-        self.SR.append(strehl if self.psf_reward is not None else strehl.clone())
-        self.wfsSignal = self.wfs.signal
-        return self._sq(self._obs), self._sq(self._reward), strehl, False, {"strehl": strehl}
 
     def calculate_strehl_AVG(self):
         """OOPAOEnvRazor.py:589-596 (mean over the episode; here also over environments and, when

@@ -44,9 +44,17 @@ class TorchWrapper(_Wrapper):
     back CPU float32 tensors; this wrapper keeps that contract with pinned staging buffers and asynchronous copies
     (`host_io=True`, default), or keeps everything on the device (`host_io=False`) for on-GPU policies."""
 
-    def __init__(self, env, host_io=True):
+    def __init__(self, env, host_io=True, lookahead=False):
+        """lookahead (host_io only, opt-in): the observation of frame t+1 does not depend on the action of step t+1 (one
+        frame of DM lag), so `step(t, a_t)` applies a_t and then already runs frame t+1 (WFS, reconstruction), starts
+        its download and issues the atmosphere of frame t+2; the next call returns obs(t+1) without waiting for the
+        GPU.  Same numbers as the strict path, but the simulation runs ahead of what was returned: call `flush()` (or
+        `reset_soft()`) before touching the environment's objects between steps."""
         super().__init__(env)
         self.host_io = host_io
+        self.lookahead = bool(lookahead)
+        self._ahead = None
+        self._atm_ahead = False
         self._pinned = {}
         self._flip = {}
         self._copy_stream = None
@@ -59,10 +67,11 @@ class TorchWrapper(_Wrapper):
         (callers that keep observations longer — e.g. a replay buffer — copy them, as they do with the reference's
         arrays)."""
         key = tuple((tuple(t.shape), t.dtype) for t in tensors)
+        sets = 3 if self.lookahead else 2
         if key not in self._pinned:
-            self._pinned[key] = [[torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors] for _ in range(2)]
+            self._pinned[key] = [[torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors] for _ in range(sets)]
             self._flip[key] = 0
-        self._flip[key] ^= 1
+        self._flip[key] = (self._flip[key] + 1) % sets
         return self._pinned[key][self._flip[key]]
 
     def _to_host(self, *tensors):
@@ -73,27 +82,30 @@ class TorchWrapper(_Wrapper):
         torch.cuda.current_stream(self._env.device).synchronize()
         return bufs
 
-    def _step_pipelined(self, i, action):
-        """Host tensors in / out with the copies off the critical path: the action goes up on a copy stream while
-        the atmosphere and the WFS of this frame run (the command update waits for it), and the observation comes down
-        on the copy stream while the command update and the next DM surface are computed."""
-        env, dev = self._env, self._env.device
-        main = torch.cuda.current_stream(dev)
+    def _upload(self, action):
+        """Action -> device on the copy stream; returns (device tensor, event to wait for or None)."""
+        dev = self._env.device
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(dev)
         a = torch.as_tensor(action)
-        ready = None
-        if a.device.type == "cpu":
-            a = a.to(torch.float32)
-            if self._act_dev is None or self._act_dev[0].shape != a.shape:
-                self._act_dev = [torch.empty(a.shape, dtype=torch.float32, device=dev) for _ in range(2)]
-            self._act_slot ^= 1
-            a_dev = self._act_dev[self._act_slot]          # the other buffer may still be read by the last command update
-            with torch.cuda.stream(self._copy_stream):
-                a_dev.copy_(a, non_blocking=True)
-                ready = self._copy_stream.record_event()
-            a = a_dev
-        out = {}
+        if a.device.type != "cpu":
+            return a, None
+        a = a.to(torch.float32)
+        if self._act_dev is None or self._act_dev[0].shape != a.shape:
+            self._act_dev = [torch.empty(a.shape, dtype=torch.float32, device=dev) for _ in range(2)]
+        self._act_slot ^= 1
+        a_dev = self._act_dev[self._act_slot]              # the other buffer may still be read by the last command update
+        with torch.cuda.stream(self._copy_stream):
+            a_dev.copy_(a, non_blocking=True)
+            ready = self._copy_stream.record_event()
+        return a_dev, ready
+
+    def _download_hook(self, out):
+        """Callback for the point of the stream where obs / reward / Strehl are final: copies them to pinned host
+        buffers on the copy stream and leaves the completion event in `out`."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self._env.device)
+        main = torch.cuda.current_stream(self._env.device)
 
         def after_observe(obs, reward, strehl):
             seen = main.record_event()
@@ -105,10 +117,41 @@ class TorchWrapper(_Wrapper):
                     p_.copy_(t, non_blocking=True)
                 out["ready"] = self._copy_stream.record_event()
             out["bufs"], out["keep"] = bufs, tensors
+        return after_observe
 
-        env._step_views(i, a, action_ready=ready, after_observe=after_observe)
+    def _step_pipelined(self, i, action):
+        """Host tensors in / out with the copies off the critical path: the action goes up on a copy stream while
+        the atmosphere and the WFS of this frame run (the command update waits for it), and the observation comes down
+        on the copy stream while the command update and the next DM surface are computed."""
+        a_dev, ready = self._upload(action)
+        out = {}
+        self._env._step_views(i, a_dev, action_ready=ready, after_observe=self._download_hook(out))
         out["ready"].synchronize()
         return out["bufs"]
+
+    def _step_lookahead(self, i, action):
+        """Stream order per call:  command(t), DM surface(t), WFS + reconstruction(t+1) -> download, atmosphere(t+2).
+        The atmosphere of the frame after next depends on nothing the host decides, so it fills the time the host
+        needs to turn obs(t+1) into action(t+1) and upload it."""
+        env = self._env
+        if self._ahead is None:                            # first step after a reset: measure this frame now
+            self._ahead = {}
+            env._measure_frame(i, self._download_hook(self._ahead), atmosphere_done=self._atm_ahead)
+            env.atm.update()
+            self._atm_ahead = True
+        cur = self._ahead
+        a_dev, ready = self._upload(action)
+        env._apply_command(a_dev, ready)
+        self._ahead = {}
+        env._measure_frame(None if i is None else i + 1, self._download_hook(self._ahead), atmosphere_done=True)
+        env.atm.update()
+        cur["ready"].synchronize()
+        return cur["bufs"]
+
+    def flush(self):
+        """Drops the frame measured ahead (lookahead mode): the next step measures again from the current state (the
+        atmosphere stays one update ahead)."""
+        self._ahead = None
 
     def step(self, i, action):
         dev = self._env.device
@@ -121,7 +164,10 @@ class TorchWrapper(_Wrapper):
         # small batches are launch-bound: the extra stream / event traffic of the pipelined path costs more than the
         # copies it hides
         big = self._env.n_envs * self._env.nActuator ** 2 >= 65536
-        if big and "_step_views" in type(self._env).__dict__:
+        bare = "_step_views" in type(self._env).__dict__
+        if self.lookahead and bare:
+            obs_h, reward_h, strehl_h = self._step_lookahead(i, action)
+        elif big and bare:
             obs_h, reward_h, strehl_h = self._step_pipelined(i, action)
         else:                                           # e.g. an env wrapped in TimeDelayEnv goes through its own step()
             a = torch.as_tensor(action)
@@ -134,6 +180,8 @@ class TorchWrapper(_Wrapper):
         return obs_h, reward_h, strehl_h, False, [("strehl", torch.as_tensor(strehl_h, dtype=torch.float32))]
 
     def reset_soft(self):
+        self._ahead = None
+        self._atm_ahead = False            # episode boundary: the caller has just drawn new screens (or accepts a skipped frame)
         obs = self._env.reset_soft()
         return self._to_host(obs)[0] if self.host_io else obs
 

@@ -202,3 +202,27 @@ def test_gymnasium_signature_history_and_delay(dev):
     # a second reset with the same seed replays the episode
     obs2, _ = g.reset(seed=12)
     assert torch.equal(obs2[:, 0], hist[-1])
+
+
+def test_lookahead_wrapper_returns_the_same_numbers(dev):
+    """TorchWrapper(lookahead=True) measures frame t+1 while the host is still working on step t; observations,
+    rewards and Strehl ratios are those of the strict path, step by step."""
+    from rlao_b200.PO4AO.util_simple import TorchWrapper
+    cfg = CONFIGS["tiny"]()
+    strict = TorchWrapper(build_env(cfg, n_envs=300, rng="philox", seed=4, device=dev))           # pipelined path (big batch)
+    ahead = TorchWrapper(build_env(cfg, n_envs=300, rng="philox", seed=4, device=dev), lookahead=True)
+    new_episode(strict._env, 9)
+    new_episode(ahead._env, 9)
+    oa, ob = strict.reset_soft(), ahead.reset_soft()
+    assert torch.equal(oa, ob)
+    for i in range(8):
+        oa, ra, sa, _, _ = strict.step(i, cfg.gainCL * oa)
+        ob, rb, sb, _, _ = ahead.step(i, cfg.gainCL * ob)
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(sa, sb), i
+    # a new episode discards the frame measured ahead
+    new_episode(strict._env, 10)
+    new_episode(ahead._env, 10)
+    oa, ob = strict.reset_soft(), ahead.reset_soft()
+    oa, *_ = strict.step(0, cfg.gainCL * oa)
+    ob, *_ = ahead.step(0, cfg.gainCL * ob)
+    assert torch.equal(oa, ob)
