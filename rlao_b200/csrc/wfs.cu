@@ -113,22 +113,13 @@ __device__ __forceinline__ float poisson_draw(float lam, uint32_t w0, uint32_t w
   return rintf(lam);
 }
 
-// OOPAO/Detector.py:279-301 (integrate) then :232-276 (readout), one pixel.
-__device__ __forceinline__ float detector_pixel(float x, const aoenv_detector_t& d, uint32_t pixel, uint32_t env) {
-  const PixelRng rng(d.seed, pixel, env, d.frame_counter);
-  const uint4 r0 = rng.block(0);
-  if (d.photon_noise) x = poisson_draw(x, r0.x, r0.y, rng, 16);
-  x *= d.qe;
-  if (d.dark_electrons > 0.f) {
-    const uint4 r1 = rng.block(1);
-    x += poisson_draw(d.dark_electrons, r1.x, r1.y, rng, 32);
-  }
+// OOPAO/Detector.py:279-301 (integrate) then :232-276 (readout), one pixel, split around the photon draw:
+//   electrons = Poisson(flux) * QE + Poisson(dark); clip to the full well; (+ EM gain); + round(N(0,1) RON); gain; ADC.
+__device__ __forceinline__ float detector_finish(float photons, float dark, float ron, const aoenv_detector_t& d) {
+  float x = photons * d.qe + dark;
   if (d.has_fwc) x = fminf(fmaxf(x, 0.f), d.fwc);
   if (d.sensor_emccd) x *= d.gain;
-  if (d.readout_noise != 0.f) {           // Box-Muller with the SFU logarithm / cosine: the draw is rounded to whole electrons
-    const float g = sqrtf(-2.0f * __logf(u32_to_unit(r0.z))) * __cosf(6.283185307179586f * u32_to_unit(r0.w));
-    x += rintf(g * d.readout_noise);
-  }
+  x += ron;
   if (!d.sensor_emccd) x *= d.gain;
   if (d.bits > 0) {
     const float full = (float)((1u << d.bits) - 1u);
@@ -138,43 +129,80 @@ __device__ __forceinline__ float detector_pixel(float x, const aoenv_detector_t&
   return x;
 }
 
-// The camera as its own pass over the noise-free frame.  One block per (row of lenslets, environment): the n frame
-// rows of that lenslet row are one contiguous run of n*R floats, staged through shared memory, and the work items are
-// ordered pixel-position-major (item w = position-in-lenslet * nS + lenslet), so the lanes of a warp hold the SAME
-// pixel position of neighbouring lenslets.  In closed loop those pixels carry similar flux, so a warp stays in one
-// regime of the Poisson sampler (inversion for the dim rim, PTRS for the core) instead of paying for both, and the
-// rejection loops of its lanes have similar lengths.  The random stream of a pixel depends only on (pixel, env,
-// frame counter), not on this ordering.
-__global__ void __launch_bounds__(256, 6)
-shwfs_detector_kernel(float* __restrict__ frame, const uint8_t* __restrict__ valid, int nS, int n, float inv_nS, float inv_n,
+// The camera as its own pass over the noise-free frame.  A warp walks kDetPerLane * 32 consecutive pixels (coalesced
+// loads and stores, no block barrier).  Every lane does the cheap, uniform part of a pixel — one Philox block, the
+// read-out normal, the dark-current draw, and the photon draw when the flux is below 12 (sequential inversion).  Pixels
+// in the transformed-rejection regime (the bright cores, ~10 % of the frame) are queued in the warp's shared-memory list
+// and drawn afterwards by consecutive lanes, so the long PTRS path runs on full warps instead of on the two or three
+// lanes per warp that need it (ncu before: 4 active threads on average in that code, a third of all instructions).
+// The random stream of a pixel depends only on (pixel, env, frame counter): block 0 -> photon words x, y / normal z, w;
+// the dark current takes word y when the photon draw did not need it, block 1 otherwise; PTRS retries use blocks 16...
+constexpr int kDetPerLane = 8;
+struct DetQueued { float lam, ron; uint32_t w0, w1; int pix; };
+
+__global__ void __launch_bounds__(256)
+shwfs_detector_kernel(float* __restrict__ frame, const uint8_t* __restrict__ valid, int nS, int n, float inv_R, float inv_n,
                       const __grid_constant__ aoenv_detector_t det, int shared_max, int32_t* __restrict__ envmax) {
-  extern __shared__ float tile[];                // [n][R]
-  const int R = nS * n, count = n * R;
-  const int li = blockIdx.x, b = blockIdx.y;
-  const size_t base = (size_t)b * R * R + (size_t)li * count;
-  for (int i = threadIdx.x; i < count; i += blockDim.x) tile[i] = frame[base + i];
-  __syncthreads();
+  __shared__ DetQueued queue[8][kDetPerLane * 32];
+  const int R = nS * n, P = R * R;
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int first = (blockIdx.x * 8 + warp) * (kDetPerLane * 32);
+  float* __restrict__ img = frame + (size_t)b * P;
+  DetQueued* __restrict__ q = queue[warp];
+  int queued = 0;                                   // warp-uniform
   float vmax = -INFINITY;
-  for (int w = threadIdx.x; w < count; w += blockDim.x) {
-    const int pos = (int)(((float)w + 0.5f) * inv_nS);       // exact: the fraction is >= 1/(2 nS) away from an integer
-    const int lens = w - pos * nS;
-    const int p = (int)(((float)pos + 0.5f) * inv_n);
-    const int q = pos - p * n;
-    const int local = p * R + lens * n + q;
-    const float val = detector_pixel(tile[local], det, (uint32_t)(li * count + local), (uint32_t)b);
-    tile[local] = val;
-    if (valid[li * nS + lens]) vmax = fmaxf(vmax, val);
+  const bool has_dark = det.dark_electrons > 0.f;
+  const float dark_p0 = has_dark ? __expf(-det.dark_electrons) : 1.f;
+
+  auto is_lit = [&](int pix) {
+    const int y = (int)(((float)pix + 0.5f) * inv_R);          // exact: P < 2^24, fraction >= 1/(2R) from an integer
+    const int x = pix - y * R;
+    const int li = (int)(((float)y + 0.5f) * inv_n), lj = (int)(((float)x + 0.5f) * inv_n);
+    return valid[li * nS + lj] != 0;
+  };
+
+#pragma unroll 2
+  for (int j = 0; j < kDetPerLane; ++j) {
+    const int pix = first + j * 32 + lane;
+    const bool in = pix < P;
+    float lam = in ? img[pix] : 0.f;
+    const PixelRng rng(det.seed, (uint32_t)pix, (uint32_t)b, det.frame_counter);
+    const uint4 r0 = rng.block(0);
+    float ron = 0.f;
+    if (det.readout_noise != 0.f)       // Box-Muller with the SFU logarithm / cosine: the draw is rounded to whole electrons
+      ron = rintf(sqrtf(-2.0f * __logf(u32_to_unit(r0.z))) * __cosf(6.283185307179586f * u32_to_unit(r0.w)) * det.readout_noise);
+    const bool ptrs = in && det.photon_noise && lam >= 12.f;
+    if (!ptrs && in) {
+      const float photons = det.photon_noise ? poisson_draw(lam, r0.x, 0u, rng, 16) : lam;
+      float dark = 0.f;
+      if (has_dark) {                   // almost always zero: one comparison against exp(-dark)
+        const float u = u32_to_unit(r0.y) * 0.99999994f;
+        dark = u <= dark_p0 ? 0.f : poisson_draw(det.dark_electrons, r0.y, 0u, rng, 32);
+      }
+      const float val = detector_finish(photons, dark, ron, det);
+      img[pix] = val;
+      if (is_lit(pix)) vmax = fmaxf(vmax, val);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, ptrs);
+    if (ptrs) q[queued + __popc(m & ((1u << lane) - 1u))] = {lam, ron, r0.x, r0.y, pix};
+    queued += __popc(m);
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < count; i += blockDim.x) frame[base + i] = tile[i];
+  __syncwarp();
+  for (int e = lane; e < queued; e += 32) {
+    const DetQueued it = q[e];
+    const PixelRng rng(det.seed, (uint32_t)it.pix, (uint32_t)b, det.frame_counter);
+    const float photons = poisson_draw(it.lam, it.w0, it.w1, rng, 16);
+    float dark = 0.f;
+    if (has_dark) {
+      const uint4 r1 = rng.block(1);
+      dark = poisson_draw(det.dark_electrons, r1.x, r1.y, rng, 32);
+    }
+    const float val = detector_finish(photons, dark, it.ron, det);
+    img[it.pix] = val;
+    if (is_lit(it.pix)) vmax = fmaxf(vmax, val);
+  }
   vmax = warp_max(vmax);
-  __shared__ float sm[8];
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = vmax;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) vmax = fmaxf(vmax, sm[w]);
-    if (vmax > -INFINITY) atomicMax(&envmax[shared_max ? 0 : b], float_to_ordered(vmax));
-  }
+  if (lane == 0 && vmax > -INFINITY) atomicMax(&envmax[shared_max ? 0 : b], float_to_ordered(vmax));
 }
 
 template <int n>
@@ -716,9 +744,9 @@ int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil
   AOENV_LAUNCH_CHECK("shwfs_frame");
   if (det) {
     const int R = nS * n;
-    dim3 gd(nS, B);
-    shwfs_detector_kernel<<<gd, 256, sizeof(float) * (size_t)n * R, s>>>(frame, valid, nS, n, 1.0f / (float)nS, 1.0f / (float)n,
-                                                                       *det, shared_max, envmax);
+    AOENV_CHECK_ARG(R * R < (1 << 24), "shwfs_frame: frame of %d x %d pixels is too large for the camera pass", R, R);
+    dim3 gd((R * R + 8 * kDetPerLane * 32 - 1) / (8 * kDetPerLane * 32), B);
+    shwfs_detector_kernel<<<gd, 256, 0, s>>>(frame, valid, nS, n, 1.0f / (float)R, 1.0f / (float)n, *det, shared_max, envmax);
     AOENV_LAUNCH_CHECK("shwfs_detector");
   }
   return 0;
