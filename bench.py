@@ -25,6 +25,8 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (nSubap, nLayers, envs per GPU, description, options)
     "cfg3": (40, 3, 1024, "8m 40x40 SH-WFS, 41x41 DM (1353 act), 3-layer VK atmosphere, integrator, noise off", {}),
+    "cfg3noise": (40, 3, 1024, "cfg3 with the reference environment's default camera: photon noise, RON 14 e-, QE 0.56, dark 5, "
+                               "FWC 1e4, 10-bit ADC (OOPAOEnvRazor.py:243-250,332-333)", {"noise": True}),
     "cfg2": (20, 1, 1024, "8m 20x20 SH-WFS, 21x21 DM (357 act), 1-layer VK atmosphere, integrator, noise off", {}),
     "cfg4": (20, 1, 4096, "8m 20x20 SH-WFS, 21x21 DM, 1 layer, Razor-like camera: photon noise, RON 14 e-, QE 0.56, dark 5, "
                           "FWC 1e4, 10-bit ADC", {"noise": True}),

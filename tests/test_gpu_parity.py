@@ -555,3 +555,31 @@ def test_poisson_sampler_matches_the_poisson_pmf(dev):
             assert abs(s.mean() - lam) < 5 * np.sqrt(lam / s.size) + 1e-3 * lam, (mag, lam, s.mean())
             checked.append(lam)
     assert min(checked) < 1.0 and max(checked) > 1000 and any(8 < c < 12 for c in checked) and any(12 < c < 20 for c in checked)
+
+
+def test_extruded_screens_keep_the_von_karman_structure_function(dev):
+    """After the window has been regenerated several times over by add_row (float32 maps, split-bf16 tensor-core GEMM for
+    X = A Z + B xi), the phase structure function of the maps must still be the von Karman one the operators were
+    built for (OOPAO/phaseStats.py:70-133): D(r) = 2 (C(0) - C(r))."""
+    from oracle.ao_oracle import vk_covariance_matrix
+    from rlao_b200.Atmosphere import Atmosphere
+    from rlao_b200.Source import Source
+    from rlao_b200.Telescope import Telescope
+    R, D, L0, r0, B = 48, 8.0, 25.0, 0.13, 512
+    tel = Telescope(R, D, 1 / 500, n_envs=B, device=dev)
+    Source("I", 8) * tel
+    atm = Atmosphere(tel, r0, L0, [45.0], [1.0], [35.0], [0.0], rng="philox", seed=11)
+    atm.initializeAtmosphere(tel)
+    ps = atm.ps_loop
+    steps = int(4 * atm._M / (45.0 / 500 / ps)) + 1           # the wind carries four window widths of fresh screen in
+    for _ in range(steps):
+        atm.update()
+    m = atm._layers[0].mapShift.double()                       # [B, M, M] radians at 500 nm
+    assert torch.isfinite(m).all()
+    for sep in (1, 3, 8, 20):
+        want = 2 * (vk_covariance_matrix(np.array([0j]), np.array([0j]), L0, r0)[0, 0]
+                    - vk_covariance_matrix(np.array([0j]), np.array([sep * ps + 0j]), L0, r0)[0, 0])
+        dx = float(((m[:, :, sep:] - m[:, :, :-sep]) ** 2).mean())
+        dy = float(((m[:, sep:, :] - m[:, :-sep, :]) ** 2).mean())
+        tol = 0.04 if sep <= 8 else 0.08
+        assert abs(dx / want - 1) < tol and abs(dy / want - 1) < tol, (sep, dx / want, dy / want)
