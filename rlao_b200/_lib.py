@@ -85,7 +85,20 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr(device=None):
+    """cudaStream_t of torch's current stream on `device` (called before every C-ABI launch: the raw accessor is ~20x
+    cheaper than building a torch.cuda.Stream object)."""
+    if _raw_stream is not None:
+        if device is None:
+            idx = torch.cuda.current_device()
+        else:
+            idx = device.index if isinstance(device, torch.device) else torch.device(device).index
+            if idx is None:
+                idx = torch.cuda.current_device()
+        return C.c_void_p(_raw_stream(idx))
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
