@@ -9,6 +9,9 @@ Default workload (BASELINE.json configs[2], the one the 1e6 env-steps/s target i
 Prints ONE JSON line (see the task contract): value = device-timed throughput with inputs resident in HBM,
 e2e = same metric through the host-facing TorchWrapper (pinned host action in, host obs/reward/Strehl out,
 copies inside the timed region), roofline of the dominant kernel, cpu_baseline (oracle port on host cores).
+Extra keys: `e2e_lookahead` (the same loop through TorchWrapper(lookahead=True), opt-in), `kernels` (per C-ABI entry point,
+CUDA events, separate pass), `roofline.fp32` when the dominant kernel is the FMA-bound SH-WFS transform.
+Other workloads: --workload cfg1|cfg2|cfg3noise|cfg4|cfg4lowflux|cfg5|cfg5psf|tiny; --policy po4ao runs ConvPolicy rollouts.
 """
 import argparse
 import json
