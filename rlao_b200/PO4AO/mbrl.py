@@ -65,7 +65,30 @@ class _RolloutPolicy:
     channels [n_h, 2 n_h - 1)  action ring:      slot p_a holds the newest action
     """
 
-    def __init__(self, policy, past_obs, past_act, n_history):
+    @classmethod
+    def attach(cls, policy, past_obs, past_act, n_history, graph=True):
+        """One instance (and one pair of captured graphs) per policy and batch shape, reused from episode to episode:
+        the graphs read the weights through their storage, which the optimiser updates in place."""
+        key = (tuple(past_obs.shape), str(past_obs.device), n_history, bool(graph))
+        cache = policy.__dict__.setdefault("_rollout_cache", {})
+        inst = cache.get(key)
+        if inst is None or inst.w0 is not policy.net[0].weight:
+            inst = cache[key] = cls(policy, past_obs, past_act, n_history, graph)
+        else:
+            inst.load(past_obs, past_act)
+        return inst
+
+    def load(self, past_obs, past_act):
+        """Start of an episode: histories into the rings (past_obs[j], 0 = oldest, in slot j; the next state goes to slot d)."""
+        self.inp[:, :self.d] = past_obs
+        self.inp[:, self.d] = 0
+        self.inp[:, self.nH:] = past_act
+        self.p_o, self.p_a = self.d - 1, self.d - 1
+        if self._graphs is not None:
+            self._po.fill_(self.p_o)
+            self._pa.fill_(self.p_a)
+
+    def __init__(self, policy, past_obs, past_act, n_history, graph=True):
         B, d, nA = past_obs.shape[0], n_history - 1, past_obs.shape[-1]
         dev = past_obs.device
         self.policy, self.nH, self.d = policy, n_history, d
@@ -87,10 +110,58 @@ class _RolloutPolicy:
         ref_o = torch.where(age_o == n_history - 1, torch.zeros_like(age_o), age_o + 1).expand(n_history, d, n_history)
         ref_a = (n_history + (slot_a - pa - 1) % d).expand(n_history, d, d)
         self.perm = torch.cat([ref_o, ref_a], dim=2).to(dev)             # [n_h, d, 2 n_h - 1]
+        self._graphs = None
+        if graph and dev.type == "cuda":
+            self._capture(B, nA, dev)
+
+    # ---- CUDA-graph path: ring positions live on the device, so one captured graph serves every step ------------
+    def _act_body(self):
+        self._po.add_(1).remainder_(self.nH)
+        self.inp.index_copy_(1, self._po, self._obs_in.unsqueeze(1))
+        row = self.perm.view(self.nH * self.d, -1).index_select(0, self._po * self.d + self._pa)
+        w = self.w0.index_select(1, row[0])
+        out = torch.nn.functional.conv2d(self.inp, w, self.b0, padding=1)
+        self._act_out.copy_(self.policy.project(self.rest(out))[:, 0])
+
+    def _record_body(self):
+        self._pa.add_(1).remainder_(self.d)
+        self.inp.index_copy_(1, self._pa + self.nH, self._act_in.unsqueeze(1))
+
+    def _capture(self, B, nA, dev):
+        """Warm up on a side stream, restore the rings, capture the two step bodies.  Any failure leaves the eager path."""
+        try:
+            self._po = torch.tensor([self.p_o], dtype=torch.long, device=dev)
+            self._pa = torch.tensor([self.p_a], dtype=torch.long, device=dev)
+            self._obs_in = torch.zeros((B, nA, nA), dtype=torch.float32, device=dev)
+            self._act_in = torch.zeros((B, nA, nA), dtype=torch.float32, device=dev)
+            self._act_out = torch.zeros((B, nA, nA), dtype=torch.float32, device=dev)
+            saved = (self.inp.clone(), self._po.clone(), self._pa.clone())
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    self._act_body()
+                    self._record_body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            g_act, g_rec = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_act):
+                self._act_body()
+            with torch.cuda.graph(g_rec):
+                self._record_body()
+            self.inp.copy_(saved[0])
+            self._po.copy_(saved[1])
+            self._pa.copy_(saved[2])
+            self._graphs = (g_act, g_rec)
+        except Exception:
+            self._graphs = None
 
     def act(self, obs):
         """obs [B, nAct, nAct] (the current state) -> action [B, nAct, nAct]."""
         self.p_o = (self.p_o + 1) % self.nH
+        if self._graphs is not None:
+            self._obs_in.copy_(obs)
+            self._graphs[0].replay()
+            return self._act_out.clone()
         self.inp[:, self.p_o] = obs
         w = self.w0.index_select(1, self.perm[self.p_o, self.p_a])
         out = torch.nn.functional.conv2d(self.inp, w, self.b0, padding=1)
@@ -98,6 +169,10 @@ class _RolloutPolicy:
 
     def record(self, action):
         self.p_a = (self.p_a + 1) % self.d
+        if self._graphs is not None:
+            self._act_in.copy_(action)
+            self._graphs[1].replay()
+            return
         self.inp[:, self.nH + self.p_a] = action
 
     def histories(self):
@@ -135,7 +210,7 @@ def run(env, past_obs, past_act, obs, replay, policy, dynamics, n_history, max_t
     use_policy = episode >= warmup_ts
     fast = use_policy and n_history > 1 and hasattr(policy, "project") and hasattr(policy, "net")
     if fast:
-        roll = _RolloutPolicy(policy, past_obs, past_act, n_history)
+        roll = _RolloutPolicy.attach(policy, past_obs, past_act, n_history)
     else:
         h_obs, h_act = _History(past_obs), _History(past_act)
     rewards = torch.empty((max_ts, B), dtype=torch.float32, device=dev)
