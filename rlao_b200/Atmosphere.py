@@ -192,7 +192,7 @@ class Atmosphere:
     def _win_ptr(self, i, buf=None, org=None):
         buf = self._cur[i] if buf is None else buf
         oy, ox = self._org[i] if org is None else org
-        return C.c_void_p(self._maps[i, buf].data_ptr() + 4 * (oy * self._pitch + ox))
+        return self._maps[i, buf].data_ptr() + 4 * (oy * self._pitch + ox)
 
     def _compact(self, i):
         """Re-centres layer i's window into the other canvas buffer."""

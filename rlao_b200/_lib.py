@@ -82,7 +82,7 @@ def check(rc, what=""):
 
 def ptr(t):
     """Device (or host) address of a tensor, or NULL."""
-    return None if t is None else C.c_void_p(t.data_ptr())
+    return None if t is None else t.data_ptr()          # plain int: ctypes converts it for a c_void_p parameter
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
@@ -98,8 +98,8 @@ def stream_ptr(device=None):
             idx = device.index if isinstance(device, torch.device) else torch.device(device).index
             if idx is None:
                 idx = torch.cuda.current_device()
-        return C.c_void_p(_raw_stream(idx))
-    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        return _raw_stream(idx)
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def launch_count():
