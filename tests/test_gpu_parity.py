@@ -69,6 +69,29 @@ def test_gemm_rejects_bad_arguments(dev):
     assert rc != 0 and b"multiple of 16" in _lib.load().aoenv_last_error()
 
 
+def test_entry_points_reject_bad_arguments(dev):
+    """Every entry point validates shapes before launching: negative return code, message in aoenv_last_error, no launch."""
+    lib = _lib.load()
+    z = torch.zeros(4096, device=dev)
+    zp, st = _lib.ptr(z), _lib.stream_ptr(dev)
+    n0 = _lib.launch_count()
+    cases = [
+        (lib.aoenv_atm_gather(zp, 1, 10, 12, 120, 2, 0, zp, 8, 36, None, 0, 0, zp, 64, None, 3, st), b"shift"),
+        (lib.aoenv_atm_ring(zp, 1, 10, 12, 120, 0, 35, zp, 36, zp, zp, 0, st), b"ring has"),
+        (lib.aoenv_shwfs_frame(zp, None, zp, zp, zp, 1, 4, 5, 1.0, None, 0, zp, zp, None, st), b"pixels per lenslet"),
+        (lib.aoenv_shwfs_slopes(zp, zp, 0, zp, 4, zp, 1.0, 0.01, 1, 4, 6, zp, 4, None, 2, st), b"shwfs_slopes"),
+        (lib.aoenv_gemm_tn_tc(zp, zp, 12, 2, zp, 8, 4, 4, 12, 1.0, st), b"gemm_tn_tc"),
+        (lib.aoenv_split_bf16(zp, 16, 4, 16, 5, zp, 16, st), b"parts"),
+        (lib.aoenv_psf_peak(zp, None, zp, zp, zp, zp, 1, 7, 21, 1, 8, 1.0, zp, 16, zp, None, zp, st), b"psf_peak"),
+        (lib.aoenv_dm_surface_separable(zp, 2, zp, 4, 2, zp, zp, zp, zp, None, None, None, None, 0, 1, 8, zp, st), b"dm_surface_separable"),
+    ]
+    for rc, needle in cases:
+        assert rc < 0, needle
+    # the message of the last failure is retrievable; nothing was launched
+    assert b"dm_surface_separable" in lib.aoenv_last_error()
+    assert _lib.launch_count() == n0
+
+
 # ---------------------------------------------------------------------------------------------------------
 def _tiny_objects(dev, n_envs=1, cfg=None):
     from rlao_b200.Atmosphere import Atmosphere
