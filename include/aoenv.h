@@ -141,6 +141,11 @@ typedef struct {
   uint64_t frame_counter;  /* advances once per call: independent draws per step                            */
 } aoenv_detector_t;
 
+/* OOPAO/Detector.py:279-301 + 232-276 (integrate + readout) applied in place to B frames of rows x cols photons
+ * (the camera pass of aoenv_shwfs_frame as a stand-alone call: Poisson photon noise, QE, dark current, full well,
+ * read-out noise, gain, ADC).  One Philox stream per (pixel, frame index, det->seed, det->frame_counter). */
+int aoenv_detector_integrate(float* frame, int B, int rows, int cols, const aoenv_detector_t* det, void* stream);
+
 /* Selects the implementation of the n = 6 frame kernel: 0 = term-by-term pruned DFT (default), 1 = factorised
  * (radix 2 x Good-Thomas 2 x 3).  Same frame to float32 rounding; returns the previous setting. */
 int aoenv_set_wfs6_variant(int factorised);

@@ -1,6 +1,8 @@
 """Detector — mirror of OOPAO/Detector.py for the WFS camera: a parameter holder whose noise chain
 (photon -> QE -> dark -> full well -> read noise -> gain -> ADC, Detector.py:232-301) runs inside the WFS
-kernel (rlao_b200/csrc/wfs.cu: detector_pixel), one Philox stream per pixel, environment and frame."""
+camera pass (rlao_b200/csrc/wfs.cu: shwfs_detector_kernel), one Philox stream per pixel, environment and frame."""
+import ctypes
+
 import numpy as np
 import torch
 
@@ -63,3 +65,18 @@ class Detector:
         d.frame_counter = self.frame_counter
         self.frame_counter += 1
         return d
+
+    def integrate(self, frame):
+        """Detector.py:279-301: applies the camera to a frame of photons ([rows, cols] or [B, rows, cols], CUDA float32) and
+        stores / returns `self.frame`.  Every call advances the frame counter of the random streams."""
+        f = torch.as_tensor(frame, dtype=torch.float32)
+        if f.device.type != "cuda":
+            raise _lib.AOEnvLibraryError("Detector.integrate needs a CUDA tensor (there is no CPU path)")
+        out = (f.unsqueeze(0) if f.ndim == 2 else f).contiguous().clone()
+        det = self.as_struct()
+        if det is not None:
+            _lib.check(_lib.load().aoenv_detector_integrate(_lib.ptr(out), out.shape[0], out.shape[1], out.shape[2],
+                                                            ctypes.byref(det), _lib.stream_ptr(out.device)), "detector_integrate")
+        self.frame = out[0] if f.ndim == 2 else out
+        return self.frame
+

@@ -142,9 +142,10 @@ struct DetQueued { float lam, ron; uint32_t w0, w1; int pix; };
 
 __global__ void __launch_bounds__(256)
 shwfs_detector_kernel(float* __restrict__ frame, const uint8_t* __restrict__ valid, int nS, int n, float inv_R, float inv_n,
-                      const __grid_constant__ aoenv_detector_t det, int shared_max, int32_t* __restrict__ envmax) {
+                      const __grid_constant__ aoenv_detector_t det, int shared_max, int32_t* __restrict__ envmax,
+                      int n_pixels) {
   __shared__ DetQueued queue[8][kDetPerLane * 32];
-  const int R = nS * n, P = R * R;
+  const int R = nS * n, P = n_pixels > 0 ? n_pixels : R * R;
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int first = (blockIdx.x * 8 + warp) * (kDetPerLane * 32);
   float* __restrict__ img = frame + (size_t)b * P;
@@ -155,6 +156,7 @@ shwfs_detector_kernel(float* __restrict__ frame, const uint8_t* __restrict__ val
   const float dark_p0 = has_dark ? __expf(-det.dark_electrons) : 1.f;
 
   auto is_lit = [&](int pix) {
+    if (valid == nullptr) return envmax != nullptr;            // stand-alone camera: every pixel counts
     const int y = (int)(((float)pix + 0.5f) * inv_R);          // exact: P < 2^24, fraction >= 1/(2R) from an integer
     const int x = pix - y * R;
     const int li = (int)(((float)y + 0.5f) * inv_n), lj = (int)(((float)x + 0.5f) * inv_n);
@@ -201,8 +203,10 @@ shwfs_detector_kernel(float* __restrict__ frame, const uint8_t* __restrict__ val
     img[it.pix] = val;
     if (is_lit(it.pix)) vmax = fmaxf(vmax, val);
   }
-  vmax = warp_max(vmax);
-  if (lane == 0 && vmax > -INFINITY) atomicMax(&envmax[shared_max ? 0 : b], float_to_ordered(vmax));
+  if (envmax != nullptr) {
+    vmax = warp_max(vmax);
+    if (lane == 0 && vmax > -INFINITY) atomicMax(&envmax[shared_max ? 0 : b], float_to_ordered(vmax));
+  }
 }
 
 template <int n>
@@ -746,9 +750,22 @@ int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil
     const int R = nS * n;
     AOENV_CHECK_ARG(R * R < (1 << 24), "shwfs_frame: frame of %d x %d pixels is too large for the camera pass", R, R);
     dim3 gd((R * R + 8 * kDetPerLane * 32 - 1) / (8 * kDetPerLane * 32), B);
-    shwfs_detector_kernel<<<gd, 256, 0, s>>>(frame, valid, nS, n, 1.0f / (float)R, 1.0f / (float)n, *det, shared_max, envmax);
+    shwfs_detector_kernel<<<gd, 256, 0, s>>>(frame, valid, nS, n, 1.0f / (float)R, 1.0f / (float)n, *det, shared_max, envmax, 0);
     AOENV_LAUNCH_CHECK("shwfs_detector");
   }
+  return 0;
+}
+
+int aoenv_detector_integrate(float* frame, int B, int rows, int cols, const aoenv_detector_t* det, void* stream) {
+  AOENV_CHECK_ARG(B > 0 && B <= 65535 && rows > 0 && cols > 0 && (long long)rows * cols < (1 << 24), "detector_integrate: bad shape");
+  AOENV_CHECK_ARG(det != nullptr, "detector_integrate: no detector given");
+  AOENV_CHECK_ARG(!(det->bits > 0 && !det->has_fwc), "detector_integrate: ADC without a full-well capacity is not supported");
+  AOENV_CHECK_ARG(det->bits >= 0 && det->bits < 31, "detector_integrate: bits=%d", det->bits);
+  const int P = rows * cols;
+  dim3 gd((P + 8 * kDetPerLane * 32 - 1) / (8 * kDetPerLane * 32), B);
+  // the kernel only needs P = R * R pixels per frame when no lenslet mask is given: pass nS * n = 1 * P via (nS, n) = (P, 1)
+  shwfs_detector_kernel<<<gd, 256, 0, (cudaStream_t)stream>>>(frame, nullptr, 1, 1, 1.0f, 1.0f, *det, 0, nullptr, P);
+  AOENV_LAUNCH_CHECK("detector_integrate");
   return 0;
 }
 

@@ -47,6 +47,9 @@ class FakeLib:
     def aoenv_last_error(self):
         return b""
 
+    def aoenv_detector_integrate(self, *a):
+        raise NotImplementedError("fake backend: detector_integrate")
+
     def aoenv_set_wfs6_variant(self, factorised):
         return 0
 

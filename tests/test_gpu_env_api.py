@@ -226,3 +226,19 @@ def test_lookahead_wrapper_returns_the_same_numbers(dev):
     oa, *_ = strict.step(0, cfg.gainCL * oa)
     ob, *_ = ahead.step(0, cfg.gainCL * ob)
     assert torch.equal(oa, ob)
+
+
+def test_detector_integrate_standalone(dev):
+    """OOPAO/Detector.py:279-301 as a stand-alone call: Poisson statistics, QE, ADC; frames differ from call to call."""
+    from rlao_b200.Detector import Detector
+    cam = Detector(photonNoise=True, QE=0.5, seed=3)
+    flux = torch.full((64, 40, 50), 200.0, device=dev)
+    a = cam.integrate(flux)
+    b = cam.integrate(flux)
+    assert a.shape == flux.shape and float((a - b).abs().max()) > 0
+    e = a / 0.5                                                   # photo-electrons before QE
+    assert torch.equal(e.round(), e) and abs(float(e.mean()) - 200) < 0.5 and abs(float(e.var()) / 200 - 1) < 0.05
+    cam2 = Detector(readoutNoise=3.0, FWC=1000, bits=8, seed=1)
+    q = cam2.integrate(torch.full((30, 30), 500.0, device=dev))
+    assert q.shape == (30, 30) and float(q.max()) <= 255 and abs(float(q.mean()) - 500 / 1000 * 255) < 1.5
+    assert torch.equal(Detector().integrate(flux), flux)          # ideal detector
