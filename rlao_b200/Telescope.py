@@ -181,6 +181,10 @@ class Telescope:
         mx = psf.amax(dim=(-2, -1), keepdim=True)
         self.PSF_norma = self._squeeze(psf / mx)
 
+    def _materialise_psf(self):
+        p = self.PSF
+        return p if p.ndim == 3 else p.unsqueeze(0)
+
     # ---- operators --------------------------------------------------------------------------------------
     def __mul__(self, obj):
         """Telescope.py:457-564, dispatch on obj.tag."""
@@ -193,8 +197,20 @@ class Telescope:
             self._opd_np = dm_opd
             self._lazy = None
         elif tag == "detector":
-            raise NotImplementedError("tel*detector (science camera on the PSF) is out of scope (SURVEY.md section 8 f-4); "
-                                      "use tel.computePSF(zp) / env.psf_strehl(zp, window)")
+            # Telescope.py:487-500: science camera on the PSF (short exposures of one AO frame; no cropping / stacking)
+            full = int(obj.psf_sampling * self.resolution)
+            if obj.resolution is not None and int(obj.resolution) != full:
+                raise NotImplementedError("cropped science frames (Detector.nRes != psf_sampling * resolution) are out of scope")
+            if obj.integrationTime is None:
+                obj.integrationTime = self.samplingTime
+            if obj.integrationTime < self.samplingTime:
+                raise ValueError("The Detector integration time is smaller than the AO loop sampling Time. ")
+            if obj.integrationTime > self.samplingTime:
+                raise NotImplementedError("stacking several AO frames per exposure is out of scope (SURVEY.md section 8 f-4)")
+            self.computePSF(obj.psf_sampling)
+            obj._integrated_time += self.samplingTime
+            obj.integrate(self._materialise_psf())
+            self.PSF = obj.frame
         else:
             raise AttributeError(f"Telescope cannot be propagated to an object with tag {tag!r}")
         return self

@@ -242,3 +242,23 @@ def test_detector_integrate_standalone(dev):
     q = cam2.integrate(torch.full((30, 30), 500.0, device=dev))
     assert q.shape == (30, 30) and float(q.max()) <= 255 and abs(float(q.mean()) - 500 / 1000 * 255) < 1.5
     assert torch.equal(Detector().integrate(flux), flux)          # ideal detector
+
+
+def test_science_camera_on_the_psf(dev):
+    """tel*cam (Telescope.py:487-500): computePSF(cam.psf_sampling) then the detector chain; photon noise keeps the flux."""
+    from rlao_b200.Detector import Detector
+    from rlao_b200.Source import Source
+    from rlao_b200.Telescope import Telescope
+    tel = Telescope(48, 8, 1 / 500, n_envs=3, device=dev)
+    Source("I", 8) * tel
+    tel.resetOPD()
+    tel.computePSF(4)
+    ideal = tel.PSF.clone()
+    cam = Detector(psf_sampling=4, photonNoise=True, seed=2)
+    tel * cam
+    assert tel.PSF is cam.frame and cam.frame.shape == ideal.shape
+    assert torch.equal(cam.frame.round(), cam.frame) and float((cam.frame - ideal).abs().max()) > 0
+    assert abs(float(cam.frame.sum()) / float(ideal.sum()) - 1) < 5e-3
+    assert float((cam.frame[0] - cam.frame[1]).abs().max()) > 0          # independent draws per environment
+    with pytest.raises(ValueError):
+        tel * Detector(psf_sampling=4, integrationTime=1e-4)
