@@ -146,6 +146,8 @@ class TorchWrapper(_Wrapper):
         env._measure_frame(None if i is None else i + 1, self._download_hook(self._ahead), atmosphere_done=True)
         env.atm.update()
         cur["ready"].synchronize()
+        if ready is not None:
+            ready.synchronize()            # the caller may reuse its action buffer as soon as step returns
         return cur["bufs"]
 
     def flush(self):
