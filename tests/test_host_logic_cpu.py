@@ -179,3 +179,32 @@ def test_po4ao_rollout_host_logic_on_cpu(fake):
     assert torch.equal(past_obs[:, -1], st[1, -1]) and torch.equal(past_act[:, -1], rp.action().reshape(2, max_ts, B, nA, nA)[1, -1])
     loss = mbrl.train_dynamics(nH, max_ts, 4, dynamics, torch.optim.Adam(dynamics.parameters()), rp, dyn_iters=1, device="cpu")
     assert np.isfinite(loss)
+
+
+def test_shift_bookkeeping_matches_oracle_for_random_winds(fake):
+    """Integer / fractional wind bookkeeping of updateLayer (OOPAO/Atmosphere.py:350-404): number of add_row events per
+    frame and the sub-pixel remainder `buff` for random wind speeds and directions, in lock-step with the oracle."""
+    from oracle.ao_oracle import AtmosphereOracle, telescope_pupil
+    from rlao_b200.Atmosphere import Atmosphere
+    from rlao_b200.Source import Source
+    from rlao_b200.Telescope import Telescope
+    rs = np.random.RandomState(4)
+    for trial in range(4):
+        cfg = CONFIGS["tiny"]()
+        cfg.windSpeed = list(rs.uniform(3, 70, size=2))
+        cfg.windDirection = list(rs.uniform(0, 360, size=2))
+        tel = Telescope(cfg.resolution, cfg.diameter, cfg.samplingTime, n_envs=1)
+        Source(cfg.opticalBand, cfg.magnitude) * tel
+        atm = Atmosphere(tel, cfg.r0, cfg.L0, cfg.windSpeed, cfg.fractionalR0, cfg.windDirection, cfg.altitude,
+                         rng="reference", canvas_slack=8)
+        atm.initializeAtmosphere(tel)
+        orc = AtmosphereOracle(cfg, telescope_pupil(cfg.resolution))
+        for k in range(25):
+            before = [ly.events for ly in atm._layers]
+            n_draws = len(orc.xi_log)
+            atm.update()
+            orc.update()
+            assert sum(ly.events for ly in atm._layers) - sum(before) == len(orc.xi_log) - n_draws, (trial, k)
+            for ly, lo in zip(atm._layers, orc.layers):
+                assert np.allclose(ly.buff, lo.buff, rtol=0, atol=1e-12), (trial, k)
+        assert rel_err(atm.OPD_no_pupil.numpy(), orc.OPD_no_pupil) < 1e-4
