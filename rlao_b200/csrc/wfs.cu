@@ -542,28 +542,37 @@ shwfs_frame6_kernel(const float* __restrict__ opd_a, const float* __restrict__ o
   }
 }
 
-// centroid + slopes: one thread per (valid lenslet, environment)
+// centroid + slopes: one thread per (valid lenslet, environment).  n is a template parameter so that the 6 x 6 (4 x 4,
+// 8 x 8) spot is read with fully unrolled 64-bit loads (tile rows start on even columns: lj * n with n even).
+template <int n>
 __global__ void __launch_bounds__(128)
 shwfs_slopes_kernel(const float* __restrict__ frame, const int32_t* __restrict__ envmax, int shared_max,
                     const int32_t* __restrict__ valid_idx, int nV, const float* __restrict__ ref_xy, float inv_units,
-                    float threshold_cog, int nS, int n, float* __restrict__ slopes, int lds,
+                    float threshold_cog, int nS, float* __restrict__ slopes, int lds,
                     __nv_bfloat16* __restrict__ planes, int parts) {
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nV) return;
   const int R = nS * n;
   const int k = __ldg(&valid_idx[t]);
-  const int li = k / nS, lj = k % nS;
+  const int li = k / nS, lj = k - li * nS;
   const float thr = threshold_cog * ordered_to_float(__ldg(&envmax[shared_max ? 0 : b]));
   const float* __restrict__ f = frame + (size_t)b * R * R + (size_t)(li * n) * R + lj * n;
-  float s = 0.f, sx = 0.f, sy = 0.f;
+  float2 v[n][n / 2];
+#pragma unroll
   for (int p = 0; p < n; ++p)
+#pragma unroll
+    for (int h = 0; h < n / 2; ++h) v[p][h] = __ldg(reinterpret_cast<const float2*>(f + (size_t)p * R) + h);
+  float s = 0.f, sx = 0.f, sy = 0.f;
+#pragma unroll
+  for (int p = 0; p < n; ++p)
+#pragma unroll
     for (int q = 0; q < n; ++q) {
-      float v = __ldg(f + (size_t)p * R + q);
-      v = v < thr ? 0.f : v;
-      s += v;
-      sx = fmaf(v, (float)p, sx);   // axis 1 of maps_intensity -> centroid[:,0] -> SX (ShackHartmann.py:321,596)
-      sy = fmaf(v, (float)q, sy);   // axis 2 -> centroid[:,1] -> SY
+      float x = (q & 1) ? v[p][q >> 1].y : v[p][q >> 1].x;
+      x = x < thr ? 0.f : x;
+      s += x;
+      sx = fmaf(x, (float)p, sx);   // axis 1 of maps_intensity -> centroid[:,0] -> SX (ShackHartmann.py:321,596)
+      sy = fmaf(x, (float)q, sy);   // axis 2 -> centroid[:,1] -> SY
     }
   float cx = sx / s, cy = sy / s;
   if (!isfinite(cx)) cx = 0.f;      // ShackHartmann.py:583-593
@@ -773,10 +782,21 @@ int aoenv_shwfs_slopes(const float* frame, const int32_t* envmax, int shared_max
                        const float* ref_xy, float inv_units, float threshold_cog, int B, int nS, int n, float* slopes,
                        int lds, void* slope_planes, int parts, void* stream) {
   AOENV_CHECK_ARG(B > 0 && B <= 65535 && nV > 0 && lds >= 2 * nV, "shwfs_slopes: bad shape B=%d nV=%d lds=%d", B, nV, lds);
+  AOENV_CHECK_ARG(n == 4 || n == 6 || n == 8, "shwfs_slopes: %d pixels per lenslet is not a compiled size (4, 6, 8)", n);
+  AOENV_CHECK_ARG((reinterpret_cast<uintptr_t>(frame) & 7) == 0, "shwfs_slopes: frame must be 8-byte aligned");
   dim3 grid((nV + 127) / 128, B);
-  shwfs_slopes_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(frame, envmax, shared_max, valid_idx, nV, ref_xy,
-                                                              inv_units, threshold_cog, nS, n, slopes, lds,
-                                                              (__nv_bfloat16*)slope_planes, parts);
+#define AOENV_SLOPES_CASE(NN)                                                                                          \
+  case NN:                                                                                                             \
+    shwfs_slopes_kernel<NN><<<grid, 128, 0, (cudaStream_t)stream>>>(frame, envmax, shared_max, valid_idx, nV, ref_xy,   \
+                                                                    inv_units, threshold_cog, nS, slopes, lds,          \
+                                                                    (__nv_bfloat16*)slope_planes, parts);               \
+    break;
+  switch (n) {
+    AOENV_SLOPES_CASE(4)
+    AOENV_SLOPES_CASE(6)
+    AOENV_SLOPES_CASE(8)
+  }
+#undef AOENV_SLOPES_CASE
   AOENV_LAUNCH_CHECK("shwfs_slopes");
   return 0;
 }
