@@ -241,23 +241,32 @@ shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ op
 #pragma unroll
     for (int bb = 0; bb < n; ++bb) {
 #pragma unroll
-      for (int aa = 0; aa < n; ++aa) {
-        const int o = bb * R + aa;
-        const float a = __ldg(pa + o);
-        const float t = pb ? a + __ldg(pb + o) : a;
-        const float pu = __ldg(pupil + tile + o);
-        const float in_pupil = pu > 0.f ? 1.f : 0.f;
-        const float da = (a - ka) * in_pupil, dt = (t - kt) * in_pupil;
-        f0 += da; f1 = fmaf(da, da, f1); f2 += dt; f3 = fmaf(dt, dt, f3);
-        // phase / 2pi reduced to [-1/2, 1/2] exactly, then the SFU sine/cosine (abs. error ~4e-7 on [-pi, pi])
-        const float turns = t * pu * phase_turns;
-        // nearest integer by the 1.5 * 2^23 trick (two FADDs; rintf would go through the transcendental pipe, which the
-        // sine and cosine already load): exact for |turns| < 2^22
-        const float ang = (turns - ((turns + 12582912.0f) - 12582912.0f)) * 6.283185307179586f;
-        const float sn = __sinf(ang), cs = __cosf(ang);
-        const float am = lit ? __ldg(amp + tile + o) : 0.f;
-        if ((bb & 1) == 0) { er2[aa][bb >> 1].x = am * cs; ei2[aa][bb >> 1].x = am * sn; }
-        else { er2[aa][bb >> 1].y = am * cs; ei2[aa][bb >> 1].y = am * sn; }
+      for (int a2 = 0; a2 < n / 2; ++a2) {
+        // two neighbouring pixels per 64-bit load (tile rows start on even columns: lj * n with n even, R even)
+        const int o2 = bb * R + 2 * a2;
+        const float2 av = __ldg(reinterpret_cast<const float2*>(pa + o2));
+        const float2 bv = pb ? __ldg(reinterpret_cast<const float2*>(pb + o2)) : make_float2(0.f, 0.f);
+        const float2 pv = __ldg(reinterpret_cast<const float2*>(pupil + tile + o2));
+        const float2 mv = lit ? __ldg(reinterpret_cast<const float2*>(amp + tile + o2)) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int aa = 2 * a2 + e;
+          const float a = e ? av.y : av.x;
+          const float t = a + (e ? bv.y : bv.x);
+          const float pu = e ? pv.y : pv.x;
+          const float in_pupil = pu > 0.f ? 1.f : 0.f;
+          const float da = (a - ka) * in_pupil, dt = (t - kt) * in_pupil;
+          f0 += da; f1 = fmaf(da, da, f1); f2 += dt; f3 = fmaf(dt, dt, f3);
+          // phase / 2pi reduced to [-1/2, 1/2] exactly, then the SFU sine/cosine (abs. error ~4e-7 on [-pi, pi])
+          const float turns = t * pu * phase_turns;
+          // nearest integer by the 1.5 * 2^23 trick (two FADDs; rintf would go through the transcendental pipe, which
+          // the sine and cosine already load): exact for |turns| < 2^22
+          const float ang = (turns - ((turns + 12582912.0f) - 12582912.0f)) * 6.283185307179586f;
+          const float sn = __sinf(ang), cs = __cosf(ang);
+          const float am = e ? mv.y : mv.x;
+          if ((bb & 1) == 0) { er2[aa][bb >> 1].x = am * cs; ei2[aa][bb >> 1].x = am * sn; }
+          else { er2[aa][bb >> 1].y = am * cs; ei2[aa][bb >> 1].y = am * sn; }
+        }
       }
     }
   }
