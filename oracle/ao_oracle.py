@@ -2,7 +2,7 @@
 through OOPAO (Shack-Hartmann path).  TEST INFRASTRUCTURE ONLY.
 
 Only tests/, __graft_entry__.smoke(), bench.py's `cpu_baseline` / `--impl reference` legs and
-oracle/make_golden.py may import this module; the product (rlao_b200) never does and has no CPU
+oracle/make_golden*.py may import this module; the product (rlao_b200) never does and has no CPU
 fallback.  Every function cites the reference lines it restates (paths under
 /root/reference/drl4ao/: OOPAO/ = AO_OOPAO/OOPAO/, MAIN/ = MAIN_CODE/).
 

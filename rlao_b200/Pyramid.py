@@ -1,0 +1,253 @@
+"""Pyramid — mirror of OOPAO/Pyramid.py for the configuration the drl4ao papyrus environment instantiates
+(MAIN_CODE/OOPAOEnv/OOPAOEnv.py:239-249): 4-sided pyramid, PSF centred on four pixels, circular tip-tilt modulation,
+`slopesMaps` post-processing; batched over environments (first step).
+
+The two transforms per modulation point (Pyramid.py:469-504: FFT of the padded field, focal-plane mask, inverse FFT)
+go through cuFFT (`torch.fft`) — the reference's own GPU path does the same through CuPy — over all environments and a
+chunk of modulation points at once; the field formation, mask, intensity accumulation, detector binning and the
+quadrant arithmetic are batched tensor operations around them.  Detector noise uses the camera kernel of the SH path
+(`Detector.integrate` -> aoenv_detector_integrate).  Hand-written transform kernels are future work; parity is pinned
+through oracle/pyramid_oracle.py, itself pinned against the unmodified reference (tests/golden/pyramid.npz).
+Unsupported reference options raise NotImplementedError.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .Detector import Detector
+
+
+class Pyramid:
+    def __init__(self, nSubap, telescope, modulation, lightRatio, postProcessing="slopesMaps", psfCentering=True,
+                 n_pix_separation=2, calibModulation=50, n_pix_edge=None, extraModulationFactor=0, binning=1,
+                 nTheta_user_defined=None, userValidSignal=None, old_mask=False, rooftop=None, delta_theta=0,
+                 user_modulation_path=None, pupilSeparationRatio=None, edgePixel=None, zeroPadding=None,
+                 max_points_per_pass=8):
+        tel = telescope
+        self.telescope = tel
+        self.device = tel.device
+        self.n_envs = tel.n_envs
+        if (tel.resolution / nSubap) % 2 != 0:
+            raise ValueError("The resolution should be an even number and be a multiple of 2**i where i>=2")
+        if tel.src is None:
+            raise AttributeError("The telescope was not coupled to any source object! Make sure to couple it with an src object using src*tel")
+        for name, val, default in (("postProcessing", postProcessing, "slopesMaps"), ("psfCentering", psfCentering, True),
+                                   ("binning", binning, 1), ("userValidSignal", userValidSignal, None),
+                                   ("old_mask", old_mask, False), ("rooftop", rooftop, None),
+                                   ("user_modulation_path", user_modulation_path, None),
+                                   ("pupilSeparationRatio", pupilSeparationRatio, None), ("edgePixel", edgePixel, None),
+                                   ("zeroPadding", zeroPadding, None)):
+            if val != default:
+                raise NotImplementedError(f"Pyramid({name}={val!r}) is out of scope; only {default!r} is supported")
+        self.tag = "pyramid"
+        self.nSubap = int(nSubap)
+        self.postProcessing = postProcessing
+        self.psfCentering = True
+        self.binning = 1
+        self.delta_theta = delta_theta
+        self.extraModulationFactor = extraModulationFactor
+        self.nTheta_user_defined = nTheta_user_defined
+        self.n_pix_separation = n_pix_separation
+        self.n_pix_edge = n_pix_separation // 2 if n_pix_edge is None else n_pix_edge                 # Pyramid.py:237-240
+        R = tel.resolution
+        self.nRes = int((self.nSubap * 2 + self.n_pix_separation + self.n_pix_edge * 2) * R / self.nSubap)   # :250
+        self.zeroPaddingFactor = self.nRes / R
+        self.zeroPadding = (self.nRes - R) // 2
+        self.center = self.nRes // 2
+        self.cam = Detector(round(self.nSubap * self.zeroPaddingFactor))                              # :254
+        self.lightRatio = lightRatio
+        self.calibModulation = R / 2 - 1 if calibModulation >= R / 2 else calibModulation             # :258-261
+        self.delta_Tip = self.delta_Tilt = 0
+        self.fov = 206265 * self.nRes / self.zeroPaddingFactor * (tel.src.wavelength / tel.D)
+        self.max_points_per_pass = int(max_points_per_pass)
+        dev = self.device
+        lin = np.linspace(-np.pi, np.pi, R)
+        tip, tilt = np.meshgrid(lin, lin)                                                             # :285-288
+        self._Tip = torch.as_tensor(tip * tel.pupil, dtype=torch.float64, device=dev)
+        self._Tilt = torch.as_tensor(tilt * tel.pupil, dtype=torch.float64, device=dev)
+        k = torch.arange(self.nRes, dtype=torch.float64, device=dev)
+        ph1 = torch.polar(torch.ones_like(k), -math.pi * (self.nRes + 1) / self.nRes * k)             # :291-292, separable
+        self._phasor = ph1[:, None] * ph1[None, :]
+        self.m = self._phase_mask()
+        self._mask = torch.polar(torch.ones_like(self.m), self.m)                                     # :318-323
+        self.mask = self._mask
+        self.slopesUnits = 1
+        self.referenceSignal = 0
+        self.referenceSignal_2D = 0
+        self.isInitialized = self.isCalibrated = False
+        self._signal = self._signal_2D = None
+        self.modulation = modulation
+        self.initialization(tel)                                                                      # :301-303
+        self.modulation = modulation
+        self.wfs_calibration(tel)
+        tel.resetOPD()
+        self.wfs_measure()
+
+    # ---- static geometry ----------------------------------------------------------------------------------
+    def _phase_mask(self):
+        """Pyramid.py:368-388 (get_phase_mask, psf_centering=True)."""
+        n_tot, nS = self.nRes, self.nSubap
+        norma = (nS + self.n_pix_separation) * (self.telescope.resolution / nS)
+        lim = np.pi / 4 - (np.pi / 4) / (n_tot // 2)
+        tip, tilt = np.meshgrid(np.linspace(-lim, lim, n_tot // 2), np.linspace(-lim, lim, n_tot // 2))
+        h = n_tot // 2
+        m = np.zeros((n_tot, n_tot))
+        m[:h, :h] = tip * norma + tilt * norma
+        m[:h, -h:] = -tip * norma + tilt * norma
+        m[-h:, -h:] = -tip * norma - tilt * norma
+        m[-h:, :h] = tip * norma - tilt * norma
+        return torch.as_tensor(-m, dtype=torch.float64, device=self.device)
+
+    # ---- modulation ---------------------------------------------------------------------------------------
+    @property
+    def modulation(self):
+        return self._modulation
+
+    @modulation.setter
+    def modulation(self, val):
+        """Pyramid.py:941-984: modulation path, per-point tip/tilt phases; re-calibrates the reference slopes."""
+        self._modulation = val
+        if val >= self.telescope.resolution // 2:
+            raise ValueError("Error the modulation radius is too large for this resolution! Consider using a larger telescope resolution!")
+        if val != 0:
+            perimeter = np.pi * 2 * val
+            self.nTheta = (4 * int(self.extraModulationFactor + np.ceil(perimeter / 4)) if self.nTheta_user_defined is None
+                           else self.nTheta_user_defined)
+            self.thetaModulation = np.linspace(0 + self.delta_theta, 2 * np.pi + self.delta_theta, self.nTheta, endpoint=False)
+            self.modulation_path = [[val * np.cos(t) + self.delta_Tip, val * np.sin(t) + self.delta_Tilt] for t in self.thetaModulation]
+            px = torch.as_tensor([p[0] for p in self.modulation_path], dtype=torch.float64, device=self.device)
+            py = torch.as_tensor([p[1] for p in self.modulation_path], dtype=torch.float64, device=self.device)
+            # the reference keeps these phases in float32 (:960-961)
+            self._phase_mod = (px[:, None, None] * self._Tip + py[:, None, None] * self._Tilt).to(torch.float32)
+        else:
+            self.nTheta = 1
+            self._phase_mod = torch.zeros((1,) + tuple(self._Tip.shape), dtype=torch.float32, device=self.device)
+        if getattr(self, "isCalibrated", False):
+            self.slopesUnits = 1
+            self.referenceSignal = 0
+            self.referenceSignal_2D = 0
+            self.wfs_calibration(self.telescope)
+
+    # ---- propagation --------------------------------------------------------------------------------------
+    def _frames(self, phase, precise=False):
+        """phase [F, R, R] (radians, pupil-masked) -> detector frames [F, n_cam, n_cam] before the camera chain:
+        sum over the modulation points of |IFFT(FFT(padded field * phasor) * mask)|^2 (Pyramid.py:469-504, 581-603),
+        binned to the detector pixels (:987-1002, tools.py:409-416)."""
+        tel = self.telescope
+        R, N, F = tel.resolution, self.nRes, phase.shape[0]
+        rdt, cdt = (torch.float64, torch.complex128) if precise else (torch.float32, torch.complex64)
+        amp = (torch.as_tensor(np.sqrt(tel.src.fluxMap / self.nTheta) * tel.pupilReflectivity, device=self.device)).to(rdt)
+        phasor, mask = self._phasor.to(cdt), self._mask.to(cdt)
+        lo = self.center - R // 2
+        out = torch.zeros((F, N, N), dtype=rdt, device=self.device)
+        step = max(1, self.max_points_per_pass)
+        for t0 in range(0, self.nTheta, step):
+            pm = self._phase_mod[t0:t0 + step].to(rdt)                                     # [T, R, R]
+            field = torch.polar(amp.expand(F, pm.shape[0], R, R), phase.to(rdt)[:, None] + pm[None])
+            support = torch.zeros((F, pm.shape[0], N, N), dtype=cdt, device=self.device)
+            support[:, :, lo:lo + R, lo:lo + R] = field
+            ft = torch.fft.fft2(support * phasor)
+            out += (torch.fft.ifft2(ft * mask).abs() ** 2).sum(dim=1)
+        n, b = self.cam.resolution, int(round(N / self.cam.resolution))
+        return out.reshape(F, n, b, n, b).sum(dim=(2, 4))
+
+    def _camera(self, frames):
+        """self*self.cam (:987-1002): detector chain on the binned frames."""
+        self.pyramidFrame = frames
+        if self.cam.integrationTime is None:
+            self.cam.integrationTime = self.telescope.samplingTime
+        if self.cam.is_ideal():
+            self.cam.frame = frames[0] if (self.n_envs == 1 and frames.shape[0] == 1) else frames
+        else:
+            out = self.cam.integrate(frames.to(torch.float32))
+            self.cam.frame = out[0] if (self.n_envs == 1 and out.shape[0] == 1) else out
+        return self.cam.frame
+
+    def grabQuadrant(self, n, cameraFrame=None):
+        """Pyramid.py:774-791 (4-sided pyramid, binning 1), on [..., n_cam, n_cam]."""
+        f = self.cam.frame if cameraFrame is None else cameraFrame
+        e = int(np.round(self.n_pix_separation / 2))
+        c = int(np.round(self.cam.resolution / 2))
+        m = int(np.ceil(self.nSubap))
+        if n == 3:
+            return f[..., e + c:e + c + m, e + c:e + c + m]
+        if n == 4:
+            return f[..., e + c:e + c + m, -e + c - m:-e + c]
+        if n == 1:
+            return f[..., -e + c - m:-e + c, -e + c - m:-e + c]
+        if n == 2:
+            return f[..., -e + c - m:-e + c, e + c:e + c + m]
+        raise ValueError("quadrant index must be 1..4")
+
+    def signalProcessing(self, cameraFrame=None):
+        """Pyramid.py:685-701 (slopesMaps): returns (slopes maps [..., 2 nSubap, nSubap], slopes [..., nSignal])."""
+        f = self.cam.frame if cameraFrame is None else cameraFrame
+        v = self._valid_t.to(f.dtype)
+        I1, I2, I3, I4 = (self.grabQuadrant(k, f) * v for k in (1, 2, 3, 4))
+        I4Q = I1 + I2 + I3 + I4
+        self.norma = I4Q[..., self._valid_t].mean(dim=-1)
+        norma = self.norma[..., None, None] if I4Q.ndim == 3 else self.norma
+        Sx = (I1 - I2 + I4 - I3) / norma
+        Sy = (I1 - I4 + I2 - I3) / norma
+        maps = (torch.cat([Sx, Sy], dim=-2) - self.referenceSignal_2D) * self.slopesUnits
+        return maps, maps[..., self._valid_signal_t]
+
+    # ---- reference-facing API -----------------------------------------------------------------------------
+    def initialization(self, telescope):
+        """Pyramid.py:408-450: valid pixels from the flux at a large modulation."""
+        telescope.resetOPD()
+        self.modulation = self.calibModulation
+        zero = torch.zeros((1, telescope.resolution, telescope.resolution), dtype=torch.float64, device=self.device)
+        self.initFrame = self._frames(zero, precise=True)[0]
+        quads = [self.grabQuadrant(k, self.initFrame) for k in (1, 2, 3, 4)]
+        self.I4Q = quads[0] + quads[1] + quads[2] + quads[3]
+        self._valid_t = self.I4Q >= self.lightRatio * self.I4Q.max()
+        self._valid_signal_t = torch.cat([self._valid_t, self._valid_t], dim=0)
+        self.validI4Q = self._valid_t.cpu().numpy()
+        self.validSignal = self._valid_signal_t.cpu().numpy()
+        self.nSignal = int(self.validSignal.sum())
+        self.isInitialized = True
+
+    def wfs_calibration(self, telescope):
+        """Pyramid.py:454-466: reference slopes of the flat wavefront at the working modulation (float64)."""
+        zero = torch.zeros((1, telescope.resolution, telescope.resolution), dtype=torch.float64, device=self.device)
+        frame = self._frames(zero, precise=True)[0]
+        self.referenceSignal_2D = 0
+        ref2d, ref = self.signalProcessing(frame)
+        self.referenceSignal_2D, self.referenceSignal = ref2d, ref
+        self.referencePyramidFrame = frame
+        self.isCalibrated = True
+
+    def wfs_measure(self, phase_in=None):
+        """Pyramid.py:516-603, single-frame branches, for every environment."""
+        tel = self.telescope
+        lam = tel.src.wavelength
+        if phase_in is not None:
+            ph = torch.as_tensor(phase_in, dtype=torch.float32, device=self.device)
+            tel.OPD = (ph.unsqueeze(0) if ph.ndim == 2 else ph) * (lam / (2 * math.pi))
+        opd = tel._materialise() * tel._pupil_f
+        frames = self._frames(opd * (2 * math.pi / lam))
+        self._camera(frames)
+        frame = self.cam.frame if self.cam.frame.ndim == 3 else self.cam.frame.unsqueeze(0)
+        maps, sig = self.signalProcessing(frame.to(torch.float64) if self.cam.is_ideal() else frame.to(torch.float32))
+        self._signal_2D, self._signal = maps, sig
+        self.pyramidSignal_2D, self.pyramidSignal = self.signal_2D, self.signal
+
+    def pyramid_propagation(self, telescope):
+        self.wfs_measure()
+
+    @property
+    def signal(self):
+        return self._signal[0] if self.n_envs == 1 else self._signal
+
+    @property
+    def signal_2D(self):
+        return self._signal_2D[0] if self.n_envs == 1 else self._signal_2D
+
+    def __mul__(self, obj):
+        if getattr(obj, "tag", None) != "detector":
+            raise AttributeError("Error light propagated to the wrong type of object")
+        self._camera(self.pyramidFrame)
+        return -1

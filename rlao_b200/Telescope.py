@@ -189,7 +189,7 @@ class Telescope:
     def __mul__(self, obj):
         """Telescope.py:457-564, dispatch on obj.tag."""
         tag = getattr(obj, "tag", None)
-        if tag == "shackHartmann":
+        if tag in ("shackHartmann", "pyramid"):               # Telescope.py:476-485
             obj.telescope = self
             obj.wfs_measure()
         elif tag == "deformableMirror":
