@@ -62,6 +62,14 @@ def main():
         wfs.wfs_measure(phase_in=phases[0])
     g["referenceSignal_2D_unmodulated"] = np.asarray(wfs.referenceSignal_2D, dtype=np.float64)
     g["signal_unmodulated_0"] = np.asarray(wfs.signal, dtype=np.float64)
+    with rh.quiet():
+        tel.resetOPD()
+        wfs2 = Pyramid(nSubap=s["nSubap"], telescope=tel, modulation=s["modulation"], lightRatio=s["lightRatio"],
+                       n_pix_separation=s["n_pix_separation"], n_pix_edge=s["n_pix_edge"],
+                       postProcessing="slopesMaps_incidence_flux", binning=1)
+        wfs2.wfs_measure(phase_in=phases[1])
+    g["incidence_referenceSignal_2D"] = np.asarray(wfs2.referenceSignal_2D, dtype=np.float64)
+    g["incidence_signal_1"] = np.asarray(wfs2.signal, dtype=np.float64)
     np.savez_compressed(OUT, **g)
     print("wrote", OUT, os.path.getsize(OUT) // 1024, "KiB; nRes", wfs.nRes, "nTheta", int(g["nTheta"]), "nSignal", wfs.nSignal)
 

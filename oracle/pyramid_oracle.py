@@ -1,10 +1,10 @@
 """CPU oracle for the Pyramid WFS (OOPAO/Pyramid.py) — TEST INFRASTRUCTURE ONLY, groundwork for SURVEY.md section 8 f-3.
 
 float64 numpy restatement of the path the drl4ao papyrus environment uses (MAIN_CODE/OOPAOEnv/OOPAOEnv.py:239-249):
-4-sided pyramid, PSF centred on 4 pixels (`psfCentering=True`), circular tip-tilt modulation, `slopesMaps`
-post-processing, ideal detector, binning 1.  Every function cites the reference lines it follows.  Pinned against the
-unmodified reference by oracle/make_golden_pyramid.py -> tests/golden/pyramid.npz (tests/test_pyramid_oracle.py).
-The product has no Pyramid yet: nothing under rlao_b200/ imports this module.
+4-sided pyramid, PSF centred on 4 pixels (`psfCentering=True`), circular tip-tilt modulation, `slopesMaps` /
+`slopesMaps_incidence_flux` post-processing, ideal detector, binning 1.  Every function cites the reference lines it
+follows.  Pinned against the unmodified reference by oracle/make_golden_pyramid.py -> tests/golden/pyramid.npz
+(tests/test_pyramid_oracle.py).  Nothing under rlao_b200/ imports this module.
 """
 from __future__ import annotations
 
@@ -34,7 +34,9 @@ class PyramidOracle:
     phase [R, R] in radians (already masked by the pupil) and returns the slopes vector; `frame`, `signal_2D` are kept."""
 
     def __init__(self, pupil, fluxMap, nSubap, modulation, lightRatio, n_pix_separation=2, n_pix_edge=None,
-                 calibModulation=50, reflectivity=None):
+                 calibModulation=50, reflectivity=None, postProcessing="slopesMaps"):
+        assert postProcessing in ("slopesMaps", "slopesMaps_incidence_flux")
+        self.postProcessing = postProcessing
         self.pupil = np.asarray(pupil).astype(bool)
         self.R = self.pupil.shape[0]
         if (self.R / nSubap) % 2 != 0:
@@ -125,10 +127,11 @@ class PyramidOracle:
         return f[-n_extra + c - n:-n_extra + c, n_extra + c:n_extra + c + n]
 
     def signal_processing(self):
-        """Pyramid.py:685-701 (slopesMaps)."""
+        """Pyramid.py:685-701 (slopesMaps) and :703-726 (slopesMaps_incidence_flux)."""
         I1, I2, I3, I4 = (self.grab_quadrant(k) * self.validI4Q for k in (1, 2, 3, 4))
         I4Q = I1 + I2 + I3 + I4
-        self.norma = np.mean(I4Q[self.validI4Q])
+        # :689-691 global normalisation; :713-716 `slopesMaps_incidence_flux` normalises by the mean of the camera frame
+        self.norma = np.mean(I4Q[self.validI4Q]) if self.postProcessing == "slopesMaps" else np.float64(self.frame.mean())
         Sx = I1 - I2 + I4 - I3
         Sy = I1 - I4 + I2 - I3
         maps = (np.concatenate((Sx, Sy) / self.norma) - self.referenceSignal_2D) * self.slopesUnits

@@ -33,7 +33,9 @@ class Pyramid:
             raise ValueError("The resolution should be an even number and be a multiple of 2**i where i>=2")
         if tel.src is None:
             raise AttributeError("The telescope was not coupled to any source object! Make sure to couple it with an src object using src*tel")
-        for name, val, default in (("postProcessing", postProcessing, "slopesMaps"), ("psfCentering", psfCentering, True),
+        if postProcessing not in ("slopesMaps", "slopesMaps_incidence_flux"):
+            raise NotImplementedError(f"Pyramid(postProcessing={postProcessing!r}) is out of scope (full-frame signals)")
+        for name, val, default in (("psfCentering", psfCentering, True),
                                    ("binning", binning, 1), ("userValidSignal", userValidSignal, None),
                                    ("old_mask", old_mask, False), ("rooftop", rooftop, None),
                                    ("user_modulation_path", user_modulation_path, None),
@@ -182,12 +184,16 @@ class Pyramid:
         raise ValueError("quadrant index must be 1..4")
 
     def signalProcessing(self, cameraFrame=None):
-        """Pyramid.py:685-701 (slopesMaps): returns (slopes maps [..., 2 nSubap, nSubap], slopes [..., nSignal])."""
+        """Pyramid.py:685-726 (slopesMaps, slopesMaps_incidence_flux): returns (slopes maps [..., 2 nSubap, nSubap],
+        slopes [..., nSignal])."""
         f = self.cam.frame if cameraFrame is None else cameraFrame
         v = self._valid_t.to(f.dtype)
         I1, I2, I3, I4 = (self.grabQuadrant(k, f) * v for k in (1, 2, 3, 4))
         I4Q = I1 + I2 + I3 + I4
-        self.norma = I4Q[..., self._valid_t].mean(dim=-1)
+        if self.postProcessing == "slopesMaps":                         # :689-691
+            self.norma = I4Q[..., self._valid_t].mean(dim=-1)
+        else:                                                           # :713-716 mean of the camera frame
+            self.norma = f.mean(dim=(-2, -1))
         norma = self.norma[..., None, None] if I4Q.ndim == 3 else self.norma
         Sx = (I1 - I2 + I4 - I3) / norma
         Sy = (I1 - I4 + I2 - I3) / norma

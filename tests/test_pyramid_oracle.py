@@ -54,6 +54,15 @@ def test_unmodulated(g, wfs):
     assert _rel(wfs.measure(g["phase_0"]), g["signal_unmodulated_0"]) < 1e-8
 
 
+def test_incidence_flux_normalisation(g):
+    """postProcessing='slopesMaps_incidence_flux' (the papyrus parameter file, parameterFile_oopao_parser.py:68)."""
+    R, nS, mod, sep, edge = (int(x) for x in g["setup"])
+    w = PyramidOracle(g["pupil"].astype(bool), g["fluxMap"], nS, mod, float(g["lightRatio"]), n_pix_separation=sep,
+                      n_pix_edge=edge, postProcessing="slopesMaps_incidence_flux")
+    assert _rel(w.referenceSignal_2D, g["incidence_referenceSignal_2D"]) < 1e-9
+    assert _rel(w.measure(g["phase_1"]), g["incidence_signal_1"]) < 1e-8
+
+
 # ---- product class (torch / cuFFT implementation) against the same fixture --------------------------------------
 def _build_product(g, device, n_envs=1):
     from rlao_b200.Pyramid import Pyramid
@@ -93,6 +102,19 @@ def _check_product(g, tel, wfs, tol_frame, tol_sig):
         for k in range(2):
             assert _rel(wfs.cam.frame[k].cpu().numpy(), g[f"frame_{k}"]) < tol_frame
             assert _rel(wfs.signal[k].cpu().numpy(), g[f"signal_{k}"]) < tol_sig
+
+
+def test_product_incidence_flux_on_cpu_stand_in(g, monkeypatch):
+    import fake_backend
+    from rlao_b200.Pyramid import Pyramid
+    fake_backend.install(monkeypatch)
+    tel, src, _ = _build_product(g, None)
+    R, nS, mod, sep, edge = (int(x) for x in g["setup"])
+    w = Pyramid(nS, tel, mod, float(g["lightRatio"]), n_pix_separation=sep, n_pix_edge=edge,
+                postProcessing="slopesMaps_incidence_flux")
+    assert _rel(w.referenceSignal_2D.numpy(), g["incidence_referenceSignal_2D"]) < 1e-9
+    w.wfs_measure(phase_in=g["phase_1"])
+    assert _rel(w.signal.numpy(), g["incidence_signal_1"]) < 2e-4
 
 
 def test_product_pyramid_on_cpu_stand_in(g, monkeypatch):
