@@ -54,6 +54,11 @@ def initializeParameterFile(args):
     param["cam_readoutNoise"] = 14 if noisy else 0                   # OOPAOEnvRazor.py:332-333
     if noisy:                                                        # OOPAOEnvRazor.py:243-250
         param.update(cam_sensor="CMOS", cam_FWC=10000, cam_bits=10, cam_QE=0.56, cam_darkCurrent=5)
+    # Pyramid WFS (only read when the environment is built with wfs_type="pyramid"; Conf/parameterFile_oopao_parser.py:64-68)
+    param["modulation"] = g("modulation", 3)
+    param["n_pix_separation"] = 4
+    param["lightThreshold"] = 0.1
+    param["postProcessing"] = g("postProcessing", "slopesMaps_incidence_flux")
     # control
     param["nZernike"] = g("nZernike", 50)
     param["nMeasurements"] = 25

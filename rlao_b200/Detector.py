@@ -66,14 +66,14 @@ class Detector:
         self.frame_counter += 1
         return d
 
-    def integrate(self, frame):
+    def integrate(self, frame, env_offset=0):
         """Detector.py:279-301: applies the camera to a frame of photons ([rows, cols] or [B, rows, cols], CUDA float32) and
         stores / returns `self.frame`.  Every call advances the frame counter of the random streams."""
         f = torch.as_tensor(frame, dtype=torch.float32)
         if f.device.type != "cuda":
             raise _lib.AOEnvLibraryError("Detector.integrate needs a CUDA tensor (there is no CPU path)")
         out = (f.unsqueeze(0) if f.ndim == 2 else f).contiguous().clone()
-        det = self.as_struct()
+        det = self.as_struct(env_offset)
         if det is not None:
             _lib.check(_lib.load().aoenv_detector_integrate(_lib.ptr(out), out.shape[0], out.shape[1], out.shape[2],
                                                             ctypes.byref(det), _lib.stream_ptr(out.device)), "detector_integrate")

@@ -67,9 +67,10 @@ class OOPAO:
 
     def set_params(self, args=None, wfs_type="shackhartmann", modal_basis="zernike", gainCL=0.5, n_envs=1, device=None,
                    rng="philox", seed=0, env_offset=0, warp_kernel="lagrange018", canvas_slack=96):
-        """OOPAOEnvRazor.py:91-339 (SH branch)."""
-        if wfs_type != "shackhartmann":
-            raise NotImplementedError("only the Shack-Hartmann WFS is implemented (Pyramid: SURVEY.md section 8 f-3)")
+        """OOPAOEnvRazor.py:91-339 (SH branch; `wfs_type="pyramid"` builds the Pyramid of OOPAOEnv.py:239-249 instead)."""
+        if wfs_type not in ("shackhartmann", "pyramid"):
+            raise NotImplementedError(f"wfs_type {wfs_type!r}: only 'shackhartmann' and 'pyramid' are implemented")
+        self.wfs_type = wfs_type
         args = args if args is not None else types.SimpleNamespace()
         self.gainCL = gainCL
         self.n_envs = int(n_envs)
@@ -106,9 +107,16 @@ class OOPAO:
             self.dm_mask = np.asarray(param["boolActMask"]).astype(int)
         self.xvalid, self.yvalid = np.nonzero(self.dm_mask)
         self.tel - self.atm
-        self.wfs = ShackHartmann(telescope=self.tel, nSubap=param["nSubaperture"], lightRatio=param.get("lightRatio", 0.5),
-                                 threshold_cog=param.get("threshold_cog", 0.01), is_geometric=False,
-                                 shannon_sampling=param.get("shannon_sampling", True))
+        if wfs_type == "pyramid":                                                                    # OOPAOEnv.py:239-246
+            from ..Pyramid import Pyramid
+            self.wfs = Pyramid(nSubap=param["nSubaperture"], telescope=self.tel, lightRatio=param.get("lightThreshold", 0.1),
+                               modulation=param.get("modulation", 3), binning=1,
+                               n_pix_separation=param.get("n_pix_separation", 4), n_pix_edge=2,
+                               postProcessing=param.get("postProcessing", "slopesMaps"))
+        else:
+            self.wfs = ShackHartmann(telescope=self.tel, nSubap=param["nSubaperture"], lightRatio=param.get("lightRatio", 0.5),
+                                     threshold_cog=param.get("threshold_cog", 0.01), is_geometric=False,
+                                     shannon_sampling=param.get("shannon_sampling", True))
         cam = self.wfs.cam
         cam.sensor = param.get("cam_sensor", cam.sensor)
         cam.FWC = param.get("cam_FWC", cam.FWC)
@@ -145,8 +153,8 @@ class OOPAO:
         self._nLoop = nLoop
         self.total = torch.zeros((nLoop, self.n_envs), dtype=torch.float32, device=self.device) if nLoop else None
         self.residual = torch.zeros((nLoop, self.n_envs), dtype=torch.float32, device=self.device) if nLoop else None
-        cam.photonNoise = param.get("cam_photonNoise", True)                                         # :332-333
-        cam.readoutNoise = param.get("cam_readoutNoise", 14)
+        cam.photonNoise = param.get("cam_photonNoise", True)                                         # :332-333 (OOPAOEnv.py:379)
+        cam.readoutNoise = param.get("cam_readoutNoise", 14 if wfs_type == "shackhartmann" else 0)
         self.set_reconstructor(M2C @ calib.M)                                                        # :336
         self.F = M2C @ torch.linalg.pinv(M2C)                                                        # :337
         self._F32 = self.F.to(torch.float32)

@@ -79,9 +79,14 @@ class Pyramid:
         self.referenceSignal = 0
         self.referenceSignal_2D = 0
         self.isInitialized = self.isCalibrated = False
-        self._signal = self._signal_2D = None
+        self._signal64 = self._signal_2D = None
+        self._signal_is_multi = False
+        self._signal_planes = None                      # the environment's reconstruction GEMM splits `_signal` itself
         self.modulation = modulation
         self.initialization(tel)                                                                      # :301-303
+        self._lds = (self.nSignal + 15) // 16 * 16
+        self._signal = torch.zeros((self.n_envs, self._lds), dtype=torch.float32, device=self.device)
+        self._stats = torch.zeros((self.n_envs, 4), dtype=torch.float64, device=self.device)
         self.modulation = modulation
         self.wfs_calibration(tel)
         tel.resetOPD()
@@ -155,7 +160,7 @@ class Pyramid:
         n, b = self.cam.resolution, int(round(N / self.cam.resolution))
         return out.reshape(F, n, b, n, b).sum(dim=(2, 4))
 
-    def _camera(self, frames):
+    def _camera(self, frames, env_offset=0):
         """self*self.cam (:987-1002): detector chain on the binned frames."""
         self.pyramidFrame = frames
         if self.cam.integrationTime is None:
@@ -163,7 +168,7 @@ class Pyramid:
         if self.cam.is_ideal():
             self.cam.frame = frames[0] if (self.n_envs == 1 and frames.shape[0] == 1) else frames
         else:
-            out = self.cam.integrate(frames.to(torch.float32))
+            out = self.cam.integrate(frames.to(torch.float32), env_offset)
             self.cam.frame = out[0] if (self.n_envs == 1 and out.shape[0] == 1) else out
         return self.cam.frame
 
@@ -227,26 +232,66 @@ class Pyramid:
         self.isCalibrated = True
 
     def wfs_measure(self, phase_in=None):
-        """Pyramid.py:516-603, single-frame branches, for every environment."""
+        """Pyramid.py:516-603, single-frame branches, for every environment (a stack of k wavefronts other than n_envs
+        goes through the multi-frame branch :604-676 and yields signal [nSignal, k])."""
         tel = self.telescope
         lam = tel.src.wavelength
         if phase_in is not None:
             ph = torch.as_tensor(phase_in, dtype=torch.float32, device=self.device)
             tel.OPD = (ph.unsqueeze(0) if ph.ndim == 2 else ph) * (lam / (2 * math.pi))
-        opd = tel._materialise() * tel._pupil_f
-        frames = self._frames(opd * (2 * math.pi / lam))
-        self._camera(frames)
+        a, b = tel._terms()
+        if a.shape[0] != self.n_envs:
+            self._multi_signal = self.measure_frames(a if b is None else a + b)
+            self._signal_is_multi = True
+            return
+        self._measure_terms(a, b)
+
+    def _measure_terms(self, opd_a, opd_b, env_offset=0):
+        """Per-environment measurement on OPD_no_pupil = opd_a (+ opd_b): what tel*wfs and the environment's step run.
+        Also leaves the operands of the environment's reconstruction / reward kernels: `_signal` [B, lds] float32 (zero
+        padded) and the pupil statistics `_stats` [B, 4] (sum and sum of squares of the atmosphere-only and of the total
+        OPD inside the pupil, relative to the value at the pupil centre — the definition of aoenv_shwfs_frame)."""
+        tel = self.telescope
+        lam, R = tel.src.wavelength, tel.resolution
+        opd = opd_a if opd_b is None else opd_a + opd_b
+        pupil = tel._pupil_f
+        frames = self._frames(opd * pupil * (2 * math.pi / lam))
+        self._camera(frames, env_offset)
         frame = self.cam.frame if self.cam.frame.ndim == 3 else self.cam.frame.unsqueeze(0)
+        self._frame = frame
         maps, sig = self.signalProcessing(frame.to(torch.float64) if self.cam.is_ideal() else frame.to(torch.float32))
-        self._signal_2D, self._signal = maps, sig
+        self._signal_2D, self._signal64 = maps, sig
+        self._signal[:, :self.nSignal] = sig.to(torch.float32)
+        inside = pupil > 0
+        ka = opd_a[:, R // 2, R // 2].double()[:, None]
+        da = (opd_a.double().reshape(opd_a.shape[0], -1) - ka) * inside.reshape(-1)
+        kt = opd[:, R // 2, R // 2].double()[:, None]
+        dt = (opd.double().reshape(opd.shape[0], -1) - kt) * inside.reshape(-1)
+        self._stats[:, 0], self._stats[:, 1] = da.sum(dim=1), (da * da).sum(dim=1)
+        self._stats[:, 2], self._stats[:, 3] = dt.sum(dim=1), (dt * dt).sum(dim=1)
+        self._signal_is_multi = False
         self.pyramidSignal_2D, self.pyramidSignal = self.signal_2D, self.signal
+
+    def measure_frames(self, opd):
+        """Multi-frame branch (Pyramid.py:604-676): k wavefronts [k, R, R] (OPD_no_pupil, metres), ideal detector, every
+        frame processed on its own.  Returns signal [k, nSignal] in float64 (the calibration path)."""
+        if not self.cam.is_ideal() and (self.cam.photonNoise or self.cam.readoutNoise):
+            raise NotImplementedError("noisy multi-frame measurements are not supported (calibrate with noise='off')")
+        tel = self.telescope
+        out = []
+        for s0 in range(0, opd.shape[0], 16):                      # bounded memory: 16 wavefronts x nTheta points per pass
+            ph = opd[s0:s0 + 16].double() * tel._pupil_f.double() * (2 * math.pi / tel.src.wavelength)
+            out.append(self.signalProcessing(self._frames(ph, precise=True))[1])
+        return torch.cat(out, dim=0)
 
     def pyramid_propagation(self, telescope):
         self.wfs_measure()
 
     @property
     def signal(self):
-        return self._signal[0] if self.n_envs == 1 else self._signal
+        if self._signal_is_multi:
+            return self._multi_signal.T                                # [nSignal, k] as Pyramid.py:676
+        return self._signal64[0] if self.n_envs == 1 else self._signal64
 
     @property
     def signal_2D(self):

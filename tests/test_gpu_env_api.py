@@ -262,3 +262,22 @@ def test_science_camera_on_the_psf(dev):
     assert float((cam.frame[0] - cam.frame[1]).abs().max()) > 0          # independent draws per environment
     with pytest.raises(ValueError):
         tel * Detector(psf_sampling=4, integrationTime=1e-4)
+
+
+def test_pyramid_environment_on_gpu(dev):
+    """OOPAOEnv.py-style environment with the Pyramid WFS on the GPU: photon-noise camera, 6-tuple step, closed loop."""
+    from rlao_b200.OOPAOEnv.OOPAOEnv import OOPAO
+    cfg = CONFIGS["tiny"]()
+    cfg.nSubap = 12
+    p = param_from_config(cfg)
+    p.update(modulation=3, n_pix_separation=4, lightThreshold=0.1, postProcessing="slopesMaps_incidence_flux", nLoop=64,
+             cam_photonNoise=True, cam_readoutNoise=0, nZernike=20)
+    env = OOPAO()
+    env.set_params_file(p, "")
+    env.set_params(types.SimpleNamespace(), gainCL=0.4, n_envs=4, rng="philox", seed=1, device=dev)
+    obs = new_episode(env, 5)
+    for i in range(30):
+        obs, wfsf, reward, strehl, done, info = env.step(i, env.gainCL * obs)
+    assert wfsf.shape == (4, env.wfs.cam.resolution, env.wfs.cam.resolution) and torch.equal(wfsf.round(), wfsf)
+    assert float(env.residual[29].mean()) < 0.5 * float(env.total[29].mean())
+    assert float((obs[0] - obs[1]).abs().max()) > 0

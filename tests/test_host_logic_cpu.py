@@ -2,6 +2,7 @@
 are driven on the CPU through tests/fake_backend.py (a numpy stand-in for the C ABI) and compared with the
 oracle; plus: the shared library loads and exports every symbol include/aoenv.h declares."""
 import ctypes
+import types
 import os
 import re
 
@@ -208,3 +209,31 @@ def test_shift_bookkeeping_matches_oracle_for_random_winds(fake):
             for ly, lo in zip(atm._layers, orc.layers):
                 assert np.allclose(ly.buff, lo.buff, rtol=0, atol=1e-12), (trial, k)
         assert rel_err(atm.OPD_no_pupil.numpy(), orc.OPD_no_pupil) < 1e-4
+
+
+def test_pyramid_environment_closes_the_loop_on_cpu(fake):
+    """The papyrus-style environment (OOPAOEnv.py: Pyramid WFS, 6-tuple step) on the CPU stand-in: interaction matrix
+    through the multi-frame branch, reconstruction, leaky integrator — the residual must drop well below the turbulence."""
+    from rlao_b200.OOPAOEnv.OOPAOEnv import OOPAO
+    cfg = CONFIGS["tiny"]()
+    cfg.nSubap = 12                                        # 48 px pupil / 12 = 4 px per Pyramid subaperture
+    p = param_from_config_for_pyramid(cfg)
+    env = OOPAO()
+    env.set_params_file(p, "")
+    env.set_params(types.SimpleNamespace(), gainCL=0.4, n_envs=2, rng="philox", seed=1)
+    assert env.wfs.tag == "pyramid" and env.wfs.nSignal == 2 * int(env.wfs.validI4Q.sum())
+    assert env.reconstructor.shape == (env.dm.nValidAct, env.wfs.nSignal)
+    obs = new_episode(env, 5)
+    for i in range(25):
+        obs, wfsf, reward, strehl, done, info = env.step(i, env.gainCL * obs)
+    assert wfsf.shape == (2, env.wfs.cam.resolution, env.wfs.cam.resolution)
+    assert float(env.residual[24].mean()) < 0.5 * float(env.total[24].mean())
+    assert float(strehl.min()) > 0 and done is False
+
+
+def param_from_config_for_pyramid(cfg):
+    from parity_util import param_from_config
+    p = param_from_config(cfg)
+    p.update(modulation=3, n_pix_separation=4, lightThreshold=0.1, postProcessing="slopesMaps_incidence_flux", nLoop=64,
+             cam_photonNoise=False, cam_readoutNoise=0, nZernike=20)
+    return p
