@@ -12,7 +12,6 @@ environment, PO4AO.util.Dynamics) are replaced by empty stand-ins in sys.modules
 """
 import os
 import sys
-import types
 from unittest import mock
 
 import numpy as np

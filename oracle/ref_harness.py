@@ -9,7 +9,6 @@ import io
 import math
 import os
 import sys
-import types
 
 import numpy as np
 

@@ -3,7 +3,6 @@
 camera pass (rlao_b200/csrc/wfs.cu: shwfs_detector_kernel), one Philox stream per pixel, environment and frame."""
 import ctypes
 
-import numpy as np
 import torch
 
 from . import _lib

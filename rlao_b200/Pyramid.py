@@ -15,7 +15,6 @@ import math
 import numpy as np
 import torch
 
-from . import _lib
 from .Detector import Detector
 
 

@@ -3,12 +3,10 @@
 include/aoenv.h on raw host addresses with numpy, following the oracle's arithmetic.  It is test
 infrastructure: the product never imports it and has no CPU path."""
 import ctypes as C
-import math
 
 import numpy as np
 import torch
 
-from oracle.ao_oracle import ShackHartmannOracle
 
 
 def _arr(ptr, shape, dtype=np.float32):

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle.golden_configs import CONFIGS, EPISODE_SEED
+from oracle.golden_configs import CONFIGS
 from parity_util import build_env, new_episode, param_from_config, rel_err
 
 pytestmark = pytest.mark.gpu

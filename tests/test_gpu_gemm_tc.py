@@ -1,5 +1,4 @@
 """tcgen05 split-bf16 GEMM (aoenv_gemm_tn_tc) against float64 and against the FP32 SIMT kernel."""
-import numpy as np
 import pytest
 import torch
 

@@ -1,7 +1,6 @@
 """Parity of the CUDA path (through the C ABI, via the rlao_b200 host layer) against the CPU oracle and the
 golden fixtures recorded from the unmodified reference.  Tolerances (north_star): noise-free slopes and DM
 surfaces rel. 1e-4 (of the array's max), Strehl rel. 1e-3, on identical inputs; noisy runs: statistics."""
-import ctypes
 import math
 import os
 
@@ -9,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle.ao_oracle import (AOConfig, AtmosphereOracle, DetectorConfig, EnvOracle, ShackHartmannOracle, compute_psf,
+from oracle.ao_oracle import (AOConfig, AtmosphereOracle, EnvOracle, ShackHartmannOracle, compute_psf,
                               dm_geometry, dm_modes, flux_map, source_properties, telescope_pupil)
 from oracle.golden_configs import CONFIGS, EPISODE_SEED, STEPS
 from oracle.warp018 import warp_translate

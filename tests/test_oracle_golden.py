@@ -3,7 +3,6 @@
 import os
 
 import numpy as np
-import pytest
 
 from oracle.replay import replay_oracle
 

@@ -1,5 +1,5 @@
 """Operator-level profile of a PO4AO rollout (torch.profiler): where the time of mbrl.run goes."""
-import sys, os, types
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from torch.profiler import profile, ProfilerActivity
