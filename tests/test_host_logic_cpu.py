@@ -237,3 +237,24 @@ def param_from_config_for_pyramid(cfg):
     p.update(modulation=3, n_pix_separation=4, lightThreshold=0.1, postProcessing="slopesMaps_incidence_flux", nLoop=64,
              cam_photonNoise=False, cam_readoutNoise=0, nZernike=20)
     return p
+
+
+def test_product_never_touches_the_oracle_or_the_reference():
+    """The oracle is test infrastructure: nothing under rlao_b200/ may import it or read /root/reference, and bench.py may
+    reach it only in its CPU arms."""
+    pkg = os.path.join(ROOT, "rlao_b200")
+    offenders = []
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
+                src = open(os.path.join(dp, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M) or "/root/reference" in src:
+                    offenders.append(os.path.join(dp, f))
+    assert offenders == []
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    uses = [m.start() for m in re.finditer(r"from oracle", bench)]
+    assert uses and all(bench.rfind("\ndef ", 0, u) >= 0 for u in uses)
+    for u in uses:                                       # every use sits inside a CPU-arm helper
+        fn = bench[bench.rfind("\ndef ", 0, u):u].split("(")[0]
+        assert fn.strip().split()[-1] in ("oracle_config", "cpu_env"), fn
+    assert "/root/reference" not in bench
