@@ -283,6 +283,82 @@ class OOPAO:
                                             coefs.stride(0), st), "command_update")          # :492-493
         self.dm._set_coefs_batch(coefs)                                    # coefs setter side effect: next surface
 
+    def step_wfs(self, i, action):
+        """OOPAOEnvRazor.py:553-586 (the definition that is in effect: the second `def step_wfs`): the observation is the
+        WFS camera frame, the command accumulates without leak and the action is applied as given (metres)."""
+        self._measure_frame(i)
+        frame = self._sq(self.wfs._frame).clone()
+        leak, self.leak = self.leak, 1.0
+        try:
+            self._apply_command(torch.as_tensor(action, dtype=torch.float32, device=self.device) * 1e6)   # the kernel scales by 1e-6
+        finally:
+            self.leak = leak
+        strehl = self.SR[-1]
+        reward = self._sq(-torch.linalg.vector_norm(frame.reshape(self.n_envs, -1).float(), dim=1))
+        return frame, reward, strehl, False, {"strehl": strehl}
+
+    def _get_reward(self, slopes=None, type="volt"):
+        """OOPAOEnvRazor.py:607-614: S2V is never set on this path, so the reward is the Strehl ratio."""
+        if getattr(self, "S2V", None) is not None and type != "sh":
+            v = torch.as_tensor(slopes, dtype=torch.float64, device=self.device) @ torch.as_tensor(self.S2V, dtype=torch.float64, device=self.device).T
+            return -torch.linalg.vector_norm(v, dim=-1)
+        return self.get_strehl()
+
+    def compute_dm_proj(self):
+        """OOPAOEnvRazor.py:676-680: (modes^T modes)^-1 modes^T, the least-squares projector of an OPD map on the DM."""
+        modes = self.dm.modes.double()
+        self.dm_proj = torch.linalg.solve(modes.T @ modes, modes.T)
+        return self.dm_proj
+
+    def OPD_on_dm(self):
+        """OOPAOEnvRazor.py:683-689: the part of tel.OPD the DM can reproduce."""
+        if getattr(self, "dm_proj", None) is None:
+            self.compute_dm_proj()
+        res = self.tel.resolution
+        opd = (self.tel._materialise() * self.tel._pupil_f).double().reshape(self.n_envs, res * res)
+        out = ((opd @ self.dm_proj.T) @ self.dm.modes.double().T).reshape(self.n_envs, res, res)
+        return self._sq(out)
+
+    def set_modalBasis(self, mode="zernike"):
+        """OOPAOEnvRazor.py:393-425: recompute the zonal interaction matrix and the modal (50 Zernike) calibration."""
+        if mode != "zernike":
+            raise NotImplementedError("only the Zernike basis is built by the reference (OOPAOEnvRazor.py:394)")
+        paired = self.tel.isPaired
+        self.tel - self.atm
+        Z = Zernike(self.tel, 50)
+        Z.computeZernike(self.tel)
+        M2C = torch.linalg.pinv(self.dm.modes[self.tel._pupil_idx, :].double()) @ Z.modes
+        eye = torch.eye(self.dm.nValidAct, dtype=torch.float64, device=self.device)
+        self.imat = InteractionMatrix(ngs=self.source, atm=self.atm, tel=self.tel, dm=self.dm, wfs=self.wfs, M2C=eye,
+                                      stroke=1e-9, nMeasurements=25, noise="off")
+        self.calib_CL = CalibrationVault(self.imat.D @ M2C)
+        self.M2C_CL = M2C
+        self.tel.resetOPD()
+        self.dm.coefs = 0
+        self.source * self.tel * self.dm * self.wfs
+        if paired:
+            self.tel + self.atm
+
+    def set_wfs(self, param, type="pyramid"):
+        """OOPAOEnvRazor.py:342-391: replace the WFS (the calibration is NOT redone, as in the reference: call
+        set_modalBasis / set_reconstructor afterwards)."""
+        self.tel - self.atm
+        if type == "pyramid":
+            from ..Pyramid import Pyramid
+            if param.get("psfCentering", True) is not True:
+                raise NotImplementedError("Pyramid(psfCentering=False) is out of scope")
+            self.wfs = Pyramid(nSubap=param["nSubaperture"], telescope=self.tel, modulation=param["modulation"],
+                               lightRatio=param["lightThreshold"], n_pix_separation=param["n_pix_separation"],
+                               postProcessing=param["postProcessing"])
+        elif type == "shackhartmann":
+            self.wfs = ShackHartmann(telescope=self.tel, nSubap=param["nSubaperture"], lightRatio=param.get("lightRatio", 0.5),
+                                     threshold_cog=param.get("threshold_cog", 0.01), is_geometric=False,
+                                     shannon_sampling=param.get("shannon_sampling", True))
+        else:
+            raise NotImplementedError(f"wfs type {type!r}")
+        self.wfs_type = type
+        self.tel * self.wfs
+
     def calculate_strehl_AVG(self):
         """OOPAOEnvRazor.py:589-596 (mean over the episode; here also over environments and, when
         torch.distributed is initialised, over ranks)."""

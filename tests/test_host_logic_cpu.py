@@ -258,3 +258,37 @@ def test_product_never_touches_the_oracle_or_the_reference():
         fn = bench[bench.rfind("\ndef ", 0, u):u].split("(")[0]
         assert fn.strip().split()[-1] in ("oracle_config", "cpu_env"), fn
     assert "/root/reference" not in bench
+
+
+def test_remaining_environment_methods(fake):
+    """step_wfs (frame observation, no leak, action in metres), OPD_on_dm / compute_dm_proj, _get_reward, set_modalBasis,
+    set_wfs (OOPAOEnvRazor.py:342-425, 553-586, 607-614, 676-689)."""
+    cfg = CONFIGS["tiny"]()
+    env = build_env(cfg, n_envs=2, rng="philox")
+    new_episode(env, 3)
+    coefs0 = env.dm_prev.clone()
+    act = torch.zeros((2, cfg.nSubap + 1, cfg.nSubap + 1))
+    act[:, env.xvalid[5], env.yvalid[5]] = 2e-8
+    frame, reward, strehl, done, info = env.step_wfs(0, act)
+    assert frame.shape == (2, cfg.resolution, cfg.resolution) and reward.shape == (2,) and done is False
+    assert torch.allclose(env.dm_prev - coefs0, env.img_to_vec(act).float(), rtol=1e-5, atol=1e-14)      # += action, no leak
+    assert env.leak == cfg.leak
+    assert torch.equal(env._get_reward(), env.get_strehl())
+    # projection of an OPD that lies in the DM space gives it back
+    c = torch.zeros((2, env.dm.nValidAct), dtype=torch.float64)
+    c[:, 7], c[:, 20] = 3e-8, -1e-8
+    opd = (c @ env.dm.modes.double().T).reshape(2, cfg.resolution, cfg.resolution)
+    env.tel.OPD_no_pupil = opd.float()
+    pupil = torch.as_tensor(env.tel.pupil, dtype=torch.float64)
+    back = env.OPD_on_dm()
+    want = ((opd * pupil).reshape(2, -1) @ env.dm_proj.T) @ env.dm.modes.double().T
+    assert rel_err(back.reshape(2, -1).numpy(), want.numpy()) < 2e-6          # tel.OPD is float32
+    R0 = env.reconstructor.clone()
+    env.set_modalBasis("zernike")
+    assert env.calib_CL.M.shape[1] == env.wfs.nSignal and env.M2C_CL.shape == (env.dm.nValidAct, 50)
+    assert torch.equal(env.reconstructor, R0)                       # the reference does not touch the reconstructor here
+    with pytest.raises(NotImplementedError):
+        env.set_modalBasis("KL")
+    p = dict(env.param)
+    env.set_wfs(p, "shackhartmann")
+    assert env.wfs.tag == "shackHartmann" and env.wfs.telescope is env.tel
