@@ -138,3 +138,17 @@ def test_product_pyramid_on_gpu_batched(g):
     tel * wfs
     assert torch.equal(wfs.cam.frame.round(), wfs.cam.frame)
     assert float((wfs.signal - ideal).abs().max()) > 0 and float((wfs.signal - ideal).abs().max()) < 0.2
+
+
+def test_product_modulation_setter_recalibrates(g, monkeypatch):
+    """wfs.modulation = 0 on the fly (Pyramid.py:941-984): new reference slopes, unmodulated measurement."""
+    import fake_backend
+    fake_backend.install(monkeypatch)
+    tel, src, wfs = _build_product(g, None)
+    wfs.modulation = 0
+    assert wfs.nTheta == 1
+    assert _rel(wfs.referenceSignal_2D.numpy(), g["referenceSignal_2D_unmodulated"]) < 1e-9
+    wfs.wfs_measure(phase_in=g["phase_0"])
+    assert _rel(wfs.signal.numpy(), g["signal_unmodulated_0"]) < 5e-4
+    with pytest.raises(ValueError):
+        wfs.modulation = tel.resolution
