@@ -146,6 +146,13 @@ typedef struct {
  * read-out noise, gain, ADC).  One Philox stream per (pixel, frame index, det->seed, det->frame_counter). */
 int aoenv_detector_integrate(float* frame, int B, int rows, int cols, const aoenv_detector_t* det, void* stream);
 
+/* The camera of the WFS as its own step: the same chain applied in place to B noise-free frames of nS x nS lenslets of
+ * n x n pixels, and envmax [B] (or [1] when shared_max) = maximum over the pixels of the valid lenslets AFTER the
+ * camera (the centroiding threshold of ShackHartmann.py:314-316 is taken on the detector output).  This is the second
+ * half of aoenv_shwfs_frame with a detector; aoenv_shwfs_fused + this + aoenv_shwfs_slopes is the noisy step. */
+int aoenv_shwfs_camera(float* frame, const uint8_t* valid, int B, int nS, int n, const aoenv_detector_t* det, int shared_max,
+                       int32_t* envmax, void* stream);
+
 /* Selects the implementation of the n = 6 frame kernel: 0 = term-by-term pruned DFT (default), 1 = factorised
  * (radix 2 x Good-Thomas 2 x 3).  Same frame to float32 rounding; returns the previous setting. */
 int aoenv_set_wfs6_variant(int factorised);
@@ -175,6 +182,43 @@ int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil
 int aoenv_shwfs_slopes(const float* frame, const int32_t* envmax, int shared_max, const int32_t* valid_idx,
                        int nV, const float* ref_xy, float inv_units, float threshold_cog, int B, int nS, int n,
                        float* slopes, int lds, void* slope_planes, int parts, void* stream);
+
+/* The three steps DM surface -> lenslet spots -> slopes of one frame as ONE kernel (thread-block cluster per
+ * environment; the production path of env.step): DeformableMirror.py:534-570 (separable default geometry, see
+ * aoenv_dm_surface_separable), ShackHartmann.py:340-353,529-577 (ideal detector), :314-324,580-601, and the pupil
+ * statistics of MAIN/OOPAOEnv/OOPAOEnvRazor.py:484,502,604-605.  Neither the DM surface nor atmosphere + DM are
+ * written to memory; the camera frame only when `frame` is non-null.
+ *   opd_a [B][R][R]: first OPD term (atmosphere, metres, no pupil).  Second term: either `dm` (commands + banded
+ *   tables of the separable geometry) or `opd_b` [B][R][R] (any surface), or neither.
+ *   pupil8 [R][R]: 1 inside the pupil (the flux must be uniform over the pupil: amp0 = sqrt(fluxMap) there).
+ *   cluster: CTAs per environment (divides nS; > 8 needs the non-portable cluster size); CTA r owns lenslet rows
+ *   [r nS/cluster, (r+1) nS/cluster).  order [cluster][nS/cluster * nS]: lenslet ids inside each strip
+ *   (row_in_strip * nS + column), the lit ones first; nlit [cluster]: how many are lit.  slot_of [nS*nS]: position of
+ *   a lenslet in the valid list (= its slope index), -1 if invalid.  groups: warp groups per CTA (2 or 4).
+ *   slopes (nullable; then only the frame is produced, envmax is reset for the camera pass) / slope_planes / ref_xy /
+ *   inv_units / threshold_cog / envmax / stats: as in aoenv_shwfs_slopes and aoenv_shwfs_frame, except that stats
+ *   holds the plain sums {sum a, sum a^2, sum t, sum t^2} over the pupil (a = opd_a, t = opd_a + DM). */
+typedef struct {
+  const float* coefs;            /* [B][ldc] commands of the valid actuators (metres); NULL = no separable DM         */
+  const int32_t* act_pos;        /* [nA] row * nAct + col of each valid actuator (row-major order)                     */
+  const int32_t* act_row_start;  /* [nAct + 1] index in the valid list of the first actuator of each grid row          */
+  const float* wx;               /* [R][W]  weights of pixel column x, first actuator column j0x[x]                    */
+  const int32_t* j0x;            /* [R]                                                                                 */
+  const float* wyp;              /* [R/2][2][W] weights of the pixel-row pair (2k, 2k+1), first actuator row i0y[k]     */
+  const int32_t* i0y;            /* [R/2], non-decreasing                                                               */
+  int32_t ldc, nA, nAct, W;      /* W = 12 or 16                                                                        */
+  int32_t t_rows;                /* max over strips of the actuator rows a strip's bands touch                          */
+  int32_t reserved;
+} aoenv_dm_sep_t;
+
+int aoenv_shwfs_fused(const float* opd_a, const float* opd_b, const aoenv_dm_sep_t* dm, const uint8_t* pupil8, float amp0,
+                      const int32_t* order, const int32_t* nlit, const int32_t* slot_of, int B, int nS, int n, int cluster,
+                      int groups, float phase_scale, const float* ref_xy, int nV, float inv_units, float threshold_cog,
+                      float* frame, float* slopes, int lds, void* slope_planes, int parts, int32_t* envmax, double* stats,
+                      void* stream);
+/* Shared memory per CTA (bytes) the kernel above needs for a configuration, or -1 for an invalid one (t_rows = 0: no
+ * separable DM).  The limit is 227 KB. */
+int aoenv_shwfs_fused_smem(int nS, int n, int cluster, int groups, int t_rows, int nAct, int W);
 
 /* Calibration-grade measurement (init only): the two steps above in float64 with the ideal detector, for the
  * reference slopes / slope units (ShackHartmann.py:254-312) and the interaction matrix pushes

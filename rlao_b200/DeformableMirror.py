@@ -20,6 +20,26 @@ from . import _lib, gemm
 from .MisRegistration import MisRegistration
 
 
+class DMSurfaceRef:
+    """A DM surface that may not have been written to memory yet: (mirror, slot).  The fused step kernel
+    (aoenv_shwfs_fused) evaluates the surface of the separable geometry in shared memory straight from the commands;
+    anybody else who needs the [n_envs, R, R] tensor calls `.tensor()`, which runs the surface kernel on demand."""
+
+    def __init__(self, dm, slot):
+        self.dm, self.slot = dm, slot
+
+    def tensor(self):
+        return self.dm._slot_surface(self.slot)
+
+    @property
+    def coefs(self):
+        return self.dm._coefs_of[self.slot]
+
+    @property
+    def shape(self):
+        return self.dm._opd[self.slot].shape
+
+
 class DeformableMirror:
     def __init__(self, telescope, nSubap, mechCoupling=0.35, coordinates=None, pitch=None, modes=None, misReg=None,
                  M4_param=None, nJobs=30, nThreads=20, print_dm_properties=True, floating_precision=64, altitude=None):
@@ -82,6 +102,11 @@ class DeformableMirror:
         self._sep = self._separable_tables() if (modes is None and coordinates is None) else None
         self._opd = torch.zeros((2, self.n_envs, R, R), dtype=torch.float32, device=self.device)   # ping-pong
         self._slot = 0
+        # lazy surfaces: with the separable geometry env.step never writes the surface (the fused WFS kernel builds it
+        # in shared memory from the commands); _opd[slot] is brought up to date only when somebody reads it
+        self.lazy_surface = True
+        self._coefs_of = [None, None]
+        self._valid = [True, True]
         self._multi = None            # [k, R, R] surfaces of a [nValidAct, k] command matrix (calibration)
         self._coefs = torch.zeros((self.n_envs, self._Kp), dtype=torch.float32, device=self.device)
         self._coefs_matrix = None
@@ -151,8 +176,10 @@ class DeformableMirror:
         rows, cols = np.nonzero(np.reshape(self.validAct, (n, n)))
         t = lambda arr, dt: torch.as_tensor(np.ascontiguousarray(arr), dtype=dt, device=dev)
         bx, by, gxv, gyv = bands(ex), bands(ey), np.exp(-ex), np.exp(-ey)
+        row_start = np.searchsorted(rows, np.arange(n + 1)).astype(np.int32)      # valid actuators are listed row-major
         out = dict(gx=t(gxv, torch.float32), gy=t(gyv, torch.float32), band_x=t(bx, torch.int32), band_y=t(by, torch.int32),
-                   act_pos=t((rows * n + cols).astype(np.int32), torch.int32), W=0, wx=None, j0x=None, wyp=None, i0y=None)
+                   act_pos=t((rows * n + cols).astype(np.int32), torch.int32), act_row_start=t(row_start, torch.int32),
+                   W=0, wx=None, j0x=None, wyp=None, i0y=None, i0y_host=None, nAct=n)
         # fixed-width band tables for the unrolled kernel: per pixel column, and per PAIR of pixel rows
         if R % 2 == 0:
             pair_lo = np.minimum(by[0::2, 0], by[1::2, 0])
@@ -170,7 +197,7 @@ class DeformableMirror:
                         lo, hi = by[2 * k + h]
                         wyp[k, h, lo - pair_lo[k]:hi - pair_lo[k] + 1] = gyv[lo:hi + 1, 2 * k + h]
                 out.update(W=W, wx=t(wx, torch.float32), j0x=t(bx[:, 0], torch.int32), wyp=t(wyp, torch.float32),
-                           i0y=t(pair_lo.astype(np.int32), torch.int32))
+                           i0y=t(pair_lo.astype(np.int32), torch.int32), i0y_host=pair_lo.astype(np.int64))
         return out
 
     def _set_modes(self, modes64):
@@ -221,10 +248,32 @@ class DeformableMirror:
         self._multi = None
         self._coefs_matrix = None
         self._slot ^= 1
-        self._surface(coefs_padded, self._opd[self._slot])
+        self._coefs_of[self._slot] = coefs_padded
+        if self.lazy_surface and self.fused_tables() is not None:
+            self._valid[self._slot] = False       # evaluated inside aoenv_shwfs_fused, or on demand
+        else:
+            self._surface(coefs_padded, self._opd[self._slot])
+            self._valid[self._slot] = True
+
+    def fused_tables(self):
+        """Banded tables of the separable geometry in the form aoenv_shwfs_fused takes, or None."""
+        t = self._sep
+        if t is None or t["W"] not in (12, 16) or self.surface_backend not in ("auto", "separable"):
+            return None
+        return t
+
+    def _slot_surface(self, slot):
+        if not self._valid[slot]:
+            self._surface(self._coefs_of[slot], self._opd[slot])
+            self._valid[slot] = True
+        return self._opd[slot]
+
+    def surface_ref(self):
+        """The current surface as a (possibly not yet materialised) reference."""
+        return DMSurfaceRef(self, self._slot)
 
     def _previous_surface(self):
-        return self._opd[self._slot ^ 1]
+        return self._slot_surface(self._slot ^ 1)
 
     @property
     def coefs(self):
@@ -271,12 +320,12 @@ class DeformableMirror:
     def OPD(self):
         if self._multi is not None:
             return self._multi
-        o = self._opd[self._slot]
+        o = self._slot_surface(self._slot)
         return o[0] if self.n_envs == 1 else o
 
     def dm_propagation(self, telescope, OPD_in=None, i_source=None):
         """DeformableMirror.py:452-478: OPD_no_pupil leaving the mirror (a new tensor)."""
-        dm_opd = self._multi if self._multi is not None else self._opd[self._slot]
+        dm_opd = self._multi if self._multi is not None else self._slot_surface(self._slot)
         if telescope.isPaired:
             base = telescope._materialise() if OPD_in is None else OPD_in
             if dm_opd.shape[0] != base.shape[0]:

@@ -33,7 +33,20 @@ class Detector:
         self._integrated_time = 0
         self.seed = int(seed)
         self.frame_counter = 0
-        self.frame = None
+        self._frame, self._frame_src = None, None
+
+    @property
+    def frame(self):
+        """The last camera frame.  A WFS that did not write the frame of its last measurement registers a producer in
+        `_frame_src`; it runs the first time the frame is read."""
+        if self._frame_src is not None:
+            src, self._frame_src = self._frame_src, None
+            self._frame = src()
+        return self._frame
+
+    @frame.setter
+    def frame(self, val):
+        self._frame, self._frame_src = val, None
 
     def is_ideal(self):
         """True when the chain is the identity (the default WFS camera, ShackHartmann.py:166-168)."""

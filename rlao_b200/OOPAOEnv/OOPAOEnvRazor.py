@@ -125,6 +125,7 @@ class OOPAO:
         cam.darkCurrent = param.get("cam_darkCurrent", cam.darkCurrent)
         cam.integrationTime = param["samplingTime"]
         cam.seed = seed
+        self.wfs.env_offset = self.env_offset       # every shard draws its own camera noise, also outside step()
         self.tel * self.wfs
         # modal basis and calibration
         nZ = param.get("nZernike", 50)
@@ -227,7 +228,7 @@ class OOPAO:
 
     def reset_soft_wfs(self):
         self.action_buffer = []
-        return self._sq(self.wfs._frame).clone()
+        return self.wfs.cam.frame.clone()
 
     def step(self, i, action):
         """OOPAOEnvRazor.py:474-514.  Returns fresh tensors (the reference returns fresh arrays)."""
@@ -254,7 +255,7 @@ class OOPAO:
         frame has already been issued (it depends on nothing the step computes)."""
         if not atmosphere_done:
             self.atm.update()                                              # :482 -> tel.OPD = atm.OPD (lazy)
-        dm_surface = self.dm._opd[self.dm._slot]                           # surface commanded at the previous step
+        dm_surface = self.dm.surface_ref()                                 # surface commanded at the previous step
         self.tel._set_lazy(self.atm._opd, dm_surface)                      # :488 tel*dm
         self.wfs._measure_terms(self.atm._opd, dm_surface, self.env_offset)  # :488 *wfs  (+ stats for :484,502,506)
         self._observe(True)                                                # :496-506
@@ -287,7 +288,7 @@ class OOPAO:
         """OOPAOEnvRazor.py:553-586 (the definition that is in effect: the second `def step_wfs`): the observation is the
         WFS camera frame, the command accumulates without leak and the action is applied as given (metres)."""
         self._measure_frame(i)
-        frame = self._sq(self.wfs._frame).clone()
+        frame = self.wfs.cam.frame.clone()
         leak, self.leak = self.leak, 1.0
         try:
             self._apply_command(torch.as_tensor(action, dtype=torch.float32, device=self.device) * 1e6)   # the kernel scales by 1e-6

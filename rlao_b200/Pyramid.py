@@ -245,13 +245,16 @@ class Pyramid:
             return
         self._measure_terms(a, b)
 
-    def _measure_terms(self, opd_a, opd_b, env_offset=0):
+    def _measure_terms(self, opd_a, opd_b, env_offset=None):
         """Per-environment measurement on OPD_no_pupil = opd_a (+ opd_b): what tel*wfs and the environment's step run.
         Also leaves the operands of the environment's reconstruction / reward kernels: `_signal` [B, lds] float32 (zero
         padded) and the pupil statistics `_stats` [B, 4] (sum and sum of squares of the atmosphere-only and of the total
         OPD inside the pupil, relative to the value at the pupil centre — the definition of aoenv_shwfs_frame)."""
         tel = self.telescope
         lam, R = tel.src.wavelength, tel.resolution
+        env_offset = getattr(self, "env_offset", 0) if env_offset is None else env_offset
+        if opd_b is not None and not torch.is_tensor(opd_b):
+            opd_b = opd_b.tensor()                                  # DMSurfaceRef: the surface kernel runs now
         opd = opd_a if opd_b is None else opd_a + opd_b
         pupil = tel._pupil_f
         frames = self._frames(opd * pupil * (2 * math.pi / lam))

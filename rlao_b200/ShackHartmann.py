@@ -7,11 +7,13 @@ calibration push as in ShackHartmann.py:674), `wfs.signal_2D`, `wfs.cam.frame`.
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
 
 from . import _lib, gemm
+from .DeformableMirror import DMSurfaceRef
 from .Detector import Detector
 
 _SUPPORTED_N = (4, 6, 8)
@@ -62,6 +64,15 @@ class ShackHartmann:
         self.fov_pixel_arcsec = self.fov_lenslet_arcsec / self.n_pix_subap
         self.fov_pixel_binned_arcsec = self.fov_lenslet_arcsec / self.n_pix_subap_init
         self.get_camera_frame_multi = False
+        # One fused kernel (DM surface + spots + slopes, aoenv_shwfs_fused) when the flux is uniform over a binary pupil;
+        # otherwise (or with use_fused = False / AOENV_WFS=legacy) the frame and slopes kernels.  keep_frame: write the
+        # camera frame at every measurement; when False (default) `wfs.cam.frame` is produced on demand from the inputs
+        # of the last measurement, and env.step never spends the HBM traffic on it.
+        self.env_offset = 0          # global index of this shard's first environment (seeds of the camera streams)
+        self.use_fused = os.environ.get("AOENV_WFS", "fused") != "legacy"
+        self.keep_frame = False
+        self._fused_plans = {}
+        self._last_inputs = None
         ii, jj = np.meshgrid(np.arange(self.nSubap), np.arange(self.nSubap), indexing="ij")
         self.index_x, self.index_y = ii.reshape(-1), jj.reshape(-1)
         self.initialize_flux()
@@ -84,6 +95,14 @@ class ShackHartmann:
         self._amp = torch.as_tensor(np.sqrt(flux), dtype=torch.float32, device=self.device).contiguous()
         self.current_nPhoton = src.nPhoton
         self._flux_version = getattr(src, "_flux_version", 0)
+        # fused-kernel form: binary pupil mask + one amplitude (valid only when the flux is uniform over the pupil)
+        pup = np.asarray(self.telescope.pupil)
+        inside = pup > 0
+        vals = flux[inside]
+        self._uniform_flux = bool(inside.any() and np.all((pup == 0) | (pup == 1)) and np.all(flux[~inside] == 0)
+                                  and np.all(vals == vals[0]))
+        self._amp0 = float(np.sqrt(vals[0])) if self._uniform_flux else 0.0
+        self._pupil8 = torch.as_tensor(inside.astype(np.uint8), device=self.device).contiguous()
 
     def _select_valid(self):
         nS = self.nSubap
@@ -98,6 +117,10 @@ class ShackHartmann:
         dev = self.device
         self._valid_u8 = torch.as_tensor(self.valid_subapertures_1D.astype(np.uint8), device=dev).contiguous()
         self._valid_idx = torch.as_tensor(np.nonzero(self.valid_subapertures_1D)[0].astype(np.int32), device=dev).contiguous()
+        slot = np.full(nS * nS, -1, dtype=np.int32)
+        slot[np.nonzero(self.valid_subapertures_1D)[0]] = np.arange(self.nValidSubaperture, dtype=np.int32)
+        self._slot_of = torch.as_tensor(slot, device=dev).contiguous()
+        self._fused_plans = {}
 
     @property
     def lightRatio(self):
@@ -122,10 +145,108 @@ class ShackHartmann:
             raise NotImplementedError("geometric SH-WFS is out of scope")
 
     # ---- kernels ------------------------------------------------------------------------------------------
+    def _fused_plan(self, dm_tables):
+        """Launch shape of aoenv_shwfs_fused: CTAs per environment (cluster), warp groups, the lit-first lenslet order of
+        every strip and the number of actuator rows a strip's bands touch."""
+        key = id(dm_tables) if dm_tables is not None else 0
+        plan = self._fused_plans.get(key)
+        if plan is not None:
+            return plan
+        lib, nS, n = _lib.load(), self.nSubap, self.n_pix_subap
+        groups = int(os.environ.get("AOENV_WFS_GROUPS", "4"))
+
+        def t_rows_for(C_):
+            if dm_tables is None:
+                return 0
+            i0, W, nAct = dm_tables["i0y_host"], dm_tables["W"], dm_tables["nAct"]
+            pp = (nS // C_) * n // 2                      # pixel-row pairs per strip
+            first, last = i0[0::pp][:C_], i0[pp - 1::pp][:C_]
+            return int((np.minimum(last + W - 1, nAct - 1) - first + 1).max())
+
+        def smem_for(C_):
+            return lib.aoenv_shwfs_fused_smem(nS, n, C_, groups, t_rows_for(C_), dm_tables["nAct"] if dm_tables else 0,
+                                              dm_tables["W"] if dm_tables else 12)
+        forced = os.environ.get("AOENV_WFS_CLUSTER")
+        divisors = [c for c in range(1, min(16, nS) + 1) if nS % c == 0]
+        limit = 227 * 1024
+        if forced:
+            cluster = int(forced)
+        else:
+            # portable cluster sizes first: the largest one that leaves >= 96 lenslets per CTA, else a single CTA;
+            # configurations whose strip does not fit in shared memory take the largest cluster (<= 16) that does
+            fit8 = [c for c in divisors if c <= 8 and 0 < smem_for(c) <= limit]
+            good = [c for c in fit8 if nS * nS // c >= 96]
+            if good:
+                cluster = max(good)
+            elif fit8:
+                cluster = min(fit8)
+            else:
+                fit16 = [c for c in divisors if 0 < smem_for(c) <= limit]
+                if not fit16:
+                    raise NotImplementedError(f"{nS} x {nS} lenslets of {n} px do not fit the fused WFS kernel")
+                cluster = max(fit16)
+        rows = nS // cluster
+        valid = self.valid_subapertures
+        order = np.zeros((cluster, rows * nS), dtype=np.int32)
+        nlit = np.zeros(cluster, dtype=np.int32)
+        for r in range(cluster):
+            v = valid[r * rows:(r + 1) * rows].reshape(-1)
+            order[r] = np.concatenate([np.nonzero(v)[0], np.nonzero(~v)[0]])
+            nlit[r] = int(v.sum())
+        dev = self.device
+        plan = dict(cluster=cluster, groups=groups, t_rows=t_rows_for(cluster),
+                    order=torch.as_tensor(order, device=dev).contiguous(), nlit=torch.as_tensor(nlit, device=dev).contiguous())
+        self._fused_plans[key] = plan
+        return plan
+
+    def _fused_ok(self, opd_a):
+        return self.use_fused and self._uniform_flux and opd_a.dtype == torch.float32 and opd_a.is_contiguous()
+
+    def _run_fused(self, opd_a, opd_b, scale, det, frame, envmax, stats, slopes, ref_xy, inv_units, slope_planes, want_frame):
+        """aoenv_shwfs_fused (+ the camera pass and the slopes kernel when a noisy detector sits in between).
+        opd_b: None, a tensor, or a DMSurfaceRef whose mirror has the separable tables."""
+        lib, st = _lib.load(), _lib.stream_ptr(self.device)
+        F = opd_a.shape[0]
+        dm_struct, tables, b_tensor = None, None, None
+        if isinstance(opd_b, DMSurfaceRef):
+            tables = opd_b.dm.fused_tables()
+            if tables is None:
+                b_tensor = opd_b.tensor()
+        elif opd_b is not None:
+            b_tensor = opd_b
+        plan = self._fused_plan(tables)
+        if tables is not None:
+            coefs = opd_b.coefs
+            dm_struct = _lib.DmSepStruct()
+            dm_struct.coefs, dm_struct.ldc = coefs.data_ptr(), coefs.stride(0)
+            dm_struct.act_pos, dm_struct.act_row_start = tables["act_pos"].data_ptr(), tables["act_row_start"].data_ptr()
+            dm_struct.wx, dm_struct.j0x = tables["wx"].data_ptr(), tables["j0x"].data_ptr()
+            dm_struct.wyp, dm_struct.i0y = tables["wyp"].data_ptr(), tables["i0y"].data_ptr()
+            dm_struct.nA, dm_struct.nAct, dm_struct.W = opd_b.dm.nValidAct, tables["nAct"], tables["W"]
+            dm_struct.t_rows = plan["t_rows"]
+        noisy = det is not None
+        write_frame = want_frame or noisy
+        _lib.check(lib.aoenv_shwfs_fused(
+            _lib.ptr(opd_a), _lib.ptr(b_tensor), C.byref(dm_struct) if dm_struct is not None else None, _lib.ptr(self._pupil8),
+            C.c_float(self._amp0), _lib.ptr(plan["order"]), _lib.ptr(plan["nlit"]), _lib.ptr(self._slot_of), F, self.nSubap,
+            self.n_pix_subap, plan["cluster"], plan["groups"], C.c_float(scale), _lib.ptr(ref_xy), self.nValidSubaperture,
+            C.c_float(inv_units), C.c_float(self.threshold_cog), _lib.ptr(frame) if write_frame else None,
+            None if (noisy or slopes is None) else _lib.ptr(slopes), slopes.stride(0) if slopes is not None else 0,
+            None if noisy else _lib.ptr(slope_planes), 2, _lib.ptr(envmax), _lib.ptr(stats), st), "shwfs_fused")
+        if noisy:
+            _lib.check(lib.aoenv_shwfs_camera(_lib.ptr(frame), _lib.ptr(self._valid_u8), F, self.nSubap, self.n_pix_subap,
+                                              C.byref(det), 0, _lib.ptr(envmax), st), "shwfs_camera")
+            _lib.check(lib.aoenv_shwfs_slopes(_lib.ptr(frame), _lib.ptr(envmax), 0, _lib.ptr(self._valid_idx),
+                                              self.nValidSubaperture, _lib.ptr(ref_xy), C.c_float(inv_units),
+                                              C.c_float(self.threshold_cog), F, self.nSubap, self.n_pix_subap,
+                                              _lib.ptr(slopes), slopes.stride(0), _lib.ptr(slope_planes), 2, st), "shwfs_slopes")
+
     def _run(self, opd_a, opd_b, pupil, scale, shared_max, det, frame, envmax, stats, slopes, ref_xy, inv_units,
              slope_planes=None):
         lib, st = _lib.load(), _lib.stream_ptr(self.device)
         F = opd_a.shape[0]
+        if isinstance(opd_b, DMSurfaceRef):
+            opd_b = opd_b.tensor()
         _lib.check(lib.aoenv_shwfs_frame(_lib.ptr(opd_a), _lib.ptr(opd_b), _lib.ptr(pupil), _lib.ptr(self._amp),
                                          _lib.ptr(self._valid_u8), F, self.nSubap, self.n_pix_subap, C.c_float(scale),
                                          C.byref(det) if det is not None else None, int(shared_max), _lib.ptr(frame),
@@ -135,17 +256,37 @@ class ShackHartmann:
                                           C.c_float(self.threshold_cog), F, self.nSubap, self.n_pix_subap,
                                           _lib.ptr(slopes), slopes.stride(0), _lib.ptr(slope_planes), 2, st), "shwfs_slopes")
 
-    def _measure_terms(self, opd_a, opd_b, env_offset=0):
-        """Per-environment measurement (single-frame branch, ShackHartmann.py:522-601) on OPD = opd_a + opd_b."""
+    def _measure_terms(self, opd_a, opd_b, env_offset=None):
+        """Per-environment measurement (single-frame branch, ShackHartmann.py:522-601) on OPD = opd_a + opd_b
+        (opd_b: tensor, None, or a DMSurfaceRef = a DM surface that exists only as commands)."""
         if self._flux_version != getattr(self.telescope.src, "_flux_version", 0) or self.current_nPhoton != self.telescope.src.nPhoton:
             self.initialize_flux()                                       # ShackHartmann.py:515-517,534
         tel = self.telescope
+        env_offset = self.env_offset if env_offset is None else env_offset
         det = self.cam.as_struct(env_offset)
-        self._run(opd_a, opd_b, tel._pupil_f, 2 * math.pi / tel.src.wavelength, False, det, self._frame, self._envmax,
-                  self._stats, self._signal, self._ref_xy, 1.0 / self.slopes_units,
-                  slope_planes=self._signal_planes if gemm.uses_tensor_cores() else None)
+        scale = 2 * math.pi / tel.src.wavelength
+        planes = self._signal_planes if gemm.uses_tensor_cores() else None
+        if self._fused_ok(opd_a):
+            keep = self.keep_frame or det is not None
+            self._run_fused(opd_a, opd_b, scale, det, self._frame, self._envmax, self._stats, self._signal, self._ref_xy,
+                            1.0 / self.slopes_units, planes, keep)
+            if keep:
+                self.cam.frame = self._frame[0] if self.n_envs == 1 else self._frame
+            else:
+                self._last_inputs = (opd_a, opd_b, scale)
+                self.cam._frame_src = self._frame_on_demand
+        else:
+            self._run(opd_a, opd_b, tel._pupil_f, scale, False, det, self._frame, self._envmax, self._stats, self._signal,
+                      self._ref_xy, 1.0 / self.slopes_units, slope_planes=planes)
+            self.cam.frame = self._frame[0] if self.n_envs == 1 else self._frame
         self._signal_is_multi = False
-        self.cam.frame = self._frame[0] if self.n_envs == 1 else self._frame
+
+    def _frame_on_demand(self):
+        """`wfs.cam.frame` of a measurement that did not write it: the fused kernel again, frame only, on the inputs of
+        that measurement (the atmosphere OPD buffer and the DM commands are unchanged until the next step)."""
+        opd_a, opd_b, scale = self._last_inputs
+        self._run_fused(opd_a, opd_b, scale, None, self._frame, None, None, None, self._ref_xy, 1.0, None, True)
+        return self._frame[0] if self.n_envs == 1 else self._frame
 
     def _measure_f64(self, opd, shared_max, ref_xy64, inv_units):
         """Calibration-grade float64 measurement of F wavefronts [F, R, R] with the ideal detector
@@ -180,10 +321,12 @@ class ShackHartmann:
             ph = ph.unsqueeze(0) if ph.ndim == 2 else ph
             lam = tel.src.wavelength
             tel.OPD = ph * (lam / (2 * math.pi))
-        a, b = tel._terms()
+        a, b = tel._terms(resolve=False)
         if a.shape[0] == self.n_envs:
             self._measure_terms(a, b)
         else:
+            if isinstance(b, DMSurfaceRef):
+                b = b.tensor()
             opd = a if b is None else a + b
             self._multi_signal = self.measure_frames(opd)
             self._signal_is_multi = True
@@ -228,8 +371,13 @@ class ShackHartmann:
         f32 = dict(dtype=torch.float32, device=dev)
         fr32, em32 = torch.empty((1, R, R), **f32), torch.zeros((1,), dtype=torch.int32, device=dev)
         raw32 = torch.zeros((1, self._lds), **f32)
-        self._run(torch.zeros((1, R, R), **f32), None, tel._pupil_f, 2 * math.pi / lam, False, None, fr32, em32, None,
-                  raw32, torch.zeros((2, nV), **f32), 1.0)
+        zero32 = torch.zeros((1, R, R), **f32)
+        if self._fused_ok(zero32):
+            self._run_fused(zero32, None, 2 * math.pi / lam, None, fr32, em32, None, raw32, torch.zeros((2, nV), **f32), 1.0,
+                            None, False)
+        else:
+            self._run(zero32, None, tel._pupil_f, 2 * math.pi / lam, False, None, fr32, em32, None, raw32,
+                      torch.zeros((2, nV), **f32), 1.0)
         self._ref_xy = raw32[0, :2 * nV].reshape(2, nV).contiguous()
         ref2d = np.zeros((2 * nS, nS))
         f = flat.cpu().numpy()

@@ -79,15 +79,21 @@ class Telescope:
     def _materialise(self):
         if self._opd_np is None:
             a, b = self._lazy
+            if b is not None and not torch.is_tensor(b):
+                b = b.tensor()                                # DMSurfaceRef: the surface kernel runs now
             self._opd_np = a.clone() if b is None else a + b
             self._lazy = None
         return self._opd_np
 
-    def _terms(self):
-        """(opd_a, opd_b) such that OPD_no_pupil = opd_a + opd_b, without forcing a materialisation."""
+    def _terms(self, resolve=True):
+        """(opd_a, opd_b) such that OPD_no_pupil = opd_a + opd_b, without forcing a materialisation of the sum.
+        resolve=False may return opd_b as a DeformableMirror.DMSurfaceRef (a surface not yet written to memory)."""
         if self._opd_np is not None:
             return self._opd_np, None
-        return self._lazy
+        a, b = self._lazy
+        if resolve and b is not None and not torch.is_tensor(b):
+            b = b.tensor()
+        return a, b
 
     def _squeeze(self, t):
         return t[0] if (self.n_envs == 1 and t.shape[0] == 1) else t

@@ -26,6 +26,16 @@ class DetectorStruct(C.Structure):
     ]
 
 
+class DmSepStruct(C.Structure):
+    """aoenv_dm_sep_t (include/aoenv.h)."""
+    _fields_ = [
+        ("coefs", C.c_void_p), ("act_pos", C.c_void_p), ("act_row_start", C.c_void_p), ("wx", C.c_void_p),
+        ("j0x", C.c_void_p), ("wyp", C.c_void_p), ("i0y", C.c_void_p),
+        ("ldc", C.c_int32), ("nA", C.c_int32), ("nAct", C.c_int32), ("W", C.c_int32), ("t_rows", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
 MAX_LAYERS = 8          # AOENV_MAX_LAYERS (include/aoenv.h)
 
 _vp, _i, _f, _u64, _d, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_uint64, C.c_double, C.c_int64
@@ -44,8 +54,12 @@ PROTOTYPES = {
     "aoenv_dm_surface_separable": [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
     "aoenv_set_wfs6_variant": [_i],
     "aoenv_detector_integrate": [_vp, _i, _i, _i, _vp, _vp],
+    "aoenv_shwfs_camera": [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp],
     "aoenv_shwfs_frame": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i, _vp, _vp, _vp, _vp],
     "aoenv_shwfs_slopes": [_vp, _vp, _i, _vp, _i, _vp, _f, _f, _i, _i, _i, _vp, _i, _vp, _i, _vp],
+    "aoenv_shwfs_fused": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _i, _f, _f, _vp, _vp, _i, _vp, _i,
+                          _vp, _vp, _vp],
+    "aoenv_shwfs_fused_smem": [_i, _i, _i, _i, _i, _i, _i],
     "aoenv_shwfs_measure_f64": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _d, _d, _i, _i, _i, _d, _i, _vp, _vp, _vp, _i, _vp],
     "aoenv_command_update": [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _i, _vp],
     "aoenv_observe": [_vp, _i, _vp, _i, _i, _i, _vp, _d, _f, _vp, _vp, _vp, _vp, _vp, _vp],

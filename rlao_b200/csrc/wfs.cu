@@ -179,7 +179,15 @@ shwfs_detector_kernel(float* __restrict__ frame, const uint8_t* __restrict__ val
       float dark = 0.f;
       if (has_dark) {                   // almost always zero: one comparison against exp(-dark)
         const float u = u32_to_unit(r0.y) * 0.99999994f;
-        dark = u <= dark_p0 ? 0.f : poisson_draw(det.dark_electrons, r0.y, 0u, rng, 32);
+        if (u > dark_p0) {
+          // small means: inversion continues from the same uniform; large means (PTRS) need two fresh words
+          if (det.dark_electrons < 12.f) {
+            dark = poisson_draw(det.dark_electrons, r0.y, 0u, rng, 32);
+          } else {
+            const uint4 r1 = rng.block(1);
+            dark = poisson_draw(det.dark_electrons, r1.x, r1.y, rng, 32);
+          }
+        }
       }
       const float val = detector_finish(photons, dark, ron, det);
       img[pix] = val;
@@ -771,6 +779,23 @@ int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil
     shwfs_detector_kernel<<<gd, 256, 0, s>>>(frame, valid, nS, n, 1.0f / (float)R, 1.0f / (float)n, *det, shared_max, envmax, 0);
     AOENV_LAUNCH_CHECK("shwfs_detector");
   }
+  return 0;
+}
+
+int aoenv_shwfs_camera(float* frame, const uint8_t* valid, int B, int nS, int n, const aoenv_detector_t* det, int shared_max,
+                       int32_t* envmax, void* stream) {
+  AOENV_CHECK_ARG(B > 0 && B <= 65535 && nS > 0 && n > 0, "shwfs_camera: bad shape B=%d nS=%d", B, nS);
+  AOENV_CHECK_ARG(det != nullptr && valid != nullptr && envmax != nullptr, "shwfs_camera: detector, lenslet mask and envmax are required");
+  AOENV_CHECK_ARG(!(det->bits > 0 && !det->has_fwc), "shwfs_camera: ADC without a full-well capacity is not supported");
+  AOENV_CHECK_ARG(det->bits >= 0 && det->bits < 31, "shwfs_camera: bits=%d", det->bits);
+  const int R = nS * n;
+  AOENV_CHECK_ARG(R * R < (1 << 24), "shwfs_camera: frame of %d x %d pixels is too large for the camera pass", R, R);
+  cudaStream_t s = (cudaStream_t)stream;
+  envmax_init_kernel<<<(B + 255) / 256, 256, 0, s>>>(envmax, shared_max ? 1 : B);
+  AOENV_LAUNCH_CHECK("envmax_init");
+  dim3 gd((R * R + 8 * kDetPerLane * 32 - 1) / (8 * kDetPerLane * 32), B);
+  shwfs_detector_kernel<<<gd, 256, 0, s>>>(frame, valid, nS, n, 1.0f / (float)R, 1.0f / (float)n, *det, shared_max, envmax, 0);
+  AOENV_LAUNCH_CHECK("shwfs_detector");
   return 0;
 }
 

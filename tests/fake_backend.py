@@ -222,6 +222,116 @@ class FakeLib:
                 em[e] = _f2o(maxes[e])
         return 0
 
+    def aoenv_shwfs_fused_smem(self, nS, n, cluster, groups, t_rows, nAct, W):
+        if nS % cluster:
+            return -1
+        R, rows_px = nS * n, (nS // cluster) * n
+        up = lambda v: (v + 127) & ~127
+        o = up(rows_px * R * 4)
+        o = up(o + rows_px * R)
+        o = up(o + groups * n * n * 256)
+        if t_rows > 0:
+            o = up(o + t_rows * R * 4)
+            o = up(o + t_rows * nAct * 4)
+            o = up(o + (rows_px // 2) * 2 * W * 4)
+            o = up(o + (rows_px // 2) * 4)
+        return up(o + 512)
+
+    def aoenv_shwfs_fused(self, opd_a, opd_b, dm, pupil8, amp0, order, nlit, slot_of, B, nS, n, cluster, groups, phase_scale,
+                          ref_xy, nV, inv_units, thr, frame, slopes, lds, slope_planes, parts, envmax, stats, stream):
+        """Strip by strip, like the kernel: the DM surface of a strip from the banded tables and the commands of the
+        actuator rows [tBase, tBase + t_rows), lenslets visited through `order` / `nlit`, slopes scattered by `slot_of`."""
+        self.launches += 1
+        R, rows = nS * n, nS // cluster
+        LPC = rows * nS
+        a = _arr(opd_a, (B, R, R))
+        b_ = _arr(opd_b, (B, R, R))
+        pu = _arr(pupil8, (R, R), np.uint8).astype(bool)
+        od, nl = _arr(order, (cluster, LPC), np.int32), _arr(nlit, (cluster,), np.int32)
+        so = _arr(slot_of, (nS * nS,), np.int32)
+        fr = _arr(frame, (B, R, R))
+        sl = _arr(slopes, (B, lds)) if slopes else None
+        ref = _arr(ref_xy, (2, nV)) if sl is not None else None
+        em = _arr(envmax, (B,), np.int32)
+        st = _arr(stats, (B, 4), np.float64)
+        scale, a0 = np.float32(_val(phase_scale)), float(_val(amp0))
+        d = dm._obj if hasattr(dm, "_obj") else dm
+        sep = d is not None and d.coefs
+        if sep:
+            W, nAct, nA = d.W, d.nAct, d.nA
+            c = _arr(d.coefs, (B, d.ldc))
+            pos, rs = _arr(d.act_pos, (nA,), np.int32), _arr(d.act_row_start, (nAct + 1,), np.int32)
+            wx, j0x = _arr(d.wx, (R, W)).astype(np.float64), _arr(d.j0x, (R,), np.int32)
+            wyp, i0y = _arr(d.wyp, (R // 2, 2, W)).astype(np.float64), _arr(d.i0y, (R // 2,), np.int32)
+        N = 2 * n
+        k = np.arange(N)
+        xx, yy = np.meshgrid(k, k)
+        phasor = np.exp(-(1j * np.pi * (N + 1) / N) * (xx + yy))
+        lo = N // 2 - n // 2
+        for e in range(B):
+            total = a[e].astype(np.float32).copy()
+            if b_ is not None:
+                total = total + b_[e]
+            spots_img = np.zeros((R, R), dtype=np.float64)
+            lit_max = -np.inf
+            for r in range(cluster):
+                y0, y1 = r * rows * n, (r + 1) * rows * n
+                if sep:
+                    tBase = int(i0y[y0 // 2])
+                    r_end = min(nAct, tBase + d.t_rows)
+                    Cimg = np.zeros((d.t_rows, nAct))
+                    for kk in range(rs[tBase], rs[r_end]):
+                        Cimg[pos[kk] // nAct - tBase, pos[kk] % nAct] = c[e, kk]
+                    Trow = np.zeros((d.t_rows, R))
+                    for x in range(R):
+                        cols = np.minimum(j0x[x] + np.arange(W), nAct - 1)
+                        Trow[:, x] = Cimg[:, cols] @ wx[x]
+                    for y in range(y0, y1):
+                        i0 = int(i0y[y // 2])
+                        rows_i = np.minimum(i0 + np.arange(W), nAct - 1) - tBase
+                        assert rows_i.max() < d.t_rows, "t_rows too small for this strip"
+                        total[y] = total[y] + (wyp[y // 2, y % 2] @ Trow[rows_i]).astype(np.float32)
+                ph = (total[y0:y1] * np.float32(scale)).astype(np.float64)
+                field_px = np.where(pu[y0:y1], a0 * np.exp(1j * ph), 0)
+                for i in range(LPC):
+                    lens = int(od[r, i])
+                    lr, l = lens // nS, lens % nS
+                    if i >= nl[r]:
+                        continue
+                    tile = field_px[lr * n:(lr + 1) * n, l * n:(l + 1) * n].T
+                    fld = np.zeros((N, N), dtype=complex)
+                    fld[lo:lo + n, lo:lo + n] = tile
+                    I = np.abs(np.fft.fft2(fld * phasor) / N) ** 2
+                    sp = I.reshape(n, 2, n, 2).sum(axis=(1, 3))
+                    spots_img[y0 + lr * n:y0 + (lr + 1) * n, l * n:(l + 1) * n] = sp
+                    lit_max = max(lit_max, np.float32(sp.max()))
+            if st is not None:
+                av, tv = a[e][pu].astype(np.float64), total[pu].astype(np.float64)
+                st[e] = [av.sum(), (av ** 2).sum(), tv.sum(), (tv ** 2).sum()]
+            if fr is not None:
+                fr[e] = spots_img.astype(np.float32)
+            if em is not None:
+                em[e] = _f2o(lit_max if sl is not None else -np.inf)
+            if sl is not None:
+                f32 = spots_img.astype(np.float32).astype(np.float64)
+                for kk in np.nonzero(so >= 0)[0]:
+                    li, lj = kk // nS, kk % nS
+                    im = f32[li * n:(li + 1) * n, lj * n:(lj + 1) * n].copy()
+                    im[im < np.float32(_val(thr)) * np.float32(lit_max)] = 0
+                    with np.errstate(invalid="ignore", divide="ignore"):
+                        s_ = im.sum()
+                        cx = (im * np.arange(n)[:, None]).sum() / s_
+                        cy = (im * np.arange(n)[None, :]).sum() / s_
+                    cx = cx if np.isfinite(cx) else 0.0
+                    cy = cy if np.isfinite(cy) else 0.0
+                    t = so[kk]
+                    sl[e, t] = (cx - ref[0, t]) * np.float32(_val(inv_units))
+                    sl[e, nV + t] = (cy - ref[1, t]) * np.float32(_val(inv_units))
+        return 0
+
+    def aoenv_shwfs_camera(self, *a):
+        raise NotImplementedError("fake backend: detector chain not modelled")
+
     def aoenv_shwfs_slopes(self, frame, envmax, shared_max, valid_idx, nV, ref_xy, inv_units, thr, B, nS, n, slopes, lds,
                            slope_planes, parts, stream):
         self.launches += 1
