@@ -76,7 +76,7 @@ class ClockSampler:
     falls back to an `nvidia-smi` poller when the NVML binding is missing."""
     Q = "index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-    PERIOD = 0.05
+    PERIOD = 0.004
 
     def __init__(self, gpu_index):
         self.rows, self.gpu, self.proc, self.nvml, self._stop = [], gpu_index, None, None, threading.Event()
@@ -171,6 +171,15 @@ def cpu_env(nSubap, nLayers, reconstructor=None, opts=None):
     return EnvOracle(oracle_config(nSubap, nLayers, opts), reconstructor=reconstructor)
 
 
+def reference_env(nSubap, nLayers, opts=None):
+    """The UNMODIFIED reference (OOPAO + the drl4ao Razor environment) from the build container's reference tree or, on
+    the GPU box, from the copy build() staged under oracle/_ref/; None when neither is there."""
+    from oracle import ref_harness
+    if not ref_harness.reference_available():
+        return None
+    return ref_harness.ReferenceStepper(oracle_config(nSubap, nLayers, opts))
+
+
 def time_cpu(env, n_procs, n_steps):
     """`n_procs` forked workers (read-only operators shared copy-on-write), one environment each, one BLAS
     thread each; returns env-steps/s summed over workers."""
@@ -190,8 +199,10 @@ def time_cpu(env, n_procs, n_steps):
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; the Python reference itself cannot travel to
-    the GPU box) on all host cores, same metric/config keys."""
+    """--impl reference: the reference's own CPU implementation of the step on all host cores (the unmodified OOPAO +
+    drl4ao environment staged under oracle/_ref/ by build(); the oracle port only if that copy is missing), same
+    metric/config keys.  A "step" of this arm is one env.step of every worker process's environment; the line reports
+    the steps it really timed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -199,20 +210,28 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     n_procs = max(1, min(cores, 64))
     t_init = time.perf_counter()
-    env = cpu_env(nS, nL, opts=opts)
+    env, kind = None, "reference"
+    try:
+        env = reference_env(nS, nL, opts)
+    except Exception as ex:
+        print(f"reference import failed ({ex!r}); timing the oracle port", file=sys.stderr)
+    if env is None:
+        env, kind = cpu_env(nS, nL, opts=opts), "port"
     t_init = time.perf_counter() - t_init
-    per_step = 0.12 if nS >= 40 else 0.02
-    n_steps = max(3, int(min(20.0, 8.0 * max(1, args.steps)) / per_step / 4))
-    for _ in range(max(1, args.warmup // 3)):
-        time_cpu(env, n_procs, 2)
+    per_step = {8: 0.004, 20: 0.02, 40: 0.12, 80: 0.8}.get(nS, 0.1)          # s per env-step of one process (survey figures)
+    n_steps = max(2, int(min(30.0, 1.0 * max(1, args.steps)) / per_step))     # bounded sample: <= 30 s of stepping per worker
+    n_warm = max(1, min(args.warmup, 3))
+    time_cpu(env, n_procs, n_warm)
     value, worst, wall = time_cpu(env, n_procs, n_steps)
+    note = ("UNMODIFIED reference (OOPAO + MAIN_CODE/OOPAOEnv/OOPAOEnvRazor.py, numpy float64; skimage.transform.warp through the "
+            "documented restatement oracle/warp018.py)" if kind == "reference" else "oracle port (numpy float64) of the OOPAO/drl4ao step")
     line = {
         "impl": "reference", "metric": "closed-loop AO env-steps/sec (batched envs)", "value": value, "unit": "env-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * worst / n_steps,
+        "n_gpus": args.gpus, "steps": n_steps, "warmup": n_warm + 3, "ms_per_step": 1e3 * worst / n_steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "envs": n_procs,
-                   "note": "oracle port (numpy float64) of the OOPAO/drl4ao step, one env per host process"},
-        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": n_procs, "kind": "port",
+        "config": {"workload": args.workload, "description": desc, "envs": n_procs, "requested_steps": args.steps,
+                   "note": note + ", one environment per host process"},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": n_procs, "kind": kind,
                          "sample": f"{n_procs} processes x {n_steps} steps of one env each (1 BLAS thread), init {t_init:.1f}s excluded"},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

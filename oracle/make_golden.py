@@ -16,7 +16,7 @@ import numpy as np
 from numpy.random import RandomState
 
 from . import ref_harness as rh
-from .golden_configs import COMPACT, CONFIGS, STEPS, EPISODE_SEED
+from .golden_configs import COMPACT, CONFIGS, LITE, STEPS, EPISODE_SEED
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 DET_SEED = 1234
@@ -56,6 +56,17 @@ def generate(name):
     g["psf_atm_max"] = np.float64(env.tel.PSF.max())
     g["psf_atm_crop"] = env.tel.PSF[c - 8:c + 8, c - 8:c + 8].copy()
     g["psf_atm_phase"] = env.tel.src.phase.copy()
+    if name in LITE:
+        # PSF of a wavefront given by a formula (golden_configs.psf_formula_opd), so that the test can rebuild the input
+        # without a 0.9 MB phase map in the fixture: peak and central 32 x 32 window of tel.computePSF(4)
+        from .golden_configs import psf_formula_opd
+        env.tel.OPD = psf_formula_opd(cfg.resolution) * env.tel.pupil
+        with rh.quiet():
+            env.tel.computePSF(4)
+        c = env.tel.PSF.shape[0] // 2
+        g["psf_formula_max"] = np.float64(env.tel.PSF.max())
+        g["psf_formula_win"] = env.tel.PSF[c - 16:c + 16, c - 16:c + 16].copy()
+        env.tel.resetOPD()
 
     if cfg.detector.photonNoise or cfg.detector.readoutNoise:
         env.wfs.cam.random_state_photon_noise = RandomState(DET_SEED)
@@ -78,26 +89,41 @@ def generate(name):
     tr = dict(obs=np.zeros((n, nA, nA)), reward=np.zeros(n), strehl=np.zeros(n), signal=np.zeros((n, env.wfs.nSignal)),
               coefs=np.zeros((n, env.dm.nValidAct)))
     snaps = {}
+    lite = name in LITE
+    knife = np.zeros((n, env.wfs.nValidSubaperture), dtype=bool)
+    rows = slice(0, None, 3) if lite else slice(None)
     for i in range(n):
         with rh.quiet():
             obs, reward, strehl, done, info = env.step(i, env.gainCL * obs)
         tr["obs"][i], tr["reward"][i], tr["strehl"][i] = obs, reward, strehl
         tr["signal"][i] = env.wfs.signal
         tr["coefs"][i] = env.dm.coefs
+        if lite:     # lenslets with a pixel within 1e-4 (relative) of the centroiding threshold, from the reference's spots
+            maps = env.wfs.maps_intensity
+            thr = env.wfs.threshold_cog * maps.max()
+            knife[i] = (np.abs(maps - thr) < 1e-4 * thr).any(axis=(1, 2))
         if i in ((n - 1,) if name in COMPACT else (0, n // 2, n - 1)):
             ft = np.float32 if name in COMPACT else np.float64
-            snaps[f"atm_OPD_{i}"] = env.atm.OPD.astype(ft)
-            snaps[f"tel_OPD_{i}"] = env.tel.OPD.astype(ft)
-            snaps[f"frame_{i}"] = np.asarray(env.wfs.cam.frame).astype(ft)
+            snaps[f"atm_OPD_{i}"] = env.atm.OPD.astype(ft)[rows]
+            snaps[f"tel_OPD_{i}"] = env.tel.OPD.astype(ft)[rows]
+            snaps[f"frame_{i}"] = np.asarray(env.wfs.cam.frame).astype(ft)[rows]
     for k, v in tr.items():
         g["trace_" + k] = v
     g["trace_total"] = env.total[:n].copy()
     g["trace_residual"] = env.residual[:n].copy()
     g.update(snaps)
     g["snap_steps"] = np.array([n - 1] if name in COMPACT else [0, n // 2, n - 1])
+    if lite:
+        g["knife_edge"] = np.packbits(knife, axis=1)
+        g["snap_row_step"] = np.int64(3)
+        for k in ("frame0", "psf_atm_phase", "psf_atm_crop"):
+            g.pop(k, None)
+        g["trace_obs"] = g["trace_obs"].astype(np.float32)
+        g["obs0"] = g["obs0"].astype(np.float32)
     if name in COMPACT:
         for k in ("frame0", "trace_signal", "trace_coefs", "psf_atm_phase", "signal_after_build", "signal0", "reference_slopes_maps"):
-            g[k] = np.asarray(g[k]).astype(np.float32)
+            if k in g:
+                g[k] = np.asarray(g[k]).astype(np.float32)
     for i in range(env.atm.nLayer):
         ly = getattr(env.atm, f"layer_{i + 1}")
         g[f"final_buff_{i}"] = ly.buff.copy()

@@ -12,8 +12,31 @@ import sys
 
 import numpy as np
 
-REF_ROOT = "/root/reference/drl4ao"
-_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_shims")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIMS = os.path.join(_HERE, "ref_shims")
+# The reference lives in /root/reference in the build container.  __graft_entry__.build() stages an UNMODIFIED copy of
+# the files of the path (OOPAO package + the Razor environment) under the git-ignored oracle/_ref/, which travels to
+# the GPU box with the built library, so that bench.py's CPU arm can time the reference itself there.
+STAGED_ROOT = os.path.join(_HERE, "_ref", "drl4ao")
+REF_ROOT = ("/root/reference/drl4ao" if os.path.isdir("/root/reference/drl4ao/AO_OOPAO/OOPAO")
+            and os.environ.get("AOENV_REF_ROOT") != "staged" else STAGED_ROOT)
+STAGED_FILES = ("AO_OOPAO/OOPAO", "MAIN_CODE/OOPAOEnv/OOPAOEnvRazor.py", "MAIN_CODE/OOPAOEnv/__load__oopao.py")
+
+
+def stage_reference(src_root="/root/reference/drl4ao"):
+    """Copies the reference files of the path, byte for byte, into oracle/_ref/ (build-time; outputs only there)."""
+    import shutil
+    if not os.path.isdir(os.path.join(src_root, "AO_OOPAO", "OOPAO")):
+        return False
+    for rel in STAGED_FILES:
+        src, dst = os.path.join(src_root, rel), os.path.join(STAGED_ROOT, rel)
+        if os.path.isdir(src):
+            shutil.copytree(src, dst, dirs_exist_ok=True,
+                            ignore=shutil.ignore_patterns("__pycache__", "*.pyc", "*.npy", "*.fits", "*.png", "*.jpg"))
+        elif os.path.exists(src):
+            os.makedirs(os.path.dirname(dst), exist_ok=True)
+            shutil.copyfile(src, dst)
+    return True
 
 
 def reference_available():
@@ -108,6 +131,28 @@ def build_reference_env(cfg, verbose=False):
         wfs.cam.photonNoise = d.photonNoise
         wfs.cam.readoutNoise = d.readoutNoise
     return env
+
+
+class ReferenceStepper:
+    """The reference environment behind the two calls bench.py's CPU arm uses (new_episode / step), following the caller
+    pattern of MAIN_CODE/integrator_oopao_razor.py:46-70."""
+
+    def __init__(self, cfg):
+        self.env = build_reference_env(cfg)
+        self.gainCL = cfg.gainCL
+
+    def new_episode(self, seed):
+        env = self.env
+        with quiet():
+            env.atm.generateNewPhaseScreen(seed)
+            env.dm.coefs = 0
+            env.dm_prev = env.dm.coefs.copy()
+            env.tel * env.dm * env.wfs
+            return env.reset_soft()
+
+    def step(self, i, action):
+        with quiet():
+            return self.env.step(i, action)
 
 
 def record_xi(env):

@@ -5,6 +5,8 @@ from .OOPAOEnvRazor import OOPAO as _RazorOOPAO
 
 
 class OOPAO(_RazorOOPAO):
+    returns_frame = True          # step() is a 6-tuple: wrappers must not take the step apart and drop the frame
+
     def set_params(self, args=None, wfs_type="pyramid", modal_basis="zernike", gainCL=0.5, **kw):
         """OOPAOEnv.py:93-404."""
         return super().set_params(args, wfs_type, modal_basis, gainCL, **kw)

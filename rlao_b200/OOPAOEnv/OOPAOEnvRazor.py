@@ -27,6 +27,7 @@ from ..Telescope import Telescope
 from ..Zernike import Zernike
 from ..calibration.CalibrationVault import CalibrationVault
 from ..calibration.InteractionMatrix import InteractionMatrix
+from ..tools import linalg
 
 
 class OOPAO:
@@ -132,7 +133,7 @@ class OOPAO:
         if nZ and nZ > 0:
             Z = Zernike(self.tel, nZ)
             Z.computeZernike(self.tel)
-            M2C = torch.linalg.pinv(self.dm.modes[self.tel._pupil_idx, :].double()) @ Z.modes       # :261
+            M2C = linalg.pinv(self.dm.modes[self.tel._pupil_idx, :].double()) @ Z.modes              # :261
         else:
             M2C = torch.eye(self.dm.nValidAct, dtype=torch.float64, device=self.device)
         calib_zonal = InteractionMatrix(ngs=self.source, atm=self.atm, tel=self.tel, dm=self.dm, wfs=self.wfs,
@@ -157,7 +158,7 @@ class OOPAO:
         cam.photonNoise = param.get("cam_photonNoise", True)                                         # :332-333 (OOPAOEnv.py:379)
         cam.readoutNoise = param.get("cam_readoutNoise", 14 if wfs_type == "shackhartmann" else 0)
         self.set_reconstructor(M2C @ calib.M)                                                        # :336
-        self.F = M2C @ torch.linalg.pinv(M2C)                                                        # :337
+        self.F = M2C @ linalg.pinv(M2C)                                                              # :337
         self._F32 = self.F.to(torch.float32)
         self.dm.free_float64()
         # device-side index tables and outputs
@@ -328,7 +329,7 @@ class OOPAO:
         self.tel - self.atm
         Z = Zernike(self.tel, 50)
         Z.computeZernike(self.tel)
-        M2C = torch.linalg.pinv(self.dm.modes[self.tel._pupil_idx, :].double()) @ Z.modes
+        M2C = linalg.pinv(self.dm.modes[self.tel._pupil_idx, :].double()) @ Z.modes
         eye = torch.eye(self.dm.nValidAct, dtype=torch.float64, device=self.device)
         self.imat = InteractionMatrix(ngs=self.source, atm=self.atm, tel=self.tel, dm=self.dm, wfs=self.wfs, M2C=eye,
                                       stroke=1e-9, nMeasurements=25, noise="off")

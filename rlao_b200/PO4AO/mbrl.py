@@ -225,7 +225,8 @@ def run(env, past_obs, past_act, obs, replay, policy, dynamics, n_history, max_t
             history = torch.cat([h_obs.window(), h_act.window()], dim=1) if n_history > 1 else None
             action = policy(obs.unsqueeze(1), history)[:, 0]
         action = action.to(torch.float32)
-        next_obs, reward, strehl, done, _ = env.step(t, squeeze(action))
+        out = env.step(t, squeeze(action))          # 5-tuple, or 6 with the camera frame second (mbrl.py:76)
+        next_obs, (reward, strehl, done) = out[0], out[-4:-1]
         next_obs = torch.as_tensor(next_obs, device=dev).reshape(B, nA, nA)
         if fast:                                               # :79-80 (the state is already in its ring slot)
             roll.record(action)

@@ -155,18 +155,37 @@ class TorchWrapper(_Wrapper):
         atmosphere stays one update ahead)."""
         self._ahead = None
 
+    @staticmethod
+    def _split(out):
+        """(obs, frame or None, reward, strehl, done, info) from a 5-tuple (Razor environment, OOPAOEnvRazor.py:514) or a
+        6-tuple with the WFS camera frame in second place (papyrus environment, OOPAOEnv.py:536)."""
+        if len(out) == 6:
+            return out
+        obs, reward, strehl, done, info = out
+        return obs, None, reward, strehl, done, info
+
+    def _bare_step_env(self):
+        """True when self._env IS an environment whose step can be taken apart (_step_views) — not a wrapper around one
+        (TimeDelayEnv must see every action) and not one that also returns the camera frame."""
+        from ..OOPAOEnv.OOPAOEnvRazor import OOPAO as _Razor
+        return isinstance(self._env, _Razor) and not getattr(self._env, "returns_frame", False)
+
     def step(self, i, action):
+        """util_simple.py:209-213: same arity as the wrapped environment's step (the camera frame, when the environment
+        returns one, stays second)."""
         dev = self._env.device
         if not self.host_io:
             a = torch.as_tensor(action)
             if a.device != dev:
                 a = a.to(dev, dtype=torch.float32, non_blocking=True)
-            obs, reward, strehl, done, info = self._env.step(i, a)
-            return obs, reward, strehl, done, [(k, v) for k, v in info.items()]
+            obs, frame, reward, strehl, done, info = self._split(self._env.step(i, a))
+            info = [(k, v) for k, v in info.items()]
+            return (obs, reward, strehl, done, info) if frame is None else (obs, frame, reward, strehl, done, info)
         # small batches are launch-bound: the extra stream / event traffic of the pipelined path costs more than the
         # copies it hides
         big = self._env.n_envs * self._env.nActuator ** 2 >= 65536
-        bare = "_step_views" in type(self._env).__dict__
+        bare = self._bare_step_env()
+        frame_h = None
         if self.lookahead and bare:
             obs_h, reward_h, strehl_h = self._step_lookahead(i, action)
         elif big and bare:
@@ -175,11 +194,17 @@ class TorchWrapper(_Wrapper):
             a = torch.as_tensor(action)
             if a.device != dev:
                 a = a.to(dev, dtype=torch.float32, non_blocking=True)
-            obs, reward, strehl, done, info = self._env.step(i, a)
-            obs_h, reward_h, strehl_h = self._to_host(obs, reward, strehl)
+            obs, frame, reward, strehl, done, info = self._split(self._env.step(i, a))
+            if frame is None:
+                obs_h, reward_h, strehl_h = self._to_host(obs, reward, strehl)
+            else:
+                obs_h, reward_h, strehl_h, frame_h = self._to_host(obs, reward, strehl, frame)
         if self._env.n_envs == 1:
             reward_h, strehl_h = float(reward_h), float(strehl_h)
-        return obs_h, reward_h, strehl_h, False, [("strehl", torch.as_tensor(strehl_h, dtype=torch.float32))]
+        info = [("strehl", torch.as_tensor(strehl_h, dtype=torch.float32))]
+        if frame_h is not None:
+            return obs_h, frame_h, reward_h, strehl_h, False, info
+        return obs_h, reward_h, strehl_h, False, info
 
     def reset_soft(self):
         self._ahead = None

@@ -2,6 +2,8 @@
 and its (optionally truncated) pseudo-inverse.  float64 torch tensors on the matrix's device."""
 import torch
 
+from ..tools import linalg
+
 
 class CalibrationVault:
     def __init__(self, D, nTrunc=0, display=False, print_details=False, invert=True):
@@ -9,7 +11,7 @@ class CalibrationVault:
         if not invert:
             self.D = D
             return
-        U, s, V = torch.linalg.svd(D, full_matrices=False)
+        U, s, V = linalg.svd(D)
         self.s = s
         self.S = torch.diag(s)
         self.eigenValues = s

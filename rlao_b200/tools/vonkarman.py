@@ -8,6 +8,8 @@ import math
 
 import numpy as np
 import torch
+
+from . import linalg
 from numpy.random import RandomState
 from scipy.special import kv
 
@@ -52,7 +54,7 @@ class VKOperators:
         ZZt = torch.as_tensor(_vk_cov(zi, zi, L0, r0_def), **f64)
         self.ZXt = torch.as_tensor(_vk_cov(zi, zo, L0, r0_def), **f64)
         self.XXt = torch.as_tensor(_vk_cov(zo, zo, L0, r0_def), **f64)
-        ZZt_inv = torch.linalg.pinv(ZZt, hermitian=False)
+        ZZt_inv = linalg.pinv(ZZt)
         s = (r0_def / r0) ** (5.0 / 3)
         self.A = (self.ZXt * s).T @ (ZZt_inv / s)
         self.B = self.innovation_factor(r0)

@@ -231,6 +231,34 @@ def test_pyramid_environment_closes_the_loop_on_cpu(fake):
     assert float(strehl.min()) > 0 and done is False
 
 
+def test_torch_wrapper_keeps_the_camera_frame_of_the_papyrus_env(fake, monkeypatch):
+    """MAIN_CODE/PO4AO/util_simple.py:209-213 and mbrl.py:76: TorchWrapper.step of the papyrus environment is a 6-tuple
+    (obs, wfsf, reward, strehl, done, info), with and without TimeDelayEnv in between; the Razor environment stays a
+    5-tuple; mbrl.run accepts both."""
+    from rlao_b200.OOPAOEnv.OOPAOEnv import OOPAO
+    from rlao_b200.PO4AO import util_simple
+    from rlao_b200.PO4AO.util_simple import TimeDelayEnv, TorchWrapper
+    monkeypatch.setattr(util_simple.TorchWrapper, "_to_host", lambda self, *t: [x.clone() for x in t])   # no pinned memory on CPU
+    cfg = CONFIGS["tiny"]()
+    cfg.nSubap = 12
+    env = OOPAO()
+    env.set_params_file(param_from_config_for_pyramid(cfg), "")
+    env.set_params(types.SimpleNamespace(), gainCL=0.4, n_envs=2, rng="philox", seed=1)
+    new_episode(env, 5)
+    R = env.wfs.cam.resolution
+    for wrapped in (TorchWrapper(env, host_io=False), TorchWrapper(env, host_io=True),
+                    TorchWrapper(TimeDelayEnv(env, 1), host_io=True), TorchWrapper(TimeDelayEnv(env, 2), host_io=False)):
+        obs = wrapped.reset_soft()
+        out = wrapped.step(0, env.gainCL * obs)
+        assert len(out) == 6
+        obs, wfsf, reward, strehl, done, info = out
+        assert wfsf.shape == (2, R, R) and obs.shape == (2, env.nActuator, env.nActuator) and info[0][0] == "strehl"
+    razor = build_env(CONFIGS["tiny"](), n_envs=2, rng="philox", seed=1)
+    new_episode(razor, 5)
+    w = TorchWrapper(TimeDelayEnv(razor, 1), host_io=True)
+    assert len(w.step(0, razor.gainCL * w.reset_soft())) == 5
+
+
 def param_from_config_for_pyramid(cfg):
     from parity_util import param_from_config
     p = param_from_config(cfg)
@@ -256,7 +284,7 @@ def test_product_never_touches_the_oracle_or_the_reference():
     assert uses and all(bench.rfind("\ndef ", 0, u) >= 0 for u in uses)
     for u in uses:                                       # every use sits inside a CPU-arm helper
         fn = bench[bench.rfind("\ndef ", 0, u):u].split("(")[0]
-        assert fn.strip().split()[-1] in ("oracle_config", "cpu_env"), fn
+        assert fn.strip().split()[-1] in ("oracle_config", "cpu_env", "reference_env"), fn
     assert "/root/reference" not in bench
 
 
