@@ -246,6 +246,16 @@ int aoenv_observe(const float* rec, int ldr, const int32_t* act_idx, int B, int 
                   const double* stats, double n_pupil, float phase_scale,
                   float* obs, float* reward, float* strehl, float* total, float* residual, void* stream);
 
+/* Exploration noise (MAIN/OOPAOEnv/OOPAOEnvRazor.py:616-619: F @ np.random.normal(0, sigma, nValidAct), as an actuator
+ * image): aoenv_normal_fill draws z [rows][ld] = sigma * N(0, 1) (columns >= cols are zero) from Philox4x32-10 keyed by
+ * `seed` with `counter` = the call number, as float32 and (planes non-null) as the split-bf16 operand of
+ * aoenv_gemm_tn_tc; the product with F is that GEMM; aoenv_vec_to_img scatters vec [B][ldv] * scale into
+ * img [B][nAct2] (zero at invalid actuators; vec_to_img of OOPAOEnvRazor.py:621-630). */
+int aoenv_normal_fill(uint64_t seed, uint64_t counter, int rows, int cols, int ld, float sigma, float* out, void* planes,
+                      int parts, void* stream);
+int aoenv_vec_to_img(const float* vec, int ldv, const int32_t* act_idx, int B, int nA, int nAct2, float scale, float* img,
+                     void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Science-path PSF Strehl — OOPAO/Telescope.py:260-360 (computePSF(zp) -> PropagateField), PSF.max()
  * The reference pads the pupil field to N = os*zp*R (os = 2 for even image sizes), takes |FFT/N|^2 and bins

@@ -159,7 +159,10 @@ class OOPAO:
         cam.readoutNoise = param.get("cam_readoutNoise", 14 if wfs_type == "shackhartmann" else 0)
         self.set_reconstructor(M2C @ calib.M)                                                        # :336
         self.F = M2C @ linalg.pinv(M2C)                                                              # :337
-        self._F32 = self.F.to(torch.float32)
+        nA_, Kp_ = self.dm.nValidAct, self.dm._Kp
+        self._F32 = torch.zeros((nA_, Kp_), dtype=torch.float32, device=self.device)      # K-padded operand of F @ z
+        self._F32[:, :nA_] = self.F.to(torch.float32)
+        self._F_op = gemm.Operator(self._F32, parts=2)
         self.dm.free_float64()
         # device-side index tables and outputs
         B, nA = self.n_envs, self.dm.nValidAct
@@ -171,8 +174,11 @@ class OOPAO:
         self._total_now = torch.zeros((B,), dtype=torch.float32, device=self.device)
         self._residual_now = torch.zeros((B,), dtype=torch.float32, device=self.device)
         self._phase_scale = 2 * math.pi / self.source.wavelength
-        self._noise_gen = torch.Generator(device=self.device)
-        self._noise_gen.manual_seed(seed * 7919 + env_offset + 5)
+        self._noise_seed = (seed * 7919 + 5) & 0xFFFFFFFFFFFFFFFF
+        self._noise_calls = 0
+        self._noise_z = torch.zeros((B, self.dm._Kp), dtype=torch.float32, device=self.device)
+        self._noise_planes = torch.zeros((2, B, self.dm._Kp), dtype=torch.bfloat16, device=self.device)
+        self._noise_vec = torch.zeros((B, (nA + 3) // 4 * 4), dtype=torch.float32, device=self.device)
 
     def set_reconstructor(self, R):
         """reconstructor [nValidAct, nSignal] (float64 kept for inspection, padded float32 copy for the step GEMM)."""
@@ -388,8 +394,19 @@ class OOPAO:
 
     def sample_noise(self, sigma, use_torch=True):
         """OOPAOEnvRazor.py:616-619: F @ (sigma * N(0, I)), as an actuator image per environment."""
-        z = torch.randn((self.n_envs, self.dm.nValidAct), generator=self._noise_gen, device=self.device) * sigma
-        return self.vec_to_img(z @ self._F32.T)
+        lib, st, B, nA = _lib.load(), _lib.stream_ptr(self.device), self.n_envs, self.dm.nValidAct
+        tc = gemm.uses_tensor_cores()
+        # Philox normals (counter = call number; environments of other shards sit at other rows of the stream) ...
+        _lib.check(lib.aoenv_normal_fill(ctypes.c_uint64(self._noise_seed + (self.env_offset << 20)), ctypes.c_uint64(self._noise_calls),
+                                         B, nA, self.dm._Kp, ctypes.c_float(float(sigma)), _lib.ptr(self._noise_z),
+                                         _lib.ptr(self._noise_planes) if tc else None, 2, st), "normal_fill")
+        self._noise_calls += 1
+        # ... times F on the tensor cores, scattered to actuator images
+        gemm.gemm_tn(self._noise_z, self._F_op, self._noise_vec, B, nA, x_planes=self._noise_planes if tc else None)
+        img = torch.empty((B, self.nActuator, self.nActuator), dtype=torch.float32, device=self.device)
+        _lib.check(lib.aoenv_vec_to_img(_lib.ptr(self._noise_vec), self._noise_vec.stride(0), _lib.ptr(self._act_idx), B, nA,
+                                        self.nActuator ** 2, ctypes.c_float(1.0), _lib.ptr(img), st), "vec_to_img")
+        return self._sq(img)
 
     def vec_to_img(self, action_vec, use_torch=True):
         """OOPAOEnvRazor.py:621-630."""

@@ -409,6 +409,21 @@ class FakeLib:
         p[:, :nA] = new
         return 0
 
+    def aoenv_normal_fill(self, seed, counter, rows, cols, ld, sigma, out, planes, parts, stream):
+        self.launches += 1
+        o = _arr(out, (rows, ld))
+        o[:] = 0
+        rs = np.random.RandomState((int(_val(seed)) * 1000003 + int(_val(counter))) % (2 ** 32))
+        o[:, :cols] = rs.normal(size=(rows, cols)) * np.float32(_val(sigma))
+        return 0
+
+    def aoenv_vec_to_img(self, vec, ldv, act_idx, B, nA, nAct2, scale, img, stream):
+        self.launches += 1
+        v, idx, o = _arr(vec, (B, ldv)), _arr(act_idx, (nA,), np.int32), _arr(img, (B, nAct2))
+        o[:] = 0
+        o[:, idx] = v[:, :nA] * np.float32(_val(scale))
+        return 0
+
     def aoenv_observe(self, rec, ldr, act_idx, B, nA, nAct2, stats, n_pupil, phase_scale, obs, reward, strehl, total,
                       residual, stream):
         self.launches += 1

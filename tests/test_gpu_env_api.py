@@ -71,6 +71,43 @@ def test_sample_noise_lives_in_the_controlled_subspace(dev):
     assert rel_err((v @ env.F.T).cpu().numpy(), v.cpu().numpy()) < 1e-5
     assert torch.equal(env.vec_to_img(env.img_to_vec(z)), z)
     assert 0.0 < float(v.std()) < 0.05
+    # the pieces: Philox normals (aoenv_normal_fill) x F on the tensor cores (aoenv_gemm_tn_tc) -> aoenv_vec_to_img
+    nA = env.dm.nValidAct
+    draws = env._noise_z[:, :nA].double()
+    assert rel_err(v.cpu().numpy(), (draws @ env.F.T).cpu().numpy()) < 1e-4
+    assert float(env._noise_z[:, nA:].abs().max()) == 0.0            # padding columns stay zero
+    z2 = env.sample_noise(0.05)
+    assert not torch.equal(z2, z)                                     # the call counter advances the stream
+
+
+def test_sample_noise_statistics(dev):
+    """sigma * N(0, I) before the projection: mean 0, variance sigma^2, no correlation between environments, actuators or
+    calls; after it the covariance is sigma^2 F F^T (checked through its trace)."""
+    cfg = CONFIGS["tiny"]()
+    B = 512
+    env = build_env(cfg, n_envs=B, rng="philox", device=dev)
+    nA, sigma = env.dm.nValidAct, 0.2
+    zs, vs = [], []
+    for _ in range(8):
+        img = env.sample_noise(sigma)
+        zs.append(env._noise_z[:, :nA].double().cpu().numpy().copy())
+        vs.append(env.img_to_vec(img).double().cpu().numpy())
+    z = np.concatenate(zs)                                            # [8 B, nA]
+    n = z.size
+    assert abs(z.mean()) < 5 * sigma / np.sqrt(n)
+    assert abs(z.std() / sigma - 1) < 5 / np.sqrt(2 * n)
+    k4 = ((z / sigma) ** 4).mean()
+    assert abs(k4 - 3) < 0.1                                          # Gaussian kurtosis
+    c_env = np.corrcoef(z[:B].T[:, :200].T)                           # environments x environments (one call)
+    assert np.abs(c_env - np.eye(B)).max() < 0.5
+    c_act = np.corrcoef(z.T)                                          # actuators x actuators
+    assert np.abs(c_act - np.eye(nA)).max() < 6 / np.sqrt(z.shape[0])
+    assert abs(np.corrcoef(zs[0].reshape(-1), zs[1].reshape(-1))[0, 1]) < 5 / np.sqrt(zs[0].size)
+    v = np.concatenate(vs)
+    F = env.F.cpu().numpy()
+    want = sigma ** 2 * np.trace(F @ F.T)
+    got = (v ** 2).sum(axis=1).mean()
+    assert abs(got / want - 1) < 0.03
 
 
 def test_psf_strehl_reward(dev):
