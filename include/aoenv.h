@@ -80,6 +80,26 @@ int aoenv_atm_ring_multi(void* const* wins, const int64_t* win_offsets, void* co
 int aoenv_atm_compact(const float* src_win, float* dst_win, int B, int M, int pitch, int64_t env_stride, uint64_t* ext,
                       int64_t pos_delta, void* stream);
 
+/* Episode reset (Atmosphere.py:560-592 -> OOPAO/phaseStats.py:190-318, ft_phase_screen + ft_sh_phase_screen): S von
+ * Karman screens of N x N points, written into the interior of S layer windows (dst = window row 1, column 1 of
+ * environment 0; pitch floats per row, env_stride floats per environment).  N = R + 4 is not a power of two, so the
+ * transform fftshift(fft2(fftshift(cn))) runs as two dense products with the DFT matrix on the tensor cores (the
+ * fftshifts folded into signs), with a transposition in between; the three 3 x 3 sub-harmonic grids and the removal of
+ * their mean are applied by the last kernel.  Five launches.
+ *   cn = (n_re + i n_im) sqrt(PSD) del_f with n ~ N(0, 1) from Philox4x32-10 (seed; counter = stream position, screen0 + s),
+ *   or from `inject` [S][2][N][N] (real-part draws then imaginary-part draws, in the reference's order) when non-null.
+ *   As in the reference, the sub-harmonic coefficients reuse the first 54 positions of the real-part stream
+ *   (phaseStats.py:268,272 seed both generators alike).
+ *   amp [N][N] = sqrt(PSD) del_f (-1)^(a+b);  wa_planes: split-bf16 planes [parts][2N][Kp] of
+ *   [[Wr, -Wi], [Wi, Wr]], W[y][a] = (-1)^y exp(-2 pi i y a / N);  wb_planes: [parts][N][Kp] of [Wr | -Wi];  Kp >= 2N, % 16.
+ *   sh_ex / sh_ey: float2 [3][2][N] = exp(2 pi i g x), g in {-1/(3^p D), 0}; h_amp [3][2][2], h_mx / h_my [3][2][2] (HOST):
+ *   sub-harmonic amplitudes sqrt(PSD) df and the grid means of sh_ex / sh_ey.
+ *   Workspaces (caller-owned): work_planes bf16 [parts][S*N][Kp], work_a [S*N][lda >= 2N], work_b [S*N][ldb >= N]. */
+int aoenv_vk_screens(uint64_t seed, uint32_t screen0, int S, int N, const float* amp, const float* inject, const void* wa_planes,
+                     const void* wb_planes, int Kp, int parts, const float* sh_ex, const float* sh_ey, const float* h_amp,
+                     const float* h_mx, const float* h_my, void* work_planes, float* work_a, int lda, float* work_b, int ldb,
+                     float* dst, int pitch, int64_t env_stride, void* stream);
+
 /* updateLayer tail + fill_phase_support + set_OPD (Atmosphere.py:406-407,439-450,474-478): for each layer the
  * bicubic (4x4 tap) sub-pixel shift of the map, clipped to the map's [min,max], cropped to the R x R pupil
  * footprint, weighted by sqrt(fractionalR0) and summed; opd_out [B][R][R] = sum * opd_scale (lambda/2pi).

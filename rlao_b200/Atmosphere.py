@@ -96,6 +96,7 @@ class Atmosphere:
         self.canvas_slack = max(1, int(canvas_slack))   # add_row events between two re-centrings of a layer's canvas
         self.xi_queue = None        # optional iterator of [B, nO] tensors: injected innovations (parity runs)
         self.xi_log = None          # set to [] to record every innovation block used
+        self.screen_inject = None   # optional [nLayer][B, 2, N, N] normal draws for the next generateNewPhaseScreen (parity runs)
 
     # ------------------------------------------------------------------------------------------------
     def initializeAtmosphere(self, telescope):
@@ -167,15 +168,22 @@ class Atmosphere:
                 phase = torch.as_tensor(ph, dtype=torch.float32, device=dev)
                 ly.host_rng = [RandomState(ring_seed(i) + 104729 * (self.env_offset + e)) for e in range(B)]
             else:
-                g = torch.Generator(device=dev)
-                g.manual_seed((self.seed * 1000003 + screen_seed(i) * 7919 + self.env_offset * 104729 + 12345) % (2 ** 63))
-                phase = vk.screens_device_rng(self._r0, self._L0, N, delta, B, g, dev)
+                phase = None                       # synthesised on the device straight into the canvas (below)
                 ly.philox_seed = (self.seed * 1000003 + ring_seed(i)) & 0xFFFFFFFFFFFFFFFF
                 ly.events = 0
             self._cur[i] = 0
             self._org[i] = self._fresh_origin(i)
             oy, ox = self._org[i]
-            self._maps[i, 0, :, oy + 1:oy + self._M - 1, ox + 1:ox + self._M - 1] = phase
+            if phase is not None:
+                self._maps[i, 0, :, oy + 1:oy + self._M - 1, ox + 1:ox + self._M - 1] = phase
+            else:
+                key = (float(self._r0), float(self._L0))
+                if getattr(self, "_synth_key", None) != key:
+                    self._synth, self._synth_key = vk.ScreenSynth(self._r0, self._L0, N, delta, dev), key
+                sseed = (self.seed * 1000003 + screen_seed(i) * 7919 + 12345) & 0xFFFFFFFFFFFFFFFF
+                dst = self._maps[i, 0].data_ptr() + 4 * ((oy + 1) * self._pitch + ox + 1)
+                self._synth.generate(sseed, self.env_offset, B, dst, self._pitch, self._env_stride,
+                                     inject=self.screen_inject[i] if self.screen_inject is not None else None)
             self._extrude(i, 0, 0, force_rescan=True)
             ly.notDoneOnce = True
 

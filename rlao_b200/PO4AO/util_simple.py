@@ -142,6 +142,9 @@ class TorchWrapper(_Wrapper):
         cur = self._ahead
         a_dev, ready = self._upload(action)
         env._apply_command(a_dev, ready)
+        # the next observe overwrites the output buffers: it must not start before the download of the frame measured
+        # ahead has read them (the upload event orders this only when the action comes from the host)
+        torch.cuda.current_stream(env.device).wait_event(cur["ready"])
         self._ahead = {}
         env._measure_frame(None if i is None else i + 1, self._download_hook(self._ahead), atmosphere_done=True)
         env.atm.update()

@@ -1,7 +1,9 @@
 """Dense contractions of the step: D[x][w] = alpha * sum_k X[x][k] W[w][k] (include/aoenv.h).
 
-Two hand-written CUDA back ends, both FP32-accurate:
-  "tc"   tcgen05 tensor cores on split-bf16 operands (aoenv_gemm_tn_tc) — the production path;
+Two hand-written CUDA back ends:
+  "tc"   tcgen05 tensor cores on split-bf16 operands (aoenv_gemm_tn_tc) — the production path; relative error of a
+         product ~2^-17 of sum |x||w| with parts=2 (DM surface, reconstruction, exploration noise, PSF rows) and ~2^-24
+         (FP32 grade) with parts=3 (add_row, screen synthesis);
   "simt" FP32 FMA kernel (aoenv_gemm_tn) — kept as the on-device cross-check of the tensor-core path.
 Select with rlao_b200.gemm.BACKEND or the AOENV_GEMM environment variable."""
 import os
@@ -36,7 +38,9 @@ _workspaces = {}
 
 
 def _x_planes(X, parts):
-    key = (X.device, X.shape[0], X.stride(0), parts)      # one workspace per shape: calls are stream-ordered
+    # one workspace per shape AND stream: calls on one stream are ordered, two streams (or two environments driven from
+    # two streams) must not share the planes between the split and the GEMM that reads them
+    key = (X.device, X.shape[0], X.stride(0), parts, torch.cuda.current_stream(X.device).cuda_stream if X.is_cuda else 0)
     ws = _workspaces.get(key)
     if ws is None:
         ws = torch.empty((parts, X.shape[0], X.stride(0)), dtype=torch.bfloat16, device=X.device)

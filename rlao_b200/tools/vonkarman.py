@@ -136,6 +136,78 @@ def screens_device_rng(r0, L0, N, delta, n, generator, device, l0=1e-10):
     return out
 
 
+class ScreenSynth:
+    """Device-side synthesis of the episode's first screens (aoenv_vk_screens: Philox spectrum, two DFT-matrix GEMMs on the
+    tensor cores, sub-harmonics) — OOPAO/phaseStats.py:190-318 for a batch of screens.  Holds the operators of one
+    (r0, L0, N, delta): signed spectral amplitude, the two DFT operators in split-bf16 form, the sub-harmonic tables."""
+
+    def __init__(self, r0, L0, N, delta, device, parts=3, l0=1e-10):
+        from .. import gemm
+        self.N, self.parts, self.device = int(N), parts, device
+        N = self.N
+        del_f = 1.0 / (N * delta)
+        f1 = np.arange(-N / 2.0, N / 2.0) * del_f
+        fx, fy = np.meshgrid(f1, f1)
+        psd = _psd(np.sqrt(fx ** 2 + fy ** 2), r0, L0, l0)
+        psd[N // 2, N // 2] = 0
+        k = np.arange(N)
+        sign = 1.0 - 2.0 * ((k[:, None] + k[None, :]) % 2)
+        t32 = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device=device)
+        self.amp = t32(np.sqrt(psd) * del_f * sign)
+        # W[y][a] = (-1)^y exp(-2 pi i y a / N), exponent reduced mod N in integers
+        ang = -2.0 * np.pi * ((k[:, None] * k[None, :]) % N) / N
+        sy = (1.0 - 2.0 * (k % 2))[:, None]
+        Wr, Wi = np.cos(ang) * sy, np.sin(ang) * sy
+        self.Kp = (2 * N + 15) // 16 * 16
+        WA = np.zeros((2 * N, self.Kp))
+        WA[:N, :N], WA[:N, N:2 * N] = Wr, -Wi           # Ur = Gr Wr - Gi Wi
+        WA[N:, :N], WA[N:, N:2 * N] = Wi, Wr            # Ui = Gr Wi + Gi Wr
+        WB = np.zeros((N, self.Kp))
+        WB[:, :N], WB[:, N:2 * N] = Wr, -Wi             # Re(U W)
+        self.WA, self.WB = gemm.Operator(t32(WA), parts=parts), gemm.Operator(t32(WB), parts=parts)
+        # sub-harmonic grids p = 1..3: frequencies (j - 1) df along x, (i - 1) df along y, only i, j in {0, 1} are used
+        D = N * delta
+        c = np.arange(-N / 2, N / 2) * delta
+        ex = np.zeros((3, 2, N), dtype=complex)
+        amp_lo = np.zeros((3, 2, 2))
+        for p in range(1, 4):
+            df = 1 / (3 ** p * D)
+            g = np.arange(-1, 2) * df
+            gx, gy = np.meshgrid(g, g)
+            ps = _psd(np.sqrt(gx ** 2 + gy ** 2), r0, L0, l0)
+            ps[1, 1] = 0
+            amp_lo[p - 1] = (np.sqrt(ps) * df)[:2, :2]
+            for j in range(2):
+                ex[p - 1, j] = np.exp(2j * np.pi * g[j] * c)
+        pack = lambda z: np.stack([z.real, z.imag], axis=-1)
+        self.sh_ex = t32(pack(ex))                      # the y tables are the same numbers (square grid)
+        self.h_amp = np.ascontiguousarray(amp_lo, dtype=np.float32)
+        self.h_mean = np.ascontiguousarray(pack(ex.mean(axis=2)), dtype=np.float32)
+
+    def generate(self, seed, screen0, S, dst_ptr, pitch, env_stride, inject=None):
+        """Writes S screens into the windows starting at device address dst_ptr (row 1 / column 1 of environment 0)."""
+        import ctypes as C
+        from .. import _lib
+        lib, N, Kp, dev = _lib.load(), self.N, self.Kp, self.device
+        lda, ldb = (2 * N + 3) // 4 * 4, (N + 3) // 4 * 4
+        per_screen = self.parts * N * Kp * 2 + N * (lda + ldb) * 4
+        chunk = max(1, min(S, 32767, (768 << 20) // per_screen))
+        planes = torch.empty((self.parts, chunk * N, Kp), dtype=torch.bfloat16, device=dev)
+        wa = torch.empty((chunk * N, lda), dtype=torch.float32, device=dev)
+        wb = torch.empty((chunk * N, ldb), dtype=torch.float32, device=dev)
+        f = lambda a: a.ctypes.data_as(C.c_void_p)
+        for s0 in range(0, S, chunk):
+            m = min(chunk, S - s0)
+            inj = None
+            if inject is not None:
+                inj = torch.as_tensor(inject[s0:s0 + m], dtype=torch.float32, device=dev).contiguous()
+            _lib.check(lib.aoenv_vk_screens(
+                C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), C.c_uint32((screen0 + s0) & 0xFFFFFFFF), m, N, _lib.ptr(self.amp),
+                _lib.ptr(inj), _lib.ptr(self.WA.planes()), _lib.ptr(self.WB.planes()), Kp, self.parts, _lib.ptr(self.sh_ex),
+                _lib.ptr(self.sh_ex), f(self.h_amp), f(self.h_mean), f(self.h_mean), _lib.ptr(planes), _lib.ptr(wa), lda,
+                _lib.ptr(wb), ldb, dst_ptr + 4 * s0 * env_stride, pitch, env_stride, _lib.stream_ptr(dev)), "vk_screens")
+
+
 def cubic_tap_weights(buff, kernel="lagrange018"):
     """Tap offset (relative to the output pixel) and the four float64 weights of the separable cubic
     interpolation that shifts a map by `buff` pixels (|buff| < 1) along one axis.

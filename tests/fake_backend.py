@@ -130,6 +130,38 @@ class FakeLib:
         u[:] = (u & np.uint64(0xffffffff00000000)) | ((u & np.uint64(0xffffffff)) + np.uint64(pos_delta % (1 << 32))) & np.uint64(0xffffffff)
         return 0
 
+    def aoenv_vk_screens(self, seed, screen0, S, N, amp, inject, wa, wb, Kp, parts, sh_ex, sh_ey, h_amp, h_mx, h_my, wp, wa_, lda,
+                         wb_, ldb, dst, pitch, env_stride, stream):
+        """numpy FFT of the same spectrum (the kernels run it as two DFT-matrix products); sub-harmonics from the tables."""
+        self.launches += 5
+        a = _arr(amp, (N, N)).astype(np.float64)                    # sqrt(PSD) del_f (-1)^(a+b)
+        k = np.arange(N)
+        sign = 1.0 - 2.0 * ((k[:, None] + k[None, :]) % 2)
+        inj = _arr(inject, (S, 2, N, N))
+        ex = _arr(sh_ex, (3, 2, N, 2)).astype(np.float64)
+        ex = ex[..., 0] + 1j * ex[..., 1]
+        ey = _arr(sh_ey, (3, 2, N, 2)).astype(np.float64)
+        ey = ey[..., 0] + 1j * ey[..., 1]
+        la = _arr(h_amp, (3, 2, 2))
+        out = self._window(dst, S, N, pitch, env_stride)
+        for s_ in range(S):
+            if inj is not None:
+                re, im = inj[s_, 0].astype(np.float64), inj[s_, 1].astype(np.float64)
+            else:
+                rs = np.random.RandomState((int(_val(seed)) * 7919 + int(_val(screen0)) + s_) % (2 ** 32))
+                re, im = rs.normal(size=(N, N)), rs.normal(size=(N, N))
+            cn = (re + 1j * im) * a * sign                          # amp carries the fftshift signs: undo them
+            hi = np.fft.fftshift(np.fft.fft2(np.fft.fftshift(cn))).real
+            flat = re.reshape(-1)
+            lo = np.zeros((N, N), dtype=complex)
+            for p in range(3):
+                for i in range(2):
+                    for j in range(2):
+                        c = (flat[18 * p + 3 * i + j] + 1j * flat[18 * p + 9 + 3 * i + j]) * la[p, i, j]
+                        lo += c * ey[p, i][:, None] * ex[p, j][None, :]
+            out[s_] = (hi + lo.real - lo.real.mean()).astype(np.float32)
+        return 0
+
     def aoenv_atm_phase(self, h_canvas, h_ext, h_org, L, B, R, M, Mc, pitch, fp_off, roff, coff, wr, wc, wt, opd_scale,
                         opd_out, stream):
         self.launches += 1
@@ -155,6 +187,10 @@ class FakeLib:
         return 0
 
     # ---- gemm ------------------------------------------------------------------------------------------
+    def aoenv_split_bf16(self, src, lds, rows, K, parts, dst, ldk, stream):
+        self.launches += 1          # operand planes are never read by this stand-in (its GEMMs take the float32 operands)
+        return 0
+
     def aoenv_gemm_tn(self, X, ldx, W, ldw, D, ldd, M, N, K, alpha, stream):
         self.launches += 1
         assert K % 16 == 0
