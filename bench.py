@@ -440,6 +440,7 @@ def run_gpu_arm(args):
                               "note": "TorchWrapper(lookahead=True), opt-in; `e2e` is the strict wrapper"},
             "gpu_launches": launches,
             "roofline": roofline,
+            "step_roofline": step_roofline(env, B, ms_max / args.steps),
             "cpu_baseline": cpu_baseline,
             "kernels": kernels,
         }
@@ -467,7 +468,7 @@ def dominant_roofline(kernels, env, B):
     try:     # DRAM bytes per launch from the committed ncu capture of this workload (profiles/)
         t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_cfg3.json")))
         if t.get("envs_per_gpu") == B and (R, L) == (240, 3):
-            traffic = t.get(top)
+            traffic = t.get(top)          # null until an ncu capture of this kernel is committed
     except Exception:
         pass
     if top.startswith("aoenv_gemm_tn"):
@@ -488,6 +489,7 @@ def dominant_roofline(kernels, env, B):
         "aoenv_dm_surface_separable": P * 4 + nA * 4,
         "aoenv_atm_phase": L * M * M * 4 + P * 4,
         "aoenv_shwfs_frame": 3 * P * 4,
+        "aoenv_shwfs_fused": P * 4 + nA * 4 + nSig * 4,
         "aoenv_shwfs_slopes": P * 4 + nSig * 4,
         "aoenv_atm_ring": 2 * (4 * M - 4) * 4,
         "aoenv_atm_compact": 2 * M * M * 4,
@@ -502,18 +504,47 @@ def dominant_roofline(kernels, env, B):
     # algorithmic HBM GB/s of every streaming kernel of the step (same definition as `achieved`)
     out["all_streaming_kernels_gbs"] = {k: round(per_env_all[k] * B / (kernels[k]["ms_per_call"] * 1e-3) / 1e9, 1)
                                         for k in kernels if k in per_env_all}
-    if top == "aoenv_shwfs_frame":
-        # FP32 work of the frame kernel: two DFT passes on the n non-zero inputs, radix-2 split
+    if top in ("aoenv_shwfs_frame", "aoenv_shwfs_fused"):
+        # This kernel is bound by the FP32 FMA pipe (ncu: profiles/), so the roofline is the FP32 one: algorithmic flops =
+        # the two pruned DFT passes on the n non-zero inputs with the radix-2 split (4 n^3 + 8 n^3 FMA per lit lenslet,
+        # DESIGN.md section 4) and, for the fused kernel, the banded DM surface (W FMA per pixel + the T = C gx stage).
+        # Field generation, |.|^2, binning, statistics and centroids are not counted.  The HBM figures stay as
+        # `hbm_model` (algorithmic bytes: OPD in, commands in, slopes out; the camera frame only when it is written).
         n = env.wfs.n_pix_subap if hasattr(env.wfs, "n_pix_subap") else R // env.wfs.nSubap
-        fma = 4 * n ** 3 + 8 * n ** 3                         # complex MACs x 4, pass 1 + pass 2, per lit lenslet
-        lit = int(env.wfs.nValidSubaperture)
-        tflops = 2.0 * fma * lit * B / (ms * 1e-3) / 1e12
-        out["fp32"] = {"achieved_tflops": tflops, "peak_tflops": 72.3, "frac": tflops / 72.3,
-                       "peak_source": "tools/microbench/ffma2_rate.cu on this pool's B200 (FFMA and FFMA2 both 72 TFLOP/s)"}
-        out["note"] = ("this kernel is bound by the FP32 FMA pipe, not by HBM: ncu (profiles/r1_v12_ncu_wfs_ffma2.md) shows the "
-                       "FMA pipe 65 % active, issue slots 53 %, DRAM 30 %; `fp32` is the DFT arithmetic alone against the "
-                       "measured FP32 peak")
+        fma = (4 * n ** 3 + 8 * n ** 3) * int(env.wfs.nValidSubaperture)
+        what = "pruned DFT passes"
+        if top == "aoenv_shwfs_fused":
+            tb = env.dm.fused_tables()
+            if tb is not None:
+                fma += tb["W"] * P + tb["W"] * env.dm.nAct * R
+                what += " + banded DM surface"
+        tflops = 2.0 * fma * B / (ms * 1e-3) / 1e12
+        out = {"kernel": top, "bound": "fp32", "achieved": tflops, "peak": 72.3, "unit": "TFLOP/s", "frac": tflops / 72.3,
+               "traffic": traffic, "flops_counted": what,
+               "peak_source": "FP32 FMA peak measured on this pool's B200 (tools/microbench/ffma2_rate.cu: FFMA and FFMA2 both "
+                              "72.3 TFLOP/s; nominal 148 SM x 128 x 2 x 1.965 GHz = 74.4); MEASURED_PEAKS.json holds no FP32 figure",
+               "hbm_model": {"algorithmic_bytes_per_launch": per_env * B, "achieved_gbs": ach, "frac_of_hbm_peak": ach / hbm_peak,
+                             "hbm_peak_gbs": hbm_peak, "peak_source": src},
+               "all_streaming_kernels_gbs": out["all_streaming_kernels_gbs"]}
     return out
+
+
+def step_roofline(env, B, ms_per_step):
+    """Whole-step HBM figure on SURVEY.md section 8(d)'s compulsory bytes per env-step: every layer map read once, one map
+    write-back per expected add_row, commands, slopes, observation, reward and Strehl."""
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    R, L, M = env.tel.resolution, env.atm.nLayer, env.atm._M
+    nA, nSig, nAct2 = env.dm.nValidAct, env.wfs.nSignal, env.nActuator ** 2
+    f = sum(float(abs(ly.ratio).max()) for ly in env.atm._layers)
+    per_env = L * M * M * 4 + f * M * M * 4 + 3 * nA * 4 + nSig * 4 + nAct2 * 4 + 8
+    gbs = per_env * B / (ms_per_step * 1e-3) / 1e9
+    return {"algorithmic_bytes_per_env_step": per_env, "add_row_events_per_step": f, "achieved_gbs": gbs, "peak_gbs": hbm_peak,
+            "frac": gbs / hbm_peak, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"}
 
 
 def run_po4ao_arm(args):
