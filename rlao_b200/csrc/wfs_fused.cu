@@ -153,7 +153,7 @@ __host__ __device__ inline FusedSmem fused_smem_layout(int nS, int n, int rows_p
   s.off_C = o;      o = up(o + (sep ? t_rows * nAct * 4 : 0));
   s.off_Wy = o;     o = up(o + (sep ? (rows_px / 2) * 2 * W * 4 : 0));
   s.off_I0 = o;     o = up(o + (sep ? (rows_px / 2) * 4 : 0));
-  s.off_misc = o;   o = up(o + 512);
+  s.off_misc = o;   o = up(o + 1536);                          // FusedMisc
   s.total = o;
   return s;
 }
@@ -166,7 +166,7 @@ struct FusedMisc {
   float warp_max[32];
   double warp_stats[32][4];
 };
-static_assert(sizeof(FusedMisc) <= 8 + 32 + 8 + 128 + 1024 + 64, "misc block");
+static_assert(sizeof(FusedMisc) <= 1536, "misc block must fit the bytes fused_smem_layout reserves for it");
 
 template <int n, int NG, int W>
 __global__ void __launch_bounds__(NG * (n / 2) * 32, (NG * (n / 2) * 32 <= 384) ? 2 : 1)

@@ -271,7 +271,7 @@ class FakeLib:
             o = up(o + t_rows * nAct * 4)
             o = up(o + (rows_px // 2) * 2 * W * 4)
             o = up(o + (rows_px // 2) * 4)
-        return up(o + 512)
+        return up(o + 1536)
 
     def aoenv_shwfs_fused(self, opd_a, opd_b, dm, pupil8, amp0, order, nlit, slot_of, B, nS, n, cluster, groups, phase_scale,
                           ref_xy, nV, inv_units, thr, frame, slopes, lds, slope_planes, parts, envmax, stats, stream):
