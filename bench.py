@@ -489,7 +489,8 @@ def dominant_roofline(kernels, env, B):
         "aoenv_dm_surface_separable": P * 4 + nA * 4,
         "aoenv_atm_phase": L * M * M * 4 + P * 4,
         "aoenv_shwfs_frame": 3 * P * 4,
-        "aoenv_shwfs_fused": P * 4 + nA * 4 + nSig * 4,
+        "aoenv_shwfs_fused": P * 4 + nSig * 4 + (env.dm.nAct + 14) * R * 4,      # OPD in, slopes out, T = C gx rows in
+        "aoenv_dm_rows": nA * 4 + env.dm.nAct * R * 4,
         "aoenv_shwfs_slopes": P * 4 + nSig * 4,
         "aoenv_atm_ring": 2 * (4 * M - 4) * 4,
         "aoenv_atm_compact": 2 * M * M * 4,
@@ -516,8 +517,9 @@ def dominant_roofline(kernels, env, B):
         if top == "aoenv_shwfs_fused":
             tb = env.dm.fused_tables()
             if tb is not None:
-                fma += tb["W"] * P + tb["W"] * env.dm.nAct * R
-                what += " + banded DM surface"
+                plan = env.wfs._fused_plans.get(id(tb))
+                fma += (plan["WL"] if plan else 14) * P          # row half of the separable surface (the column half is aoenv_dm_rows)
+                what += " + banded DM surface (row half)"
         tflops = 2.0 * fma * B / (ms * 1e-3) / 1e12
         out = {"kernel": top, "bound": "fp32", "achieved": tflops, "peak": 72.3, "unit": "TFLOP/s", "frac": tflops / 72.3,
                "traffic": traffic, "flops_counted": what,

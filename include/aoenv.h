@@ -208,37 +208,41 @@ int aoenv_shwfs_slopes(const float* frame, const int32_t* envmax, int shared_max
  * aoenv_dm_surface_separable), ShackHartmann.py:340-353,529-577 (ideal detector), :314-324,580-601, and the pupil
  * statistics of MAIN/OOPAOEnv/OOPAOEnvRazor.py:484,502,604-605.  Neither the DM surface nor atmosphere + DM are
  * written to memory; the camera frame only when `frame` is non-null.
- *   opd_a [B][R][R]: first OPD term (atmosphere, metres, no pupil).  Second term: either `dm` (commands + banded
- *   tables of the separable geometry) or `opd_b` [B][R][R] (any surface), or neither.
- *   pupil8 [R][R]: 1 inside the pupil (the flux must be uniform over the pupil: amp0 = sqrt(fluxMap) there).
- *   cluster: CTAs per environment (divides nS; > 8 needs the non-portable cluster size); CTA r owns lenslet rows
- *   [r nS/cluster, (r+1) nS/cluster).  order [cluster][nS/cluster * nS]: lenslet ids inside each strip
- *   (row_in_strip * nS + column), the lit ones first; nlit [cluster]: how many are lit.  slot_of [nS*nS]: position of
- *   a lenslet in the valid list (= its slope index), -1 if invalid.  groups: warp groups per CTA (2 or 4).
+ *   opd_a [B][R][R]: first OPD term (atmosphere, metres, no pupil).  Second term: either `dm` (the column half
+ *   T = C gx of the separable surface from aoenv_dm_rows + the row weights) or `opd_b` [B][R][R] (any surface), or neither.
+ *   pupil8 [R][R]: 1 inside the pupil (the flux must be uniform over the pupil: amp0 = sqrt(fluxMap) there).  R % 4 == 0.
+ *   cluster: CTAs per environment (<= 16; > 8 needs the non-portable cluster size); CTA r owns the lenslet rows
+ *   [h_row_start[r], h_row_start[r+1]) (HOST array of cluster + 1 entries, 0 ... nS).  order [cluster][rows_max * nS]
+ *   (rows_max = tallest strip): lenslet ids inside each strip (row_in_strip * nS + column), the lit ones first;
+ *   nlit [cluster]: how many are lit.  slot_of [nS*nS]: position of a lenslet in the valid list (= its slope index), -1
+ *   if invalid.  groups: warp groups per CTA.
  *   slopes (nullable; then only the frame is produced, envmax is reset for the camera pass) / slope_planes / ref_xy /
  *   inv_units / threshold_cog / envmax / stats: as in aoenv_shwfs_slopes and aoenv_shwfs_frame, except that stats
  *   holds the plain sums {sum a, sum a^2, sum t, sum t^2} over the pupil (a = opd_a, t = opd_a + DM). */
 typedef struct {
-  const float* coefs;            /* [B][ldc] commands of the valid actuators (metres); NULL = no separable DM         */
-  const int32_t* act_pos;        /* [nA] row * nAct + col of each valid actuator (row-major order)                     */
-  const int32_t* act_row_start;  /* [nAct + 1] index in the valid list of the first actuator of each grid row          */
-  const float* wx;               /* [R][W]  weights of pixel column x, first actuator column j0x[x]                    */
-  const int32_t* j0x;            /* [R]                                                                                 */
-  const float* wyp;              /* [R/2][2][W] weights of the pixel-row pair (2k, 2k+1), first actuator row i0y[k]     */
-  const int32_t* i0y;            /* [R/2], non-decreasing                                                               */
-  int32_t ldc, nA, nAct, W;      /* W = 12 or 16                                                                        */
-  int32_t t_rows;                /* max over strips of the actuator rows a strip's bands touch                          */
+  const float* rows;             /* [B][nActP][R] T = C gx from aoenv_dm_rows (rows >= nAct are zero); NULL = no separable DM */
+  const float* wlr;              /* [R][2 * pad4((WL+1)/2)] weights of pixel row y on the actuator rows ilr[y / n] + t, t < WL,  */
+                                 /* stored as two halves of (WL+1)/2 entries, each padded to a multiple of 4 floats               */
+  const int32_t* ilr;            /* [nS] first actuator row of the window of every lenslet row, non-decreasing                   */
+  int32_t nActP;                 /* rows per environment in `rows` (>= nAct + WL)                                                */
+  int32_t WL;                    /* window height: 14 or 18                                                                      */
+  int32_t t_rows;                /* max over strips of ilr[last row] + WL - ilr[first row]                                       */
   int32_t reserved;
 } aoenv_dm_sep_t;
 
 int aoenv_shwfs_fused(const float* opd_a, const float* opd_b, const aoenv_dm_sep_t* dm, const uint8_t* pupil8, float amp0,
-                      const int32_t* order, const int32_t* nlit, const int32_t* slot_of, int B, int nS, int n, int cluster,
-                      int groups, float phase_scale, const float* ref_xy, int nV, float inv_units, float threshold_cog,
-                      float* frame, float* slopes, int lds, void* slope_planes, int parts, int32_t* envmax, double* stats,
-                      void* stream);
-/* Shared memory per CTA (bytes) the kernel above needs for a configuration, or -1 for an invalid one (t_rows = 0: no
- * separable DM).  The limit is 227 KB. */
-int aoenv_shwfs_fused_smem(int nS, int n, int cluster, int groups, int t_rows, int nAct, int W);
+                      const int32_t* h_row_start, const int32_t* order, const int32_t* nlit, const int32_t* slot_of, int B,
+                      int nS, int n, int cluster, int groups, float phase_scale, const float* ref_xy, int nV, float inv_units,
+                      float threshold_cog, float* frame, float* slopes, int lds, void* slope_planes, int parts,
+                      int32_t* envmax, double* stats, void* stream);
+/* Shared memory per CTA (bytes) the kernel above needs when its tallest strip has rows_max lenslet rows, or -1 for an
+ * invalid configuration (t_rows = 0: no separable DM).  The limit is 227 KB. */
+int aoenv_shwfs_fused_smem(int nS, int n, int rows_max, int groups, int t_rows, int WL);
+/* Column half of the separable DM surface, once per command: rows [B][nActP][R], rows[b][i][x] = sum_q C_b[i][j0x[x] + q]
+ * wx[x][q] for i < nAct (C_b = command image of environment b, see aoenv_dm_surface_separable for the tables; W = 12 or
+ * 16); rows i >= nAct are not written (the caller keeps them zero). */
+int aoenv_dm_rows(const float* coefs, int ldc, const int32_t* act_pos, int nA, int nAct, int nActP, const float* wx,
+                  const int32_t* j0x, int W, int B, int R, float* rows, void* stream);
 
 /* Calibration-grade measurement (init only): the two steps above in float64 with the ideal detector, for the
  * reference slopes / slope units (ShackHartmann.py:254-312) and the interaction matrix pushes
@@ -293,6 +297,16 @@ int aoenv_vec_to_img(const float* vec, int ldv, const int32_t* act_idx, int B, i
 int aoenv_psf_peak(const float* opd_a, const float* opd_b, const float* pupil, const float* amp,
                    const void* w1_planes, const float* g2, int B, int R, int N, int os, int win, float phase_scale,
                    void* field_planes, int ldk, float* scratch, float* psf_win, float* psf_max, void* stream);
+
+/* The whole PSF image (tel.computePSF(zp) / computePSF(detector=cam): Telescope.py:260-360 with img_resolution = win):
+ * the central win x win binned pixels, any win up to N / os.  Both transforms are tensor-core GEMMs with the operator of
+ * aoenv_psf_peak (w_planes [2][2*Wu][ldk], Wu = os * win; the DFT kernel is the same along both axes), with a
+ * transposition in between; five launches.  Workspaces (caller-owned): field_planes bf16 [2][B*R][ldk] (columns
+ * [2R, ldk) zero), work_t [B*R][2*Wu], planes_u bf16 [2][B*Wu][ldk] (columns [2R, ldk) zero), work_f [B*Wu][2*Wu].
+ * psf [B][win][win]; psf_max [B]. */
+int aoenv_psf_image(const float* opd_a, const float* opd_b, const float* pupil, const float* amp, const void* w_planes, int B,
+                    int R, int N, int os, int win, float phase_scale, void* field_planes, int ldk, float* work_t, void* planes_u,
+                    float* work_f, float* psf, float* psf_max, void* stream);
 
 #ifdef __cplusplus
 }

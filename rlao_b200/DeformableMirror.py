@@ -36,6 +36,11 @@ class DMSurfaceRef:
         return self.dm._coefs_of[self.slot]
 
     @property
+    def rows(self):
+        """T = C gx [n_envs, nAct + 18, R] of this surface (aoenv_dm_rows), the DM operand of aoenv_shwfs_fused."""
+        return self.dm._rows_of(self.slot)
+
+    @property
     def shape(self):
         return self.dm._opd[self.slot].shape
 
@@ -107,6 +112,8 @@ class DeformableMirror:
         self.lazy_surface = True
         self._coefs_of = [None, None]
         self._valid = [True, True]
+        self._rows = None                 # [2][n_envs, nAct + 18, R]: column half of the separable surface, per slot
+        self._rows_valid = [False, False]
         self._multi = None            # [k, R, R] surfaces of a [nValidAct, k] command matrix (calibration)
         self._coefs = torch.zeros((self.n_envs, self._Kp), dtype=torch.float32, device=self.device)
         self._coefs_matrix = None
@@ -179,7 +186,8 @@ class DeformableMirror:
         row_start = np.searchsorted(rows, np.arange(n + 1)).astype(np.int32)      # valid actuators are listed row-major
         out = dict(gx=t(gxv, torch.float32), gy=t(gyv, torch.float32), band_x=t(bx, torch.int32), band_y=t(by, torch.int32),
                    act_pos=t((rows * n + cols).astype(np.int32), torch.int32), act_row_start=t(row_start, torch.int32),
-                   W=0, wx=None, j0x=None, wyp=None, i0y=None, i0y_host=None, nAct=n)
+                   W=0, wx=None, j0x=None, wyp=None, i0y=None, i0y_host=None, nAct=n, by_host=by.astype(np.int64),
+                   gy_host=gyv)
         # fixed-width band tables for the unrolled kernel: per pixel column, and per PAIR of pixel rows
         if R % 2 == 0:
             pair_lo = np.minimum(by[0::2, 0], by[1::2, 0])
@@ -249,8 +257,10 @@ class DeformableMirror:
         self._coefs_matrix = None
         self._slot ^= 1
         self._coefs_of[self._slot] = coefs_padded
+        self._rows_valid[self._slot] = False
         if self.lazy_surface and self.fused_tables() is not None:
             self._valid[self._slot] = False       # evaluated inside aoenv_shwfs_fused, or on demand
+            self._rows_of(self._slot)             # T = C gx now (39 KB per environment instead of the 230 KB surface)
         else:
             self._surface(coefs_padded, self._opd[self._slot])
             self._valid[self._slot] = True
@@ -261,6 +271,24 @@ class DeformableMirror:
         if t is None or t["W"] not in (12, 16) or self.surface_backend not in ("auto", "separable"):
             return None
         return t
+
+    ROWS_PAD = 18                     # zero rows after the last actuator row: windows may run past it without clamping
+
+    def _rows_of(self, slot):
+        t = self.fused_tables()
+        if self._rows is None:
+            self._rows = torch.zeros((2, self.n_envs, self.nAct + self.ROWS_PAD, self.resolution), dtype=torch.float32,
+                                     device=self.device)
+        if not self._rows_valid[slot]:
+            c = self._coefs_of[slot]
+            if c is None:
+                c = torch.zeros((self.n_envs, self._Kp), dtype=torch.float32, device=self.device)
+            _lib.check(_lib.load().aoenv_dm_rows(_lib.ptr(c), c.stride(0), _lib.ptr(t["act_pos"]), self.nValidAct, self.nAct,
+                                                 self.nAct + self.ROWS_PAD, _lib.ptr(t["wx"]), _lib.ptr(t["j0x"]), t["W"],
+                                                 self.n_envs, self.resolution, _lib.ptr(self._rows[slot]),
+                                                 _lib.stream_ptr(self.device)), "dm_rows")
+            self._rows_valid[slot] = True
+        return self._rows[slot]
 
     def _slot_surface(self, slot):
         if not self._valid[slot]:

@@ -146,61 +146,106 @@ class ShackHartmann:
 
     # ---- kernels ------------------------------------------------------------------------------------------
     def _fused_plan(self, dm_tables):
-        """Launch shape of aoenv_shwfs_fused: CTAs per environment (cluster), warp groups, the lit-first lenslet order of
-        every strip and the number of actuator rows a strip's bands touch."""
+        """Launch shape of aoenv_shwfs_fused: CTAs per environment (cluster) and the strip of lenslet rows each owns (cut
+        so that rows + lit lenslets are even), warp groups, the lit-first lenslet order of every strip, and — with a
+        separable DM — the window tables: first actuator row of every lenslet row's band, row weights relative to it."""
         key = id(dm_tables) if dm_tables is not None else 0
         plan = self._fused_plans.get(key)
         if plan is not None:
             return plan
-        lib, nS, n = _lib.load(), self.nSubap, self.n_pix_subap
+        lib, nS, n, dev = _lib.load(), self.nSubap, self.n_pix_subap, self.device
+        R = nS * n
         groups = int(os.environ.get("AOENV_WFS_GROUPS", "4"))
+        valid = self.valid_subapertures
+        lit_row = valid.sum(axis=1).astype(np.float64)
+        WL, ilr, wlr = 0, None, None
+        if dm_tables is not None:
+            by, gy = dm_tables["by_host"], dm_tables["gy_host"]            # [R, 2] band of every pixel row, [nAct, R] weights
+            lo = by[:, 0].reshape(nS, n).min(axis=1)
+            hi = by[:, 1].reshape(nS, n).max(axis=1)
+            need = int((hi - lo + 1).max())
+            WL = 14 if need <= 14 else (18 if need <= 18 else 0)
+            if WL == 0:
+                raise NotImplementedError(f"DM influence bands of {need} actuator rows per lenslet row are too wide for the fused kernel")
+            half = (WL + 1) // 2
+            hp = (half + 3) // 4 * 4
+            wl = np.zeros((R, 2 * hp), dtype=np.float32)
+            for y in range(R):
+                i0 = lo[y // n]
+                for i in range(by[y, 0], by[y, 1] + 1):
+                    t = i - i0
+                    wl[y, (t // half) * hp + t % half] = gy[i, y]
+            ilr = lo.astype(np.int32)
+            wlr = wl
 
-        def t_rows_for(C_):
-            if dm_tables is None:
+        def t_rows_for(rs):
+            if ilr is None:
                 return 0
-            i0, W, nAct = dm_tables["i0y_host"], dm_tables["W"], dm_tables["nAct"]
-            pp = (nS // C_) * n // 2                      # pixel-row pairs per strip
-            first, last = i0[0::pp][:C_], i0[pp - 1::pp][:C_]
-            return int((np.minimum(last + W - 1, nAct - 1) - first + 1).max())
+            return int(max(ilr[rs[k + 1] - 1] + WL - ilr[rs[k]] for k in range(len(rs) - 1)))
 
-        def smem_for(C_):
-            return lib.aoenv_shwfs_fused_smem(nS, n, C_, groups, t_rows_for(C_), dm_tables["nAct"] if dm_tables else 0,
-                                              dm_tables["W"] if dm_tables else 12)
+        # contiguous strips minimising the largest cost: phase D is paid per lenslet row, the transforms per lit lenslet
+        # (one row of phase D ~ 0.26 nS lit lenslets); one dynamic programme serves every cluster size
+        Cmax = min(16, nS)
+        cost = 0.26 * nS + lit_row
+        pre = np.concatenate([[0.0], np.cumsum(cost)])
+        seg = pre[None, :] - pre[:, None]                                   # seg[s0, e] = cost of rows [s0, e)
+        best = np.full((Cmax + 1, nS + 1), np.inf)
+        arg = np.zeros((Cmax + 1, nS + 1), dtype=np.int64)
+        best[0, 0] = 0.0
+        for c in range(1, Cmax + 1):
+            for e in range(c, nS + 1):
+                v = np.maximum(best[c - 1, c - 1:e], seg[c - 1:e, e])
+                k = int(np.argmin(v))
+                best[c, e], arg[c, e] = v[k], c - 1 + k
+
+        def partition(C_):
+            rs, e = [nS], nS
+            for c in range(C_, 0, -1):
+                e = int(arg[c, e])
+                rs.append(e)
+            return rs[::-1]
+
+        def smem_for(rs):
+            rows_max = max(rs[k + 1] - rs[k] for k in range(len(rs) - 1))
+            return lib.aoenv_shwfs_fused_smem(nS, n, rows_max, groups, t_rows_for(rs), WL)
         forced = os.environ.get("AOENV_WFS_CLUSTER")
-        divisors = [c for c in range(1, min(16, nS) + 1) if nS % c == 0]
         limit = 227 * 1024
+        cands = {c: partition(c) for c in range(1, Cmax + 1)}
         if forced:
             cluster = int(forced)
         else:
-            # portable cluster sizes first: the largest one that leaves >= 96 lenslets per CTA, else a single CTA;
-            # configurations whose strip does not fit in shared memory take the largest cluster (<= 16) that does
-            fit8 = [c for c in divisors if c <= 8 and 0 < smem_for(c) <= limit]
+            # portable cluster sizes first: the largest one that leaves >= 96 lenslets per CTA on average, else a single
+            # CTA; configurations whose strips do not fit in shared memory take the largest cluster (<= 16) that does
+            fit8 = [c for c in cands if c <= 8 and 0 < smem_for(cands[c]) <= limit]
             good = [c for c in fit8 if nS * nS // c >= 96]
             if good:
                 cluster = max(good)
             elif fit8:
                 cluster = min(fit8)
             else:
-                fit16 = [c for c in divisors if 0 < smem_for(c) <= limit]
+                fit16 = [c for c in cands if 0 < smem_for(cands[c]) <= limit]
                 if not fit16:
                     raise NotImplementedError(f"{nS} x {nS} lenslets of {n} px do not fit the fused WFS kernel")
                 cluster = max(fit16)
-        rows = nS // cluster
-        valid = self.valid_subapertures
-        order = np.zeros((cluster, rows * nS), dtype=np.int32)
+        rs = cands[cluster]
+        rows_max = max(rs[k + 1] - rs[k] for k in range(cluster))
+        order = np.zeros((cluster, rows_max * nS), dtype=np.int32)
         nlit = np.zeros(cluster, dtype=np.int32)
         for r in range(cluster):
-            v = valid[r * rows:(r + 1) * rows].reshape(-1)
-            order[r] = np.concatenate([np.nonzero(v)[0], np.nonzero(~v)[0]])
+            v = valid[rs[r]:rs[r + 1]].reshape(-1)
+            o = np.concatenate([np.nonzero(v)[0], np.nonzero(~v)[0]])
+            order[r, :len(o)] = o
             nlit[r] = int(v.sum())
-        dev = self.device
-        plan = dict(cluster=cluster, groups=groups, t_rows=t_rows_for(cluster),
-                    order=torch.as_tensor(order, device=dev).contiguous(), nlit=torch.as_tensor(nlit, device=dev).contiguous())
+        td = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev).contiguous()
+        plan = dict(cluster=cluster, groups=groups, t_rows=t_rows_for(rs), WL=WL, row_start=(C.c_int32 * (cluster + 1))(*rs),
+                    rows=rs, order=td(order, torch.int32), nlit=td(nlit, torch.int32),
+                    ilr=td(ilr, torch.int32) if ilr is not None else None, wlr=td(wlr, torch.float32) if wlr is not None else None)
         self._fused_plans[key] = plan
         return plan
 
     def _fused_ok(self, opd_a):
-        return self.use_fused and self._uniform_flux and opd_a.dtype == torch.float32 and opd_a.is_contiguous()
+        return (self.use_fused and self._uniform_flux and self.telescope.resolution % 4 == 0 and opd_a.dtype == torch.float32
+                and opd_a.is_contiguous())
 
     def _run_fused(self, opd_a, opd_b, scale, det, frame, envmax, stats, slopes, ref_xy, inv_units, slope_planes, want_frame):
         """aoenv_shwfs_fused (+ the camera pass and the slopes kernel when a noisy detector sits in between).
@@ -216,19 +261,16 @@ class ShackHartmann:
             b_tensor = opd_b
         plan = self._fused_plan(tables)
         if tables is not None:
-            coefs = opd_b.coefs
+            rows = opd_b.rows                       # T = C gx of this surface (aoenv_dm_rows, run when it was commanded)
             dm_struct = _lib.DmSepStruct()
-            dm_struct.coefs, dm_struct.ldc = coefs.data_ptr(), coefs.stride(0)
-            dm_struct.act_pos, dm_struct.act_row_start = tables["act_pos"].data_ptr(), tables["act_row_start"].data_ptr()
-            dm_struct.wx, dm_struct.j0x = tables["wx"].data_ptr(), tables["j0x"].data_ptr()
-            dm_struct.wyp, dm_struct.i0y = tables["wyp"].data_ptr(), tables["i0y"].data_ptr()
-            dm_struct.nA, dm_struct.nAct, dm_struct.W = opd_b.dm.nValidAct, tables["nAct"], tables["W"]
-            dm_struct.t_rows = plan["t_rows"]
+            dm_struct.rows, dm_struct.wlr, dm_struct.ilr = rows.data_ptr(), plan["wlr"].data_ptr(), plan["ilr"].data_ptr()
+            dm_struct.nActP, dm_struct.WL, dm_struct.t_rows = rows.shape[1], plan["WL"], plan["t_rows"]
         noisy = det is not None
         write_frame = want_frame or noisy
         _lib.check(lib.aoenv_shwfs_fused(
             _lib.ptr(opd_a), _lib.ptr(b_tensor), C.byref(dm_struct) if dm_struct is not None else None, _lib.ptr(self._pupil8),
-            C.c_float(self._amp0), _lib.ptr(plan["order"]), _lib.ptr(plan["nlit"]), _lib.ptr(self._slot_of), F, self.nSubap,
+            C.c_float(self._amp0), plan["row_start"], _lib.ptr(plan["order"]), _lib.ptr(plan["nlit"]), _lib.ptr(self._slot_of), F,
+            self.nSubap,
             self.n_pix_subap, plan["cluster"], plan["groups"], C.c_float(scale), _lib.ptr(ref_xy), self.nValidSubaperture,
             C.c_float(inv_units), C.c_float(self.threshold_cog), _lib.ptr(frame) if write_frame else None,
             None if (noisy or slopes is None) else _lib.ptr(slopes), slopes.stride(0) if slopes is not None else 0,

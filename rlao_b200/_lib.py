@@ -29,10 +29,8 @@ class DetectorStruct(C.Structure):
 class DmSepStruct(C.Structure):
     """aoenv_dm_sep_t (include/aoenv.h)."""
     _fields_ = [
-        ("coefs", C.c_void_p), ("act_pos", C.c_void_p), ("act_row_start", C.c_void_p), ("wx", C.c_void_p),
-        ("j0x", C.c_void_p), ("wyp", C.c_void_p), ("i0y", C.c_void_p),
-        ("ldc", C.c_int32), ("nA", C.c_int32), ("nAct", C.c_int32), ("W", C.c_int32), ("t_rows", C.c_int32),
-        ("reserved", C.c_int32),
+        ("rows", C.c_void_p), ("wlr", C.c_void_p), ("ilr", C.c_void_p),
+        ("nActP", C.c_int32), ("WL", C.c_int32), ("t_rows", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -59,14 +57,16 @@ PROTOTYPES = {
     "aoenv_shwfs_camera": [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp],
     "aoenv_shwfs_frame": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i, _vp, _vp, _vp, _vp],
     "aoenv_shwfs_slopes": [_vp, _vp, _i, _vp, _i, _vp, _f, _f, _i, _i, _i, _vp, _i, _vp, _i, _vp],
-    "aoenv_shwfs_fused": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _i, _f, _f, _vp, _vp, _i, _vp, _i,
+    "aoenv_shwfs_fused": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _i, _f, _f, _vp, _vp, _i, _vp, _i,
                           _vp, _vp, _vp],
-    "aoenv_shwfs_fused_smem": [_i, _i, _i, _i, _i, _i, _i],
+    "aoenv_shwfs_fused_smem": [_i, _i, _i, _i, _i, _i],
+    "aoenv_dm_rows": [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
     "aoenv_shwfs_measure_f64": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _d, _d, _i, _i, _i, _d, _i, _vp, _vp, _vp, _i, _vp],
     "aoenv_normal_fill": [_u64, _u64, _i, _i, _i, _f, _vp, _vp, _i, _vp],
     "aoenv_vec_to_img": [_vp, _i, _vp, _i, _i, _i, _f, _vp, _vp],
     "aoenv_command_update": [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _i, _vp],
     "aoenv_observe": [_vp, _i, _vp, _i, _i, _i, _vp, _d, _f, _vp, _vp, _vp, _vp, _vp, _vp],
+    "aoenv_psf_image": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "aoenv_psf_peak": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _i, _vp, _vp, _vp, _vp],
 }
 

@@ -128,9 +128,89 @@ psf_window_kernel(const float* __restrict__ T, int ldt, const float2* __restrict
   }
 }
 
+// ---- full image: both transforms on the tensor cores -----------------------------------------------------------------------
+// planes[(b, u)][c * R + x] = T[(b, x)][c * Wu + u]: the [x][u] -> [u][x] transposition between the row and the column
+// transform, through a 32 x 32 shared-memory tile, written in split-bf16 operand form (2 parts)
+__global__ void __launch_bounds__(256)
+psf_transpose_kernel(const float* __restrict__ T, int ldt, int R, int Wu, __nv_bfloat16* __restrict__ planes, int ldk,
+                     size_t plane_stride) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z >> 1, c = blockIdx.z & 1;
+  const int x0 = blockIdx.y * 32, u0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int x = x0 + r, u = u0 + tx;
+    tile[r][tx] = (x < R && u < Wu) ? __ldg(&T[((size_t)b * R + x) * ldt + c * Wu + u]) : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int u = u0 + r, x = x0 + tx;
+    if (u < Wu && x < R) {
+      const float v = tile[tx][r];
+      const size_t o = ((size_t)b * Wu + u) * ldk + c * R + x;
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      planes[o] = h;
+      planes[plane_stride + o] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+// |F|^2 / N^2 binned os x os: F[(b, u)][c * Wu + v] -> psf[b][u / os][v / os], and the maximum of every image
+__global__ void __launch_bounds__(256)
+psf_intensity_kernel(const float* __restrict__ F, int ldf, int Wu, int os, int win, float inv_n2, float* __restrict__ psf,
+                     int* __restrict__ psf_max_bits) {
+  const int b = blockIdx.z, yb = blockIdx.y;
+  const int xb = blockIdx.x * blockDim.x + threadIdx.x;
+  float val = 0.f;
+  if (xb < win) {
+    for (int i = 0; i < os; ++i) {
+      const float* __restrict__ row = F + ((size_t)b * Wu + yb * os + i) * ldf;
+      for (int j = 0; j < os; ++j) {
+        const float re = __ldg(row + xb * os + j), im = __ldg(row + Wu + xb * os + j);
+        val = fmaf(re, re, fmaf(im, im, val));
+      }
+    }
+    val *= inv_n2;
+    psf[((size_t)b * win + yb) * win + xb] = val;
+  }
+  val = warp_max(val);
+  if ((threadIdx.x & 31) == 0) atomicMax(&psf_max_bits[b], __float_as_int(val));      // val >= 0: int order == float order
+}
+
 }  // namespace aoenv
 
 using namespace aoenv;
+
+extern "C" int aoenv_psf_image(const float* opd_a, const float* opd_b, const float* pupil, const float* amp,
+                               const void* w_planes, int B, int R, int N, int os, int win, float phase_scale,
+                               void* field_planes, int ldk, float* work_t, void* planes_u, float* work_f, float* psf,
+                               float* psf_max, void* stream) {
+  AOENV_CHECK_ARG(B > 0 && 2 * B <= 65535 && R > 0 && N >= R && (N - R) % 2 == 0, "psf_image: bad shape B=%d R=%d N=%d", B, R, N);
+  AOENV_CHECK_ARG((os == 1 || os == 2) && N % os == 0, "psf_image: oversampling %d unsupported", os);
+  const int Wu = os * win;
+  AOENV_CHECK_ARG(win > 0 && Wu <= N && win <= 65535, "psf_image: image of %d pixels unsupported", win);
+  AOENV_CHECK_ARG(ldk >= 2 * R && ldk % 8 == 0 && R % 2 == 0, "psf_image: ldk=%d must be a multiple of 8 and >= 2R, R even", ldk);
+  AOENV_CHECK_ARG((long long)B * Wu < (1LL << 31) && (long long)B * R < (1LL << 31), "psf_image: batch too large");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(psf_max, 0, sizeof(float) * (size_t)B, s);
+  if (e != cudaSuccess) return fail(-3, "psf_image memset: %s", cudaGetErrorString(e));
+  psf_field_kernel<<<dim3((R + 31) / 32, (R + 63) / 64, B), 256, 0, s>>>(opd_a, opd_b, pupil, amp, R, phase_scale * 0.15915494309189535f,
+                                                                         (__nv_bfloat16*)field_planes, ldk, (size_t)B * R * ldk);
+  AOENV_LAUNCH_CHECK("psf_field");
+  // rows: T[(b, x)][(c', u)]
+  int rc = aoenv_gemm_tn_tc(field_planes, w_planes, ldk, 2, work_t, 2 * Wu, B * R, 2 * Wu, 2 * R, 1.0f, stream);
+  if (rc) return rc;
+  psf_transpose_kernel<<<dim3((Wu + 31) / 32, (R + 31) / 32, 2 * B), 256, 0, s>>>(work_t, 2 * Wu, R, Wu, (__nv_bfloat16*)planes_u, ldk,
+                                                                               (size_t)B * Wu * ldk);
+  AOENV_LAUNCH_CHECK("psf_transpose");
+  // columns: F[(b, u)][(c'', v)] — the same operator (the kernel is symmetric in the two axes)
+  rc = aoenv_gemm_tn_tc(planes_u, w_planes, ldk, 2, work_f, 2 * Wu, B * Wu, 2 * Wu, 2 * R, 1.0f, stream);
+  if (rc) return rc;
+  psf_intensity_kernel<<<dim3((win + 255) / 256, win, B), 256, 0, s>>>(work_f, 2 * Wu, Wu, os, win, 1.0f / ((float)N * (float)N), psf,
+                                                                      (int*)psf_max);
+  AOENV_LAUNCH_CHECK("psf_intensity");
+  return 0;
+}
 
 extern "C" int aoenv_psf_peak(const float* opd_a, const float* opd_b, const float* pupil, const float* amp,
                               const void* w1_planes, const float* g2, int B, int R, int N, int os, int win,

@@ -258,32 +258,47 @@ class FakeLib:
                 em[e] = _f2o(maxes[e])
         return 0
 
-    def aoenv_shwfs_fused_smem(self, nS, n, cluster, groups, t_rows, nAct, W):
-        if nS % cluster:
+    def aoenv_shwfs_fused_smem(self, nS, n, rows_max, groups, t_rows, WL):
+        if rows_max <= 0 or rows_max > nS:
             return -1
-        R, rows_px = nS * n, (nS // cluster) * n
+        R, rows_px = nS * n, rows_max * n
         up = lambda v: (v + 127) & ~127
+        wstride = 2 * (((max(WL, 14) + 1) // 2 + 3) // 4 * 4)
         o = up(rows_px * R * 4)
         o = up(o + rows_px * R)
         o = up(o + groups * n * n * 256)
         if t_rows > 0:
             o = up(o + t_rows * R * 4)
-            o = up(o + t_rows * nAct * 4)
-            o = up(o + (rows_px // 2) * 2 * W * 4)
-            o = up(o + (rows_px // 2) * 4)
-        return up(o + 1536)
+            o = up(o + rows_px * wstride * 4)
+        return up(o + 2048)
 
-    def aoenv_shwfs_fused(self, opd_a, opd_b, dm, pupil8, amp0, order, nlit, slot_of, B, nS, n, cluster, groups, phase_scale,
-                          ref_xy, nV, inv_units, thr, frame, slopes, lds, slope_planes, parts, envmax, stats, stream):
-        """Strip by strip, like the kernel: the DM surface of a strip from the banded tables and the commands of the
-        actuator rows [tBase, tBase + t_rows), lenslets visited through `order` / `nlit`, slopes scattered by `slot_of`."""
+    def aoenv_dm_rows(self, coefs, ldc, act_pos, nA, nAct, nActP, wx, j0x, W, B, R, rows, stream):
         self.launches += 1
-        R, rows = nS * n, nS // cluster
-        LPC = rows * nS
+        c = _arr(coefs, (B, ldc))
+        pos = _arr(act_pos, (nA,), np.int32)
+        w, j0 = _arr(wx, (R, W)).astype(np.float64), _arr(j0x, (R,), np.int32)
+        out = _arr(rows, (B, nActP, R))
+        for b in range(B):
+            Cimg = np.zeros((nAct, nAct + W))
+            Cimg[pos // nAct, pos % nAct] = c[b, :nA]
+            for x in range(R):
+                out[b, :nAct, x] = Cimg[:, j0[x]:j0[x] + W] @ w[x]
+        return 0
+
+    def aoenv_shwfs_fused(self, opd_a, opd_b, dm, pupil8, amp0, row_start, order, nlit, slot_of, B, nS, n, cluster, groups,
+                          phase_scale, ref_xy, nV, inv_units, thr, frame, slopes, lds, slope_planes, parts, envmax, stats, stream):
+        """Strip by strip, like the kernel: the DM surface of a strip from the window tables and the rows of T the strip
+        may read ([ilr[first row], ilr[first row] + t_rows)), lenslets visited through `order` / `nlit`, slopes scattered
+        by `slot_of`."""
+        self.launches += 1
+        R = nS * n
+        rs = [int(row_start[k]) for k in range(cluster + 1)]
+        assert rs[0] == 0 and rs[-1] == nS
+        rows_max = max(rs[k + 1] - rs[k] for k in range(cluster))
         a = _arr(opd_a, (B, R, R))
         b_ = _arr(opd_b, (B, R, R))
         pu = _arr(pupil8, (R, R), np.uint8).astype(bool)
-        od, nl = _arr(order, (cluster, LPC), np.int32), _arr(nlit, (cluster,), np.int32)
+        od, nl = _arr(order, (cluster, rows_max * nS), np.int32), _arr(nlit, (cluster,), np.int32)
         so = _arr(slot_of, (nS * nS,), np.int32)
         fr = _arr(frame, (B, R, R))
         sl = _arr(slopes, (B, lds)) if slopes else None
@@ -292,13 +307,12 @@ class FakeLib:
         st = _arr(stats, (B, 4), np.float64)
         scale, a0 = np.float32(_val(phase_scale)), float(_val(amp0))
         d = dm._obj if hasattr(dm, "_obj") else dm
-        sep = d is not None and d.coefs
+        sep = d is not None and d.rows
         if sep:
-            W, nAct, nA = d.W, d.nAct, d.nA
-            c = _arr(d.coefs, (B, d.ldc))
-            pos, rs = _arr(d.act_pos, (nA,), np.int32), _arr(d.act_row_start, (nAct + 1,), np.int32)
-            wx, j0x = _arr(d.wx, (R, W)).astype(np.float64), _arr(d.j0x, (R,), np.int32)
-            wyp, i0y = _arr(d.wyp, (R // 2, 2, W)).astype(np.float64), _arr(d.i0y, (R // 2,), np.int32)
+            WL, half = d.WL, (d.WL + 1) // 2
+            hp = (half + 3) // 4 * 4
+            trows = _arr(d.rows, (B, d.nActP, R)).astype(np.float64)
+            wlr, ilr = _arr(d.wlr, (R, 2 * hp)).astype(np.float64), _arr(d.ilr, (nS,), np.int32)
         N = 2 * n
         k = np.arange(N)
         xx, yy = np.meshgrid(k, k)
@@ -311,25 +325,18 @@ class FakeLib:
             spots_img = np.zeros((R, R), dtype=np.float64)
             lit_max = -np.inf
             for r in range(cluster):
-                y0, y1 = r * rows * n, (r + 1) * rows * n
+                y0, y1 = rs[r] * n, rs[r + 1] * n
                 if sep:
-                    tBase = int(i0y[y0 // 2])
-                    r_end = min(nAct, tBase + d.t_rows)
-                    Cimg = np.zeros((d.t_rows, nAct))
-                    for kk in range(rs[tBase], rs[r_end]):
-                        Cimg[pos[kk] // nAct - tBase, pos[kk] % nAct] = c[e, kk]
-                    Trow = np.zeros((d.t_rows, R))
-                    for x in range(R):
-                        cols = np.minimum(j0x[x] + np.arange(W), nAct - 1)
-                        Trow[:, x] = Cimg[:, cols] @ wx[x]
+                    tBase = int(ilr[rs[r]])
+                    assert int(ilr[rs[r + 1] - 1]) + WL - tBase <= d.t_rows, "t_rows too small for this strip"
+                    assert tBase + d.t_rows <= d.nActP + WL
                     for y in range(y0, y1):
-                        i0 = int(i0y[y // 2])
-                        rows_i = np.minimum(i0 + np.arange(W), nAct - 1) - tBase
-                        assert rows_i.max() < d.t_rows, "t_rows too small for this strip"
-                        total[y] = total[y] + (wyp[y // 2, y % 2] @ Trow[rows_i]).astype(np.float32)
+                        i0 = int(ilr[y // n])
+                        w = np.array([wlr[y, (t // half) * hp + t % half] for t in range(WL)])
+                        total[y] = total[y] + (w @ trows[e, i0:i0 + WL]).astype(np.float32)
                 ph = (total[y0:y1] * np.float32(scale)).astype(np.float64)
                 field_px = np.where(pu[y0:y1], a0 * np.exp(1j * ph), 0)
-                for i in range(LPC):
+                for i in range((rs[r + 1] - rs[r]) * nS):
                     lens = int(od[r, i])
                     lr, l = lens // nS, lens % nS
                     if i >= nl[r]:

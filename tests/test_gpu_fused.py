@@ -96,7 +96,7 @@ def test_fused_equals_unfused_kernels_and_oracle(dev, nS, n):
         assert rel_err(sig_f[e], want) < 1e-4, (e, "slopes")
 
 
-@pytest.mark.parametrize("cluster,groups", [(1, 4), (2, 4), (4, 2), (5, 4), (10, 6), (10, 2)])
+@pytest.mark.parametrize("cluster,groups", [(1, 4), (2, 4), (4, 2), (5, 4), (7, 4), (10, 6), (13, 2)])
 def test_fused_cluster_and_group_shapes_agree(dev, monkeypatch, cluster, groups):
     nS, n, B = 20, 6, 4
     cfg, tel, wfs, dm = _objects(dev, nS, n, B)
@@ -125,7 +125,10 @@ def test_fused_benchmark_size_properties(dev):
     zero = torch.zeros((B, R, R), device=dev)
     dm.coefs = 0
     sig, _ = _measure(wfs, zero, dm.surface_ref(), True)
-    assert next(iter(wfs._fused_plans.values()))["cluster"] == 8
+    plan = wfs._fused_plans[id(dm.fused_tables())]
+    assert plan["cluster"] == 8 and plan["rows"][0] == 0 and plan["rows"][-1] == 40
+    heights = np.diff(plan["rows"])
+    assert heights[0] > heights[3] and heights[-1] > heights[4]     # taller strips at the pupil edge (few lit lenslets per row)
     assert np.abs(sig).max() < 1e-5
     sig, _ = _measure(wfs, zero + 3e-7, dm.surface_ref(), True)
     assert np.abs(sig).max() < 1e-4

@@ -69,7 +69,7 @@ def test_wfs_and_dm_at_80x80_vs_oracle(dev):
     wfs.keep_frame = True
     wfs._measure_terms(a, dm.surface_ref(), 0)
     plan = next(iter(wfs._fused_plans.values()))
-    assert plan["cluster"] > 8                                                  # the 80 x 80 strip needs the large cluster
+    assert plan["cluster"] >= 8 and 80 % plan["cluster"] == 0                   # strips of at most 10 lenslet rows fit in shared memory
     sig, frame = _np(wfs.signal), _np(wfs.cam.frame)
     total = _np(a) + surf
     for e in range(B):
@@ -176,7 +176,9 @@ def test_detector_statistics_at_cfg4_size_low_flux(dev):
     s1 = _np(wfs.signal)
     tel * wfs
     f2 = wfs.cam.frame.clone()
-    assert bool((f1 == f1.round()).all()) and float(f1.min()) >= 0 and float(f1.max()) <= 1023
+    # whole counts, clipped at the top only (Detector.py:190-201 truncates towards zero and clips to [min, 2^bits - 1]:
+    # read noise around an empty pixel gives small negative counts)
+    assert bool((f1 == f1.round()).all()) and float(f1.min()) > -12 and float(f1.max()) <= 1023
     full = 1023.0 / 10000.0
     lam = ideal * 0.56 + 5.0 / 500                                               # electrons before the read noise
     mean = f1.double().mean(dim=0).cpu().numpy()

@@ -65,10 +65,10 @@ def test_philox_screens_have_the_reference_statistics(dev):
         assert abs(dx / wx - 1) < tol and abs(dy / wy - 1) < tol, (sep, dx / wx, dy / wy)
     assert abs(float(a.var()) / ref.var() - 1) < 0.15
     # independent streams: other screens, other shard offset, other seed
-    flat = a.reshape(512, -1)
-    c = np.corrcoef(flat[:64, ::7].cpu().numpy())
-    assert np.abs(c - np.eye(64)).max() < 0.5               # large-scale modes dominate: loose bound on 64 x 64 pairs
-    assert np.abs(c - np.eye(64)).mean() < 0.12
+    # (first differences: the screens themselves are dominated by a handful of large-scale modes, which correlate by chance)
+    d = (a[:64, :, 1:] - a[:64, :, :-1]).reshape(64, -1)[:, ::5].cpu().numpy()
+    c = np.corrcoef(d)
+    assert np.abs(c - np.eye(64)).max() < 0.2 and np.abs(c - np.eye(64)).mean() < 0.03
     b = _synth_screens(synth, 4, seed=5, screen0=512)
     assert not torch.equal(b[0].double(), a[0])
     again = _synth_screens(synth, 4, seed=5, screen0=0)
