@@ -173,9 +173,10 @@ int aoenv_detector_integrate(float* frame, int B, int rows, int cols, const aoen
 int aoenv_shwfs_camera(float* frame, const uint8_t* valid, int B, int nS, int n, const aoenv_detector_t* det, int shared_max,
                        int32_t* envmax, void* stream);
 
-/* Selects the implementation of the n = 6 frame kernel: 0 = term-by-term pruned DFT (default), 1 = factorised
- * (radix 2 x Good-Thomas 2 x 3).  Same frame to float32 rounding; returns the previous setting. */
-int aoenv_set_wfs6_variant(int factorised);
+/* Selects the implementation of the n = 6 frame kernel: 2 = factorised transform (radix 2 x Good-Thomas 2 x 3) on three
+ * lanes per lenslet (default), 1 = the same transform on one thread per lenslet, 0 = term-by-term pruned DFT.  Same frame
+ * to float32 rounding; returns the previous setting. */
+int aoenv_set_wfs6_variant(int variant);
 
 /* wfs_measure, diffractive branch up to the detector: per lenslet, the transposed n x n tile of
  * phase = (opd_a + opd_b) * pupil * phase_scale is zero-padded to 2n x 2n, multiplied by sqrt(flux) and the

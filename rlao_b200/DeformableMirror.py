@@ -11,6 +11,7 @@ default Cartesian grid of axis-aligned Gaussians the product factorises into two
 when the geometry allows it.
 """
 import math
+import os
 import sys
 
 import numpy as np
@@ -107,9 +108,9 @@ class DeformableMirror:
         self._sep = self._separable_tables() if (modes is None and coordinates is None) else None
         self._opd = torch.zeros((2, self.n_envs, R, R), dtype=torch.float32, device=self.device)   # ping-pong
         self._slot = 0
-        # lazy surfaces: with the separable geometry env.step never writes the surface (the fused WFS kernel builds it
-        # in shared memory from the commands); _opd[slot] is brought up to date only when somebody reads it
-        self.lazy_surface = True
+        # lazy surfaces (opt-in, AOENV_WFS=fused): with the separable geometry the fused WFS kernel builds the surface in
+        # shared memory from T = C gx; _opd[slot] is then brought up to date only when somebody reads it
+        self.lazy_surface = os.environ.get("AOENV_WFS", "kernels") == "fused"
         self._coefs_of = [None, None]
         self._valid = [True, True]
         self._rows = None                 # [2][n_envs, nAct + 18, R]: column half of the separable surface, per slot

@@ -64,12 +64,14 @@ class ShackHartmann:
         self.fov_pixel_arcsec = self.fov_lenslet_arcsec / self.n_pix_subap
         self.fov_pixel_binned_arcsec = self.fov_lenslet_arcsec / self.n_pix_subap_init
         self.get_camera_frame_multi = False
-        # One fused kernel (DM surface + spots + slopes, aoenv_shwfs_fused) when the flux is uniform over a binary pupil;
-        # otherwise (or with use_fused = False / AOENV_WFS=legacy) the frame and slopes kernels.  keep_frame: write the
-        # camera frame at every measurement; when False (default) `wfs.cam.frame` is produced on demand from the inputs
-        # of the last measurement, and env.step never spends the HBM traffic on it.
+        # Production path: the frame kernel (three lanes per lenslet for 6-pixel lenslets) + the slopes kernel.
+        # use_fused (opt-in, AOENV_WFS=fused): ONE cluster kernel for DM surface + spots + slopes (aoenv_shwfs_fused), for a
+        # uniform flux over a binary pupil; correct and tested, but measured slower on B200 (a third of its time is spent
+        # at the cluster barrier that the environment-wide centroiding threshold needs — profiles/r2_*).  With it,
+        # keep_frame = False (default) leaves the camera frame unwritten: `wfs.cam.frame` is then produced on demand from
+        # the inputs of the last measurement.
         self.env_offset = 0          # global index of this shard's first environment (seeds of the camera streams)
-        self.use_fused = os.environ.get("AOENV_WFS", "fused") != "legacy"
+        self.use_fused = os.environ.get("AOENV_WFS", "kernels") == "fused"
         self.keep_frame = False
         self._fused_plans = {}
         self._last_inputs = None

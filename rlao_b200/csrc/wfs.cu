@@ -559,6 +559,173 @@ shwfs_frame6_kernel(const float* __restrict__ opd_a, const float* __restrict__ o
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// n = 6, THREE LANES PER LENSLET (the production frame kernel): the factorised transform above, split so that no thread
+// ever holds more than a third of a lenslet.  Lane t of a lenslet owns tile rows 2t, 2t+1 = columns b = 2t, 2t+1 of the
+// transposed field: it loads those 12 pixels, forms the field (half-pixel phasor folded into the angle) and runs pass 1
+// — the 12-point DFT over a of its two columns, as two 6-point Good-Thomas DFTs packed in the FP32x2 lanes (r = 0, 1) —
+// which yields H[k][b] for all six row pairs k.  The three lanes then swap thirds through a warp-private patch of shared
+// memory (no block barrier anywhere: a __syncwarp orders the exchange): lane t keeps the row pairs k = (4t) mod 6 and
+// (3 + 4t) mod 6, for which it runs pass 2 over all six columns, the intensities and the 2x2 binning, and stores binned
+// rows k with 64-bit stores.  Every lane of a warp executes the same instruction stream (the passes do not depend on which
+// column / row pair they work on), 10 lenslets per warp, ~80 registers instead of 165, 2.1 k instead of 3.5 k FP32 pipe
+// slots per lenslet.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kS6Lenslets = 10;                     // lenslets per warp (lanes 30, 31 idle)
+constexpr int kS6Warps = 4;
+
+// dft6_half for both K1 at once on one column; outputs indexed [K1][k2]
+__device__ __forceinline__ void dft6_both(const C2 (&z)[6], C2 (&y)[2][3]) {
+  dft6_half<0>(z, y[0][0], y[0][1], y[0][2]);
+  dft6_half<1>(z, y[1][0], y[1][1], y[1][2]);
+}
+
+__global__ void __launch_bounds__(kS6Warps * 32, 4)
+shwfs_frame6s_kernel(const float* __restrict__ opd_a, const float* __restrict__ opd_b, const float* __restrict__ pupil,
+                     const float* __restrict__ amp, const uint8_t* __restrict__ valid, int nS, float phase_scale,
+                     int track_max, int shared_max, float* __restrict__ frame, int32_t* __restrict__ envmax,
+                     double* __restrict__ stats) {
+  constexpr int n = 6, N = 12;
+  constexpr float c = 0.8660254037844386f;
+  // exchange buffer: [warp][value 0..47][lane]; value = ((K1 * 3 + k2) * 2 + col) * 4 + component
+  __shared__ float xch[kS6Warps][48][33];        // row stride 33: the three lanes of a lenslet hit different banks
+  const int R = nS * n;
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slot = lane / 3, t = lane - slot * 3;                        // lenslet of the warp, third of the lenslet
+  const int k = (blockIdx.x * kS6Warps + warp) * kS6Lenslets + slot;
+  const bool active = slot < kS6Lenslets && k < nS * nS;
+  const int li = active ? k / nS : 0, lj = active ? k - li * nS : 0;
+  const bool lit = active && valid[k] != 0;
+  const float phase_turns = phase_scale * 0.15915494309189535f;
+  const size_t tile = (size_t)(li * n) * R + lj * n;
+  float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;                         // pupil statistics, see shwfs_frame_kernel
+  // ---- field of tile rows 2t, 2t+1 + pass 1 ------------------------------------------------------------------------
+  C2 y[2][2][3];                                                          // [column][K1][k2]
+  if (active) {
+    const float* __restrict__ pa = opd_a + (size_t)b * R * R + tile;
+    const float* __restrict__ pb = opd_b ? opd_b + (size_t)b * R * R + tile : nullptr;
+    const size_t centre = (size_t)b * R * R + (size_t)(R / 2) * R + R / 2;
+    const float ka = stats ? __ldg(opd_a + centre) : 0.f;
+    const float kt = stats ? (opd_b ? ka + __ldg(opd_b + centre) : ka) : 0.f;
+    // reduced phasor angle of row bb = 2t + e, in turns: -13 (bb + 3) / 24 mod 1 (literal constants, exact to 6e-8)
+    constexpr float kCf[6] = {0.375f, -0.16666667f, 0.29166667f, -0.25f, 0.20833333f, -0.33333333f};
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int bb = 2 * t + e;
+      const float cfb = e == 0 ? (t == 0 ? kCf[0] : t == 1 ? kCf[2] : kCf[4]) : (t == 0 ? kCf[1] : t == 1 ? kCf[3] : kCf[5]);
+      C2 z[6];
+#pragma unroll
+      for (int a2 = 0; a2 < 3; ++a2) {
+        const int o2 = bb * R + 2 * a2;
+        const float2 av = __ldg(reinterpret_cast<const float2*>(pa + o2));
+        const float2 bv = pb ? __ldg(reinterpret_cast<const float2*>(pb + o2)) : make_float2(0.f, 0.f);
+        const float2 pv = __ldg(reinterpret_cast<const float2*>(pupil + tile + o2));
+        const float2 mv = lit ? __ldg(reinterpret_cast<const float2*>(amp + tile + o2)) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int aa = 2 * a2 + h2;
+          const float a = h2 ? av.y : av.x;
+          const float tt = a + (h2 ? bv.y : bv.x);
+          const float pu = h2 ? pv.y : pv.x;
+          const float in_pupil = pu > 0.f ? 1.f : 0.f;
+          const float da = (a - ka) * in_pupil, dt = (tt - kt) * in_pupil;
+          f0 += da; f1 = fmaf(da, da, f1); f2 += dt; f3 = fmaf(dt, dt, f3);
+          const float turns = fmaf(tt * pu, phase_turns, kCf[aa] + cfb);
+          const float ang = (turns - ((turns + 12582912.0f) - 12582912.0f)) * 6.283185307179586f;
+          const float am = h2 ? mv.y : mv.x;
+          const float xr = am * __cosf(ang), xi = am * __sinf(ang);
+          float wr, wi;                                                   // x * W^a, W = exp(-2 pi i / 12): the r = 1 lane
+          if (aa == 0) { wr = xr; wi = xi; }
+          else if (aa == 1) { wr = fmaf(xr, c, xi * 0.5f); wi = fmaf(xi, c, xr * -0.5f); }
+          else if (aa == 2) { wr = fmaf(xr, 0.5f, xi * c); wi = fmaf(xi, 0.5f, xr * -c); }
+          else if (aa == 3) { wr = xi; wi = -xr; }
+          else if (aa == 4) { wr = fmaf(xr, -0.5f, xi * c); wi = fmaf(xi, -0.5f, xr * -c); }
+          else { wr = fmaf(xr, -c, xi * 0.5f); wi = fmaf(xi, -c, xr * -0.5f); }
+          z[aa] = {make_float2(xr, wr), make_float2(xi, wi)};
+        }
+      }
+      dft6_both(z, y[e]);
+    }
+  }
+  if (stats != nullptr) {
+    double s0 = warp_sum((double)f0), s1 = warp_sum((double)f1), s2 = warp_sum((double)f2), s3 = warp_sum((double)f3);
+    if (lane == 0) {
+      double* __restrict__ st = stats + (size_t)b * 4;
+      atomicAdd(st, s0); atomicAdd(st + 1, s1); atomicAdd(st + 2, s2); atomicAdd(st + 3, s3);
+    }
+  }
+  // ---- the three lanes of a lenslet swap thirds: lane t2 receives H[K1][k2 = t2][all six columns] ----------------------
+  float (*x)[33] = xch[warp];
+  const bool any_lit = __any_sync(0xffffffffu, lit);
+  float vmax = -INFINITY;
+  if (any_lit) {
+    if (lit) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int K1 = 0; K1 < 2; ++K1)
+#pragma unroll
+          for (int k2 = 0; k2 < 3; ++k2) {
+            // destination lane = slot * 3 + k2; written at its address, indexed by (K1, source column 2t + e)
+            const int dst = slot * 3 + k2;
+            const C2 v = y[e][K1][k2];
+            // value index: (K1 * 6 + column) * 4 + component -> 48 values per destination lane
+            // (column = 2t + e is lane-dependent: the index is computed, the stores stay conflict-free per component)
+            const int base = (K1 * 6 + 2 * t + e) * 4;
+            x[base + 0][dst] = v.r.x; x[base + 1][dst] = v.r.y; x[base + 2][dst] = v.i.x; x[base + 3][dst] = v.i.y;
+          }
+    }
+    __syncwarp();
+    if (lit) {
+      float* __restrict__ fout = frame + (size_t)b * R * R + tile;
+      const float norm = 1.0f / (float)(N * N);
+#pragma unroll
+      for (int K1 = 0; K1 < 2; ++K1) {
+        const int p = (3 * K1 + 4 * t) % 6;                              // binned row = row pair (2p, 2p + 1)
+        C2 Hr[6];
+#pragma unroll
+        for (int bcol = 0; bcol < 6; ++bcol) {
+          const int base = (K1 * 6 + bcol) * 4;
+          Hr[bcol] = {make_float2(x[base + 0][lane], x[base + 1][lane]), make_float2(x[base + 2][lane], x[base + 3][lane])};
+        }
+        C2 yw[6];
+        twiddle6(Hr, yw);
+        float row[6];
+#pragma unroll
+        for (int q1 = 0; q1 < 2; ++q1) {
+          C2 e[3], o[3];
+          if (q1 == 0) { dft6_half<0>(Hr, e[0], e[1], e[2]); dft6_half<0>(yw, o[0], o[1], o[2]); }
+          else { dft6_half<1>(Hr, e[0], e[1], e[2]); dft6_half<1>(yw, o[0], o[1], o[2]); }
+#pragma unroll
+          for (int q2 = 0; q2 < 3; ++q2) {
+            const float2 i0 = fma2(e[q2].r, e[q2].r, mul2(e[q2].i, e[q2].i));       // v = 2q
+            const float2 i1 = fma2(o[q2].r, o[q2].r, mul2(o[q2].i, o[q2].i));       // v = 2q + 1
+            const float2 tt = add2(i0, i1);
+            row[dft6_row(q1, q2)] = (tt.x + tt.y) * norm;
+          }
+        }
+#pragma unroll
+        for (int q2 = 0; q2 < 3; ++q2) {
+          *reinterpret_cast<float2*>(fout + (size_t)p * R + 2 * q2) = make_float2(row[2 * q2], row[2 * q2 + 1]);
+          vmax = fmaxf(vmax, fmaxf(row[2 * q2], row[2 * q2 + 1]));
+        }
+      }
+    }
+  }
+  if (active && !lit) {                                                   // dark lenslet: rows 2t, 2t+1 of its tile
+    float* __restrict__ fout = frame + (size_t)b * R * R + tile;
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+#pragma unroll
+      for (int q2 = 0; q2 < 3; ++q2) *reinterpret_cast<float2*>(fout + (size_t)(2 * t + e) * R + 2 * q2) = make_float2(0.f, 0.f);
+  }
+  if (track_max) {
+    vmax = warp_max(vmax);
+    if (lane == 0 && vmax > -INFINITY) atomicMax(&envmax[shared_max ? 0 : b], float_to_ordered(vmax));
+  }
+}
+
 // centroid + slopes: one thread per (valid lenslet, environment).  n is a template parameter so that the 6 x 6 (4 x 4,
 // 8 x 8) spot is read with fully unrolled 64-bit loads (tile rows start on even columns: lj * n with n even).
 template <int n>
@@ -720,18 +887,19 @@ __global__ void envmax_init_kernel(int32_t* __restrict__ envmax, int count) {
 
 using namespace aoenv;
 
-// n = 6 has two implementations of the same frame: the term-by-term transform (default: faster on B200, where the kernel
-// is bound by the FP32 pipe and dependency chains rather than by instruction count) and the factorised one
-// (shwfs_frame6_kernel).  aoenv_set_wfs6_variant / AOENV_WFS6=factorised selects the latter; the tests run both.
+// n = 6 has three implementations of the same frame: the factorised transform on three lanes per lenslet
+// (shwfs_frame6s_kernel, default), the factorised transform on one thread per lenslet (shwfs_frame6_kernel) and the
+// term-by-term transform (shwfs_frame_kernel<6>).  aoenv_set_wfs6_variant / AOENV_WFS6=split|factorised|termwise selects;
+// the tests run all three against the oracle.
 static std::atomic<int> g_wfs6_factorised{[] {
   const char* e = getenv("AOENV_WFS6");
-  return (e && e[0] == 'f') ? 1 : 0;
+  return (e && e[0] == 'f') ? 1 : (e && e[0] == 't') ? 0 : 2;      // "factorised" / "termwise" / default: three lanes per lenslet
 }()};
 
 extern "C" {
 
-int aoenv_set_wfs6_variant(int factorised) {
-  return g_wfs6_factorised.exchange(factorised ? 1 : 0);
+int aoenv_set_wfs6_variant(int variant) {
+  return g_wfs6_factorised.exchange(variant < 0 || variant > 2 ? 2 : variant);
 }
 
 int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil, const float* amp,
@@ -762,7 +930,11 @@ int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil
     AOENV_WFS_CASE(4)
     AOENV_WFS_CASE(8)
     case 6:
-      if (g_wfs6_factorised.load(std::memory_order_relaxed))
+      if (g_wfs6_factorised.load(std::memory_order_relaxed) == 2) {
+        dim3 g3((nS * nS + kS6Warps * kS6Lenslets - 1) / (kS6Warps * kS6Lenslets), B);
+        shwfs_frame6s_kernel<<<g3, kS6Warps * 32, 0, s>>>(opd_a, opd_b, pupil, amp, valid, nS, phase_scale, det == nullptr,
+                                                          shared_max, frame, envmax, stats);
+      } else if (g_wfs6_factorised.load(std::memory_order_relaxed) == 1)
         shwfs_frame6_kernel<<<grid, 128, 0, s>>>(opd_a, opd_b, pupil, amp, valid, nS, phase_scale, det == nullptr, shared_max,
                                                  frame, envmax, stats);
       else

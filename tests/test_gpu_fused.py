@@ -33,6 +33,8 @@ def _objects(dev, nS, n, B, with_dm=True):
     Source(cfg.opticalBand, cfg.magnitude) * tel
     wfs = ShackHartmann(nS, tel, cfg.lightRatio)
     dm = DeformableMirror(tel, nS, cfg.mechCoupling) if with_dm else None
+    if dm is not None:
+        dm.lazy_surface = True                  # the opt-in mode these tests are about (AOENV_WFS=fused)
     return cfg, tel, wfs, dm
 
 

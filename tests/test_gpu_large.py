@@ -66,16 +66,20 @@ def test_wfs_and_dm_at_80x80_vs_oracle(dev):
     surf = _np(dm.OPD)
     assert rel_err(surf, want_surf) < 2e-6
     a = torch.as_tensor(opd, dtype=torch.float32, device=dev).contiguous()
-    wfs.keep_frame = True
-    wfs._measure_terms(a, dm.surface_ref(), 0)
-    plan = next(iter(wfs._fused_plans.values()))
-    assert plan["cluster"] >= 8 and 80 % plan["cluster"] == 0                   # strips of at most 10 lenslet rows fit in shared memory
-    sig, frame = _np(wfs.signal), _np(wfs.cam.frame)
     total = _np(a) + surf
-    for e in range(B):
-        want = orc.measure(total[e] * pupil * 2 * np.pi / wl) * orc.slopes_units / wfs.slopes_units
-        assert rel_err(frame[e], orc.frame) < 2e-5, (e, "frame")
-        assert rel_err(sig[e], want) < 1e-4, (e, "slopes")
+    for mode in ("kernels", "fused"):
+        if mode == "fused":                       # opt-in cluster kernel: DM surface + spots + slopes in one launch
+            wfs.use_fused, wfs.keep_frame, dm.lazy_surface = True, True, True
+            dm.coefs = torch.as_tensor(coefs, dtype=torch.float32, device=dev)
+        wfs._measure_terms(a, dm.surface_ref(), 0)
+        if mode == "fused":
+            plan = wfs._fused_plans[id(dm.fused_tables())]
+            assert plan["cluster"] >= 8 and plan["rows"][-1] == 80       # strips of at most ~10 lenslet rows fit in shared memory
+        sig, frame = _np(wfs.signal), _np(wfs.cam.frame)
+        for e in range(B):
+            want = orc.measure(total[e] * pupil * 2 * np.pi / wl) * orc.slopes_units / wfs.slopes_units
+            assert rel_err(frame[e], orc.frame) < 2e-5, (mode, e, "frame")
+            assert rel_err(sig[e], want) < 1e-4, (mode, e, "slopes")
 
 
 def test_atmosphere_phase_at_480px_five_layers_vs_warp_restatement(dev):
@@ -179,15 +183,21 @@ def test_detector_statistics_at_cfg4_size_low_flux(dev):
     # whole counts, clipped at the top only (Detector.py:190-201 truncates towards zero and clips to [min, 2^bits - 1]:
     # read noise around an empty pixel gives small negative counts)
     assert bool((f1 == f1.round()).all()) and float(f1.min()) > -12 and float(f1.max()) <= 1023
-    full = 1023.0 / 10000.0
-    lam = ideal * 0.56 + 5.0 / 500                                               # electrons before the read noise
     mean = f1.double().mean(dim=0).cpu().numpy()
     var = f1.double().var(dim=0).cpu().numpy()
     lit = ideal > 0.2 * ideal.max()
-    # ADC truncation: E[floor(x)] ~ E[x] - 1/2 once the spread covers several counts (read noise 14 e- = 1.4 counts)
-    assert abs((mean[lit] + 0.5).mean() / (lam[lit] * full).mean() - 1) < 0.02
-    want_var = (ideal * 0.56 ** 2 + 5.0 / 500 + 14.0 ** 2) * full ** 2 + 1.0 / 12   # Poisson x QE^2 + dark + RON^2 (+ quantisation)
-    assert abs(var[lit].mean() / want_var[lit].mean() - 1) < 0.05
+    # expectation of the chain (Detector.py:190-301) by Monte Carlo in float64, pixel by pixel: Poisson(photons) x QE +
+    # Poisson(dark), full well, + round(N(0,1) RON), ADC frame / FWC * (2^bits - 1) truncated towards zero.  At this flux
+    # (a few electrons per pixel under 14 e- of read noise) the truncation is not a plain -1/2 count.
+    rs = np.random.RandomState(3)
+    lam = ideal[lit]
+    K = 4096
+    e = rs.poisson(lam[None, :], size=(K, lam.size)) * 0.56 + rs.poisson(5.0 / 500, size=(K, lam.size))
+    e = np.clip(e, 0, 10000) + np.round(rs.normal(size=(K, lam.size)) * 14)
+    adu = np.trunc(e / 10000 * 1023)
+    assert abs(mean[lit].mean() - adu.mean()) < 0.02 * adu.std() + 4 * adu.std() / np.sqrt(K * lam.size / 50)
+    assert abs(var[lit].mean() / adu.var(axis=0).mean() - 1) < 0.03
+    assert np.corrcoef(mean[lit], adu.mean(axis=0))[0, 1] > 0.5                # brighter pixels read brighter
     d1, d2 = (f1.double() - f1.double().mean(dim=0)), (f2.double() - f2.double().mean(dim=0))
     sel = torch.as_tensor(lit, device=dev)
     c_frames = float((d1[:, sel] * d2[:, sel]).mean() / (d1[:, sel].std() * d2[:, sel].std()))

@@ -264,21 +264,26 @@ def test_shack_hartmann_vs_oracle(dev, nS, n):
     s2d = _np(wfs.signal_2D)
     assert rel_err(s2d[2], orc.signal_2D) < SLOPE_TOL
     if n == 6:
-        # the factorised implementation of the n = 6 transform (radix 2 x Good-Thomas 2 x 3) gives the same frame
+        # the other two implementations of the n = 6 transform (one thread per lenslet: factorised radix 2 x Good-Thomas
+        # 2 x 3, and term by term) give the same frame as the default (three lanes per lenslet)
         lib = _lib.load()
-        wfs.use_fused = False                      # the unfused frame kernel has the two n = 6 implementations
-        prev = lib.aoenv_set_wfs6_variant(1)
-        try:
-            tel * wfs
-            alt_sig, alt_frame = _np(wfs.signal), _np(wfs.cam.frame)
-        finally:
-            lib.aoenv_set_wfs6_variant(prev)
-            wfs.use_fused = True
-        assert rel_err(alt_frame, got_frame) < 5e-6
-        assert rel_err(alt_sig, got_sig) < 2e-5
-        for e in range(3):
-            orc.measure(opd32[e] * pupil * 2 * np.pi / wl)
-            assert rel_err(alt_frame[e], orc.frame) < 2e-5, (e, "frame, factorised")
+        wfs.use_fused = False
+        tel * wfs
+        got_sig, got_frame = _np(wfs.signal), _np(wfs.cam.frame)
+        for variant in (1, 0):
+            prev = lib.aoenv_set_wfs6_variant(variant)
+            assert prev == 2
+            try:
+                tel * wfs
+                alt_sig, alt_frame = _np(wfs.signal), _np(wfs.cam.frame)
+            finally:
+                lib.aoenv_set_wfs6_variant(prev)
+            assert rel_err(alt_frame, got_frame) < 5e-6, variant
+            assert rel_err(alt_sig, got_sig) < 2e-5, variant
+            for e in range(3):
+                orc.measure(opd32[e] * pupil * 2 * np.pi / wl)
+                assert rel_err(alt_frame[e], orc.frame) < 2e-5, (e, "frame", variant)
+                assert rel_err(got_frame[e], orc.frame) < 2e-5, (e, "frame", "three lanes per lenslet")
 
 
 def test_shack_hartmann_flat_wavefront_gives_zero_signal_at_full_size(dev):

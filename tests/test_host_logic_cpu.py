@@ -47,9 +47,14 @@ def fake(monkeypatch):
     return fake_backend.install(monkeypatch)
 
 
-def test_env_step_sequence_matches_oracle_on_cpu(fake):
+@pytest.mark.parametrize("wfs_mode", ["kernels", "fused"])
+def test_env_step_sequence_matches_oracle_on_cpu(fake, monkeypatch, wfs_mode):
+    """`fused` = the opt-in single-launch path (AOENV_WFS=fused): lazy DM surfaces (T = C gx through aoenv_dm_rows), balanced
+    strips, window tables and the lit-first lenslet order are host logic, exercised here on the CPU stand-in."""
+    monkeypatch.setenv("AOENV_WFS", wfs_mode)
     cfg = CONFIGS["tiny"]()
     env = build_env(cfg, n_envs=1, rng="reference")
+    assert env.wfs.use_fused == (wfs_mode == "fused") and env.dm.lazy_surface == (wfs_mode == "fused")
     orc = EnvOracle(cfg)
     assert env.dm.nValidAct == orc.nValidAct
     assert np.array_equal(env.wfs.valid_subapertures, orc.wfs.valid)

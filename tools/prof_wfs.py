@@ -24,6 +24,7 @@ tel = Telescope(R, 8.0, 1 / 500, n_envs=B, device=dev)
 Source("I", 8) * tel
 wfs = ShackHartmann(nS, tel, 0.5)
 dm = DeformableMirror(tel, nS, 0.35)
+dm.lazy_surface = True
 g = torch.Generator(device=dev).manual_seed(1)
 opd = (torch.randn((B, R, R), device=dev, generator=g) * 1e-7).contiguous()
 coefs = torch.zeros((B, dm._Kp), device=dev)
