@@ -156,7 +156,8 @@ typedef struct {
   float fwc;
   float gain;
   float readout_noise;     /* e- rms; round(N(0,1) * RON)                                 (:218-221)        */
-  uint32_t reserved;
+  uint32_t reserved;       /* stages to run, 0 = all: 1 integrate (photon noise, QE), 2 dark + full well + EM gain,
+                              4 read noise + gain + ADC (long exposures: :279-301 per sub-frame, :232-276 once) */
   uint64_t seed;           /* Philox key                                                                    */
   uint64_t frame_counter;  /* advances once per call: independent draws per step                            */
 } aoenv_detector_t;

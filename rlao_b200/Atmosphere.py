@@ -103,8 +103,9 @@ class Atmosphere:
         """Atmosphere.py:145-190."""
         tel = telescope
         self.fov, self.fov_rad = tel.fov, tel.fov_rad
-        if tel.fov != 0:
-            raise NotImplementedError("fov > 0 is out of scope")
+        if tel.fov != 0 and any(a != 0 for a in self.altitude):
+            # layers in altitude grow with the field of view (Atmosphere.py:215-218: one set of operators per layer)
+            raise NotImplementedError("fov > 0 with layers in altitude is out of scope (ground layers only)")
         dev, B, R = self.device, self.n_envs, tel.resolution
         if self.hasNotBeenInitialized:
             self.initial_r0 = self._r0
@@ -375,8 +376,19 @@ class Atmosphere:
             self * self.telescope
 
     def __mul__(self, obj):
-        """atm*tel (Atmosphere.py:632-668)."""
-        if getattr(obj, "tag", None) != "telescope":
+        """atm*tel / atm*src (Atmosphere.py:632-668).  atm*src points the paired telescope at `src` (which must lie inside
+        the field of view) and returns the telescope, so that atm*src*tel*cam chains as in the reference."""
+        tag = getattr(obj, "tag", None)
+        if tag == "source":
+            if obj.coordinates[0] > self.fov / 2:
+                raise ValueError(f"The source object zenith ({obj.coordinates[0]}\") is outside of the telescope fov ({self.fov // 2}\")! "
+                                 "You can:\n - Reduce the zenith of the source \n - Re-initialize the atmosphere object using a telescope "
+                                 "with a larger fov")
+            if obj.coordinates[0] != 0 and any(a != 0 for a in self.altitude):
+                raise NotImplementedError("off-axis sources through layers in altitude (anisoplanatism) are out of scope")
+            obj * self.telescope                       # tel.src = src (flux, wavelength)
+            obj = self.telescope
+        elif tag != "telescope":
             raise AttributeError("The atmosphere can be multiplied only with a Telescope or a Source object!")
         self.telescope = obj
         obj._set_lazy(self._opd, None)

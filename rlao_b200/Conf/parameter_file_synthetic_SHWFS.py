@@ -36,6 +36,7 @@ def initializeParameterFile(args):
     param["sizeSubaperture"] = param["diameter"] / param["nSubaperture"]
     param["samplingTime"] = g("samplingTime", 1 / 500)
     param["centralObstruction"] = 0
+    param["fov"] = g("fov", 0)                                       # arcsec; the papyrus environment asks for 1 (OOPAOEnv.py:126)
     # guide star
     param["magnitude"], param["opticalBand"] = g("magnitude", 8), g("opticalBand", "I")
     # deformable mirror: Fried geometry, DeformableMirror(nSubap=nSubaperture) (OOPAO/DeformableMirror.py:286-305)

@@ -31,6 +31,8 @@ class Detector:
         self.backgroundNoiseMap = backgroundNoiseMap
         self.tag = "detector"
         self._integrated_time = 0
+        self._buffer_sum, self.n_buffered, self._env_offset, self._squeeze_out = None, 0, 0, False
+        self.fov_arcsec = self.fov_rad = self.pixel_size_rad = self.pixel_size_arcsec = None
         self.seed = int(seed)
         self.frame_counter = 0
         self._frame, self._frame_src = None, None
@@ -59,8 +61,8 @@ class Detector:
             return None
         if self.backgroundNoise:
             raise NotImplementedError("background noise maps are out of scope")
-        if self.binning != 1:
-            raise NotImplementedError("detector binning is out of scope")
+        if self.binning != 1 and not getattr(self, "_staged", False):
+            raise NotImplementedError("detector binning inside the WFS camera pass is out of scope")
         if self.bits is not None and self.FWC is None:
             raise NotImplementedError("ADC without FWC needs the frame maximum (Detector.py:192-193); not supported")
         d = _lib.DetectorStruct()
@@ -78,17 +80,57 @@ class Detector:
         self.frame_counter += 1
         return d
 
+    def _chain(self, frame, stages, env_offset):
+        """The camera kernel on `frame` [B, rows, cols] in place, restricted to `stages` (aoenv_detector_t.reserved)."""
+        self._staged = True
+        try:
+            det = self.as_struct(env_offset)
+        finally:
+            self._staged = False
+        if det is None:
+            return
+        det.reserved = stages
+        _lib.check(_lib.load().aoenv_detector_integrate(_lib.ptr(frame), frame.shape[0], frame.shape[1], frame.shape[2],
+                                                        ctypes.byref(det), _lib.stream_ptr(frame.device)), "detector_integrate")
+
     def integrate(self, frame, env_offset=0):
-        """Detector.py:279-301: applies the camera to a frame of photons ([rows, cols] or [B, rows, cols], CUDA float32) and
-        stores / returns `self.frame`.  Every call advances the frame counter of the random streams."""
+        """Detector.py:279-301: one sub-frame of photons ([rows, cols] or [B, rows, cols], CUDA float32) — photon noise, QE —
+        is added to the exposure buffer; when the integrated time reaches `integrationTime` (the caller advances
+        `_integrated_time`, Telescope.py:495) the buffer is read out (`readout`, Detector.py:232-276) into `self.frame`.
+        Every kernel call advances the frame counter of the random streams."""
         f = torch.as_tensor(frame, dtype=torch.float32)
-        if f.device.type != "cuda":
-            raise _lib.AOEnvLibraryError("Detector.integrate needs a CUDA tensor (there is no CPU path)")
-        out = (f.unsqueeze(0) if f.ndim == 2 else f).contiguous().clone()
-        det = self.as_struct(env_offset)
-        if det is not None:
-            _lib.check(_lib.load().aoenv_detector_integrate(_lib.ptr(out), out.shape[0], out.shape[1], out.shape[2],
-                                                            ctypes.byref(det), _lib.stream_ptr(out.device)), "detector_integrate")
-        self.frame = out[0] if f.ndim == 2 else out
+        _lib.require_cuda(f.device)                                       # raises: there is no CPU path
+        self._squeeze_out = f.ndim == 2
+        sub = (f.unsqueeze(0) if f.ndim == 2 else f).contiguous().clone()
+        self.perfect_frame = sub[0] if self._squeeze_out else sub
+        self.flux_max_px = sub.amax(dim=(-2, -1))
+        self.signal = self.QE * self.flux_max_px
+        self._chain(sub, 1, env_offset)                                   # photon noise, QE
+        self._buffer_sum = sub if self._buffer_sum is None else self._buffer_sum + sub
+        self.n_buffered += 1
+        self._env_offset = env_offset
+        if self.integrationTime is None or self._integrated_time >= self.integrationTime:
+            self.readout()
         return self.frame
+
+    def readout(self):
+        """Detector.py:232-276: sum of the buffered sub-frames -> dark current, full well, [EM gain] -> hardware binning ->
+        read noise, gain, ADC; resets the buffer and the integrated time."""
+        out = self._buffer_sum
+        self._chain(out, 2, self._env_offset)                             # dark shot noise, saturation, EM gain
+        if self.binning != 1:                                             # tools.py:409-416 (sum)
+            b = int(self.binning)
+            B, r, c = out.shape
+            if r % b != 0:
+                raise ValueError("the frame size must be a multiple of the detector binning")
+            out = out.reshape(B, r // b, b, c // b, b).sum(dim=(2, 4)).contiguous()
+        self._chain(out, 4, self._env_offset)                             # read-out noise, gain, quantisation
+        self.frame = out[0] if self._squeeze_out else out
+        if self.resolution is None:
+            self.resolution = out.shape[-1]
+        if self.fov_arcsec is not None:
+            self.pixel_size_rad = self.fov_rad / self.resolution
+            self.pixel_size_arcsec = self.fov_arcsec / self.resolution
+        self.n_frames_last_exposure = self.n_buffered
+        self._buffer_sum, self.n_buffered, self._integrated_time = None, 0, 0
 

@@ -79,7 +79,8 @@ class OOPAO:
         param = self._load_param(args)
         self.param = param
         self.tel = Telescope(resolution=param["resolution"], diameter=param["diameter"], samplingTime=param["samplingTime"],
-                             centralObstruction=param["centralObstruction"], n_envs=n_envs, device=device)
+                             centralObstruction=param["centralObstruction"], fov=param.get("fov", 0), n_envs=n_envs,
+                             device=device)
         self.device = self.tel.device
         self.source = Source(optBand=param["opticalBand"], magnitude=param["magnitude"])
         self.source * self.tel

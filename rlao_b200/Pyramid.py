@@ -167,6 +167,7 @@ class Pyramid:
         if self.cam.is_ideal():
             self.cam.frame = frames[0] if (self.n_envs == 1 and frames.shape[0] == 1) else frames
         else:
+            self.cam._integrated_time += self.telescope.samplingTime       # Pyramid.py:989
             out = self.cam.integrate(frames.to(torch.float32), env_offset)
             self.cam.frame = out[0] if (self.n_envs == 1 and out.shape[0] == 1) else out
         return self.cam.frame

@@ -26,8 +26,9 @@ class Source:
                  chromatic_shift=None):
         if optBand not in _PHOTOMETRY:
             raise ValueError("Error: Wrong name for the photometry object")     # Source.py:233-238 prints + returns -1
-        if coordinates[0] != 0:
-            raise NotImplementedError("off-axis sources are not supported (SURVEY.md section 8 f-4)")
+        # Off-axis sources (coordinates = [zenith arcsec, azimuth deg], Source.py:15-24) are accepted; the Atmosphere
+        # propagates them when every layer is at the ground (altitude 0: the footprint does not move,
+        # OOPAO/Atmosphere.py:222-230) and refuses layers in altitude (anisoplanatism is out of scope).
         self.optBand = optBand
         self.wavelength, self.bandwidth, zp = _PHOTOMETRY[optBand]
         self.zeroPoint = zp / 368

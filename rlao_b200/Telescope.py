@@ -146,10 +146,12 @@ class Telescope:
         src._flux_version = getattr(src, "_flux_version", 0) + 1
 
     # ---- PSF ------------------------------------------------------------------------------------------
-    def psf_geometry(self, zeroPaddingFactor):
-        """Sizes PropagateField derives (Telescope.py:296-326): (N, oversampling, img_size)."""
+    def psf_geometry(self, zeroPaddingFactor, img_resolution=None):
+        """Sizes PropagateField derives (Telescope.py:296-326): (N, oversampling, img_size, pad, img_resolution)."""
         R = self.resolution
-        img_res = int(zeroPaddingFactor * R)
+        img_res = int(zeroPaddingFactor * R) if img_resolution is None else int(img_resolution)
+        if img_res > zeroPaddingFactor * R:
+            raise ValueError("Error: image has too many pixels for this pupil sampling. Try using a pupil mask with more pixels")
         os_ = 1
         if zeroPaddingFactor * os_ < 2:
             os_ = int(math.ceil(2.0 / zeroPaddingFactor))
@@ -161,31 +163,24 @@ class Telescope:
         return R + 2 * pad, os_, img_size, pad, img_res
 
     def computePSF(self, zeroPaddingFactor=2, detector=None, img_resolution=None):
-        """Telescope.py:260-360: full PSF image(s) in `tel.PSF` ([n_envs, S, S], squeezed for one env).
-        Uses torch.fft (cuFFT); the per-step Strehl reward uses the pruned-DFT kernel in `psf_peak`."""
+        """Telescope.py:260-293 -> PropagateField :296-360: PSF image(s) in `tel.PSF` ([n_envs, S, S], squeezed for one
+        env), S = img_resolution (default zeroPaddingFactor * resolution; a detector brings its own sampling and size).
+        Runs on the library's kernels (aoenv_psf_image: both transforms are tensor-core GEMMs)."""
+        from .psf import psf_image
+        if detector is not None:
+            zeroPaddingFactor = detector.psf_sampling
+            img_resolution = detector.resolution
         if self.src is None:
             raise AttributeError("The telescope was not coupled to any source object! Make sure to couple it with an src object using src*tel")
-        if detector is not None or img_resolution is not None:
-            raise NotImplementedError("science detector sampling is out of scope (SURVEY.md section 8 f-4)")
-        N, os_, img_size, pad, img_res = self.psf_geometry(zeroPaddingFactor)
-        phase = self._materialise() * self._pupil_f * (2 * math.pi / self.src.wavelength)
-        amp = self._pupil_f * torch.as_tensor(self.pupilReflectivity, dtype=torch.float32, device=self.device) * self.src._amp_dev
-        field = torch.polar(amp.expand_as(phase), phase)
-        sup = torch.nn.functional.pad(field, (pad, pad, pad, pad))
-        k = torch.arange(N, device=self.device, dtype=torch.float64)
-        ph1 = torch.polar(torch.ones_like(k), -math.pi / N * k * (1 - img_res % 2)).to(torch.complex64)
-        sup = sup * (ph1[:, None] * ph1[None, :])
-        emf = torch.fft.fftshift(torch.fft.fft2(torch.fft.ifftshift(sup, dim=(-2, -1))) / N, dim=(-2, -1))
-        shift_pix = 0 if N % 2 == img_size % 2 else (1 if N % 2 == 0 else -1)
-        lo = int(math.ceil(N / 2) - img_size // 2 + (1 - N % 2) - 1)
-        hi = int(math.ceil(N / 2) + img_size // 2 + shift_pix)
-        psf = emf[:, lo:hi, lo:hi].abs() ** 2
-        if os_ != 1:
-            m = psf.shape[-1] // os_
-            psf = psf.reshape(-1, m, os_, m, os_).sum(dim=(2, 4))
+        a, b = self._terms()
+        psf, peak = psf_image(self, a.contiguous(), None if b is None else b.contiguous(), zeroPaddingFactor, img_resolution)
+        img = psf.shape[-1]
+        conv = (180 / math.pi) * 3600
+        half = (self.src.wavelength / self.D) * (img / 2 / zeroPaddingFactor)
+        self.xPSF_rad = self.yPSF_rad = [-half, half]
+        self.xPSF_arcsec = self.yPSF_arcsec = [-conv * half, conv * half]
         self.PSF = self._squeeze(psf)
-        mx = psf.amax(dim=(-2, -1), keepdim=True)
-        self.PSF_norma = self._squeeze(psf / mx)
+        self.PSF_norma = self._squeeze(psf / peak[:, None, None])
 
     def _materialise_psf(self):
         p = self.PSF
@@ -203,20 +198,19 @@ class Telescope:
             self._opd_np = dm_opd
             self._lazy = None
         elif tag == "detector":
-            # Telescope.py:487-500: science camera on the PSF (short exposures of one AO frame; no cropping / stacking)
-            full = int(obj.psf_sampling * self.resolution)
-            if obj.resolution is not None and int(obj.resolution) != full:
-                raise NotImplementedError("cropped science frames (Detector.nRes != psf_sampling * resolution) are out of scope")
-            if obj.integrationTime is None:
-                obj.integrationTime = self.samplingTime
-            if obj.integrationTime < self.samplingTime:
+            # Telescope.py:487-500: the science camera looks at the PSF with its own sampling and size; every tel*cam adds
+            # one AO frame to the exposure, which is read out when the integration time is reached
+            self.computePSF(detector=obj)
+            obj.fov_arcsec = self.xPSF_arcsec[1] - self.xPSF_arcsec[0]
+            obj.fov_rad = self.xPSF_rad[1] - self.xPSF_rad[0]
+            if obj.integrationTime is not None and obj.integrationTime < self.samplingTime:
                 raise ValueError("The Detector integration time is smaller than the AO loop sampling Time. ")
-            if obj.integrationTime > self.samplingTime:
-                raise NotImplementedError("stacking several AO frames per exposure is out of scope (SURVEY.md section 8 f-4)")
-            self.computePSF(obj.psf_sampling)
             obj._integrated_time += self.samplingTime
             obj.integrate(self._materialise_psf())
-            self.PSF = obj.frame
+            if obj.frame is not None:
+                self.PSF = obj.frame
+        elif tag == "telescope":
+            pass                                   # `atm*src*tel*cam` (OOPAOEnv.py:207,315): atm*src already returned the telescope
         else:
             raise AttributeError(f"Telescope cannot be propagated to an object with tag {tag!r}")
         return self

@@ -115,16 +115,26 @@ __device__ __forceinline__ float poisson_draw(float lam, uint32_t w0, uint32_t w
 
 // OOPAO/Detector.py:279-301 (integrate) then :232-276 (readout), one pixel, split around the photon draw:
 //   electrons = Poisson(flux) * QE + Poisson(dark); clip to the full well; (+ EM gain); + round(N(0,1) RON); gain; ADC.
-__device__ __forceinline__ float detector_finish(float photons, float dark, float ron, const aoenv_detector_t& d) {
-  float x = photons * d.qe + dark;
-  if (d.has_fwc) x = fminf(fmaxf(x, 0.f), d.fwc);
-  if (d.sensor_emccd) x *= d.gain;
-  x += ron;
-  if (!d.sensor_emccd) x *= d.gain;
-  if (d.bits > 0) {
-    const float full = (float)((1u << d.bits) - 1u);
-    x = truncf(x / d.fwc * full);
-    x = fminf(x, full);
+// `stages` (aoenv_detector_t.reserved; 0 = all): bit 0 = integrate (photon noise, QE: Detector.py:279-301), bit 1 = first
+// half of readout (dark current, full well, EM gain: :232-251), bit 2 = second half (read noise, gain, ADC: :256-268).
+// Long exposures integrate sub-frames into a buffer (bit 0 each), then read the sum out once (bits 1 | 2); detector
+// binning (:252-254) sits between the two halves.
+__device__ __forceinline__ float detector_finish(float photons, float dark, float ron, const aoenv_detector_t& d, uint32_t stages) {
+  float x = photons;
+  if (stages & 1u) x *= d.qe;
+  if (stages & 2u) {
+    x += dark;
+    if (d.has_fwc) x = fminf(fmaxf(x, 0.f), d.fwc);
+    if (d.sensor_emccd) x *= d.gain;
+  }
+  if (stages & 4u) {
+    x += ron;
+    if (!d.sensor_emccd) x *= d.gain;
+    if (d.bits > 0) {
+      const float full = (float)((1u << d.bits) - 1u);
+      x = truncf(x / d.fwc * full);
+      x = fminf(x, full);
+    }
   }
   return x;
 }
@@ -152,7 +162,10 @@ shwfs_detector_kernel(float* __restrict__ frame, const uint8_t* __restrict__ val
   DetQueued* __restrict__ q = queue[warp];
   int queued = 0;                                   // warp-uniform
   float vmax = -INFINITY;
-  const bool has_dark = det.dark_electrons > 0.f;
+  const uint32_t stages = det.reserved ? det.reserved : 7u;
+  const bool photon_noise = det.photon_noise && (stages & 1u);
+  const bool has_dark = det.dark_electrons > 0.f && (stages & 2u);
+  const bool has_ron = det.readout_noise != 0.f && (stages & 4u);
   const float dark_p0 = has_dark ? __expf(-det.dark_electrons) : 1.f;
 
   auto is_lit = [&](int pix) {
@@ -171,11 +184,11 @@ shwfs_detector_kernel(float* __restrict__ frame, const uint8_t* __restrict__ val
     const PixelRng rng(det.seed, (uint32_t)pix, (uint32_t)b, det.frame_counter);
     const uint4 r0 = rng.block(0);
     float ron = 0.f;
-    if (det.readout_noise != 0.f)       // Box-Muller with the SFU logarithm / cosine: the draw is rounded to whole electrons
+    if (has_ron)                        // Box-Muller with the SFU logarithm / cosine: the draw is rounded to whole electrons
       ron = rintf(sqrtf(-2.0f * __logf(u32_to_unit(r0.z))) * __cosf(6.283185307179586f * u32_to_unit(r0.w)) * det.readout_noise);
-    const bool ptrs = in && det.photon_noise && lam >= 12.f;
+    const bool ptrs = in && photon_noise && lam >= 12.f;
     if (!ptrs && in) {
-      const float photons = det.photon_noise ? poisson_draw(lam, r0.x, 0u, rng, 16) : lam;
+      const float photons = photon_noise ? poisson_draw(lam, r0.x, 0u, rng, 16) : lam;
       float dark = 0.f;
       if (has_dark) {                   // almost always zero: one comparison against exp(-dark)
         const float u = u32_to_unit(r0.y) * 0.99999994f;
@@ -189,7 +202,7 @@ shwfs_detector_kernel(float* __restrict__ frame, const uint8_t* __restrict__ val
           }
         }
       }
-      const float val = detector_finish(photons, dark, ron, det);
+      const float val = detector_finish(photons, dark, ron, det, stages);
       img[pix] = val;
       if (is_lit(pix)) vmax = fmaxf(vmax, val);
     }
@@ -207,7 +220,7 @@ shwfs_detector_kernel(float* __restrict__ frame, const uint8_t* __restrict__ val
       const uint4 r1 = rng.block(1);
       dark = poisson_draw(det.dark_electrons, r1.x, r1.y, rng, 32);
     }
-    const float val = detector_finish(photons, dark, it.ron, det);
+    const float val = detector_finish(photons, dark, it.ron, det, stages);
     img[it.pix] = val;
     if (is_lit(it.pix)) vmax = fmaxf(vmax, val);
   }
@@ -726,6 +739,166 @@ shwfs_frame6s_kernel(const float* __restrict__ opd_a, const float* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// n / 2 LANES PER LENSLET, term-by-term transform (all compiled n): the arithmetic of shwfs_frame_kernel — radix-2 split
+// of both pruned DFT passes, packed FP32, literal twiddles — with the lenslet spread over T = n / 2 lanes of one warp.
+// Lane t owns tile rows 2t, 2t+1 = the column pair (2t, 2t+1) of the transposed field: it forms those fields and runs
+// pass 1 for them (all n output rows u: the twiddles depend on (u, a) only, so every lane executes the same code).  The
+// lanes of a lenslet swap through a warp-private patch of shared memory (__syncwarp, no block barrier); lane p then runs
+// pass 2 for the output rows 2p, 2p+1 (and n + those), |.|^2 and the binning, and stores binned rows p and p + n/2.
+// A third of the registers of the one-thread-per-lenslet kernel -> twice the resident warps.
+// ---------------------------------------------------------------------------------------------------------
+template <int n>
+__global__ void __launch_bounds__(128, 4)
+shwfs_frame_split_kernel(const float* __restrict__ opd_a, const float* __restrict__ opd_b, const float* __restrict__ pupil,
+                         const float* __restrict__ amp, const uint8_t* __restrict__ valid, int nS, float phase_scale,
+                         int track_max, int shared_max, float* __restrict__ frame, int32_t* __restrict__ envmax,
+                         double* __restrict__ stats) {
+  constexpr int N = 2 * n, T = n / 2, h = n / 2, LPW = 32 / T, S = LPW + 1;
+  // exchange: [warp][((kind * T + k) * n + u)][slot] float2, kind = Pr, Pi, Qr, Qi of output row u, column pair k
+  __shared__ float2 xch[4][4 * T * n][S];
+  const int R = nS * n;
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slot = lane / T, t = lane - slot * T;
+  const int k = (blockIdx.x * 4 + warp) * LPW + slot;
+  const bool active = slot < LPW && k < nS * nS;
+  const int li = active ? k / nS : 0, lj = active ? k - li * nS : 0;
+  const bool lit = active && valid[k] != 0;
+  const float phase_turns = phase_scale * 0.15915494309189535f;
+  const size_t tile = (size_t)(li * n) * R + lj * n;
+  float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;                         // pupil statistics, see shwfs_frame_kernel
+  float2 er2[n], ei2[n];                                                  // (E[a][2t], E[a][2t+1])
+  if (active) {
+    const float* __restrict__ pa = opd_a + (size_t)b * R * R + tile;
+    const float* __restrict__ pb = opd_b ? opd_b + (size_t)b * R * R + tile : nullptr;
+    const size_t centre = (size_t)b * R * R + (size_t)(R / 2) * R + R / 2;
+    const float ka = stats ? __ldg(opd_a + centre) : 0.f;
+    const float kt = stats ? (opd_b ? ka + __ldg(opd_b + centre) : ka) : 0.f;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int bb = 2 * t + e;
+#pragma unroll
+      for (int a2 = 0; a2 < h; ++a2) {
+        const int o2 = bb * R + 2 * a2;
+        const float2 av = __ldg(reinterpret_cast<const float2*>(pa + o2));
+        const float2 bv = pb ? __ldg(reinterpret_cast<const float2*>(pb + o2)) : make_float2(0.f, 0.f);
+        const float2 pv = __ldg(reinterpret_cast<const float2*>(pupil + tile + o2));
+        const float2 mv = lit ? __ldg(reinterpret_cast<const float2*>(amp + tile + o2)) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int aa = 2 * a2 + h2;
+          const float a = h2 ? av.y : av.x;
+          const float tt = a + (h2 ? bv.y : bv.x);
+          const float pu = h2 ? pv.y : pv.x;
+          const float in_pupil = pu > 0.f ? 1.f : 0.f;
+          const float da = (a - ka) * in_pupil, dt = (tt - kt) * in_pupil;
+          f0 += da; f1 = fmaf(da, da, f1); f2 += dt; f3 = fmaf(dt, dt, f3);
+          const float turns = tt * pu * phase_turns;
+          const float ang = (turns - ((turns + 12582912.0f) - 12582912.0f)) * 6.283185307179586f;
+          const float am = h2 ? mv.y : mv.x;
+          const float cs = am * __cosf(ang), sn = am * __sinf(ang);
+          if (e == 0) { er2[aa].x = cs; ei2[aa].x = sn; } else { er2[aa].y = cs; ei2[aa].y = sn; }
+        }
+      }
+    }
+  }
+  if (stats != nullptr) {
+    double s0 = warp_sum((double)f0), s1 = warp_sum((double)f1), s2 = warp_sum((double)f2), s3 = warp_sum((double)f3);
+    if (lane == 0) {
+      double* __restrict__ st = stats + (size_t)b * 4;
+      atomicAdd(st, s0); atomicAdd(st + 1, s1); atomicAdd(st + 2, s2); atomicAdd(st + 3, s3);
+    }
+  }
+  float2 (*x)[S] = xch[warp];
+  const bool any_lit = __any_sync(0xffffffffu, lit);
+  float vmax = -INFINITY;
+  if (any_lit) {
+    if (lit) {
+      // pass 1 for this lane's column pair, every output row u < n (rows u + n follow by the radix-2 symmetry)
+#pragma unroll
+      for (int u = 0; u < n; ++u) {
+        float2 pr = make_float2(0.f, 0.f), pi = pr, qr = pr, qi = pr;
+#pragma unroll
+        for (int aa = 0; aa < n; ++aa) {
+          const float gx = WfsTw<n>::re(u * n + aa), gy = WfsTw<n>::im(u * n + aa);
+          if (((aa + h) & 1) == 0) {
+            pr = fma2(dup2(gx), er2[aa], fma2(dup2(-gy), ei2[aa], pr));
+            pi = fma2(dup2(gx), ei2[aa], fma2(dup2(gy), er2[aa], pi));
+          } else {
+            qr = fma2(dup2(gx), er2[aa], fma2(dup2(-gy), ei2[aa], qr));
+            qi = fma2(dup2(gx), ei2[aa], fma2(dup2(gy), er2[aa], qi));
+          }
+        }
+        x[(0 * T + t) * n + u][slot] = pr;
+        x[(1 * T + t) * n + u][slot] = pi;
+        x[(2 * T + t) * n + u][slot] = qr;
+        x[(3 * T + t) * n + u][slot] = qi;
+      }
+    }
+    __syncwarp();
+    if (lit) {
+      float* __restrict__ fout = frame + (size_t)b * R * R + tile;
+      const float norm = 1.0f / (float)(N * N);
+      float2 acc[n];                         // acc[q] = (binned row t, binned row t + n/2) at binned column q
+#pragma unroll
+      for (int q = 0; q < n; ++q) acc[q] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int du = 0; du < 2; ++du) {
+        const int u = 2 * t + du;
+        float2 yr[n], yi[n];                 // (row u: P + Q, row u + n: P - Q)
+#pragma unroll
+        for (int kk = 0; kk < T; ++kk) {
+          const float2 pr = x[(0 * T + kk) * n + u][slot], pi = x[(1 * T + kk) * n + u][slot];
+          const float2 qr = x[(2 * T + kk) * n + u][slot], qi = x[(3 * T + kk) * n + u][slot];
+          yr[2 * kk] = make_float2(pr.x + qr.x, pr.x - qr.x);
+          yr[2 * kk + 1] = make_float2(pr.y + qr.y, pr.y - qr.y);
+          yi[2 * kk] = make_float2(pi.x + qi.x, pi.x - qi.x);
+          yi[2 * kk + 1] = make_float2(pi.y + qi.y, pi.y - qi.y);
+        }
+#pragma unroll
+        for (int v = 0; v < n; ++v) {
+          float2 er_ = make_float2(0.f, 0.f), ei_ = er_, or_ = er_, oi_ = er_;
+#pragma unroll
+          for (int bb = 0; bb < n; ++bb) {
+            const float gx = WfsTw<n>::re(v * n + bb), gy = WfsTw<n>::im(v * n + bb);
+            if (((bb + h) & 1) == 0) {
+              er_ = fma2(yr[bb], dup2(gx), fma2(yi[bb], dup2(-gy), er_));
+              ei_ = fma2(yr[bb], dup2(gy), fma2(yi[bb], dup2(gx), ei_));
+            } else {
+              or_ = fma2(yr[bb], dup2(gx), fma2(yi[bb], dup2(-gy), or_));
+              oi_ = fma2(yr[bb], dup2(gy), fma2(yi[bb], dup2(gx), oi_));
+            }
+          }
+          const float2 f0r = add2(er_, or_), f0i = add2(ei_, oi_);     // F[row][v]
+          const float2 f1r = sub2(er_, or_), f1i = sub2(ei_, oi_);     // F[row][v + n]
+          acc[v >> 1] = add2(acc[v >> 1], fma2(f0r, f0r, mul2(f0i, f0i)));
+          acc[(v >> 1) + h] = add2(acc[(v >> 1) + h], fma2(f1r, f1r, mul2(f1i, f1i)));
+        }
+      }
+#pragma unroll
+      for (int q2 = 0; q2 < h; ++q2) {
+        const float2 lo = make_float2(acc[2 * q2].x * norm, acc[2 * q2 + 1].x * norm);
+        const float2 hi = make_float2(acc[2 * q2].y * norm, acc[2 * q2 + 1].y * norm);
+        *reinterpret_cast<float2*>(fout + (size_t)t * R + 2 * q2) = lo;
+        *reinterpret_cast<float2*>(fout + (size_t)(t + h) * R + 2 * q2) = hi;
+        vmax = fmaxf(vmax, fmaxf(fmaxf(lo.x, lo.y), fmaxf(hi.x, hi.y)));
+      }
+    }
+  }
+  if (active && !lit) {                                                   // dark lenslet: rows 2t, 2t+1 of its tile
+    float* __restrict__ fout = frame + (size_t)b * R * R + tile;
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+#pragma unroll
+      for (int q2 = 0; q2 < h; ++q2) *reinterpret_cast<float2*>(fout + (size_t)(2 * t + e) * R + 2 * q2) = make_float2(0.f, 0.f);
+  }
+  if (track_max) {
+    vmax = warp_max(vmax);
+    if (lane == 0 && vmax > -INFINITY) atomicMax(&envmax[shared_max ? 0 : b], float_to_ordered(vmax));
+  }
+}
+
 // centroid + slopes: one thread per (valid lenslet, environment).  n is a template parameter so that the 6 x 6 (4 x 4,
 // 8 x 8) spot is read with fully unrolled 64-bit loads (tile rows start on even columns: lj * n with n even).
 template <int n>
@@ -887,19 +1060,25 @@ __global__ void envmax_init_kernel(int32_t* __restrict__ envmax, int count) {
 
 using namespace aoenv;
 
-// n = 6 has three implementations of the same frame: the factorised transform on three lanes per lenslet
-// (shwfs_frame6s_kernel, default), the factorised transform on one thread per lenslet (shwfs_frame6_kernel) and the
-// term-by-term transform (shwfs_frame_kernel<6>).  aoenv_set_wfs6_variant / AOENV_WFS6=split|factorised|termwise selects;
-// the tests run all three against the oracle.
+// Implementations of the same frame (aoenv_set_wfs6_variant / AOENV_WFS_FRAME=termwise|factorised|split6|split):
+//   0 term-by-term transform, one thread per lenslet (shwfs_frame_kernel<n>)
+//   1 factorised transform (radix 2 x Good-Thomas 2 x 3), one thread per lenslet, n = 6 (shwfs_frame6_kernel)
+//   2 factorised transform on three lanes per lenslet, n = 6 (shwfs_frame6s_kernel)
+//   3 term-by-term transform on n / 2 lanes per lenslet (shwfs_frame_split_kernel<n>)
+// The tests run all of them against the oracle; the default is the one measured fastest on B200 (profiles/).
+constexpr int kDefaultFrameVariant = 0;
 static std::atomic<int> g_wfs6_factorised{[] {
-  const char* e = getenv("AOENV_WFS6");
-  return (e && e[0] == 'f') ? 1 : (e && e[0] == 't') ? 0 : 2;      // "factorised" / "termwise" / default: three lanes per lenslet
+  const char* e = getenv("AOENV_WFS_FRAME");      // termwise | factorised | split6 | split
+  if (e && e[0] == 'f') return 1;
+  if (e && e[0] == 's') return (e[5] == '6') ? 2 : 3;
+  if (e && e[0] == 't') return 0;
+  return kDefaultFrameVariant;
 }()};
 
 extern "C" {
 
 int aoenv_set_wfs6_variant(int variant) {
-  return g_wfs6_factorised.exchange(variant < 0 || variant > 2 ? 2 : variant);
+  return g_wfs6_factorised.exchange(variant < 0 || variant > 3 ? kDefaultFrameVariant : variant);
 }
 
 int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil, const float* amp,
@@ -921,6 +1100,14 @@ int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil
     if (e != cudaSuccess) return fail(-3, "shwfs_frame memset: %s", cudaGetErrorString(e));
   }
   dim3 grid((nS * nS + 127) / 128, B);
+  const int variant = g_wfs6_factorised.load(std::memory_order_relaxed);
+  if (variant == 3) {            // n / 2 lanes per lenslet, any compiled n
+    const int per_block = 4 * (32 / (n / 2));
+    dim3 g3((nS * nS + per_block - 1) / per_block, B);
+    if (n == 4) shwfs_frame_split_kernel<4><<<g3, 128, 0, s>>>(opd_a, opd_b, pupil, amp, valid, nS, phase_scale, det == nullptr, shared_max, frame, envmax, stats);
+    else if (n == 6) shwfs_frame_split_kernel<6><<<g3, 128, 0, s>>>(opd_a, opd_b, pupil, amp, valid, nS, phase_scale, det == nullptr, shared_max, frame, envmax, stats);
+    else shwfs_frame_split_kernel<8><<<g3, 128, 0, s>>>(opd_a, opd_b, pupil, amp, valid, nS, phase_scale, det == nullptr, shared_max, frame, envmax, stats);
+  } else
 #define AOENV_WFS_CASE(NN)                                                                                   \
   case NN:                                                                                                   \
     shwfs_frame_kernel<NN><<<grid, 128, 0, s>>>(opd_a, opd_b, pupil, amp, valid, nS, phase_scale, det == nullptr,  \
@@ -930,11 +1117,11 @@ int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil
     AOENV_WFS_CASE(4)
     AOENV_WFS_CASE(8)
     case 6:
-      if (g_wfs6_factorised.load(std::memory_order_relaxed) == 2) {
+      if (variant == 2) {
         dim3 g3((nS * nS + kS6Warps * kS6Lenslets - 1) / (kS6Warps * kS6Lenslets), B);
         shwfs_frame6s_kernel<<<g3, kS6Warps * 32, 0, s>>>(opd_a, opd_b, pupil, amp, valid, nS, phase_scale, det == nullptr,
                                                           shared_max, frame, envmax, stats);
-      } else if (g_wfs6_factorised.load(std::memory_order_relaxed) == 1)
+      } else if (variant == 1)
         shwfs_frame6_kernel<<<grid, 128, 0, s>>>(opd_a, opd_b, pupil, amp, valid, nS, phase_scale, det == nullptr, shared_max,
                                                  frame, envmax, stats);
       else

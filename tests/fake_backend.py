@@ -45,8 +45,57 @@ class FakeLib:
     def aoenv_last_error(self):
         return b""
 
-    def aoenv_detector_integrate(self, *a):
-        raise NotImplementedError("fake backend: detector_integrate")
+    def aoenv_detector_integrate(self, frame, B, rows, cols, det, stream):
+        """OOPAO/Detector.py:190-301 with numpy's generators, restricted to the stages in det.reserved (0 = all)."""
+        self.launches += 1
+        d = det._obj if hasattr(det, "_obj") else det
+        st = d.reserved or 7
+        f = _arr(frame, (B, rows, cols))
+        x = f.astype(np.float64)
+        if st & 1:
+            if d.photon_noise:
+                x = self.rs.poisson(np.maximum(x, 0)).astype(np.float64)
+            x = x * d.qe
+        if st & 2:
+            if d.dark_electrons > 0:
+                x = x + self.rs.poisson(d.dark_electrons, size=x.shape)
+            if d.has_fwc:
+                x = np.clip(x, 0, d.fwc)
+            if d.sensor_emccd:
+                x = x * d.gain
+        if st & 4:
+            if d.readout_noise:
+                x = x + np.round(self.rs.normal(size=x.shape) * d.readout_noise)
+            if not d.sensor_emccd:
+                x = x * d.gain
+            if d.bits > 0:
+                full = float((1 << d.bits) - 1)
+                x = np.minimum(np.trunc(x / d.fwc * full), full)
+        f[:] = x.astype(np.float32)
+        return 0
+
+    def aoenv_psf_image(self, opd_a, opd_b, pupil, amp, w_planes, B, R, N, os_, win, phase_scale, field_planes, ldk, work_t,
+                        planes_u, work_f, psf, psf_max, stream):
+        """OOPAO/Telescope.py:296-360 with numpy's FFT: padded field, half-pixel phasor, centred FFT / N, |.|^2, central
+        crop, oversampling binned away."""
+        self.launches += 5
+        a, b_ = _arr(opd_a, (B, R, R)), _arr(opd_b, (B, R, R))
+        pu, am = _arr(pupil, (R, R)).astype(np.float64), _arr(amp, (R, R)).astype(np.float64)
+        out, mx = _arr(psf, (B, win, win)), _arr(psf_max, (B,))
+        pad = (N - R) // 2
+        k = np.arange(N)
+        xx, yy = np.meshgrid(k, k)
+        phasor = np.exp(-1j * np.pi / N * (xx + yy))
+        size = os_ * win
+        lo = N // 2 - size // 2
+        for e in range(B):
+            t = a[e].astype(np.float64) + (b_[e] if b_ is not None else 0)
+            field = np.pad(am * np.exp(1j * t * pu * float(_val(phase_scale))), pad)
+            emf = np.fft.fftshift(np.fft.fft2(np.fft.ifftshift(field * phasor)) / N)[lo:lo + size, lo:lo + size]
+            img = (np.abs(emf) ** 2).reshape(win, os_, win, os_).sum(axis=(1, 3))
+            out[e] = img.astype(np.float32)
+            mx[e] = out[e].max()
+        return 0
 
     def aoenv_set_wfs6_variant(self, factorised):
         return 0

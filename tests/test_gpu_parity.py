@@ -263,27 +263,27 @@ def test_shack_hartmann_vs_oracle(dev, nS, n):
         assert rel_err(got_sig[e], want) < SLOPE_TOL, (e, "slopes")
     s2d = _np(wfs.signal_2D)
     assert rel_err(s2d[2], orc.signal_2D) < SLOPE_TOL
-    if n == 6:
-        # the other two implementations of the n = 6 transform (one thread per lenslet: factorised radix 2 x Good-Thomas
-        # 2 x 3, and term by term) give the same frame as the default (three lanes per lenslet)
-        lib = _lib.load()
-        wfs.use_fused = False
-        tel * wfs
-        got_sig, got_frame = _np(wfs.signal), _np(wfs.cam.frame)
-        for variant in (1, 0):
-            prev = lib.aoenv_set_wfs6_variant(variant)
-            assert prev == 2
-            try:
-                tel * wfs
-                alt_sig, alt_frame = _np(wfs.signal), _np(wfs.cam.frame)
-            finally:
-                lib.aoenv_set_wfs6_variant(prev)
-            assert rel_err(alt_frame, got_frame) < 5e-6, variant
-            assert rel_err(alt_sig, got_sig) < 2e-5, variant
-            for e in range(3):
-                orc.measure(opd32[e] * pupil * 2 * np.pi / wl)
-                assert rel_err(alt_frame[e], orc.frame) < 2e-5, (e, "frame", variant)
-                assert rel_err(got_frame[e], orc.frame) < 2e-5, (e, "frame", "three lanes per lenslet")
+    # every implementation of the frame kernel gives the same frame as the default one: 3 = term by term on n/2 lanes per
+    # lenslet (any n); for 6-pixel lenslets also 1 = factorised (radix 2 x Good-Thomas 2 x 3) on one thread per lenslet and
+    # 2 = factorised on three lanes per lenslet; 0 = term by term, one thread per lenslet
+    lib = _lib.load()
+    wfs.use_fused = False
+    tel * wfs
+    got_sig, got_frame = _np(wfs.signal), _np(wfs.cam.frame)
+    default = lib.aoenv_set_wfs6_variant(-1)
+    lib.aoenv_set_wfs6_variant(default)
+    for variant in ((0, 1, 2, 3) if n == 6 else (0, 3)):
+        prev = lib.aoenv_set_wfs6_variant(variant)
+        try:
+            tel * wfs
+            alt_sig, alt_frame = _np(wfs.signal), _np(wfs.cam.frame)
+        finally:
+            lib.aoenv_set_wfs6_variant(prev)
+        assert rel_err(alt_frame, got_frame) < 5e-6, variant
+        assert rel_err(alt_sig, got_sig) < 2e-5, variant
+        for e in range(3):
+            orc.measure(opd32[e] * pupil * 2 * np.pi / wl)
+            assert rel_err(alt_frame[e], orc.frame) < 2e-5, (e, "frame", variant)
 
 
 def test_shack_hartmann_flat_wavefront_gives_zero_signal_at_full_size(dev):

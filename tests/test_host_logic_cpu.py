@@ -264,6 +264,57 @@ def test_torch_wrapper_keeps_the_camera_frame_of_the_papyrus_env(fake, monkeypat
     assert len(w.step(0, razor.gainCL * w.reset_soft())) == 5
 
 
+def test_papyrus_science_path_on_cpu(fake):
+    """MAIN_CODE/OOPAOEnv/OOPAOEnv.py:118-196,300-339,473-482: guide star + off-axis science target, science cameras on the
+    PSF (`atm*src*tel*cam`), long-exposure PSF of render4plot; Detector exposure buffer (OOPAO/Detector.py:232-301)."""
+    from rlao_b200.Detector import Detector
+    from rlao_b200.OOPAOEnv.OOPAOEnv import OOPAO
+    from rlao_b200.Source import Source
+    cfg = CONFIGS["tiny"]()
+    cfg.nSubap = 12
+    env = OOPAO()
+    env.set_params_file(param_from_config_for_pyramid(cfg), "")
+    env.set_params(types.SimpleNamespace(), gainCL=0.4, n_envs=2, rng="philox", seed=1)
+    R = env.tel.resolution
+    assert env.tel.fov == 1 and env.ngs.coordinates == [0, 0] and env.src.coordinates == [0.4, 0]
+    assert env.tel.src is env.src                                   # the last propagation pointed the telescope at the target
+    assert env.src_cam.frame.shape == (2, 4 * R, 4 * R) and env.ngs_cam.frame.shape == (2, R, R)
+    assert env.LE_PSF.shape == (2, 4 * R, 4 * R)
+    # the WFS-path camera sees the central R x R pixels of the same PSF
+    env.atm * env.ngs * env.tel * env.src_cam
+    full = env.src_cam.frame
+    env.atm * env.ngs * env.tel * env.ngs_cam
+    lo = 2 * R - R // 2
+    assert torch.allclose(env.ngs_cam.frame, full[:, lo:lo + R, lo:lo + R], rtol=1e-5, atol=0)
+    # render4plot: running mean of log10(PSF) after the first 15 frames
+    obs = new_episode(env, 5)
+    logs = []
+    for i in range(14, 19):
+        obs, wfsf, reward, strehl, done, info = env.step(i, env.gainCL * obs)
+        le, se = env.render4plot(i)
+        if i > 15:
+            logs.append(se.clone())
+    assert torch.allclose(le, torch.stack(logs).mean(dim=0), rtol=1e-5, atol=1e-6)
+    # exposure over three AO frames, hardware binning 4: nothing is read out before the integration time is reached
+    cam = Detector(integrationTime=3 * env.tel.samplingTime, psf_sampling=2, binning=4)
+    env.tel * cam
+    env.tel * cam
+    assert cam.frame is None and cam.n_buffered == 2
+    env.tel.computePSF(2)
+    one = env.tel.PSF.clone()
+    env.tel * cam
+    assert cam.n_buffered == 0 and cam._integrated_time == 0 and cam.n_frames_last_exposure == 3
+    want = 3 * one.reshape(2, R // 2, 4, R // 2, 4).sum(dim=(2, 4))
+    assert cam.frame.shape == (2, R // 2, R // 2) and torch.allclose(cam.frame, want, rtol=1e-5)
+    # sources outside the field of view / layers in altitude are refused
+    with pytest.raises(ValueError):
+        env.atm * Source("I", 8, coordinates=[2.0, 0])
+    env.atm.altitude[0] = 5000.0
+    with pytest.raises(NotImplementedError):
+        env.atm * env.src
+    env.atm.altitude[0] = 0.0
+
+
 def param_from_config_for_pyramid(cfg):
     from parity_util import param_from_config
     p = param_from_config(cfg)
