@@ -286,6 +286,33 @@ class KernelTimer:
         return {k: {"ms_per_step": v[0] / n_steps, "calls_per_step": v[1] / n_steps, "ms_per_call": v[0] / v[1]} for k, v in out.items()}
 
 
+def pin_to_gpu_numa_node(local_rank, world):
+    """One process per GPU on one host: keep this rank's threads (and therefore its first-touch pinned buffers) on the CPUs
+    NVML reports as local to its GPU, split evenly between the ranks that share them.  Returns a short description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        ids = [int(v) for v in vis.split(",")] if vis and all(v.strip().isdigit() for v in vis.split(",")) else list(range(world))
+        words = (os.cpu_count() + 63) // 64
+        sets = []
+        for g in ids[:world]:
+            mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(g), words)
+            sets.append(frozenset(64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1))
+        mine = sets[local_rank]
+        allowed = sorted(mine & set(os.sched_getaffinity(0)))
+        sharers = [r for r in range(len(sets)) if sets[r] == mine]
+        if not allowed or len(sharers) == 0:
+            return "no NUMA information"
+        k, n = sharers.index(local_rank), len(sharers)
+        per = max(1, len(allowed) // n)
+        cpus = allowed[k * per:(k + 1) * per] or allowed
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} CPUs local to GPU {ids[local_rank]} ({cpus[0]}-{cpus[-1]})"
+    except Exception as ex:                       # affinity is an optimisation, never a requirement
+        return f"not pinned ({type(ex).__name__})"
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -296,6 +323,7 @@ def run_gpu_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    pinned = pin_to_gpu_numa_node(local, world) if world > 1 else "single rank"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -357,7 +385,7 @@ def run_gpu_arm(args):
     # ---- end-to-end through the host-facing wrapper (pinned host buffers, copies inside the timed region) ----
     # the host-side "policy" (action = gain * obs on 1.7M floats) may use this rank's share of the host cores
     # (torchrun pins OMP_NUM_THREADS=1 by default)
-    torch.set_num_threads(max(1, min(16, (os.cpu_count() or 1) // world)))
+    torch.set_num_threads(max(1, min(16, len(os.sched_getaffinity(0)) if world > 1 else (os.cpu_count() or 1))))
     wrapped = TorchWrapper(env, host_io=True)
     obs_h = wrapped.reset_soft()
     act_h = torch.empty(obs_h.shape, dtype=torch.float32, pin_memory=True)
@@ -433,7 +461,7 @@ def run_gpu_arm(args):
                        "reconstructor": "50-mode Zernike modal (the reference's default, OOPAOEnvRazor.py:256-337)",
                        "l2": "per-step working set (layer maps) %.0f MB per GPU exceeds the 126 MB L2" % (
                            env.atm._maps.numel() * 4 / 2 / 1e6),
-                       "mean_strehl_last_step": sr_mean},
+                       "mean_strehl_last_step": sr_mean, "host_affinity": pinned},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "e2e_lookahead": {"value": e2e_ahead, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

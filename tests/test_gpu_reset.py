@@ -72,7 +72,9 @@ def test_philox_screens_have_the_reference_statistics(dev):
     b = _synth_screens(synth, 4, seed=5, screen0=512)
     assert not torch.equal(b[0].double(), a[0])
     again = _synth_screens(synth, 4, seed=5, screen0=0)
-    assert torch.equal(again.double(), a[:4])               # counter-based: screen s of seed 5 does not depend on the batch
+    # counter-based: screen s of seed 5 does not depend on the batch it is generated in (to GEMM rounding: the small batch
+    # takes the split-K path of the tensor-core kernel)
+    assert rel_err(again.double().cpu().numpy(), a[:4].cpu().numpy()) < 1e-5
     other = _synth_screens(synth, 4, seed=6)
     assert not torch.equal(other.double(), a[:4])
 
