@@ -257,6 +257,24 @@ int aoenv_shwfs_measure_f64(const float* opd, const float* pupil, const float* a
                             double* slopes, int lds, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Pyramid WFS — OOPAO/Pyramid.py:469-504 (pyramid_transform), :581-603 (modulation), :987-1002 (detector binning)
+ *
+ * frame [B][N/bin][N/bin] = bin x bin sums of  sum_theta | ifft2( fft2( support_theta * phasor ) * mask ) |^2, where
+ * support_theta is the pupil field amp * exp(i (phase + px_theta Tip + py_theta Tilt)) zero padded to N x N (centred),
+ * phase = (opd_a + opd_b) * pupil * phase_scale, Tip / Tilt = lin[x] / lin[y] * pupil (lin = linspace(-pi, pi, R)),
+ * mod [nTheta][2] = (px, py), phasor = exp(-i pi (N+1)/N (x + y)).  amp [R][R] = sqrt(flux / nTheta) * reflectivity.
+ * mask_s: complex64 [N][N], the pyramid mask exp(i m) with BOTH axes in the transform's digit-scrambled order: position
+ * p = j1 * N2 + j2 holds frequency j1 + N1 * j2 (N = N1 * N2 = 16 * 18 or 16 * 8).  Hand-written FFT kernels (no
+ * library); aoenv_pyramid_supported(N) tells whether N is a compiled size.
+ * Workspaces (caller-owned): work_x1 complex64 [B][nTheta][N][R], work_yt complex64 [B][nTheta][N][N],
+ * intensity float32 [B][N][N] (the un-binned sum, also an output).
+ * ------------------------------------------------------------------------------------------------------- */
+int aoenv_pyramid_supported(int N);
+int aoenv_pyramid_frames(const float* opd_a, const float* opd_b, const float* pupil, const float* amp, const float* lin,
+                         const float* mod, const float* mask_s, int B, int R, int N, int nTheta, int bin, float phase_scale,
+                         float* work_x1, float* work_yt, float* intensity, float* frame, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Command update and observation — MAIN/OOPAOEnv/OOPAOEnvRazor.py:479,492-500,514,621-641
  * ------------------------------------------------------------------------------------------------------- */
 

@@ -15,6 +15,7 @@ import math
 import numpy as np
 import torch
 
+from . import _lib
 from .Detector import Detector
 
 
@@ -63,6 +64,9 @@ class Pyramid:
         self.delta_Tip = self.delta_Tilt = 0
         self.fov = 206265 * self.nRes / self.zeroPaddingFactor * (tel.src.wavelength / tel.D)
         self.max_points_per_pass = int(max_points_per_pass)
+        # step path: the library's own FFT kernels when the transform size is a compiled one (N = 128, 288: the 12 x 12 test
+        # system and the 20 x 20 papyrus system); other sizes, and the float64 calibration frames, go through torch.fft
+        self.use_kernels = True
         dev = self.device
         lin = np.linspace(-np.pi, np.pi, R)
         tip, tilt = np.meshgrid(lin, lin)                                                             # :285-288
@@ -158,6 +162,56 @@ class Pyramid:
             out += (torch.fft.ifft2(ft * mask).abs() ** 2).sum(dim=1)
         n, b = self.cam.resolution, int(round(N / self.cam.resolution))
         return out.reshape(F, n, b, n, b).sum(dim=(2, 4))
+
+    def _kernel_tables(self):
+        """Operands of aoenv_pyramid_frames for the current modulation: mask in the transform's digit-scrambled order
+        (position j1 N2 + j2 holds frequency j1 + 16 j2, N = 16 N2), tilt ramp, modulation path, amplitude."""
+        key = (self.nTheta, float(self._modulation), getattr(self.telescope.src, "_flux_version", 0))
+        if getattr(self, "_ktab_key", None) != key:
+            tel, N, dev = self.telescope, self.nRes, self.device
+            N1, N2 = 16, N // 16
+            pos = np.arange(N)
+            perm = torch.as_tensor((pos // N2) + N1 * (pos % N2), device=dev)
+            mask_s = self._mask.to(torch.complex64)[perm][:, perm].contiguous()
+            path = np.asarray(self.modulation_path, dtype=np.float32) if self._modulation != 0 else np.zeros((1, 2), dtype=np.float32)
+            amp = np.sqrt(tel.src.fluxMap / self.nTheta) * tel.pupilReflectivity
+            self._ktab = dict(
+                mask_s=torch.view_as_real(mask_s).contiguous(),
+                lin=torch.as_tensor(np.linspace(-np.pi, np.pi, tel.resolution), dtype=torch.float32, device=dev),
+                mod=torch.as_tensor(path, dtype=torch.float32, device=dev).contiguous(),
+                amp=torch.as_tensor(amp, dtype=torch.float32, device=dev).contiguous())
+            self._ktab_key = key
+        return self._ktab
+
+    def _frames_kernels(self, opd_a, opd_b):
+        """Detector frames [F, n_cam, n_cam] of OPD_no_pupil = opd_a (+ opd_b) through the library's own transform kernels
+        (aoenv_pyramid_frames: hand-written N = 16 x N2 FFTs, no cuFFT), environments in chunks that bound the workspaces."""
+        tel, lib = self.telescope, _lib.load()
+        R, N, F, dev = tel.resolution, self.nRes, opd_a.shape[0], self.device
+        n_cam = self.cam.resolution
+        tab = self._kernel_tables()
+        per_env = self.nTheta * N * (N + R) * 8 + N * N * 4
+        chunk = max(1, min(F, (2 << 30) // per_env))
+        ws = getattr(self, "_kernel_ws", None)
+        if ws is None or ws[0] != (chunk, self.nTheta):
+            ws = ((chunk, self.nTheta), torch.empty((chunk, self.nTheta, N, R, 2), dtype=torch.float32, device=dev),
+                  torch.empty((chunk, self.nTheta, N, N, 2), dtype=torch.float32, device=dev),
+                  torch.empty((chunk, N, N), dtype=torch.float32, device=dev))
+            self._kernel_ws = ws
+        out = torch.empty((F, n_cam, n_cam), dtype=torch.float32, device=dev)
+        for s0 in range(0, F, chunk):
+            m = min(chunk, F - s0)
+            a = opd_a[s0:s0 + m].contiguous()
+            b = None if opd_b is None else opd_b[s0:s0 + m].contiguous()
+            _lib.check(lib.aoenv_pyramid_frames(
+                _lib.ptr(a), _lib.ptr(b), _lib.ptr(tel._pupil_f), _lib.ptr(tab["amp"]), _lib.ptr(tab["lin"]), _lib.ptr(tab["mod"]),
+                _lib.ptr(tab["mask_s"]), m, R, N, self.nTheta, N // n_cam, 2 * math.pi / tel.src.wavelength, _lib.ptr(ws[1]),
+                _lib.ptr(ws[2]), _lib.ptr(ws[3]), _lib.ptr(out[s0:s0 + m]), _lib.stream_ptr(dev)), "pyramid_frames")
+        return out
+
+    def _kernels_ok(self):
+        N, n_cam = self.nRes, self.cam.resolution
+        return self.use_kernels and N % n_cam == 0 and bool(_lib.load().aoenv_pyramid_supported(N))
 
     def _camera(self, frames, env_offset=0):
         """self*self.cam (:987-1002): detector chain on the binned frames."""
@@ -258,7 +312,10 @@ class Pyramid:
             opd_b = opd_b.tensor()                                  # DMSurfaceRef: the surface kernel runs now
         opd = opd_a if opd_b is None else opd_a + opd_b
         pupil = tel._pupil_f
-        frames = self._frames(opd * pupil * (2 * math.pi / lam))
+        if self._kernels_ok() and opd_a.dtype == torch.float32:
+            frames = self._frames_kernels(opd_a, opd_b)
+        else:                                                           # transform sizes without a compiled kernel
+            frames = self._frames(opd * pupil * (2 * math.pi / lam))
         self._camera(frames, env_offset)
         frame = self.cam.frame if self.cam.frame.ndim == 3 else self.cam.frame.unsqueeze(0)
         self._frame = frame

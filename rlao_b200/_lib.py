@@ -64,6 +64,8 @@ PROTOTYPES = {
     "aoenv_shwfs_measure_f64": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _d, _d, _i, _i, _i, _d, _i, _vp, _vp, _vp, _i, _vp],
     "aoenv_normal_fill": [_u64, _u64, _i, _i, _i, _f, _vp, _vp, _i, _vp],
     "aoenv_vec_to_img": [_vp, _i, _vp, _i, _i, _i, _f, _vp, _vp],
+    "aoenv_pyramid_supported": [_i],
+    "aoenv_pyramid_frames": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp],
     "aoenv_command_update": [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _i, _vp],
     "aoenv_observe": [_vp, _i, _vp, _i, _i, _i, _vp, _d, _f, _vp, _vp, _vp, _vp, _vp, _vp],
     "aoenv_psf_image": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -535,6 +535,43 @@ class FakeLib:
             _arr(strehl, (B,))[:] = np.exp(-vt * float(_val(phase_scale)) ** 2)
         return 0
 
+    def aoenv_pyramid_supported(self, N):
+        return int(N in (128, 288))
+
+    def aoenv_pyramid_frames(self, opd_a, opd_b, pupil, amp, lin, mod, mask_s, B, R, N, nTheta, bin_, phase_scale, wx1, wyt,
+                             intensity, frame, stream):
+        """numpy FFTs of the same chain (OOPAO/Pyramid.py:469-504,581-603,987-1002); the mask arrives in the kernels'
+        digit-scrambled order and is put back in natural order here."""
+        self.launches += 4
+        a, b_ = _arr(opd_a, (B, R, R)), _arr(opd_b, (B, R, R))
+        pu, am = _arr(pupil, (R, R)).astype(np.float64), _arr(amp, (R, R)).astype(np.float64)
+        ln = _arr(lin, (R,)).astype(np.float64)
+        md = _arr(mod, (nTheta, 2)).astype(np.float64)
+        ms = _arr(mask_s, (N, N, 2)).astype(np.float64)
+        ms = ms[..., 0] + 1j * ms[..., 1]
+        N1, N2 = 16, N // 16
+        pos = np.arange(N)
+        freq = (pos // N2) + N1 * (pos % N2)                         # frequency held by each scrambled position
+        mask = np.zeros((N, N), dtype=complex)
+        mask[np.ix_(freq, freq)] = ms
+        k = np.arange(N)
+        ph1 = np.exp(-1j * np.pi * (N + 1) / N * k)
+        phasor = ph1[:, None] * ph1[None, :]
+        lo = (N - R) // 2
+        out, inten = _arr(frame, (B, N // bin_, N // bin_)), _arr(intensity, (B, N, N))
+        for e in range(B):
+            t = a[e].astype(np.float64) + (b_[e] if b_ is not None else 0)
+            acc = np.zeros((N, N))
+            for th in range(nTheta):
+                pm = (md[th, 0] * ln[None, :] + md[th, 1] * ln[:, None]) * pu
+                sup = np.zeros((N, N), dtype=complex)
+                sup[lo:lo + R, lo:lo + R] = am * np.exp(1j * (t * pu * float(_val(phase_scale)) + pm))
+                acc += np.abs(np.fft.ifft2(np.fft.fft2(sup * phasor) * mask)) ** 2
+            inten[e] = acc.astype(np.float32)
+            nc = N // bin_
+            out[e] = acc.reshape(nc, bin_, nc, bin_).sum(axis=(1, 3)).astype(np.float32)
+        return 0
+
     def aoenv_psf_peak(self, *a):
         raise NotImplementedError("fake backend: psf_peak")
 
