@@ -336,7 +336,7 @@ def run_gpu_arm(args):
     env.set_params(make_args(nS, nL, opts), args.wfs, gainCL=0.5, n_envs=B, device=dev, rng="philox", seed=1,
                    env_offset=rank * B)
     if args.wfs == "pyramid":
-        desc = desc.replace("SH-WFS", "Pyramid WFS (modulation 3 lambda/D, cuFFT transforms)")
+        desc = desc.replace("SH-WFS", "Pyramid WFS (modulation 3 lambda/D, 20 modulation points, the library's own FFT kernels)")
     env.atm.generateNewPhaseScreen(17)
     env.dm.coefs = 0
     env.tel * env.dm * env.wfs
@@ -695,7 +695,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="environments per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--wfs", default="shackhartmann", choices=["shackhartmann", "pyramid"],
-                    help="pyramid: the papyrus-style environment (cuFFT transforms; SURVEY.md section 8 f-3, first step)")
+                    help="pyramid: the papyrus-style environment (SURVEY.md section 8 f-3)")
     ap.add_argument("--policy", default="integrator", choices=["integrator", "po4ao"],
                     help="po4ao: ConvPolicy (n_history 20) rollouts through rlao_b200.PO4AO.mbrl.run with a GPU replay")
     args = ap.parse_args()

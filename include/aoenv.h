@@ -49,7 +49,7 @@ uint64_t aoenv_launch_count(void);
  * (seed, stream_id, b).  zx rows have `ldz` floats (ldz >= nI+nO; the tail is zero-filled).  `win` is the window
  * BEFORE the shift.  inner_rc [nI][2] holds (row, col) of the inner-ring pixels in window coordinates, in the
  * reference's boolean-mask (row-major) order.  zx_planes (nullable): [parts][B][ldz] bf16, the same vector in the
- * split-bf16 operand format of aoenv_gemm_tn_tc, written in the same pass. */
+ * split-bf16 operand format of aoenv_gemm_tn_tc, written in the same pass; zx may then be NULL (no float32 copy). */
 int aoenv_atm_gather(const float* win, int B, int M, int pitch, int64_t env_stride, int sx, int sy,
                      const int32_t* inner_rc, int nI, int nO, const float* xi,
                      uint64_t seed, uint64_t stream_id, float* zx, int ldz, void* zx_planes, int parts, void* stream);

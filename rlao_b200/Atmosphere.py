@@ -250,15 +250,16 @@ class Atmosphere:
             ids.append(((ly.events << 8) | i) + (self.env_offset << 40))
             ly.events += 1
         planes = _lib.ptr(self._zx_planes) if tc else None
+        zx = None if tc else _lib.ptr(self._zx)        # the tensor-core GEMM reads the bf16 planes only: no float32 copy
         if G == 1:
             _lib.check(lib.aoenv_atm_gather(wins[0], B, M, pitch, self._env_stride, sxs[0], sys_[0], _lib.ptr(self._inner_rc),
                                             self._nI, self._nO, _lib.ptr(xi), C.c_uint64(seeds[0]), C.c_uint64(ids[0]),
-                                            _lib.ptr(self._zx), self._K, planes, self._W_op.parts, st), "atm_gather")
+                                            zx, self._K, planes, self._W_op.parts, st), "atm_gather")
         else:
             _lib.check(lib.aoenv_atm_gather_multi((C.c_void_p * G)(*[w.value if hasattr(w, "value") else w for w in wins]),
                                                   (C.c_int32 * G)(*sxs), (C.c_int32 * G)(*sys_), (C.c_uint64 * G)(*seeds),
                                                   (C.c_uint64 * G)(*ids), G, B, M, pitch, self._env_stride,
-                                                  _lib.ptr(self._inner_rc), self._nI, self._nO, None, _lib.ptr(self._zx), self._K,
+                                                  _lib.ptr(self._inner_rc), self._nI, self._nO, None, zx, self._K,
                                                   planes, self._W_op.parts, st), "atm_gather_multi")
         gemm.gemm_tn(self._zx, self._W_op, self._X, G * B, self._nO, x_planes=self._zx_planes if tc else None)
         wins, offs, exts = [], [], []

@@ -49,7 +49,7 @@ atm_gather_kernel(const __grid_constant__ AtmGroup grp, int M, int pitch, size_t
       v = box_muller(r.x, r.y).x;
     }
   }
-  zx[row * ldz + k] = v;
+  if (zx != nullptr) zx[row * ldz + k] = v;        // float32 copy only for the SIMT GEMM back end / inspection
   if (planes != nullptr) store_bf16_planes(planes, (size_t)gridDim.z * gridDim.y * ldz, row * ldz + k, parts, v);
 }
 
@@ -348,6 +348,7 @@ int aoenv_atm_gather_multi(const void* const* wins, const int32_t* sx, const int
   AOENV_CHECK_ARG(B > 0 && B <= 65535 && M > 6 && pitch >= M && env_stride >= (int64_t)M * pitch, "atm_gather: bad shape B=%d M=%d pitch=%d", B, M, pitch);
   AOENV_CHECK_ARG(ldz >= nI + nO, "atm_gather: ldz=%d < nI+nO=%d", ldz, nI + nO);
   AOENV_CHECK_ARG(zx_planes == nullptr || parts == 2 || parts == 3, "atm_gather: parts must be 2 or 3");
+  AOENV_CHECK_ARG(zx != nullptr || zx_planes != nullptr, "atm_gather: neither zx nor zx_planes given");
   AtmGroup grp{};
   for (int g = 0; g < G; ++g) {
     AOENV_CHECK_ARG(sx[g] >= -1 && sx[g] <= 1 && sy[g] >= -1 && sy[g] <= 1, "atm_gather: shift must be in {-1,0,1}");

@@ -8,11 +8,48 @@
 namespace aoenv {
 namespace fftc {
 
-struct cpx { float x, y; };
+struct __align__(8) cpx { float x, y; };
 __host__ __device__ __forceinline__ cpx mk(float a, float b) { cpx c; c.x = a; c.y = b; return c; }
+// On the device a complex number lives in one 64-bit register pair and additions / subtractions / real scalings are single
+// packed FP32 instructions (Blackwell add.f32x2 / fma.rn.f32x2: two IEEE operations per issue slot).
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ unsigned long long as_u64(cpx a) { return *reinterpret_cast<unsigned long long*>(&a); }
+__device__ __forceinline__ cpx as_cpx(unsigned long long v) { return *reinterpret_cast<cpx*>(&v); }
+__device__ __forceinline__ cpx operator+(cpx a, cpx b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(as_u64(a)), "l"(as_u64(b)));
+  return as_cpx(d);
+}
+__device__ __forceinline__ cpx operator-(cpx a, cpx b) {
+  unsigned long long d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(as_u64(a)), "l"(as_u64(b)));
+  return as_cpx(d);
+}
+// a + s * b, s real
+__device__ __forceinline__ cpx axpy(float s, cpx b, cpx a) {
+  unsigned long long d;
+  const cpx ss = mk(s, s);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(as_u64(ss)), "l"(as_u64(b)), "l"(as_u64(a)));
+  return as_cpx(d);
+}
+// a + (sx * b.x, sy * b.y)
+__device__ __forceinline__ cpx axpy2(float sx, float sy, cpx b, cpx a) {
+  unsigned long long d;
+  const cpx ss = mk(sx, sy);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(as_u64(ss)), "l"(as_u64(b)), "l"(as_u64(a)));
+  return as_cpx(d);
+}
+#else
 __host__ __device__ __forceinline__ cpx operator+(cpx a, cpx b) { return mk(a.x + b.x, a.y + b.y); }
 __host__ __device__ __forceinline__ cpx operator-(cpx a, cpx b) { return mk(a.x - b.x, a.y - b.y); }
-__host__ __device__ __forceinline__ cpx cmul(cpx a, float wr, float wi) { return mk(a.x * wr - a.y * wi, a.x * wi + a.y * wr); }
+__host__ __device__ __forceinline__ cpx axpy(float s, cpx b, cpx a) { return mk(a.x + s * b.x, a.y + s * b.y); }
+__host__ __device__ __forceinline__ cpx axpy2(float sx, float sy, cpx b, cpx a) { return mk(a.x + sx * b.x, a.y + sy * b.y); }
+#endif
+__host__ __device__ __forceinline__ cpx swap(cpx a) { return mk(a.y, a.x); }
+// a * (wr + i wi) = wr * a + wi * (-a.y, a.x)
+__host__ __device__ __forceinline__ cpx cmul(cpx a, float wr, float wi) {
+  return axpy2(-wi, wi, swap(a), axpy(wr, a, mk(0.f, 0.f)));
+}
 __host__ __device__ __forceinline__ cpx mul_neg_i(cpx a) { return mk(a.y, -a.x); }     // a * (-i)
 __host__ __device__ __forceinline__ cpx conj(cpx a) { return mk(a.x, -a.y); }
 
@@ -25,11 +62,11 @@ __host__ __device__ __forceinline__ void dft2(cpx& a, cpx& b) {
 // 3-point: y0 = a + b + c; y1,2 = a - (b + c)/2 -+ i (sqrt3/2) (b - c)
 __host__ __device__ __forceinline__ void dft3(cpx& a, cpx& b, cpx& c) {
   constexpr float s = 0.8660254037844386f;
-  const cpx t = b + c, d = b - c;
-  const cpx m = mk(a.x - 0.5f * t.x, a.y - 0.5f * t.y);
+  const cpx t = b + c, d = swap(b - c);
+  const cpx m = axpy(-0.5f, t, a);
   a = a + t;
-  b = mk(m.x + s * d.y, m.y - s * d.x);         // m - i s d
-  c = mk(m.x - s * d.y, m.y + s * d.x);         // m + i s d
+  b = axpy2(s, -s, d, m);                       // m - i s (b - c)
+  c = axpy2(-s, s, d, m);                       // m + i s (b - c)
 }
 
 __host__ __device__ __forceinline__ void dft4(cpx (&x)[4]) {

@@ -101,7 +101,7 @@ struct ColsArgs {
 };
 
 template <int N1, int N2>
-__global__ void __launch_bounds__(Tile<N1, N2>::kThreads, 1)
+__global__ void __launch_bounds__(Tile<N1, N2>::kThreads, 2)
 pyr_cols_kernel(const __grid_constant__ ColsArgs p) {
   using T = Tile<N1, N2>;
   constexpr int N = T::N;
@@ -153,7 +153,7 @@ pyr_cols_kernel(const __grid_constant__ ColsArgs p) {
 
 // ---- K2 ---------------------------------------------------------------------------------------------------
 template <int N1, int N2>
-__global__ void __launch_bounds__(Tile<N1, N2>::kThreads, 1)
+__global__ void __launch_bounds__(Tile<N1, N2>::kThreads, 2)
 pyr_rows_kernel(const float2* __restrict__ X1, const float2* __restrict__ mask_s, int R, int lo, int nTheta,
                 float2* __restrict__ Yt) {
   using T = Tile<N1, N2>;
@@ -166,9 +166,19 @@ pyr_rows_kernel(const float2* __restrict__ X1, const float2* __restrict__ mask_s
   for (int r = warp; r < 32; r += T::kWarps) {
     float2* __restrict__ dst = tile + (size_t)r * T::LD;
     const float2* __restrict__ src = X1 + (img * N + u0 + r) * R;
-    for (int i = lane; i < N; i += 32) {
-      const int xx = i - lo;
-      dst[i] = (xx >= 0 && xx < R) ? __ldg(src + xx) : make_float2(0.f, 0.f);
+    if (((lo | R) & 1) == 0) {                      // two complex numbers per 128-bit load (lo, R even; rows 16-byte aligned)
+      for (int i = 2 * lane; i < N; i += 64) {
+        const int xx = i - lo;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (xx >= 0 && xx < R) v = __ldg(reinterpret_cast<const float4*>(src + xx));
+        dst[i] = make_float2(v.x, v.y);
+        dst[i + 1] = make_float2(v.z, v.w);
+      }
+    } else {
+      for (int i = lane; i < N; i += 32) {
+        const int xx = i - lo;
+        dst[i] = (xx >= 0 && xx < R) ? __ldg(src + xx) : make_float2(0.f, 0.f);
+      }
     }
   }
   __syncthreads();
@@ -202,7 +212,7 @@ pyr_rows_kernel(const float2* __restrict__ X1, const float2* __restrict__ mask_s
 
 // ---- K3 ---------------------------------------------------------------------------------------------------
 template <int N1, int N2>
-__global__ void __launch_bounds__(Tile<N1, N2>::kThreads, 1)
+__global__ void __launch_bounds__(Tile<N1, N2>::kThreads, 2)
 pyr_image_kernel(const float2* __restrict__ Yt, int nTheta, float scale, float* __restrict__ intensity) {
   using T = Tile<N1, N2>;
   constexpr int N = T::N;
@@ -218,7 +228,11 @@ pyr_image_kernel(const float2* __restrict__ Yt, int nTheta, float scale, float* 
     for (int r = warp; r < 32; r += T::kWarps) {
       float2* __restrict__ dst = tile + (size_t)r * T::LD;
       const float2* __restrict__ src = Yt + (img * N + q0 + r) * N;
-      for (int i = lane; i < N; i += 32) dst[i] = __ldg(src + i);
+      for (int i = 2 * lane; i < N; i += 64) {        // N is even and the rows are 16-byte aligned
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
+        dst[i] = make_float2(v.x, v.y);
+        dst[i + 1] = make_float2(v.z, v.w);
+      }
     }
     __syncthreads();
     if (warp < N1) T::inv2(row, warp);
