@@ -214,6 +214,19 @@ class Atmosphere:
                    "atm_compact")
         self._cur[i], self._org[i] = 1 - cur, [foy, fox]
 
+    def _rescan_extrema(self, i):
+        """Exact window extrema of layer i from the maps (after the maps were written from outside: checkpoint restore).
+        The ring kernel with force_rescan recomputes them; writing the ring back in place does not change the map."""
+        B, M, pitch = self.n_envs, self._M, self._pitch
+        oy, ox = self._org[i]
+        win = self._maps[i, self._cur[i], :, oy:oy + M, ox:ox + M]
+        ring = torch.cat([win[:, 0, :], torch.stack([win[:, 1:M - 1, 0], win[:, 1:M - 1, M - 1]], dim=2).reshape(B, -1),
+                          win[:, M - 1, :]], dim=1)                       # numpy boolean-mask order of the outer ring
+        self._X[:B, :self._nO] = ring
+        _lib.check(_lib.load().aoenv_atm_ring(self._win_ptr(i), B, M, pitch, self._env_stride, oy * pitch + ox, self._nO,
+                                              _lib.ptr(self._X), self._ldx, self._ext[i].data_ptr(), _lib.ptr(self._flag), 1,
+                                              _lib.stream_ptr(self.device)), "atm_ring")
+
     def _extrude(self, i, sx, sy, force_rescan=False):
         """add_row (Atmosphere.py:301-311) for layer i and every environment."""
         self._extrude_group([(i, sx, sy)], force_rescan)

@@ -9,9 +9,11 @@
 step plus one GEMM-triple per integer-pixel wind shift.  Arrays carry a leading n_envs
 dimension (squeezed when n_envs == 1); rewards / Strehl ratios are tensors of shape [n_envs].
 """
+import contextlib
 import ctypes
 import importlib
 import math
+import os
 import types
 
 import numpy as np
@@ -28,6 +30,22 @@ from ..Zernike import Zernike
 from ..calibration.CalibrationVault import CalibrationVault
 from ..calibration.InteractionMatrix import InteractionMatrix
 from ..tools import linalg
+
+
+_NVTX = os.environ.get("AOENV_NVTX", "0") not in ("", "0")
+
+
+@contextlib.contextmanager
+def _range(name):
+    """NVTX range around a stage of the step when AOENV_NVTX=1 (timeline profilers); free otherwise."""
+    if _NVTX:
+        torch.cuda.nvtx.range_push(name)
+        try:
+            yield
+        finally:
+            torch.cuda.nvtx.range_pop()
+    else:
+        yield
 
 
 class OOPAO:
@@ -262,11 +280,14 @@ class OOPAO:
         commanded at the previous step), reconstruction, reward, Strehl.  `atmosphere_done`: atm.update() for this
         frame has already been issued (it depends on nothing the step computes)."""
         if not atmosphere_done:
-            self.atm.update()                                              # :482 -> tel.OPD = atm.OPD (lazy)
+            with _range("aoenv.atmosphere"):
+                self.atm.update()                                          # :482 -> tel.OPD = atm.OPD (lazy)
         dm_surface = self.dm.surface_ref()                                 # surface commanded at the previous step
         self.tel._set_lazy(self.atm._opd, dm_surface)                      # :488 tel*dm
-        self.wfs._measure_terms(self.atm._opd, dm_surface, self.env_offset)  # :488 *wfs  (+ stats for :484,502,506)
-        self._observe(True)                                                # :496-506
+        with _range("aoenv.wfs"):
+            self.wfs._measure_terms(self.atm._opd, dm_surface, self.env_offset)  # :488 *wfs  (+ stats for :484,502,506)
+        with _range("aoenv.reconstruct"):
+            self._observe(True)                                            # :496-506
         if self.total is not None and i is not None and 0 <= i < self._nLoop:
             self.total[i] = self._total_now
             self.residual[i] = self._residual_now
@@ -287,10 +308,58 @@ class OOPAO:
         action = self._action_tensor(action)                               # :479 (img_to_vec * 1e-6 is in the kernel)
         coefs = self._coefs_buf[self._coefs_slot]                         # zero-padded tails, never written
         self._coefs_slot ^= 1
-        _lib.check(lib.aoenv_command_update(_lib.ptr(action), _lib.ptr(self._act_idx), B, self.dm.nValidAct,
-                                            self.nActuator ** 2, ctypes.c_float(self.leak), _lib.ptr(coefs), _lib.ptr(self._dm_prev),
-                                            coefs.stride(0), st), "command_update")          # :492-493
-        self.dm._set_coefs_batch(coefs)                                    # coefs setter side effect: next surface
+        with _range("aoenv.command"):
+            _lib.check(lib.aoenv_command_update(_lib.ptr(action), _lib.ptr(self._act_idx), B, self.dm.nValidAct,
+                                                self.nActuator ** 2, ctypes.c_float(self.leak), _lib.ptr(coefs), _lib.ptr(self._dm_prev),
+                                                coefs.stride(0), st), "command_update")      # :492-493
+            self.dm._set_coefs_batch(coefs)                                # coefs setter side effect: next surface
+
+    # ---- checkpoint / resume (the reference has none: SURVEY.md section 5) -------------------------------------------
+    def state_dict(self):
+        """Everything that evolves during an episode, as CPU tensors / plain numbers: layer windows with their shift
+        bookkeeping and generator counters, DM commands, camera and exploration-noise counters, the per-step records.
+        With the counter-based generators a restored environment continues bit for bit."""
+        atm = self.atm
+        layers = []
+        for i, ly in enumerate(atm._layers):
+            layers.append(dict(map=ly.mapShift.detach().cpu().clone(), buff=ly.buff.copy(), ratio=ly.ratio.copy(),
+                               notDoneOnce=ly.notDoneOnce, events=ly.events, philox_seed=getattr(ly, "philox_seed", 0),
+                               ext=None))
+        return dict(version=1, n_envs=self.n_envs, rng=atm.rng, layers=layers, atm_opd=atm._opd.detach().cpu().clone(),
+                    coefs=self.dm._coefs.detach().cpu().clone(), dm_prev=self._dm_prev.detach().cpu().clone(),
+                    cam_frame_counter=self.wfs.cam.frame_counter, noise_calls=self._noise_calls,
+                    SR=[s.detach().cpu().clone() for s in self.SR],
+                    total=None if self.total is None else self.total.detach().cpu().clone(),
+                    residual=None if self.residual is None else self.residual.detach().cpu().clone())
+
+    def load_state_dict(self, st):
+        """Restores a `state_dict()` of an environment built with the same configuration."""
+        if st.get("version") != 1 or st["n_envs"] != self.n_envs or st["rng"] != self.atm.rng:
+            raise ValueError("state_dict of another environment (n_envs / rng / version differ)")
+        if self.atm.rng != "philox":
+            raise NotImplementedError("host MT19937 streams (rng='reference') are not checkpointed; use rng='philox'")
+        atm, dev = self.atm, self.device
+        for i, (ly, s_) in enumerate(zip(atm._layers, st["layers"])):
+            atm._cur[i] = 0
+            atm._org[i] = atm._fresh_origin(i)
+            oy, ox = atm._org[i]
+            m = s_["map"].to(dev)
+            atm._maps[i, 0, :, oy:oy + atm._M, ox:ox + atm._M] = m if m.ndim == 3 else m.unsqueeze(0)
+            ly.buff, ly.ratio, ly.notDoneOnce = s_["buff"].copy(), s_["ratio"].copy(), s_["notDoneOnce"]
+            ly.events, ly.philox_seed = s_["events"], s_["philox_seed"]
+            atm._rescan_extrema(i)
+        atm._opd.copy_(st["atm_opd"].to(dev))
+        coefs = st["coefs"].to(dev)
+        self._dm_prev.copy_(st["dm_prev"].to(dev))
+        self._coefs_buf[self._coefs_slot].copy_(coefs)
+        self.dm._set_coefs_batch(self._coefs_buf[self._coefs_slot])
+        self._coefs_slot ^= 1
+        self.wfs.cam.frame_counter, self._noise_calls = st["cam_frame_counter"], st["noise_calls"]
+        self.SR = [s.to(dev) for s in st["SR"]]
+        if st["total"] is not None and self.total is not None:
+            self.total.copy_(st["total"].to(dev))
+            self.residual.copy_(st["residual"].to(dev))
+        self.tel._set_lazy(atm._opd, self.dm.surface_ref())
 
     def step_wfs(self, i, action):
         """OOPAOEnvRazor.py:553-586 (the definition that is in effect: the second `def step_wfs`): the observation is the

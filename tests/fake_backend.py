@@ -135,7 +135,9 @@ class FakeLib:
         z[:] = 0
         z[:, :nI] = m[:, rc[:, 0], rc[:, 1]]
         x = _arr(xi, (B, nO))
-        z[:, nI:nI + nO] = x if x is not None else self.rs.normal(size=(B, nO))
+        if x is None:       # counter-based like the kernel: the draw depends on (seed, stream id) only
+            x = np.random.RandomState((int(_val(seed)) * 1000003 + int(_val(stream_id))) % (2 ** 32)).normal(size=(B, nO))
+        z[:, nI:nI + nO] = x
         return 0
 
     def aoenv_atm_ring(self, win, B, M, pitch, env_stride, win_offset, nO, X, ldx, ext, flag, force_rescan, stream):

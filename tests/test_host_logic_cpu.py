@@ -264,6 +264,28 @@ def test_torch_wrapper_keeps_the_camera_frame_of_the_papyrus_env(fake, monkeypat
     assert len(w.step(0, razor.gainCL * w.reset_soft())) == 5
 
 
+def test_checkpoint_resume_continues_bit_for_bit(fake):
+    """state_dict / load_state_dict (checkpoint / resume; SURVEY.md section 5 lists it as ours to add): a second environment
+    restored from the snapshot of the first continues with identical observations, Strehl ratios and layer maps."""
+    cfg = CONFIGS["tiny"]()
+    a = build_env(cfg, n_envs=2, rng="philox", seed=3)
+    obs = new_episode(a, 7)
+    for i in range(6):
+        obs, *_ = a.step(i, cfg.gainCL * obs)
+    snap = a.state_dict()
+    b = build_env(cfg, n_envs=2, rng="philox", seed=3)
+    b.load_state_dict(snap)
+    obs_b = obs.clone()
+    for i in range(6, 12):
+        obs, r, s, *_ = a.step(i, cfg.gainCL * obs)
+        obs_b, r_b, s_b, *_ = b.step(i, cfg.gainCL * obs_b)
+        assert torch.equal(obs, obs_b) and torch.equal(s, s_b), i
+    for la, lb in zip(a.atm._layers, b.atm._layers):
+        assert torch.equal(la.mapShift, lb.mapShift) and np.array_equal(la.buff, lb.buff) and la.events == lb.events
+    with pytest.raises(ValueError):
+        build_env(cfg, n_envs=1, rng="philox", seed=3).load_state_dict(snap)
+
+
 def test_papyrus_science_path_on_cpu(fake):
     """MAIN_CODE/OOPAOEnv/OOPAOEnv.py:118-196,300-339,473-482: guide star + off-axis science target, science cameras on the
     PSF (`atm*src*tel*cam`), long-exposure PSF of render4plot; Detector exposure buffer (OOPAO/Detector.py:232-301)."""
