@@ -391,7 +391,7 @@ int aoenv_atm_ring_multi(void* const* wins, const int64_t* win_offsets, void* co
   cudaStream_t s = (cudaStream_t)stream;
   atm_ring_kernel<<<dim3(B, G), 256, 0, s>>>(grp, M, pitch, (size_t)env_stride, X, ldx, flag, force_rescan);
   AOENV_LAUNCH_CHECK("atm_ring");
-  const int rpb = 32;                          // >= 8 CTAs per flagged environment; unflagged ones exit at once
+  const int rpb = 32;                          // >= 8 CTAs per flagged environment; unflagged ones exit at once (8 rows per CTA measured slower: 169 vs 138 us)
   dim3 grid((M - 2 + rpb - 1) / rpb, B, G);
   atm_rescan_kernel<<<grid, 256, 0, s>>>(grp, M, pitch, (size_t)env_stride, flag, rpb);
   AOENV_LAUNCH_CHECK("atm_rescan");
