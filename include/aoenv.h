@@ -31,6 +31,10 @@ int aoenv_abi_version(void);
 const char* aoenv_last_error(void);
 /* Number of kernels launched by this library in the calling process since load (bench.py's gpu_launches). */
 uint64_t aoenv_launch_count(void);
+/* Programmatic dependent launch between the kernels of the step (default on; AOENV_PDL=0 in the environment turns it off
+ * at load).  With it the next kernel of the chain is scheduled while the last wave of the current one drains.  Results are
+ * bit-identical either way (the toggle exists for A/B timing and tests).  Returns the previous setting. */
+int aoenv_set_pdl(int enabled);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Atmosphere — OOPAO/Atmosphere.py

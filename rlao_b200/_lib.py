@@ -88,6 +88,7 @@ def load():
     lib.aoenv_abi_version.restype = C.c_int
     lib.aoenv_last_error.restype = C.c_char_p
     lib.aoenv_launch_count.restype = C.c_uint64
+    lib.aoenv_set_pdl.argtypes, lib.aoenv_set_pdl.restype = [C.c_int], C.c_int
     for name, args in PROTOTYPES.items():
         fn = getattr(lib, name)
         fn.argtypes = args

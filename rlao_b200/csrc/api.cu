@@ -1,5 +1,6 @@
 // Error plumbing, ABI version and launch accounting for libaoenv_b200.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -10,6 +11,10 @@ namespace aoenv {
 
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+int g_pdl = [] {
+  const char* v = getenv("AOENV_PDL");
+  return (v != nullptr && v[0] == '0') ? 0 : 1;
+}();
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -40,5 +45,10 @@ extern "C" {
 int aoenv_abi_version(void) { return AOENV_ABI_VERSION; }
 const char* aoenv_last_error(void) { return aoenv::g_err; }
 uint64_t aoenv_launch_count(void) { return aoenv::g_launches.load(); }
+int aoenv_set_pdl(int enabled) {
+  const int old = aoenv::g_pdl;
+  aoenv::g_pdl = enabled ? 1 : 0;
+  return old;
+}
 
 }  // extern "C"

@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(256)
 atm_gather_kernel(const __grid_constant__ AtmGroup grp, int M, int pitch, size_t env_stride,
                   const int2* __restrict__ inner_rc, int nI, int nO, const float* __restrict__ xi,
                   float* __restrict__ zx, int ldz, __nv_bfloat16* __restrict__ planes, int parts) {
+  pdl_enter();
   const int b = blockIdx.y, g = blockIdx.z;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= ldz) return;
@@ -96,6 +97,7 @@ __device__ __forceinline__ void block_reduce_ext(unsigned long long& lo, unsigne
 __global__ void __launch_bounds__(256)
 atm_ring_kernel(const __grid_constant__ AtmGroup grp, int M, int pitch, size_t env_stride,
                 const float* __restrict__ X, int ldx, int32_t* __restrict__ flag, int force_rescan) {
+  pdl_enter();
   const int b = blockIdx.x, g = blockIdx.y;
   const size_t row = (size_t)g * gridDim.x + b;
   const uint32_t win_offset = grp.win_offset[g];
@@ -136,6 +138,7 @@ atm_ring_kernel(const __grid_constant__ AtmGroup grp, int M, int pitch, size_t e
 __global__ void __launch_bounds__(256)
 atm_rescan_kernel(const __grid_constant__ AtmGroup grp, int M, int pitch, size_t env_stride,
                   const int32_t* __restrict__ flag, int rows_per_block) {
+  pdl_enter();
   const int b = blockIdx.y, g = blockIdx.z;
   if (__ldg(&flag[(size_t)g * gridDim.y + b]) == 0) return;
   const uint32_t win_offset = grp.win_offset[g];
@@ -172,6 +175,7 @@ atm_rescan_kernel(const __grid_constant__ AtmGroup grp, int M, int pitch, size_t
 __global__ void __launch_bounds__(256)
 atm_compact_kernel(const float* __restrict__ src, float* __restrict__ dst, int M, int pitch, size_t env_stride,
                    unsigned long long* __restrict__ ext, int pos_delta, int rows_per_block) {
+  pdl_enter();
   const int b = blockIdx.y;
   const float* __restrict__ s = src + (size_t)b * env_stride;
   float* __restrict__ d = dst + (size_t)b * env_stride;
@@ -257,6 +261,7 @@ __device__ __forceinline__ void phase_rows(const float* __restrict__ tbase, floa
 
 __global__ void __launch_bounds__(kPhThreadsX * kPhThreadsY)
 atm_phase_kernel(const __grid_constant__ AtmPhaseParams p, int R, float opd_scale, float* __restrict__ opd_out) {
+  pdl_enter();
   __shared__ __align__(128) float tile[2][kPhBufFloats];
   __shared__ __align__(8) uint64_t bar[2];
   const int b = blockIdx.z;
@@ -359,7 +364,7 @@ int aoenv_atm_gather_multi(const void* const* wins, const int32_t* sx, const int
     grp.stream_id[g] = stream_ids ? stream_ids[g] : 0;
   }
   dim3 grid((ldz + 255) / 256, B, G);
-  atm_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(grp, M, pitch, (size_t)env_stride, (const int2*)inner_rc, nI, nO,
+  AOENV_LAUNCH(atm_gather_kernel, grid, 256, 0, (cudaStream_t)stream, grp, M, pitch, (size_t)env_stride, (const int2*)inner_rc, nI, nO,
                                                             xi, zx, ldz, (__nv_bfloat16*)zx_planes, parts);
   AOENV_LAUNCH_CHECK("atm_gather");
   return 0;
@@ -389,11 +394,11 @@ int aoenv_atm_ring_multi(void* const* wins, const int64_t* win_offsets, void* co
     grp.win_offset[g] = (uint32_t)win_offsets[g];
   }
   cudaStream_t s = (cudaStream_t)stream;
-  atm_ring_kernel<<<dim3(B, G), 256, 0, s>>>(grp, M, pitch, (size_t)env_stride, X, ldx, flag, force_rescan);
+  AOENV_LAUNCH(atm_ring_kernel, dim3(B, G), 256, 0, s, grp, M, pitch, (size_t)env_stride, X, ldx, flag, force_rescan);
   AOENV_LAUNCH_CHECK("atm_ring");
   const int rpb = 32;                          // >= 8 CTAs per flagged environment; unflagged ones exit at once (8 rows per CTA measured slower: 169 vs 138 us)
   dim3 grid((M - 2 + rpb - 1) / rpb, B, G);
-  atm_rescan_kernel<<<grid, 256, 0, s>>>(grp, M, pitch, (size_t)env_stride, flag, rpb);
+  AOENV_LAUNCH(atm_rescan_kernel, grid, 256, 0, s, grp, M, pitch, (size_t)env_stride, flag, rpb);
   AOENV_LAUNCH_CHECK("atm_rescan");
   return 0;
 }
@@ -412,7 +417,7 @@ int aoenv_atm_compact(const float* src_win, float* dst_win, int B, int M, int pi
   AOENV_CHECK_ARG((reinterpret_cast<uintptr_t>(dst_win) & 15) == 0, "atm_compact: destination window must be 16-byte aligned");
   const int rpb = rows_per_block_for(B, M);
   dim3 grid((M + rpb - 1) / rpb, B);
-  atm_compact_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src_win, dst_win, M, pitch, (size_t)env_stride,
+  AOENV_LAUNCH(atm_compact_kernel, grid, 256, 0, (cudaStream_t)stream, src_win, dst_win, M, pitch, (size_t)env_stride,
                                                              reinterpret_cast<unsigned long long*>(ext), (int)pos_delta, rpb);
   AOENV_LAUNCH_CHECK("atm_compact");
   return 0;
@@ -456,7 +461,7 @@ int aoenv_atm_phase(const float* const* h_canvas, const uint64_t* const* h_ext, 
   }
   dim3 block(kPhThreadsX, kPhThreadsY);
   dim3 grid((R + kPhTileW - 1) / kPhTileW, (R + kPhTileH - 1) / kPhTileH, B);
-  atm_phase_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(p, R, opd_scale, opd_out);
+  AOENV_LAUNCH(atm_phase_kernel, grid, block, 0, (cudaStream_t)stream, p, R, opd_scale, opd_out);
   AOENV_LAUNCH_CHECK("atm_phase");
   return 0;
 }

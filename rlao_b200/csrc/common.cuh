@@ -29,6 +29,45 @@ int fail(int code, const char* fmt, ...);
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------
+// The step is a chain of ~13 dependent kernels on one stream; launched the ordinary way each of them starts only after
+// the previous grid has drained completely and its completion has travelled back to the front end.  With the
+// programmatic-stream-serialization attribute the next grid is scheduled as soon as every CTA of the current one has
+// been started (pdl_enter() issues griddepcontrol.launch_dependents first thing), takes the SM slots that free up while
+// the last wave drains, and parks at griddepcontrol.wait until the predecessor's memory is complete and visible.
+// EVERY thread calls pdl_enter() before anything else — in particular before any early return: a grid that could finish
+// without waiting would let ITS successor run ahead of the predecessor.
+extern int g_pdl;                       // 1 unless AOENV_PDL=0 (api.cu)
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+// setup that touches no global memory may run between the two halves (gemm_tc: barriers, TMEM allocation)
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+struct PdlLaunch {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  PdlLaunch(dim3 grid, dim3 block, size_t smem, cudaStream_t stream) {
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_pdl;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+};
+// AOENV_LAUNCH(kernel, grid, block, smem, stream, args...): kernels launched this way must start with pdl_enter().
+#define AOENV_LAUNCH(kernel, grid, block, smem, stream, ...)                  \
+  do {                                                                        \
+    ::aoenv::PdlLaunch l__(grid, block, smem, stream);                        \
+    cudaLaunchKernelEx(&l__.cfg, kernel, __VA_ARGS__);                        \
+  } while (0)
+
 // ---- monotone float <-> int encoding so atomicMax/atomicMin on int32 order floats ----------------------
 __device__ __forceinline__ int32_t float_to_ordered(float f) {
   int32_t i = __float_as_int(f);

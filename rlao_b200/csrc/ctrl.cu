@@ -7,6 +7,7 @@ namespace aoenv {
 __global__ void __launch_bounds__(256)
 command_update_kernel(const float* __restrict__ action, const int32_t* __restrict__ act_idx, int nA, int nAct2,
                       float leak, float* __restrict__ coefs, float* __restrict__ dm_prev, int ldc) {
+  pdl_enter();
   const int b = blockIdx.y;
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= nA) return;
@@ -22,6 +23,7 @@ observe_kernel(const float* __restrict__ rec, int ldr, const int32_t* __restrict
                const double* __restrict__ stats, double n_pupil, float phase_scale, float* __restrict__ obs,
                float* __restrict__ reward, float* __restrict__ strehl, float* __restrict__ total,
                float* __restrict__ residual) {
+  pdl_enter();
   const int b = blockIdx.x;
   float* __restrict__ o = obs + (size_t)b * nAct2;
   for (int i = threadIdx.x; i < nAct2; i += blockDim.x) o[i] = 0.f;
@@ -95,7 +97,7 @@ int aoenv_command_update(const float* action, const int32_t* act_idx, int B, int
                          float* coefs, float* dm_prev, int ldc, void* stream) {
   AOENV_CHECK_ARG(B > 0 && B <= 65535 && nA > 0 && ldc >= nA, "command_update: bad shape");
   dim3 grid((nA + 255) / 256, B);
-  command_update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(action, act_idx, nA, nAct2, leak, coefs, dm_prev, ldc);
+  AOENV_LAUNCH(command_update_kernel, grid, 256, 0, (cudaStream_t)stream, action, act_idx, nA, nAct2, leak, coefs, dm_prev, ldc);
   AOENV_LAUNCH_CHECK("command_update");
   return 0;
 }
@@ -122,7 +124,7 @@ int aoenv_observe(const float* rec, int ldr, const int32_t* act_idx, int B, int 
                   double n_pupil, float phase_scale, float* obs, float* reward, float* strehl, float* total,
                   float* residual, void* stream) {
   AOENV_CHECK_ARG(B > 0 && nA > 0 && ldr >= nA, "observe: bad shape");
-  observe_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(rec, ldr, act_idx, nA, nAct2, stats, n_pupil, phase_scale, obs,
+  AOENV_LAUNCH(observe_kernel, dim3(B), 256, 0, (cudaStream_t)stream, rec, ldr, act_idx, nA, nAct2, stats, n_pupil, phase_scale, obs,
                                                       reward, strehl, total, residual);
   AOENV_LAUNCH_CHECK("observe");
   return 0;

@@ -69,6 +69,7 @@ dm_separable_banded_kernel(const float* __restrict__ coefs, int ldc, const int32
                            const float* __restrict__ wx, const int32_t* __restrict__ j0x, const float* __restrict__ wyp,
                            const int32_t* __restrict__ i0y, int R, int xw, float* __restrict__ opd) {
   const int x0 = blockIdx.x * xw;                 // column slab of this CTA
+  pdl_enter();
   extern __shared__ __align__(16) float sm[];
   float* sC = sm;
   float* sT = sm + ((nAct * nAct + 3) & ~3);
@@ -184,9 +185,9 @@ extern "C" int aoenv_dm_surface_separable(const float* coefs, int ldc, const int
   cudaStream_t s = (cudaStream_t)stream;
   const dim3 grid(parts, B);
   if (which == 1)
-    dm_separable_banded_kernel<12><<<grid, 256, smem, s>>>(coefs, ldc, act_pos, nA, nAct, wx, j0x, wyp, i0y, R, xw, opd);
+    AOENV_LAUNCH(dm_separable_banded_kernel<12>, grid, 256, smem, s, coefs, ldc, act_pos, nA, nAct, wx, j0x, wyp, i0y, R, xw, opd);
   else if (which == 2)
-    dm_separable_banded_kernel<16><<<grid, 256, smem, s>>>(coefs, ldc, act_pos, nA, nAct, wx, j0x, wyp, i0y, R, xw, opd);
+    AOENV_LAUNCH(dm_separable_banded_kernel<16>, grid, 256, smem, s, coefs, ldc, act_pos, nA, nAct, wx, j0x, wyp, i0y, R, xw, opd);
   else
     dm_separable_kernel<<<grid, 256, smem, s>>>(coefs, ldc, act_pos, nA, nAct, gx, gy, (const int2*)band_x,
                                                 (const int2*)band_y, R, xw, opd);

@@ -130,6 +130,7 @@ gemm_tc_kernel(const __grid_constant__ TensorMaps maps, float* __restrict__ D, i
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
   const int kb_per = (num_kb + split_k - 1) / split_k;
 
+  pdl_trigger();                                   // the successor may be scheduled while this grid's last wave runs
   if (warp == 0 && lane == 0) {
     for (int p = 0; p < kParts; ++p) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.w[p])) : "memory");
@@ -157,6 +158,7 @@ gemm_tc_kernel(const __grid_constant__ TensorMaps maps, float* __restrict__ D, i
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                      // barriers, TMEM and tensor-map prefetch are set up; now the operands
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -346,7 +348,7 @@ static int launch(const __nv_bfloat16* Xs, const __nv_bfloat16* Ws, int ldk, flo
   }
   const int num_tiles = num_mn * split_k;
   const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
-  gemm_tc_kernel<kParts, BLOCK_N><<<grid, kThreads, C::kSmemBytes, s>>>(maps, D, ldd, MX, NW, K, alpha, split_k);
+  AOENV_LAUNCH((gemm_tc_kernel<kParts, BLOCK_N>), dim3(grid), kThreads, C::kSmemBytes, s, maps, D, ldd, MX, NW, K, alpha, split_k);
   AOENV_LAUNCH_CHECK("gemm_tc");
   return 0;
 }

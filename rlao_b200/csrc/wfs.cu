@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(256)
 shwfs_detector_kernel(float* __restrict__ frame, const uint8_t* __restrict__ valid, int nS, int n, float inv_R, float inv_n,
                       const __grid_constant__ aoenv_detector_t det, int shared_max, int32_t* __restrict__ envmax,
                       int n_pixels) {
+  pdl_enter();
   __shared__ DetQueued queue[8][kDetPerLane * 32];
   const int R = nS * n, P = n_pixels > 0 ? n_pixels : R * R;
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -237,6 +238,7 @@ shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ op
                    int track_max, int shared_max, float* __restrict__ frame,
                    int32_t* __restrict__ envmax, double* __restrict__ stats) {
   constexpr int N = 2 * n;
+  pdl_enter();
   const int R = nS * n;
   const int b = blockIdx.y;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -908,6 +910,7 @@ shwfs_slopes_kernel(const float* __restrict__ frame, const int32_t* __restrict__
                     float threshold_cog, int nS, float* __restrict__ slopes, int lds,
                     __nv_bfloat16* __restrict__ planes, int parts) {
   const int b = blockIdx.y;
+  pdl_enter();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nV) return;
   const int R = nS * n;
@@ -1051,9 +1054,13 @@ shwfs_slopes_f64_kernel(const double* __restrict__ frame, const unsigned long lo
   slopes[(size_t)b * lds + nV + t] = (cy - ref_xy[nV + t]) * inv_units;
 }
 
-__global__ void envmax_init_kernel(int32_t* __restrict__ envmax, int count) {
+// Resets the per-environment maxima and (optionally) the pupil statistics in one launch: a memset node between two kernels
+// would cut the programmatic-dependent-launch chain of the step.
+__global__ void envmax_init_kernel(int32_t* __restrict__ envmax, int count, double* __restrict__ stats, int n_stats) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) envmax[i] = float_to_ordered(-INFINITY);
+  if (stats != nullptr && i < n_stats) stats[i] = 0.0;
 }
 
 }  // namespace aoenv
@@ -1093,12 +1100,8 @@ int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil
   }
   int rc = ensure_twiddles(n, s);
   if (rc) return rc;
-  envmax_init_kernel<<<(B + 255) / 256, 256, 0, s>>>(envmax, shared_max ? 1 : B);
+  AOENV_LAUNCH(envmax_init_kernel, dim3((4 * B + 255) / 256), 256, 0, s, envmax, shared_max ? 1 : B, stats, stats ? 4 * B : 0);
   AOENV_LAUNCH_CHECK("envmax_init");
-  if (stats) {
-    cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 4 * (size_t)B, s);
-    if (e != cudaSuccess) return fail(-3, "shwfs_frame memset: %s", cudaGetErrorString(e));
-  }
   dim3 grid((nS * nS + 127) / 128, B);
   const int variant = g_wfs6_factorised.load(std::memory_order_relaxed);
   if (variant == 3) {            // n / 2 lanes per lenslet, any compiled n
@@ -1110,8 +1113,8 @@ int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil
   } else
 #define AOENV_WFS_CASE(NN)                                                                                   \
   case NN:                                                                                                   \
-    shwfs_frame_kernel<NN><<<grid, 128, 0, s>>>(opd_a, opd_b, pupil, amp, valid, nS, phase_scale, det == nullptr,  \
-                                                shared_max, frame, envmax, stats);                           \
+    AOENV_LAUNCH(shwfs_frame_kernel<NN>, grid, 128, 0, s, opd_a, opd_b, pupil, amp, valid, nS, phase_scale,        \
+                 (int)(det == nullptr), shared_max, frame, envmax, stats);                                  \
     break;
   switch (n) {
     AOENV_WFS_CASE(4)
@@ -1125,8 +1128,8 @@ int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil
         shwfs_frame6_kernel<<<grid, 128, 0, s>>>(opd_a, opd_b, pupil, amp, valid, nS, phase_scale, det == nullptr, shared_max,
                                                  frame, envmax, stats);
       else
-        shwfs_frame_kernel<6><<<grid, 128, 0, s>>>(opd_a, opd_b, pupil, amp, valid, nS, phase_scale, det == nullptr, shared_max,
-                                                   frame, envmax, stats);
+        AOENV_LAUNCH(shwfs_frame_kernel<6>, grid, 128, 0, s, opd_a, opd_b, pupil, amp, valid, nS, phase_scale,
+                     (int)(det == nullptr), shared_max, frame, envmax, stats);
       break;
   }
 #undef AOENV_WFS_CASE
@@ -1135,7 +1138,7 @@ int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil
     const int R = nS * n;
     AOENV_CHECK_ARG(R * R < (1 << 24), "shwfs_frame: frame of %d x %d pixels is too large for the camera pass", R, R);
     dim3 gd((R * R + 8 * kDetPerLane * 32 - 1) / (8 * kDetPerLane * 32), B);
-    shwfs_detector_kernel<<<gd, 256, 0, s>>>(frame, valid, nS, n, 1.0f / (float)R, 1.0f / (float)n, *det, shared_max, envmax, 0);
+    AOENV_LAUNCH(shwfs_detector_kernel, gd, 256, 0, s, frame, valid, nS, n, 1.0f / (float)R, 1.0f / (float)n, *det, shared_max, envmax, 0);
     AOENV_LAUNCH_CHECK("shwfs_detector");
   }
   return 0;
@@ -1150,7 +1153,7 @@ int aoenv_shwfs_camera(float* frame, const uint8_t* valid, int B, int nS, int n,
   const int R = nS * n;
   AOENV_CHECK_ARG(R * R < (1 << 24), "shwfs_camera: frame of %d x %d pixels is too large for the camera pass", R, R);
   cudaStream_t s = (cudaStream_t)stream;
-  envmax_init_kernel<<<(B + 255) / 256, 256, 0, s>>>(envmax, shared_max ? 1 : B);
+  AOENV_LAUNCH(envmax_init_kernel, dim3((B + 255) / 256), 256, 0, s, envmax, shared_max ? 1 : B, (double*)nullptr, 0);
   AOENV_LAUNCH_CHECK("envmax_init");
   dim3 gd((R * R + 8 * kDetPerLane * 32 - 1) / (8 * kDetPerLane * 32), B);
   shwfs_detector_kernel<<<gd, 256, 0, s>>>(frame, valid, nS, n, 1.0f / (float)R, 1.0f / (float)n, *det, shared_max, envmax, 0);
@@ -1180,9 +1183,8 @@ int aoenv_shwfs_slopes(const float* frame, const int32_t* envmax, int shared_max
   dim3 grid((nV + 127) / 128, B);
 #define AOENV_SLOPES_CASE(NN)                                                                                          \
   case NN:                                                                                                             \
-    shwfs_slopes_kernel<NN><<<grid, 128, 0, (cudaStream_t)stream>>>(frame, envmax, shared_max, valid_idx, nV, ref_xy,   \
-                                                                    inv_units, threshold_cog, nS, slopes, lds,          \
-                                                                    (__nv_bfloat16*)slope_planes, parts);               \
+    AOENV_LAUNCH(shwfs_slopes_kernel<NN>, grid, 128, 0, (cudaStream_t)stream, frame, envmax, shared_max, valid_idx, nV, \
+                 ref_xy, inv_units, threshold_cog, nS, slopes, lds, (__nv_bfloat16*)slope_planes, parts);              \
     break;
   switch (n) {
     AOENV_SLOPES_CASE(4)

@@ -103,6 +103,9 @@ class FakeLib:
     def aoenv_launch_count(self):
         return self.launches
 
+    def aoenv_set_pdl(self, enabled):
+        return 1
+
     # ---- atmosphere (sliding-window canvas) ---------------------------------------------------------------
     @staticmethod
     def _window(ptr, B, M, pitch, env_stride):
