@@ -231,12 +231,15 @@ shwfs_detector_kernel(float* __restrict__ frame, const uint8_t* __restrict__ val
   }
 }
 
-template <int n>
+// WL > 0: the second OPD term is the separable DM surface, evaluated in place from the column half T = C gx
+// (aoenv_dm_rows) and the row weights of `dm` (see aoenv_dm_sep_t) instead of being read from opd_b: each lenslet sums
+// its n x n pixels over the WL actuator rows of its lenslet row's window.  The surface is then never written to memory.
+template <int n, int WL = 0>
 __global__ void __launch_bounds__(128)
 shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ opd_b, const float* __restrict__ pupil,
                    const float* __restrict__ amp, const uint8_t* __restrict__ valid, int nS, float phase_scale,
                    int track_max, int shared_max, float* __restrict__ frame,
-                   int32_t* __restrict__ envmax, double* __restrict__ stats) {
+                   int32_t* __restrict__ envmax, double* __restrict__ stats, const __grid_constant__ aoenv_dm_sep_t dm) {
   constexpr int N = 2 * n;
   pdl_enter();
   const int R = nS * n;
@@ -257,10 +260,44 @@ shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ op
   if (active) {
     const size_t tile = (size_t)(li * n) * R + lj * n;
     const float* __restrict__ pa = opd_a + (size_t)b * R * R + tile;
-    const float* __restrict__ pb = opd_b ? opd_b + (size_t)b * R * R + tile : nullptr;
+    const float* __restrict__ pb = (WL == 0 && opd_b) ? opd_b + (size_t)b * R * R + tile : nullptr;
     const size_t centre = (size_t)b * R * R + (size_t)(R / 2) * R + R / 2;
     const float ka = stats ? __ldg(opd_a + centre) : 0.f;
-    const float kt = stats ? (opd_b ? ka + __ldg(opd_b + centre) : ka) : 0.f;
+    // (variance is shift invariant: with the in-place DM the total is centred on the atmosphere's centre value)
+    const float kt = stats ? (pb ? ka + __ldg(opd_b + centre) : ka) : 0.f;
+    // DM surface of this lenslet's tile: dmv[bb][a2] = pixels (row bb, columns 2 a2, 2 a2 + 1)
+    float2 dmv[WL > 0 ? n : 1][n / 2];
+    if (WL > 0) {
+      constexpr int half = (WL + 1) / 2, hp = (half + 3) / 4 * 4;
+#pragma unroll
+      for (int bb = 0; bb < n; ++bb)
+#pragma unroll
+        for (int a2 = 0; a2 < n / 2; ++a2) dmv[WL > 0 ? bb : 0][a2] = make_float2(0.f, 0.f);
+      const float* __restrict__ trow = dm.rows + ((size_t)b * dm.nActP + __ldg(&dm.ilr[li])) * R + lj * n;
+      const float* __restrict__ wrow = dm.wlr + (size_t)(li * n) * (2 * hp);
+#pragma unroll
+      for (int g = 0; g < 2 * hp / 4; ++g) {
+        float4 w4[n];
+#pragma unroll
+        for (int bb = 0; bb < n; ++bb) w4[bb] = __ldg(reinterpret_cast<const float4*>(wrow + (size_t)bb * (2 * hp)) + g);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = 4 * g + e, hh = j / hp, kk = j % hp;
+          if (kk >= half) continue;                      // padding entries of the weight rows
+          const int t = hh * half + kk;
+          if (t >= WL) continue;
+          float2 tv[n / 2];
+#pragma unroll
+          for (int a2 = 0; a2 < n / 2; ++a2) tv[a2] = __ldg(reinterpret_cast<const float2*>(trow + (size_t)t * R) + a2);
+#pragma unroll
+          for (int bb = 0; bb < n; ++bb) {
+            const float w = e == 0 ? w4[bb].x : (e == 1 ? w4[bb].y : (e == 2 ? w4[bb].z : w4[bb].w));
+#pragma unroll
+            for (int a2 = 0; a2 < n / 2; ++a2) dmv[WL > 0 ? bb : 0][a2] = fma2(dup2(w), tv[a2], dmv[WL > 0 ? bb : 0][a2]);
+          }
+        }
+      }
+    }
 #pragma unroll
     for (int bb = 0; bb < n; ++bb) {
 #pragma unroll
@@ -268,7 +305,8 @@ shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ op
         // two neighbouring pixels per 64-bit load (tile rows start on even columns: lj * n with n even, R even)
         const int o2 = bb * R + 2 * a2;
         const float2 av = __ldg(reinterpret_cast<const float2*>(pa + o2));
-        const float2 bv = pb ? __ldg(reinterpret_cast<const float2*>(pb + o2)) : make_float2(0.f, 0.f);
+        const float2 bv = WL > 0 ? dmv[WL > 0 ? bb : 0][a2]
+                                 : (pb ? __ldg(reinterpret_cast<const float2*>(pb + o2)) : make_float2(0.f, 0.f));
         const float2 pv = __ldg(reinterpret_cast<const float2*>(pupil + tile + o2));
         const float2 mv = lit ? __ldg(reinterpret_cast<const float2*>(amp + tile + o2)) : make_float2(0.f, 0.f);
 #pragma unroll
@@ -1088,10 +1126,20 @@ int aoenv_set_wfs6_variant(int variant) {
   return g_wfs6_factorised.exchange(variant < 0 || variant > 3 ? kDefaultFrameVariant : variant);
 }
 
-int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil, const float* amp,
-                      const uint8_t* valid, int B, int nS, int n, float phase_scale, const aoenv_detector_t* det,
-                      int shared_max, float* frame, int32_t* envmax, double* stats, void* stream) {
+static int shwfs_frame_impl(const float* opd_a, const float* opd_b, const aoenv_dm_sep_t* dm_in, const float* pupil,
+                            const float* amp, const uint8_t* valid, int B, int nS, int n, float phase_scale,
+                            const aoenv_detector_t* det, int shared_max, float* frame, int32_t* envmax, double* stats,
+                            void* stream) {
   AOENV_CHECK_ARG(B > 0 && B <= 65535 && nS > 0, "shwfs_frame: bad shape B=%d nS=%d", B, nS);
+  aoenv_dm_sep_t dm{};
+  if (dm_in != nullptr) {
+    dm = *dm_in;
+    AOENV_CHECK_ARG(opd_b == nullptr, "shwfs_frame_dm: give either the separable DM or an explicit second OPD term");
+    AOENV_CHECK_ARG(dm.rows != nullptr && dm.wlr != nullptr && dm.ilr != nullptr && dm.nActP > 0, "shwfs_frame_dm: bad DM tables");
+    AOENV_CHECK_ARG(dm.WL == 14 || dm.WL == 18, "shwfs_frame_dm: DM window of %d actuator rows (14 or 18)", dm.WL);
+    AOENV_CHECK_ARG((reinterpret_cast<uintptr_t>(dm.rows) & 7) == 0 && (reinterpret_cast<uintptr_t>(dm.wlr) & 15) == 0,
+                    "shwfs_frame_dm: DM tables must be 16-byte aligned");
+  }
   AOENV_CHECK_ARG(n == 4 || n == 6 || n == 8, "shwfs_frame: %d pixels per lenslet is not a compiled size (4, 6, 8)", n);
   cudaStream_t s = (cudaStream_t)stream;
   if (det) {
@@ -1104,7 +1152,7 @@ int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil
   AOENV_LAUNCH_CHECK("envmax_init");
   dim3 grid((nS * nS + 127) / 128, B);
   const int variant = g_wfs6_factorised.load(std::memory_order_relaxed);
-  if (variant == 3) {            // n / 2 lanes per lenslet, any compiled n
+  if (variant == 3 && dm.WL == 0) {            // n / 2 lanes per lenslet, any compiled n
     const int per_block = 4 * (32 / (n / 2));
     dim3 g3((nS * nS + per_block - 1) / per_block, B);
     if (n == 4) shwfs_frame_split_kernel<4><<<g3, 128, 0, s>>>(opd_a, opd_b, pupil, amp, valid, nS, phase_scale, det == nullptr, shared_max, frame, envmax, stats);
@@ -1113,14 +1161,28 @@ int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil
   } else
 #define AOENV_WFS_CASE(NN)                                                                                   \
   case NN:                                                                                                   \
-    AOENV_LAUNCH(shwfs_frame_kernel<NN>, grid, 128, 0, s, opd_a, opd_b, pupil, amp, valid, nS, phase_scale,        \
-                 (int)(det == nullptr), shared_max, frame, envmax, stats);                                  \
+    if (dm.WL == 14)                                                                                         \
+      AOENV_LAUNCH((shwfs_frame_kernel<NN, 14>), grid, 128, 0, s, opd_a, opd_b, pupil, amp, valid, nS, phase_scale, \
+                   (int)(det == nullptr), shared_max, frame, envmax, stats, dm);                             \
+    else if (dm.WL == 18)                                                                                    \
+      AOENV_LAUNCH((shwfs_frame_kernel<NN, 18>), grid, 128, 0, s, opd_a, opd_b, pupil, amp, valid, nS, phase_scale, \
+                   (int)(det == nullptr), shared_max, frame, envmax, stats, dm);                             \
+    else                                                                                                     \
+      AOENV_LAUNCH((shwfs_frame_kernel<NN, 0>), grid, 128, 0, s, opd_a, opd_b, pupil, amp, valid, nS, phase_scale,  \
+                   (int)(det == nullptr), shared_max, frame, envmax, stats, dm);                             \
     break;
   switch (n) {
     AOENV_WFS_CASE(4)
     AOENV_WFS_CASE(8)
     case 6:
-      if (variant == 2) {
+      if (dm.WL != 0) {
+        if (dm.WL == 14)
+          AOENV_LAUNCH((shwfs_frame_kernel<6, 14>), grid, 128, 0, s, opd_a, opd_b, pupil, amp, valid, nS, phase_scale,
+                       (int)(det == nullptr), shared_max, frame, envmax, stats, dm);
+        else
+          AOENV_LAUNCH((shwfs_frame_kernel<6, 18>), grid, 128, 0, s, opd_a, opd_b, pupil, amp, valid, nS, phase_scale,
+                       (int)(det == nullptr), shared_max, frame, envmax, stats, dm);
+      } else if (variant == 2) {
         dim3 g3((nS * nS + kS6Warps * kS6Lenslets - 1) / (kS6Warps * kS6Lenslets), B);
         shwfs_frame6s_kernel<<<g3, kS6Warps * 32, 0, s>>>(opd_a, opd_b, pupil, amp, valid, nS, phase_scale, det == nullptr,
                                                           shared_max, frame, envmax, stats);
@@ -1128,8 +1190,8 @@ int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil
         shwfs_frame6_kernel<<<grid, 128, 0, s>>>(opd_a, opd_b, pupil, amp, valid, nS, phase_scale, det == nullptr, shared_max,
                                                  frame, envmax, stats);
       else
-        AOENV_LAUNCH(shwfs_frame_kernel<6>, grid, 128, 0, s, opd_a, opd_b, pupil, amp, valid, nS, phase_scale,
-                     (int)(det == nullptr), shared_max, frame, envmax, stats);
+        AOENV_LAUNCH((shwfs_frame_kernel<6, 0>), grid, 128, 0, s, opd_a, opd_b, pupil, amp, valid, nS, phase_scale,
+                     (int)(det == nullptr), shared_max, frame, envmax, stats, dm);
       break;
   }
 #undef AOENV_WFS_CASE
@@ -1142,6 +1204,19 @@ int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil
     AOENV_LAUNCH_CHECK("shwfs_detector");
   }
   return 0;
+}
+
+int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil, const float* amp,
+                      const uint8_t* valid, int B, int nS, int n, float phase_scale, const aoenv_detector_t* det,
+                      int shared_max, float* frame, int32_t* envmax, double* stats, void* stream) {
+  return shwfs_frame_impl(opd_a, opd_b, nullptr, pupil, amp, valid, B, nS, n, phase_scale, det, shared_max, frame, envmax, stats, stream);
+}
+
+int aoenv_shwfs_frame_dm(const float* opd_a, const aoenv_dm_sep_t* dm, const float* pupil, const float* amp,
+                         const uint8_t* valid, int B, int nS, int n, float phase_scale, const aoenv_detector_t* det,
+                         int shared_max, float* frame, int32_t* envmax, double* stats, void* stream) {
+  AOENV_CHECK_ARG(dm != nullptr, "shwfs_frame_dm: no DM description");
+  return shwfs_frame_impl(opd_a, nullptr, dm, pupil, amp, valid, B, nS, n, phase_scale, det, shared_max, frame, envmax, stats, stream);
 }
 
 int aoenv_shwfs_camera(float* frame, const uint8_t* valid, int B, int nS, int n, const aoenv_detector_t* det, int shared_max,

@@ -485,6 +485,7 @@ template <int W>
 __global__ void __launch_bounds__(256)
 dm_rows_kernel(const float* __restrict__ coefs, int ldc, const int32_t* __restrict__ act_pos, int nA, int nAct, int nActP,
                const float* __restrict__ wx, const int32_t* __restrict__ j0x, int R, float* __restrict__ rows) {
+  pdl_enter();
   extern __shared__ __align__(16) float sC[];          // [nAct][nAct + W]
   const int b = blockIdx.x, ldC = nAct + W;
   for (int k = threadIdx.x; k < nAct * ldC; k += blockDim.x) sC[k] = 0.f;
@@ -558,8 +559,8 @@ int aoenv_dm_rows(const float* coefs, int ldc, const int32_t* act_pos, int nA, i
   cudaError_t e = W == 12 ? cudaFuncSetAttribute(dm_rows_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                           : cudaFuncSetAttribute(dm_rows_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(-3, "dm_rows smem attribute: %s", cudaGetErrorString(e));
-  if (W == 12) dm_rows_kernel<12><<<B, 256, smem, s>>>(coefs, ldc, act_pos, nA, nAct, nActP, wx, j0x, R, rows);
-  else dm_rows_kernel<16><<<B, 256, smem, s>>>(coefs, ldc, act_pos, nA, nAct, nActP, wx, j0x, R, rows);
+  if (W == 12) AOENV_LAUNCH(dm_rows_kernel<12>, dim3(B), 256, smem, s, coefs, ldc, act_pos, nA, nAct, nActP, wx, j0x, R, rows);
+  else AOENV_LAUNCH(dm_rows_kernel<16>, dim3(B), 256, smem, s, coefs, ldc, act_pos, nA, nAct, nActP, wx, j0x, R, rows);
   AOENV_LAUNCH_CHECK("dm_rows");
   return 0;
 }
