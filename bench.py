@@ -517,6 +517,7 @@ def dominant_roofline(kernels, env, B):
         "aoenv_dm_surface_separable": P * 4 + nA * 4,
         "aoenv_atm_phase": L * M * M * 4 + P * 4,
         "aoenv_shwfs_frame": 3 * P * 4,
+        "aoenv_shwfs_frame_dm": 2 * P * 4 + (env.dm.nAct + 14) * R * 4,           # atmosphere OPD in, frame out, T = C gx rows in
         "aoenv_shwfs_fused": P * 4 + nSig * 4 + (env.dm.nAct + 14) * R * 4,      # OPD in, slopes out, T = C gx rows in
         "aoenv_dm_rows": nA * 4 + env.dm.nAct * R * 4,
         "aoenv_shwfs_slopes": P * 4 + nSig * 4,
@@ -533,7 +534,7 @@ def dominant_roofline(kernels, env, B):
     # algorithmic HBM GB/s of every streaming kernel of the step (same definition as `achieved`)
     out["all_streaming_kernels_gbs"] = {k: round(per_env_all[k] * B / (kernels[k]["ms_per_call"] * 1e-3) / 1e9, 1)
                                         for k in kernels if k in per_env_all}
-    if top in ("aoenv_shwfs_frame", "aoenv_shwfs_fused"):
+    if top in ("aoenv_shwfs_frame", "aoenv_shwfs_frame_dm", "aoenv_shwfs_fused"):
         # This kernel is bound by the FP32 FMA pipe (ncu: profiles/), so the roofline is the FP32 one: algorithmic flops =
         # the two pruned DFT passes on the n non-zero inputs with the radix-2 split (4 n^3 + 8 n^3 FMA per lit lenslet,
         # DESIGN.md section 4) and, for the fused kernel, the banded DM surface (W FMA per pixel + the T = C gx stage).
@@ -542,11 +543,11 @@ def dominant_roofline(kernels, env, B):
         n = env.wfs.n_pix_subap if hasattr(env.wfs, "n_pix_subap") else R // env.wfs.nSubap
         fma = (4 * n ** 3 + 8 * n ** 3) * int(env.wfs.nValidSubaperture)
         what = "pruned DFT passes"
-        if top == "aoenv_shwfs_fused":
+        if top in ("aoenv_shwfs_fused", "aoenv_shwfs_frame_dm"):
             tb = env.dm.fused_tables()
             if tb is not None:
-                plan = env.wfs._fused_plans.get(id(tb))
-                fma += (plan["WL"] if plan else 14) * P          # row half of the separable surface (the column half is aoenv_dm_rows)
+                win = env.wfs._dm_windows(tb)
+                fma += (win[0] if win else 14) * P               # row half of the separable surface (the column half is aoenv_dm_rows)
                 what += " + banded DM surface (row half)"
         tflops = 2.0 * fma * B / (ms * 1e-3) / 1e12
         out = {"kernel": top, "bound": "fp32", "achieved": tflops, "peak": 72.3, "unit": "TFLOP/s", "frac": tflops / 72.3,

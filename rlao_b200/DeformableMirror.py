@@ -33,6 +33,10 @@ class DMSurfaceRef:
         return self.dm._slot_surface(self.slot)
 
     @property
+    def materialised(self):
+        return bool(self.dm._valid[self.slot])
+
+    @property
     def coefs(self):
         return self.dm._coefs_of[self.slot]
 
@@ -110,6 +114,9 @@ class DeformableMirror:
         self._slot = 0
         # lazy surfaces (opt-in, AOENV_WFS=fused): with the separable geometry the fused WFS kernel builds the surface in
         # shared memory from T = C gx; _opd[slot] is then brought up to date only when somebody reads it
+        # lazy_surface: the fast path of env.step (_set_coefs_batch) computes only T = C gx per command; the consumer either
+        # evaluates the surface in place (aoenv_shwfs_frame_dm, aoenv_shwfs_fused) or asks for the tensor, which runs the
+        # surface kernel on demand.  Set by the environment when its WFS can evaluate the surface itself.
         self.lazy_surface = os.environ.get("AOENV_WFS", "kernels") == "fused"
         self._coefs_of = [None, None]
         self._valid = [True, True]

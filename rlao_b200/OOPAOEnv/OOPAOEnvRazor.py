@@ -146,6 +146,14 @@ class OOPAO:
         cam.integrationTime = param["samplingTime"]
         cam.seed = seed
         self.wfs.env_offset = self.env_offset       # every shard draws its own camera noise, also outside step()
+        # production mode: atm.update() of frame t+1 runs on a side stream underneath the WFS of frame t (Atmosphere.prefetch)
+        pf = os.environ.get("AOENV_ATM_PREFETCH", "1")               # 0 = off, 1 = when the batch is large enough, force = always
+        self.atm.pipelined = "force" if pf == "force" else pf != "0"
+        # a Shack-Hartmann evaluates the default (separable) mirror's surface inside its frame kernel: step() then computes
+        # only T = C gx per command; the [n_envs, R, R] surface is produced on demand (dm.OPD, tel.OPD, PSF)
+        if wfs_type != "pyramid" and getattr(self.wfs, "inline_dm", False) and self.dm.fused_tables() is not None \
+                and self.wfs._dm_windows(self.dm.fused_tables()) is not None:
+            self.dm.lazy_surface = True
         self.tel * self.wfs
         # modal basis and calibration
         nZ = param.get("nZernike", 50)
@@ -286,6 +294,9 @@ class OOPAO:
         self.tel._set_lazy(self.atm._opd, dm_surface)                      # :488 tel*dm
         with _range("aoenv.wfs"):
             self.wfs._measure_terms(self.atm._opd, dm_surface, self.env_offset)  # :488 *wfs  (+ stats for :484,502,506)
+        if not atmosphere_done:
+            with _range("aoenv.atmosphere_next"):
+                self.atm.prefetch()          # the next frame's atm.update(), on a side stream underneath this frame's WFS
         with _range("aoenv.reconstruct"):
             self._observe(True)                                            # :496-506
         if self.total is not None and i is not None and 0 <= i < self._nLoop:
@@ -320,12 +331,17 @@ class OOPAO:
         bookkeeping and generator counters, DM commands, camera and exploration-noise counters, the per-step records.
         With the counter-based generators a restored environment continues bit for bit."""
         atm = self.atm
+        nxt = None
+        if atm._prefetched:                  # the layers already hold the next frame: keep its OPD with them
+            torch.cuda.current_stream(self.device).wait_event(atm._prefetch_event)
+            nxt = atm._opd_next.detach().cpu().clone()
         layers = []
         for i, ly in enumerate(atm._layers):
             layers.append(dict(map=ly.mapShift.detach().cpu().clone(), buff=ly.buff.copy(), ratio=ly.ratio.copy(),
                                notDoneOnce=ly.notDoneOnce, events=ly.events, philox_seed=getattr(ly, "philox_seed", 0),
                                ext=None))
         return dict(version=1, n_envs=self.n_envs, rng=atm.rng, layers=layers, atm_opd=atm._opd.detach().cpu().clone(),
+                    atm_opd_next=nxt,
                     coefs=self.dm._coefs.detach().cpu().clone(), dm_prev=self._dm_prev.detach().cpu().clone(),
                     cam_frame_counter=self.wfs.cam.frame_counter, noise_calls=self._noise_calls,
                     SR=[s.detach().cpu().clone() for s in self.SR],
@@ -339,6 +355,7 @@ class OOPAO:
         if self.atm.rng != "philox":
             raise NotImplementedError("host MT19937 streams (rng='reference') are not checkpointed; use rng='philox'")
         atm, dev = self.atm, self.device
+        atm._join_prefetch(consume=False)
         for i, (ly, s_) in enumerate(zip(atm._layers, st["layers"])):
             atm._cur[i] = 0
             atm._org[i] = atm._fresh_origin(i)
@@ -349,6 +366,12 @@ class OOPAO:
             ly.events, ly.philox_seed = s_["events"], s_["philox_seed"]
             atm._rescan_extrema(i)
         atm._opd.copy_(st["atm_opd"].to(dev))
+        if st.get("atm_opd_next") is not None:
+            if atm._opd_next is None:
+                atm._opd_next = torch.empty_like(atm._opd)
+                atm._side_stream = torch.cuda.Stream(dev)
+            atm._opd_next.copy_(st["atm_opd_next"].to(dev))
+            atm._prefetched, atm._prefetch_event = True, torch.cuda.current_stream(dev).record_event()
         coefs = st["coefs"].to(dev)
         self._dm_prev.copy_(st["dm_prev"].to(dev))
         self._coefs_buf[self._coefs_slot].copy_(coefs)

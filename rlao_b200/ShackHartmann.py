@@ -74,6 +74,10 @@ class ShackHartmann:
         self.use_fused = os.environ.get("AOENV_WFS", "kernels") == "fused"
         self.keep_frame = False
         self._fused_plans = {}
+        # inline_dm (default): a separable mirror's surface that exists only as commands (DMSurfaceRef of a lazy mirror) is
+        # evaluated inside the frame kernel (aoenv_shwfs_frame_dm); AOENV_WFS_INLINE_DM=0 reads the materialised surface
+        self.inline_dm = os.environ.get("AOENV_WFS_INLINE_DM", "1") != "0"
+        self._dm_window_cache = {}
         self._last_inputs = None
         ii, jj = np.meshgrid(np.arange(self.nSubap), np.arange(self.nSubap), indexing="ij")
         self.index_x, self.index_y = ii.reshape(-1), jj.reshape(-1)
@@ -147,6 +151,42 @@ class ShackHartmann:
             raise NotImplementedError("geometric SH-WFS is out of scope")
 
     # ---- kernels ------------------------------------------------------------------------------------------
+    def _dm_windows_host(self, dm_tables):
+        """Row-weight windows of a separable DM (aoenv_dm_sep_t): first actuator row of every lenslet row's window, the
+        window height WL (14 or 18; 0 = bands too wide) and the weights of every pixel row relative to its window."""
+        nS, n = self.nSubap, self.n_pix_subap
+        R = nS * n
+        by, gy = dm_tables["by_host"], dm_tables["gy_host"]            # [R, 2] band of every pixel row, [nAct, R] weights
+        lo = by[:, 0].reshape(nS, n).min(axis=1)
+        hi = by[:, 1].reshape(nS, n).max(axis=1)
+        need = int((hi - lo + 1).max())
+        WL = 14 if need <= 14 else (18 if need <= 18 else 0)
+        if WL == 0:
+            return 0, None, None
+        half = (WL + 1) // 2
+        hp = (half + 3) // 4 * 4
+        wl = np.zeros((R, 2 * hp), dtype=np.float32)
+        for y in range(R):
+            i0 = lo[y // n]
+            for i in range(by[y, 0], by[y, 1] + 1):
+                t = i - i0
+                wl[y, (t // half) * hp + t % half] = gy[i, y]
+        return WL, lo.astype(np.int32), wl
+
+    def _dm_windows(self, dm_tables):
+        """Device copy of _dm_windows_host, cached per mirror geometry; None if the windows do not fit."""
+        key = id(dm_tables)
+        hit = self._dm_window_cache.get(key)
+        if hit is None:
+            WL, ilr, wlr = self._dm_windows_host(dm_tables)
+            hit = (WL, None, None) if WL == 0 else (
+                WL, torch.as_tensor(ilr, dtype=torch.int32, device=self.device).contiguous(),
+                torch.as_tensor(wlr, dtype=torch.float32, device=self.device).contiguous())
+            self._dm_window_cache[key] = (hit, dm_tables)             # keeps the tables alive: id() stays unique
+        else:
+            hit = hit[0]
+        return hit if hit[0] != 0 else None
+
     def _fused_plan(self, dm_tables):
         """Launch shape of aoenv_shwfs_fused: CTAs per environment (cluster) and the strip of lenslet rows each owns (cut
         so that rows + lit lenslets are even), warp groups, the lit-first lenslet order of every strip, and — with a
@@ -162,23 +202,9 @@ class ShackHartmann:
         lit_row = valid.sum(axis=1).astype(np.float64)
         WL, ilr, wlr = 0, None, None
         if dm_tables is not None:
-            by, gy = dm_tables["by_host"], dm_tables["gy_host"]            # [R, 2] band of every pixel row, [nAct, R] weights
-            lo = by[:, 0].reshape(nS, n).min(axis=1)
-            hi = by[:, 1].reshape(nS, n).max(axis=1)
-            need = int((hi - lo + 1).max())
-            WL = 14 if need <= 14 else (18 if need <= 18 else 0)
+            WL, ilr, wlr = self._dm_windows_host(dm_tables)
             if WL == 0:
-                raise NotImplementedError(f"DM influence bands of {need} actuator rows per lenslet row are too wide for the fused kernel")
-            half = (WL + 1) // 2
-            hp = (half + 3) // 4 * 4
-            wl = np.zeros((R, 2 * hp), dtype=np.float32)
-            for y in range(R):
-                i0 = lo[y // n]
-                for i in range(by[y, 0], by[y, 1] + 1):
-                    t = i - i0
-                    wl[y, (t // half) * hp + t % half] = gy[i, y]
-            ilr = lo.astype(np.int32)
-            wlr = wl
+                raise NotImplementedError("DM influence bands are too wide for the fused kernel")
 
         def t_rows_for(rs):
             if ilr is None:
@@ -289,12 +315,28 @@ class ShackHartmann:
              slope_planes=None):
         lib, st = _lib.load(), _lib.stream_ptr(self.device)
         F = opd_a.shape[0]
+        dm_struct = None
         if isinstance(opd_b, DMSurfaceRef):
-            opd_b = opd_b.tensor()
-        _lib.check(lib.aoenv_shwfs_frame(_lib.ptr(opd_a), _lib.ptr(opd_b), _lib.ptr(pupil), _lib.ptr(self._amp),
-                                         _lib.ptr(self._valid_u8), F, self.nSubap, self.n_pix_subap, C.c_float(scale),
-                                         C.byref(det) if det is not None else None, int(shared_max), _lib.ptr(frame),
-                                         _lib.ptr(envmax), _lib.ptr(stats), st), "shwfs_frame")
+            # a separable mirror whose surface exists only as commands: evaluated inside the frame kernel from T = C gx
+            tables = opd_b.dm.fused_tables() if (self.inline_dm and opd_b.dm.lazy_surface) else None
+            win = self._dm_windows(tables) if tables is not None else None
+            if win is not None and not opd_b.materialised:
+                rows = opd_b.rows
+                dm_struct = _lib.DmSepStruct()
+                dm_struct.rows, dm_struct.wlr, dm_struct.ilr = rows.data_ptr(), win[2].data_ptr(), win[1].data_ptr()
+                dm_struct.nActP, dm_struct.WL, dm_struct.t_rows = rows.shape[1], win[0], 0
+            else:
+                opd_b = opd_b.tensor()
+        if dm_struct is not None:
+            _lib.check(lib.aoenv_shwfs_frame_dm(_lib.ptr(opd_a), C.byref(dm_struct), _lib.ptr(pupil), _lib.ptr(self._amp),
+                                                _lib.ptr(self._valid_u8), F, self.nSubap, self.n_pix_subap, C.c_float(scale),
+                                                C.byref(det) if det is not None else None, int(shared_max), _lib.ptr(frame),
+                                                _lib.ptr(envmax), _lib.ptr(stats), st), "shwfs_frame_dm")
+        else:
+            _lib.check(lib.aoenv_shwfs_frame(_lib.ptr(opd_a), _lib.ptr(opd_b), _lib.ptr(pupil), _lib.ptr(self._amp),
+                                             _lib.ptr(self._valid_u8), F, self.nSubap, self.n_pix_subap, C.c_float(scale),
+                                             C.byref(det) if det is not None else None, int(shared_max), _lib.ptr(frame),
+                                             _lib.ptr(envmax), _lib.ptr(stats), st), "shwfs_frame")
         _lib.check(lib.aoenv_shwfs_slopes(_lib.ptr(frame), _lib.ptr(envmax), int(shared_max), _lib.ptr(self._valid_idx),
                                           self.nValidSubaperture, _lib.ptr(ref_xy), C.c_float(inv_units),
                                           C.c_float(self.threshold_cog), F, self.nSubap, self.n_pix_subap,

@@ -505,7 +505,8 @@ dm_rows_kernel(const float* __restrict__ coefs, int ldc, const int32_t* __restri
       const float4 v = __ldg(reinterpret_cast<const float4*>(wx + (size_t)x * W) + q);
       w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
     }
-    for (int i = 0; i < nAct; ++i) {
+#pragma unroll 4
+    for (int i = 0; i < nAct; ++i) {                     // rows are independent: four FMA chains in flight
       const float* __restrict__ c = sC + i * ldC + j0;
       float t = 0.f;
 #pragma unroll

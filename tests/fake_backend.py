@@ -326,6 +326,24 @@ class FakeLib:
             o = up(o + rows_px * wstride * 4)
         return up(o + 2048)
 
+    def aoenv_shwfs_frame_dm(self, opd_a, dm, pupil, amp, valid, B, nS, n, phase_scale, det, shared_max, frame, envmax,
+                             stats, stream):
+        """The DM surface from its factored form (T rows + row-weight windows), then the ordinary frame."""
+        R = nS * n
+        d = dm._obj if hasattr(dm, "_obj") else dm
+        WL, half = d.WL, (d.WL + 1) // 2
+        hp = (half + 3) // 4 * 4
+        trows = _arr(d.rows, (B, d.nActP, R)).astype(np.float64)
+        wlr, ilr = _arr(d.wlr, (R, 2 * hp)).astype(np.float64), _arr(d.ilr, (nS,), np.int32)
+        surf = np.zeros((B, R, R), dtype=np.float32)
+        for y in range(R):
+            i0 = int(ilr[y // n])
+            w = np.array([wlr[y, (t // half) * hp + t % half] for t in range(WL)])
+            surf[:, y, :] = np.einsum("t,btx->bx", w, trows[:, i0:i0 + WL, :])
+        self._inline_dm_surface = surf                    # kept alive for the duration of the call below
+        return self.aoenv_shwfs_frame(opd_a, C.c_void_p(surf.ctypes.data), pupil, amp, valid, B, nS, n, phase_scale, det,
+                                      shared_max, frame, envmax, stats, stream)
+
     def aoenv_dm_rows(self, coefs, ldc, act_pos, nA, nAct, nActP, wx, j0x, W, B, R, rows, stream):
         self.launches += 1
         c = _arr(coefs, (B, ldc))

@@ -165,3 +165,38 @@ def test_fused_with_noisy_camera_matches_unfused_chain(dev):
     # identical noise-free inputs up to float32 rounding of the spots -> identical Poisson draws almost everywhere
     assert (frame_f != frame_u).mean() < 2e-3
     assert rel_err(sig_f, sig_u) < 5e-2
+
+
+@pytest.mark.parametrize("nS,n,coupling", [(8, 6, 0.35), (5, 4, 0.35), (4, 8, 0.35), (40, 6, 0.35), (10, 8, 0.45), (12, 4, 0.2), (20, 6, 0.6)])
+def test_frame_kernel_with_the_dm_surface_evaluated_in_place(dev, nS, n, coupling):
+    """aoenv_shwfs_frame_dm (the default of env.step): the frame kernel evaluates the separable mirror's surface for its own
+    pixels from T = C gx and the row-weight windows; frames, slopes and pupil variances must equal the path that reads the
+    materialised surface (aoenv_dm_surface_separable + aoenv_shwfs_frame), and the surface must not have been written."""
+    from rlao_b200 import _lib
+    from rlao_b200.DeformableMirror import DeformableMirror
+    B = 3
+    cfg, tel, wfs, _ = _objects(dev, nS, n, B, with_dm=False)
+    dm = DeformableMirror(tel, nS, coupling)
+    dm.lazy_surface = True
+    R = cfg.resolution
+    win = wfs._dm_windows(dm.fused_tables())
+    assert wfs.inline_dm and win is not None and win[0] in (14, 18)
+    opd = torch.as_tensor(_wavefronts(R, B, 11), dtype=torch.float32, device=dev).contiguous()
+    dm.coefs = torch.as_tensor(np.random.RandomState(4).normal(size=(B, dm.nValidAct)) * 1.5e-7, dtype=torch.float32, device=dev)
+    ref = dm.surface_ref()
+    n0 = _lib.launch_count()
+    sig_i, st_i = _measure(wfs, opd, ref, False)
+    assert not dm._valid[dm._slot]                                 # the surface was never written
+    frame_i = _np(wfs.cam.frame).copy()
+    surf = dm.OPD.reshape(B, R, R)                                 # now it is (aoenv_dm_surface_separable)
+    sig_m, st_m = _measure(wfs, opd, surf, False)
+    frame_m = _np(wfs.cam.frame).copy()
+    assert rel_err(frame_i, frame_m) < 5e-6
+    assert rel_err(sig_i, sig_m) < 2e-5
+    npup = float(tel.pixelArea)
+    var = lambda s, i: s[:, i + 1] / npup - (s[:, i] / npup) ** 2
+    for i in (0, 2):
+        assert np.allclose(var(st_i, i), var(st_m, i), rtol=5e-5, atol=0)
+    # a reference to a surface that has been materialised in the meantime is simply read
+    sig_r, _ = _measure(wfs, opd, ref, False)
+    assert np.array_equal(sig_r, sig_m)

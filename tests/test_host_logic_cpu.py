@@ -47,14 +47,17 @@ def fake(monkeypatch):
     return fake_backend.install(monkeypatch)
 
 
-@pytest.mark.parametrize("wfs_mode", ["kernels", "fused"])
+@pytest.mark.parametrize("wfs_mode", ["kernels", "materialised", "fused"])
 def test_env_step_sequence_matches_oracle_on_cpu(fake, monkeypatch, wfs_mode):
-    """`fused` = the opt-in single-launch path (AOENV_WFS=fused): lazy DM surfaces (T = C gx through aoenv_dm_rows), balanced
-    strips, window tables and the lit-first lenslet order are host logic, exercised here on the CPU stand-in."""
-    monkeypatch.setenv("AOENV_WFS", wfs_mode)
+    """`kernels` = the default: lazy DM surfaces (T = C gx through aoenv_dm_rows) evaluated inside the frame kernel
+    (aoenv_shwfs_frame_dm); `materialised` = AOENV_WFS_INLINE_DM=0, the surface kernel every step; `fused` = the opt-in
+    single-launch path (AOENV_WFS=fused): balanced strips, window tables and the lit-first lenslet order are host logic,
+    exercised here on the CPU stand-in."""
+    monkeypatch.setenv("AOENV_WFS", "fused" if wfs_mode == "fused" else "kernels")
+    monkeypatch.setenv("AOENV_WFS_INLINE_DM", "0" if wfs_mode == "materialised" else "1")
     cfg = CONFIGS["tiny"]()
     env = build_env(cfg, n_envs=1, rng="reference")
-    assert env.wfs.use_fused == (wfs_mode == "fused") and env.dm.lazy_surface == (wfs_mode == "fused")
+    assert env.wfs.use_fused == (wfs_mode == "fused") and env.dm.lazy_surface == (wfs_mode != "materialised")
     orc = EnvOracle(cfg)
     assert env.dm.nValidAct == orc.nValidAct
     assert np.array_equal(env.wfs.valid_subapertures, orc.wfs.valid)
