@@ -527,6 +527,8 @@ def dominant_roofline(kernels, env, B):
         "aoenv_command_update": 3 * nA * 4 + env.nActuator ** 2 * 4,
         "aoenv_observe": nA * 4 + env.nActuator ** 2 * 4,
     }
+    if "aoenv_dm_rows" not in kernels:             # the frame kernel read a surface from memory (no factored DM this run)
+        per_env_all["aoenv_shwfs_frame_dm"] = 3 * P * 4
     per_env = per_env_all.get(top, 0)
     ach = per_env * B / (ms * 1e-3) / 1e9
     out = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,

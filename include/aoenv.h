@@ -241,14 +241,18 @@ int aoenv_shwfs_fused(const float* opd_a, const float* opd_b, const aoenv_dm_sep
                       int nS, int n, int cluster, int groups, float phase_scale, const float* ref_xy, int nV, float inv_units,
                       float threshold_cog, float* frame, float* slopes, int lds, void* slope_planes, int parts,
                       int32_t* envmax, double* stats, void* stream);
-/* aoenv_shwfs_frame with the second OPD term given as the separable DM surface in factored form (`dm`: T = C gx from
- * aoenv_dm_rows + the row-weight windows; t_rows is not used): every lenslet evaluates the surface of its own n x n pixels
- * in registers, so DeformableMirror.py:534-570 costs one small kernel per command (aoenv_dm_rows) and the [B][R][R] surface
- * is neither written nor read.  Everything else as aoenv_shwfs_frame (stats: the total is centred on the atmosphere's
- * centre value — the variance is shift invariant). */
-int aoenv_shwfs_frame_dm(const float* opd_a, const aoenv_dm_sep_t* dm, const float* pupil, const float* amp,
-                         const uint8_t* valid, int B, int nS, int n, float phase_scale, const aoenv_detector_t* det,
-                         int shared_max, float* frame, int32_t* envmax, double* stats, void* stream);
+/* aoenv_shwfs_frame as env.step calls it.  Second OPD term: `opd_b` (a surface in memory), or `dm` (the separable DM surface
+ * in factored form: T = C gx from aoenv_dm_rows + the row-weight windows; t_rows is not used), or neither.  With `dm` every
+ * lenslet evaluates the surface of its own n x n pixels in registers, so DeformableMirror.py:534-570 costs one small kernel
+ * per command (aoenv_dm_rows) and the [B][R][R] surface is neither written nor read (stats: the total is then centred on the
+ * atmosphere's centre value — the variance is shift invariant).
+ * order (nullable) [nS*nS]: a permutation of the lenslet numbers, the valid (lit) ones first: thread k works on lenslet
+ * order[k], so whole warps are lit or dark and the dark ones skip the transform (21 % of the lenslets of a circular pupil).
+ * The variants selected by aoenv_set_wfs6_variant ignore `dm` = NULL-only and `order`. */
+int aoenv_shwfs_frame_dm(const float* opd_a, const float* opd_b, const aoenv_dm_sep_t* dm, const int32_t* order,
+                         const float* pupil, const float* amp, const uint8_t* valid, int B, int nS, int n, float phase_scale,
+                         const aoenv_detector_t* det, int shared_max, float* frame, int32_t* envmax, double* stats,
+                         void* stream);
 /* Shared memory per CTA (bytes) the kernel above needs when its tallest strip has rows_max lenslet rows, or -1 for an
  * invalid configuration (t_rows = 0: no separable DM).  The limit is 227 KB. */
 int aoenv_shwfs_fused_smem(int nS, int n, int rows_max, int groups, int t_rows, int WL);

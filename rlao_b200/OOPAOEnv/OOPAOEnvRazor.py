@@ -290,6 +290,8 @@ class OOPAO:
         if not atmosphere_done:
             with _range("aoenv.atmosphere"):
                 self.atm.update()                                          # :482 -> tel.OPD = atm.OPD (lazy)
+        else:
+            self.atm._join_prefetch(consume=True)                          # issued ahead on the side stream, if at all
         dm_surface = self.dm.surface_ref()                                 # surface commanded at the previous step
         self.tel._set_lazy(self.atm._opd, dm_surface)                      # :488 tel*dm
         with _range("aoenv.wfs"):

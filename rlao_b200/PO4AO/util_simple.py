@@ -137,7 +137,7 @@ class TorchWrapper(_Wrapper):
         if self._ahead is None:                            # first step after a reset: measure this frame now
             self._ahead = {}
             env._measure_frame(i, self._download_hook(self._ahead), atmosphere_done=self._atm_ahead)
-            env.atm.update()
+            env.atm.prefetch() or env.atm.update()
             self._atm_ahead = True
         cur = self._ahead
         a_dev, ready = self._upload(action)
@@ -147,7 +147,7 @@ class TorchWrapper(_Wrapper):
         torch.cuda.current_stream(env.device).wait_event(cur["ready"])
         self._ahead = {}
         env._measure_frame(None if i is None else i + 1, self._download_hook(self._ahead), atmosphere_done=True)
-        env.atm.update()
+        env.atm.prefetch() or env.atm.update()      # frame t+2: on the side stream when the batch is large enough
         cur["ready"].synchronize()
         if ready is not None:
             ready.synchronize()            # the caller may reuse its action buffer as soon as step returns

@@ -126,6 +126,9 @@ class ShackHartmann:
         slot = np.full(nS * nS, -1, dtype=np.int32)
         slot[np.nonzero(self.valid_subapertures_1D)[0]] = np.arange(self.nValidSubaperture, dtype=np.int32)
         self._slot_of = torch.as_tensor(slot, device=dev).contiguous()
+        v1 = np.asarray(self.valid_subapertures_1D).astype(bool).reshape(-1)
+        self._lit_first = torch.as_tensor(np.concatenate([np.nonzero(v1)[0], np.nonzero(~v1)[0]]).astype(np.int32),
+                                          device=dev).contiguous()       # lenslet order of the frame kernel: lit ones first
         self._fused_plans = {}
 
     @property
@@ -327,16 +330,12 @@ class ShackHartmann:
                 dm_struct.nActP, dm_struct.WL, dm_struct.t_rows = rows.shape[1], win[0], 0
             else:
                 opd_b = opd_b.tensor()
-        if dm_struct is not None:
-            _lib.check(lib.aoenv_shwfs_frame_dm(_lib.ptr(opd_a), C.byref(dm_struct), _lib.ptr(pupil), _lib.ptr(self._amp),
-                                                _lib.ptr(self._valid_u8), F, self.nSubap, self.n_pix_subap, C.c_float(scale),
-                                                C.byref(det) if det is not None else None, int(shared_max), _lib.ptr(frame),
-                                                _lib.ptr(envmax), _lib.ptr(stats), st), "shwfs_frame_dm")
-        else:
-            _lib.check(lib.aoenv_shwfs_frame(_lib.ptr(opd_a), _lib.ptr(opd_b), _lib.ptr(pupil), _lib.ptr(self._amp),
-                                             _lib.ptr(self._valid_u8), F, self.nSubap, self.n_pix_subap, C.c_float(scale),
-                                             C.byref(det) if det is not None else None, int(shared_max), _lib.ptr(frame),
-                                             _lib.ptr(envmax), _lib.ptr(stats), st), "shwfs_frame")
+        _lib.check(lib.aoenv_shwfs_frame_dm(_lib.ptr(opd_a), _lib.ptr(opd_b) if dm_struct is None else None,
+                                            C.byref(dm_struct) if dm_struct is not None else None, _lib.ptr(self._lit_first),
+                                            _lib.ptr(pupil), _lib.ptr(self._amp), _lib.ptr(self._valid_u8), F, self.nSubap,
+                                            self.n_pix_subap, C.c_float(scale), C.byref(det) if det is not None else None,
+                                            int(shared_max), _lib.ptr(frame), _lib.ptr(envmax), _lib.ptr(stats), st),
+                   "shwfs_frame_dm")
         _lib.check(lib.aoenv_shwfs_slopes(_lib.ptr(frame), _lib.ptr(envmax), int(shared_max), _lib.ptr(self._valid_idx),
                                           self.nValidSubaperture, _lib.ptr(ref_xy), C.c_float(inv_units),
                                           C.c_float(self.threshold_cog), F, self.nSubap, self.n_pix_subap,

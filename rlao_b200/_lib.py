@@ -56,7 +56,7 @@ PROTOTYPES = {
     "aoenv_detector_integrate": [_vp, _i, _i, _i, _vp, _vp],
     "aoenv_shwfs_camera": [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp],
     "aoenv_shwfs_frame": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i, _vp, _vp, _vp, _vp],
-    "aoenv_shwfs_frame_dm": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i, _vp, _vp, _vp, _vp],
+    "aoenv_shwfs_frame_dm": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i, _vp, _vp, _vp, _vp],
     "aoenv_shwfs_slopes": [_vp, _vp, _i, _vp, _i, _vp, _f, _f, _i, _i, _i, _vp, _i, _vp, _i, _vp],
     "aoenv_shwfs_fused": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _i, _f, _f, _vp, _vp, _i, _vp, _i,
                           _vp, _vp, _vp],

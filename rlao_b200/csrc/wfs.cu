@@ -239,13 +239,17 @@ __global__ void __launch_bounds__(128)
 shwfs_frame_kernel(const float* __restrict__ opd_a, const float* __restrict__ opd_b, const float* __restrict__ pupil,
                    const float* __restrict__ amp, const uint8_t* __restrict__ valid, int nS, float phase_scale,
                    int track_max, int shared_max, float* __restrict__ frame,
-                   int32_t* __restrict__ envmax, double* __restrict__ stats, const __grid_constant__ aoenv_dm_sep_t dm) {
+                   int32_t* __restrict__ envmax, double* __restrict__ stats, const __grid_constant__ aoenv_dm_sep_t dm,
+                   const int32_t* __restrict__ order) {
   constexpr int N = 2 * n;
   pdl_enter();
   const int R = nS * n;
   const int b = blockIdx.y;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = k < nS * nS;
+  // `order` (nullable): a permutation of the lenslet numbers with the lit ones first — warps are then all lit or all
+  // dark, and the dark ones skip the transform as a whole instead of idling in the lanes of a mixed warp
+  const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = k0 < nS * nS;
+  const int k = (active && order != nullptr) ? __ldg(&order[k0]) : k0;
   const int li = active ? k / nS : 0, lj = active ? k % nS : 0;
   const bool lit = active && valid[k] != 0;
   const float phase_turns = phase_scale * 0.15915494309189535f;      // radians -> turns
@@ -1120,13 +1124,25 @@ static std::atomic<int> g_wfs6_factorised{[] {
   return kDefaultFrameVariant;
 }()};
 
+// Experiment knob (AOENV_WFS_FRAME_SMEM_KB): dynamic shared memory the default frame kernel asks for without using it,
+// which caps its resident CTAs per SM (76 KB -> 2 instead of 3) and leaves registers / shared memory for the CTAs of the
+// atmosphere kernels running on the side stream (Atmosphere.prefetch).  0 = off.
+static int g_frame_pad_kb = [] {
+  const char* v = getenv("AOENV_WFS_FRAME_SMEM_KB");
+  return v ? atoi(v) : 0;
+}();
+template <typename K>
+static void frame_pad_attr(K kern) {
+  if (g_frame_pad_kb > 48) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_frame_pad_kb * 1024);
+}
+
 extern "C" {
 
 int aoenv_set_wfs6_variant(int variant) {
   return g_wfs6_factorised.exchange(variant < 0 || variant > 3 ? kDefaultFrameVariant : variant);
 }
 
-static int shwfs_frame_impl(const float* opd_a, const float* opd_b, const aoenv_dm_sep_t* dm_in, const float* pupil,
+static int shwfs_frame_impl(const float* opd_a, const float* opd_b, const aoenv_dm_sep_t* dm_in, const int32_t* order, const float* pupil,
                             const float* amp, const uint8_t* valid, int B, int nS, int n, float phase_scale,
                             const aoenv_detector_t* det, int shared_max, float* frame, int32_t* envmax, double* stats,
                             void* stream) {
@@ -1163,25 +1179,26 @@ static int shwfs_frame_impl(const float* opd_a, const float* opd_b, const aoenv_
   case NN:                                                                                                   \
     if (dm.WL == 14)                                                                                         \
       AOENV_LAUNCH((shwfs_frame_kernel<NN, 14>), grid, 128, 0, s, opd_a, opd_b, pupil, amp, valid, nS, phase_scale, \
-                   (int)(det == nullptr), shared_max, frame, envmax, stats, dm);                             \
+                   (int)(det == nullptr), shared_max, frame, envmax, stats, dm, order);                             \
     else if (dm.WL == 18)                                                                                    \
       AOENV_LAUNCH((shwfs_frame_kernel<NN, 18>), grid, 128, 0, s, opd_a, opd_b, pupil, amp, valid, nS, phase_scale, \
-                   (int)(det == nullptr), shared_max, frame, envmax, stats, dm);                             \
+                   (int)(det == nullptr), shared_max, frame, envmax, stats, dm, order);                             \
     else                                                                                                     \
       AOENV_LAUNCH((shwfs_frame_kernel<NN, 0>), grid, 128, 0, s, opd_a, opd_b, pupil, amp, valid, nS, phase_scale,  \
-                   (int)(det == nullptr), shared_max, frame, envmax, stats, dm);                             \
+                   (int)(det == nullptr), shared_max, frame, envmax, stats, dm, order);                             \
     break;
   switch (n) {
     AOENV_WFS_CASE(4)
     AOENV_WFS_CASE(8)
     case 6:
       if (dm.WL != 0) {
-        if (dm.WL == 14)
-          AOENV_LAUNCH((shwfs_frame_kernel<6, 14>), grid, 128, 0, s, opd_a, opd_b, pupil, amp, valid, nS, phase_scale,
-                       (int)(det == nullptr), shared_max, frame, envmax, stats, dm);
-        else
+        if (dm.WL == 14) {
+          frame_pad_attr(shwfs_frame_kernel<6, 14>);
+          AOENV_LAUNCH((shwfs_frame_kernel<6, 14>), grid, 128, (size_t)g_frame_pad_kb * 1024, s, opd_a, opd_b, pupil, amp, valid, nS, phase_scale,
+                       (int)(det == nullptr), shared_max, frame, envmax, stats, dm, order);
+        } else
           AOENV_LAUNCH((shwfs_frame_kernel<6, 18>), grid, 128, 0, s, opd_a, opd_b, pupil, amp, valid, nS, phase_scale,
-                       (int)(det == nullptr), shared_max, frame, envmax, stats, dm);
+                       (int)(det == nullptr), shared_max, frame, envmax, stats, dm, order);
       } else if (variant == 2) {
         dim3 g3((nS * nS + kS6Warps * kS6Lenslets - 1) / (kS6Warps * kS6Lenslets), B);
         shwfs_frame6s_kernel<<<g3, kS6Warps * 32, 0, s>>>(opd_a, opd_b, pupil, amp, valid, nS, phase_scale, det == nullptr,
@@ -1191,7 +1208,7 @@ static int shwfs_frame_impl(const float* opd_a, const float* opd_b, const aoenv_
                                                  frame, envmax, stats);
       else
         AOENV_LAUNCH((shwfs_frame_kernel<6, 0>), grid, 128, 0, s, opd_a, opd_b, pupil, amp, valid, nS, phase_scale,
-                     (int)(det == nullptr), shared_max, frame, envmax, stats, dm);
+                     (int)(det == nullptr), shared_max, frame, envmax, stats, dm, order);
       break;
   }
 #undef AOENV_WFS_CASE
@@ -1209,14 +1226,14 @@ static int shwfs_frame_impl(const float* opd_a, const float* opd_b, const aoenv_
 int aoenv_shwfs_frame(const float* opd_a, const float* opd_b, const float* pupil, const float* amp,
                       const uint8_t* valid, int B, int nS, int n, float phase_scale, const aoenv_detector_t* det,
                       int shared_max, float* frame, int32_t* envmax, double* stats, void* stream) {
-  return shwfs_frame_impl(opd_a, opd_b, nullptr, pupil, amp, valid, B, nS, n, phase_scale, det, shared_max, frame, envmax, stats, stream);
+  return shwfs_frame_impl(opd_a, opd_b, nullptr, nullptr, pupil, amp, valid, B, nS, n, phase_scale, det, shared_max, frame, envmax, stats, stream);
 }
 
-int aoenv_shwfs_frame_dm(const float* opd_a, const aoenv_dm_sep_t* dm, const float* pupil, const float* amp,
-                         const uint8_t* valid, int B, int nS, int n, float phase_scale, const aoenv_detector_t* det,
-                         int shared_max, float* frame, int32_t* envmax, double* stats, void* stream) {
-  AOENV_CHECK_ARG(dm != nullptr, "shwfs_frame_dm: no DM description");
-  return shwfs_frame_impl(opd_a, nullptr, dm, pupil, amp, valid, B, nS, n, phase_scale, det, shared_max, frame, envmax, stats, stream);
+int aoenv_shwfs_frame_dm(const float* opd_a, const float* opd_b, const aoenv_dm_sep_t* dm, const int32_t* order,
+                         const float* pupil, const float* amp, const uint8_t* valid, int B, int nS, int n, float phase_scale,
+                         const aoenv_detector_t* det, int shared_max, float* frame, int32_t* envmax, double* stats,
+                         void* stream) {
+  return shwfs_frame_impl(opd_a, opd_b, dm, order, pupil, amp, valid, B, nS, n, phase_scale, det, shared_max, frame, envmax, stats, stream);
 }
 
 int aoenv_shwfs_camera(float* frame, const uint8_t* valid, int B, int nS, int n, const aoenv_detector_t* det, int shared_max,

@@ -326,11 +326,20 @@ class FakeLib:
             o = up(o + rows_px * wstride * 4)
         return up(o + 2048)
 
-    def aoenv_shwfs_frame_dm(self, opd_a, dm, pupil, amp, valid, B, nS, n, phase_scale, det, shared_max, frame, envmax,
-                             stats, stream):
-        """The DM surface from its factored form (T rows + row-weight windows), then the ordinary frame."""
+    def aoenv_shwfs_frame_dm(self, opd_a, opd_b, dm, order, pupil, amp, valid, B, nS, n, phase_scale, det, shared_max, frame,
+                             envmax, stats, stream):
+        """The DM surface from its factored form (T rows + row-weight windows), then the ordinary frame (`order` only
+        changes which thread works on which lenslet)."""
         R = nS * n
+        if order:
+            o = _arr(order, (nS * nS,), np.int32)
+            va = _arr(valid, (nS * nS,), np.uint8).astype(bool)
+            assert sorted(o.tolist()) == list(range(nS * nS)) and va[o[:va.sum()]].all()
         d = dm._obj if hasattr(dm, "_obj") else dm
+        if d is None or not getattr(d, "rows", None):
+            return self.aoenv_shwfs_frame(opd_a, opd_b, pupil, amp, valid, B, nS, n, phase_scale, det, shared_max, frame,
+                                          envmax, stats, stream)
+        assert not opd_b
         WL, half = d.WL, (d.WL + 1) // 2
         hp = (half + 3) // 4 * 4
         trows = _arr(d.rows, (B, d.nActP, R)).astype(np.float64)
