@@ -117,6 +117,48 @@ int aoenv_atm_phase(const float* const* h_canvas, const uint64_t* const* h_ext, 
                     const float* h_wrow, const float* h_wcol, const float* h_weight, float opd_scale, float* opd_out,
                     void* stream);
 
+/* One frame of Atmosphere.update() (OOPAO/Atmosphere.py:350-428) sequenced on the host side of the library instead of by
+ * the Python layer: per layer the add_row steps of this frame (integer part of updateLayer), canvas re-centring, the
+ * grouped gather / GEMM / ring launches above, then aoenv_atm_phase with the tap weights of the sub-pixel remainders.
+ * `state` is shared with the caller (rlao_b200/Atmosphere.py maps it with ctypes and keeps using it for the paths that
+ * inject innovations); it is read AND updated: ratio / buff / not_done_once / events / cur / org.
+ *   ratio, buff: pixels per frame and accumulated sub-pixel shift along (x = columns, y = rows); vX, vY wind (m/s);
+ *   events: add_row count so far (Philox stream id); cur: canvas buffer in use; org: window origin (row, col).
+ *   maps[l][2]: the two canvas buffers [B][Mc][pitch] of layer l; ext[l]: extrema [B][2]; S: canvas slack (Mc = M + S);
+ *   zx / zx_planes / X / flag: the add_row workspaces for group_max * B rows; w_f32 [nO][ldz]: [A | B] (SIMT back end,
+ *   use_tc = 0); w_planes (argument: it is rebuilt when r0 changes): its split-bf16 planes [parts][nO][ldz];
+ *   weight[l] = sqrt(fractionalR0); warp_kernel: 0 = scikit-image 0.18.3 cubic, 1 = Catmull-Rom. */
+typedef struct {
+  double ratio[2];
+  double buff[2];
+  double vX, vY;
+  uint64_t events;
+  uint64_t philox_seed;
+  int32_t not_done_once;
+  int32_t cur;
+  int32_t org[2];
+} aoenv_layer_state_t;
+
+typedef struct {
+  int32_t nLayer, B, R, M, Mc, pitch, S, nI, nO, ldz, ldx, group_max, parts, fp_off, warp_kernel, use_tc;
+  int64_t env_stride;
+  uint64_t env_offset;
+  double sampling_time, ps_loop;
+  float opd_scale, reserved;
+  float weight[AOENV_MAX_LAYERS];
+  void* maps[AOENV_MAX_LAYERS][2];
+  void* ext[AOENV_MAX_LAYERS];
+  const void* inner_rc;
+  void* zx;
+  void* zx_planes;
+  void* X;
+  void* flag;
+  const void* w_f32;
+  aoenv_layer_state_t layer[AOENV_MAX_LAYERS];
+} aoenv_atm_state_t;
+
+int aoenv_atm_update(aoenv_atm_state_t* state, const void* w_planes, float* opd_out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Dense contractions — DeformableMirror.coefs setter (OOPAO/DeformableMirror.py:534-570: OPD = modes @ coefs),
  * add_row's X = A Z + B xi (OOPAO/Atmosphere.py:308), reconstruction (MAIN/OOPAOEnv/OOPAOEnvRazor.py:496-499).
@@ -261,6 +303,31 @@ int aoenv_shwfs_fused_smem(int nS, int n, int rows_max, int groups, int t_rows, 
  * 16); rows i >= nAct are not written (the caller keeps them zero). */
 int aoenv_dm_rows(const float* coefs, int ldc, const int32_t* act_pos, int nA, int nAct, int nActP, const float* wx,
                   const int32_t* j0x, int W, int B, int R, float* rows, void* stream);
+
+/* env.step after the atmosphere, as one call (MAIN/OOPAOEnv/OOPAOEnvRazor.py:488-514 with a Shack-Hartmann, the separable
+ * mirror evaluated in place, the integrator's command update): aoenv_shwfs_frame_dm -> aoenv_shwfs_slopes ->
+ * aoenv_gemm_tn(_tc) (reconstructor) -> aoenv_observe -> aoenv_command_update -> aoenv_dm_rows, on `stream`, with the
+ * arguments those entry points document.  `c` holds what does not change between steps; per call: the atmosphere OPD, the
+ * T rows of the surface commanded at the previous step (dm_rows_cur), the camera description of this frame (NULL = ideal),
+ * the action [B][nAct2], where the new commands and their T rows go, and the output tensors.  Host time is what this
+ * saves: six interpreter-driven calls become one (the step of a single small environment is launch-bound). */
+typedef struct {
+  int32_t B, nS, n, nV, lds, nA, nAct, nAct2, ldc, ldr, W, rec_parts, use_tc, reserved;
+  float phase_scale, inv_units, threshold_cog, leak;
+  double n_pupil;
+  const void *pupil, *amp, *valid, *order, *valid_idx, *ref_xy;        /* aoenv_shwfs_frame_dm / aoenv_shwfs_slopes */
+  void *frame, *envmax, *stats, *slopes, *slope_planes;
+  aoenv_dm_sep_t dm;                                                  /* wlr, ilr, nActP, WL; rows is taken per call */
+  const void *rec_planes, *rec_f32;                                   /* reconstructor [nA][lds]: bf16 planes / float32 */
+  void* rec;                                                          /* [B][ldr] */
+  const void* act_idx;
+  void* dm_prev;
+  const void *act_pos, *wx, *j0x;                                     /* aoenv_dm_rows */
+} aoenv_sh_step_t;
+
+int aoenv_sh_step(const aoenv_sh_step_t* c, const float* opd_a, const float* dm_rows_cur, const aoenv_detector_t* det,
+                  const float* action, float* coefs_next, float* dm_rows_next, float* obs, float* reward, float* strehl,
+                  float* total, float* residual, void* stream);
 
 /* Calibration-grade measurement (init only): the two steps above in float64 with the ideal detector, for the
  * reference slopes / slope units (ShackHartmann.py:254-312) and the interaction matrix pushes

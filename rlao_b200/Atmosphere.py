@@ -28,6 +28,11 @@ class _LayerView:
 
     def __init__(self, atm, index):
         self._atm, self._i = atm, index
+        # the shift bookkeeping lives in the state block shared with the library (aoenv_atm_state_t): the same numbers
+        # whether a frame is sequenced here (_plan_layer / _extrude_group) or by aoenv_atm_update
+        self._c = atm._cstate.layer[index]
+        self._ratio = np.ctypeslib.as_array(self._c.ratio)
+        self._buff = np.ctypeslib.as_array(self._c.buff)
         self.altitude = atm.altitude[index]
         self.windSpeed = atm._windSpeed[index]
         self.direction = atm._windDirection[index]
@@ -40,6 +45,15 @@ class _LayerView:
         self.D = atm._ops.layer_D
         self.seed = index
         self.events = 0           # number of add_row calls so far (Philox stream id)
+        self.philox_seed = 0
+
+    ratio = property(lambda self: self._ratio, lambda self, v: self._ratio.__setitem__(slice(None), v))
+    buff = property(lambda self: self._buff, lambda self, v: self._buff.__setitem__(slice(None), v))
+    vX = property(lambda self: self._c.vX, lambda self, v: setattr(self._c, "vX", float(v)))
+    vY = property(lambda self: self._c.vY, lambda self, v: setattr(self._c, "vY", float(v)))
+    events = property(lambda self: self._c.events, lambda self, v: setattr(self._c, "events", int(v)))
+    philox_seed = property(lambda self: self._c.philox_seed, lambda self, v: setattr(self._c, "philox_seed", int(v)))
+    notDoneOnce = property(lambda self: bool(self._c.not_done_once), lambda self, v: setattr(self._c, "not_done_once", int(bool(v))))
 
     @property
     def mapShift(self):
@@ -57,6 +71,34 @@ class _LayerView:
     @property
     def B(self):
         return self._atm._ops.B
+
+
+class _CurView:
+    """atm._cur[i]: canvas buffer in use, stored in the shared state block."""
+
+    def __init__(self, st):
+        self._st = st
+
+    def __getitem__(self, i):
+        return self._st.layer[i].cur
+
+    def __setitem__(self, i, v):
+        self._st.layer[i].cur = int(v)
+
+
+class _OrgView:
+    """atm._org[i] = [row, col]: window origin inside the canvas, stored in the shared state block."""
+
+    def __init__(self, st):
+        self._st = st
+
+    def __getitem__(self, i):
+        o = self._st.layer[i].org
+        return [o[0], o[1]]
+
+    def __setitem__(self, i, v):
+        o = self._st.layer[i].org
+        o[0], o[1] = int(v[0]), int(v[1])
 
 
 class Atmosphere:
@@ -90,6 +132,7 @@ class Atmosphere:
         self.nExtra = 2
         self.wavelength = 500e-9
         self.user_defined_opd = False
+        self.native_update = os.environ.get("AOENV_ATM_NATIVE", "1") != "0"     # frames sequenced by aoenv_atm_update
         self.pipelined = False           # set by the environment: update() of the next frame runs ahead on a side stream
         self._prefetched, self._prefetch_event, self._side_stream, self._opd_next = False, None, None, None
         self.mode = mode
@@ -130,8 +173,9 @@ class Atmosphere:
             self._upload_B()
             self._inner_rc = torch.as_tensor(ops.inner_rc, dtype=torch.int32, device=dev).contiguous()
             self._maps = torch.zeros((self.nLayer, 2, B, self._Mc, self._pitch), dtype=torch.float32, device=dev)
-            self._cur = [0] * self.nLayer
-            self._org = [[0, 0] for _ in range(self.nLayer)]          # window origin (row, col) inside the canvas
+            self._cstate = _lib.AtmState()
+            self._cur = _CurView(self._cstate)
+            self._org = _OrgView(self._cstate)                       # window origin (row, col) inside the canvas
             self._ext = torch.zeros((self.nLayer, B, 2), dtype=torch.int64, device=dev)
             # add_row workspaces hold one row per (layer of a group, environment): layers that extrude in the same
             # round of a step share the operator [A | B] and go through ONE gather / GEMM / ring sequence
@@ -143,6 +187,20 @@ class Atmosphere:
             self._opd = torch.zeros((B, R, R), dtype=torch.float32, device=dev)
             self._fp_off = 1 + (ops.layer_res // 2 - R // 2)         # crop [1:-1] + centred footprint (:231-232)
             self.ps_loop = ops.layer_D / ops.layer_res
+            st = self._cstate
+            st.nLayer, st.B, st.R, st.M, st.Mc, st.pitch, st.S = self.nLayer, B, R, self._M, self._Mc, self._pitch, self._S
+            st.nI, st.nO, st.ldz, st.ldx, st.group_max, st.parts = self._nI, self._nO, self._K, self._ldx, G, self._W_op.parts
+            st.fp_off, st.use_tc = self._fp_off, int(gemm.uses_tensor_cores())
+            st.warp_kernel = {"lagrange018": 0, "catmull_rom": 1}.get(self.warp_kernel, -1)
+            st.env_stride, st.env_offset = self._env_stride, self.env_offset
+            st.sampling_time, st.ps_loop = float(tel.samplingTime), float(self.ps_loop)
+            st.opd_scale = self.wavelength / 2 / math.pi
+            for i in range(self.nLayer):
+                st.weight[i] = math.sqrt(self.fractionalR0[i])
+                st.maps[i][0], st.maps[i][1] = self._maps[i, 0].data_ptr(), self._maps[i, 1].data_ptr()
+                st.ext[i] = self._ext[i].data_ptr()
+            st.inner_rc, st.zx, st.zx_planes = self._inner_rc.data_ptr(), self._zx.data_ptr(), self._zx_planes.data_ptr()
+            st.X, st.flag, st.w_f32 = self._X.data_ptr(), self._flag.data_ptr(), self._W.data_ptr()
             self._layers = [_LayerView(self, i) for i in range(self.nLayer)]
             for i, ly in enumerate(self._layers):
                 setattr(self, "layer_" + str(i + 1), ly)
@@ -368,6 +426,20 @@ class Atmosphere:
                                                C.c_float(self.wavelength / 2 / math.pi), _lib.ptr(out),
                                                _lib.stream_ptr(self.device)), "atm_phase")
 
+    def _advance(self, out):
+        """One frame: the add_row steps of every layer, then the sub-pixel shift into `out`.  Sequenced by the library
+        (aoenv_atm_update, a few microseconds of host time) in the production mode, by the Python methods above when
+        innovations are injected, generated on the host or recorded."""
+        if (self.native_update and self.rng == "philox" and self.xi_queue is None and self.xi_log is None
+                and self._cstate.warp_kernel >= 0):
+            tc = self._cstate.use_tc
+            self._cstate.sampling_time, self._cstate.env_offset = float(self.telescope.samplingTime), self.env_offset
+            _lib.check(_lib.load().aoenv_atm_update(C.byref(self._cstate), _lib.ptr(self._W_op.planes()) if tc else None,
+                                                    _lib.ptr(out), _lib.stream_ptr(self.device)), "atm_update")
+        else:
+            self._update_layers()
+            self._publish(out)
+
     # ---- the next frame, one step ahead, on a second stream -------------------------------------------------
     # atm.update() depends on nothing the rest of env.step computes, and its kernels are bound by HBM (sub-pixel shift,
     # ring writes) while the wavefront sensor is bound by the FP32 pipe: prefetch() issues the update of the NEXT frame on a
@@ -400,8 +472,7 @@ class Atmosphere:
         # queued on the main stream must be done before the side stream starts
         side.wait_event(main.record_event())
         with torch.cuda.stream(side):
-            self._update_layers()
-            self._publish(self._opd_next)
+            self._advance(self._opd_next)
             self._prefetch_event = side.record_event()
         self._prefetched = True
         return True
@@ -423,8 +494,7 @@ class Atmosphere:
         if OPD is None:
             self.user_defined_opd = False
             if not self._join_prefetch(consume=True):
-                self._update_layers()
-                self._publish()
+                self._advance(self._opd)
         else:
             self.user_defined_opd = True
             t = torch.as_tensor(OPD, dtype=torch.float32, device=self.device)

@@ -21,7 +21,7 @@ import torch
 
 from .. import _lib, gemm
 from ..Atmosphere import Atmosphere
-from ..DeformableMirror import DeformableMirror
+from ..DeformableMirror import DeformableMirror, DMSurfaceRef
 from ..MisRegistration import MisRegistration
 from ..ShackHartmann import ShackHartmann
 from ..Source import Source
@@ -68,6 +68,8 @@ class OOPAO:
         self.n_envs = 1
         self.device = None
         self.psf_reward = None        # (zeroPaddingFactor, window) -> Strehl from the PSF peak each step
+        self.native_step = os.environ.get("AOENV_STEP_NATIVE", "1") != "0"   # step() as two library calls when it can
+        self._native_key, self._native = None, None
 
     # ---- configuration ------------------------------------------------------------------------------------
     def set_params_file(self, param_file, oopao_path):
@@ -264,8 +266,89 @@ class OOPAO:
         self.action_buffer = []
         return self.wfs.cam.frame.clone()
 
+    # ---- the step as two library calls (aoenv_atm_update + aoenv_sh_step) ------------------------------------------
+    def _native_cfg(self):
+        """aoenv_sh_step_t for the objects as they are now, or None when this step has to go call by call: another sensor
+        or mirror model, the fused / materialised WFS modes, a PSF reward, NVTX ranges, a flux change that the sensor has
+        not picked up yet.  Rebuilt only when something it depends on has changed."""
+        wfs, dm, tel = self.wfs, self.dm, self.tel
+        if (not self.native_step or _NVTX or self.psf_reward is not None or type(wfs) is not ShackHartmann or wfs.use_fused
+                or not wfs.inline_dm or not dm.lazy_surface or self.atm.user_defined_opd or dm._multi is not None
+                or dm._coefs_matrix is not None):
+            return None
+        src = tel.src
+        if wfs._flux_version != getattr(src, "_flux_version", 0) or wfs.current_nPhoton != src.nPhoton:
+            return None                                   # wfs._measure_terms re-initialises the flux on the ordinary path
+        key = (wfs._flux_version, id(wfs._amp), id(wfs._ref_xy), wfs.slopes_units, wfs.threshold_cog, float(self.leak),
+               id(self._Rm_op), id(dm._sep), src.wavelength, id(self._coefs_buf))
+        if self._native_key == key:
+            return self._native
+        self._native_key, self._native = key, None
+        tables = dm.fused_tables()
+        win = wfs._dm_windows(tables) if tables is not None else None
+        if win is None or 2 * math.pi / src.wavelength != self._phase_scale:
+            return None
+        tc = gemm.uses_tensor_cores()
+        dm._rows_of(dm._slot)                             # allocates the T buffers, makes the current slot's rows valid
+        c = _lib.ShStepStruct()
+        c.B, c.nS, c.n, c.nV, c.lds = self.n_envs, wfs.nSubap, wfs.n_pix_subap, wfs.nValidSubaperture, wfs._signal.stride(0)
+        c.nA, c.nAct, c.nAct2 = dm.nValidAct, dm.nAct, self.nActuator ** 2
+        c.ldc, c.ldr, c.W, c.rec_parts, c.use_tc = self._coefs_buf.stride(1), self._rec.stride(0), tables["W"], self._Rm_op.parts, int(tc)
+        c.phase_scale, c.inv_units, c.threshold_cog, c.leak = self._phase_scale, 1.0 / wfs.slopes_units, wfs.threshold_cog, self.leak
+        c.n_pupil = float(tel.pixelArea)
+        keep = [tel._pupil_f, wfs._amp, wfs._valid_u8, wfs._lit_first, wfs._valid_idx, wfs._ref_xy, wfs._frame, wfs._envmax,
+                wfs._stats, wfs._signal, wfs._signal_planes, win, self._Rm, self._Rm_op, self._rec, self._act_idx, self._dm_prev,
+                tables]
+        c.pupil, c.amp, c.valid, c.order = tel._pupil_f.data_ptr(), wfs._amp.data_ptr(), wfs._valid_u8.data_ptr(), wfs._lit_first.data_ptr()
+        c.valid_idx, c.ref_xy, c.frame, c.envmax = wfs._valid_idx.data_ptr(), wfs._ref_xy.data_ptr(), wfs._frame.data_ptr(), wfs._envmax.data_ptr()
+        c.stats, c.slopes, c.slope_planes = wfs._stats.data_ptr(), wfs._signal.data_ptr(), wfs._signal_planes.data_ptr()
+        c.dm.wlr, c.dm.ilr, c.dm.nActP, c.dm.WL = win[2].data_ptr(), win[1].data_ptr(), dm._rows.shape[2], win[0]
+        c.rec_planes = self._Rm_op.planes().data_ptr() if tc else None
+        c.rec_f32, c.rec, c.act_idx, c.dm_prev = self._Rm.data_ptr(), self._rec.data_ptr(), self._act_idx.data_ptr(), self._dm_prev.data_ptr()
+        c.act_pos, c.wx, c.j0x = tables["act_pos"].data_ptr(), tables["wx"].data_ptr(), tables["j0x"].data_ptr()
+        self._native = (c, keep)
+        return self._native
+
+    def _step_native(self, i, action, native):
+        """OOPAOEnvRazor.py:474-514 through aoenv_atm_update + aoenv_sh_step; the Python objects are kept in step (slots,
+        counters, lazy frames) exactly as the call-by-call path leaves them."""
+        c = native[0]
+        dm, wfs, atm, B, dev = self.dm, self.wfs, self.atm, self.n_envs, self.device
+        slot = dm._slot
+        atm.update()                                                       # :482 (consumes a frame computed ahead)
+        self.tel._set_lazy(atm._opd, DMSurfaceRef(dm, slot))               # :488 tel*dm, lazily
+        det = wfs.cam.as_struct(self.env_offset)
+        a = self._action_tensor(action)
+        nAct = self.nActuator
+        obs = torch.empty((B, nAct, nAct), dtype=torch.float32, device=dev)
+        reward = torch.empty((B,), dtype=torch.float32, device=dev)
+        strehl = torch.empty((B,), dtype=torch.float32, device=dev)
+        coefs = self._coefs_buf[self._coefs_slot]
+        _lib.check(_lib.load().aoenv_sh_step(ctypes.byref(c), atm._opd.data_ptr(), dm._rows[slot].data_ptr(),
+                                             ctypes.byref(det) if det is not None else None, a.data_ptr(), coefs.data_ptr(),
+                                             dm._rows[slot ^ 1].data_ptr(), obs.data_ptr(), reward.data_ptr(), strehl.data_ptr(),
+                                             self._total_now.data_ptr(), self._residual_now.data_ptr(), _lib.stream_ptr(dev)),
+                   "sh_step")
+        atm.prefetch()
+        self._coefs_slot ^= 1
+        dm._coefs, dm._multi, dm._coefs_matrix, dm._slot = coefs, None, None, slot ^ 1
+        dm._coefs_of[slot ^ 1], dm._rows_valid[slot ^ 1], dm._valid[slot ^ 1] = coefs, True, False
+        wfs.cam.frame = wfs._frame[0] if B == 1 else wfs._frame
+        wfs._signal_is_multi = False
+        self._obs, self._reward, self._strehl = obs, reward, strehl
+        if self.total is not None and i is not None and 0 <= i < self._nLoop:
+            self.total[i] = self._total_now
+            self.residual[i] = self._residual_now
+        s = self._sq(strehl)
+        self.SR.append(s)
+        self.wfsSignal = wfs.signal
+        return self._sq(obs), self._sq(reward), s, False, {"strehl": s}
+
     def step(self, i, action):
         """OOPAOEnvRazor.py:474-514.  Returns fresh tensors (the reference returns fresh arrays)."""
+        native = self._native_cfg()
+        if native is not None and self.dm._rows_valid[self.dm._slot]:
+            return self._step_native(i, action, native)
         obs, reward, strehl, done, info = self._step_views(i, action)
         strehl = strehl.clone()
         self.SR[-1] = strehl

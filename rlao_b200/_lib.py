@@ -36,6 +36,38 @@ class DmSepStruct(C.Structure):
 
 MAX_LAYERS = 8          # AOENV_MAX_LAYERS (include/aoenv.h)
 
+
+class LayerState(C.Structure):
+    """aoenv_layer_state_t (include/aoenv.h)."""
+    _fields_ = [
+        ("ratio", C.c_double * 2), ("buff", C.c_double * 2), ("vX", C.c_double), ("vY", C.c_double),
+        ("events", C.c_uint64), ("philox_seed", C.c_uint64),
+        ("not_done_once", C.c_int32), ("cur", C.c_int32), ("org", C.c_int32 * 2),
+    ]
+
+
+class ShStepStruct(C.Structure):
+    """aoenv_sh_step_t (include/aoenv.h)."""
+    _fields_ = [(k, C.c_int32) for k in ("B", "nS", "n", "nV", "lds", "nA", "nAct", "nAct2", "ldc", "ldr", "W", "rec_parts",
+                                         "use_tc", "reserved")] + [
+        ("phase_scale", C.c_float), ("inv_units", C.c_float), ("threshold_cog", C.c_float), ("leak", C.c_float),
+        ("n_pupil", C.c_double)] + [(k, C.c_void_p) for k in ("pupil", "amp", "valid", "order", "valid_idx", "ref_xy", "frame",
+                                                              "envmax", "stats", "slopes", "slope_planes")] + [
+        ("dm", DmSepStruct)] + [(k, C.c_void_p) for k in ("rec_planes", "rec_f32", "rec", "act_idx", "dm_prev", "act_pos",
+                                                           "wx", "j0x")]
+
+
+class AtmState(C.Structure):
+    """aoenv_atm_state_t (include/aoenv.h): the per-layer bookkeeping of Atmosphere.update(), shared with the library."""
+    _fields_ = [(k, C.c_int32) for k in ("nLayer", "B", "R", "M", "Mc", "pitch", "S", "nI", "nO", "ldz", "ldx", "group_max",
+                                         "parts", "fp_off", "warp_kernel", "use_tc")] + [
+        ("env_stride", C.c_int64), ("env_offset", C.c_uint64), ("sampling_time", C.c_double), ("ps_loop", C.c_double),
+        ("opd_scale", C.c_float), ("reserved", C.c_float), ("weight", C.c_float * MAX_LAYERS),
+        ("maps", (C.c_void_p * 2) * MAX_LAYERS), ("ext", C.c_void_p * MAX_LAYERS), ("inner_rc", C.c_void_p),
+        ("zx", C.c_void_p), ("zx_planes", C.c_void_p), ("X", C.c_void_p), ("flag", C.c_void_p), ("w_f32", C.c_void_p),
+        ("layer", LayerState * MAX_LAYERS),
+    ]
+
 _vp, _i, _f, _u64, _d, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_uint64, C.c_double, C.c_int64
 
 # name -> argtypes, exactly the prototypes of include/aoenv.h
@@ -47,6 +79,8 @@ PROTOTYPES = {
     "aoenv_atm_compact": [_vp, _vp, _i, _i, _i, _i64, _vp, _i64, _vp],
     "aoenv_vk_screens": [_u64, C.c_uint32, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i,
                          _vp, _i, _i64, _vp],
+    "aoenv_atm_update": [_vp, _vp, _vp, _vp],
+    "aoenv_sh_step": [_vp] * 13,
     "aoenv_atm_phase": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp],
     "aoenv_gemm_tn": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _f, _vp],
     "aoenv_split_bf16": [_vp, _i, _i, _i, _i, _vp, _i, _vp],

@@ -1124,18 +1124,6 @@ static std::atomic<int> g_wfs6_factorised{[] {
   return kDefaultFrameVariant;
 }()};
 
-// Experiment knob (AOENV_WFS_FRAME_SMEM_KB): dynamic shared memory the default frame kernel asks for without using it,
-// which caps its resident CTAs per SM (76 KB -> 2 instead of 3) and leaves registers / shared memory for the CTAs of the
-// atmosphere kernels running on the side stream (Atmosphere.prefetch).  0 = off.
-static int g_frame_pad_kb = [] {
-  const char* v = getenv("AOENV_WFS_FRAME_SMEM_KB");
-  return v ? atoi(v) : 0;
-}();
-template <typename K>
-static void frame_pad_attr(K kern) {
-  if (g_frame_pad_kb > 48) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_frame_pad_kb * 1024);
-}
-
 extern "C" {
 
 int aoenv_set_wfs6_variant(int variant) {
@@ -1193,8 +1181,7 @@ static int shwfs_frame_impl(const float* opd_a, const float* opd_b, const aoenv_
     case 6:
       if (dm.WL != 0) {
         if (dm.WL == 14) {
-          frame_pad_attr(shwfs_frame_kernel<6, 14>);
-          AOENV_LAUNCH((shwfs_frame_kernel<6, 14>), grid, 128, (size_t)g_frame_pad_kb * 1024, s, opd_a, opd_b, pupil, amp, valid, nS, phase_scale,
+          AOENV_LAUNCH((shwfs_frame_kernel<6, 14>), grid, 128, 0, s, opd_a, opd_b, pupil, amp, valid, nS, phase_scale,
                        (int)(det == nullptr), shared_max, frame, envmax, stats, dm, order);
         } else
           AOENV_LAUNCH((shwfs_frame_kernel<6, 18>), grid, 128, 0, s, opd_a, opd_b, pupil, amp, valid, nS, phase_scale,

@@ -340,3 +340,133 @@ def test_checkpoint_resume_on_device(dev):
     for la, lb in zip(a.atm._layers, b.atm._layers):
         assert torch.equal(la.mapShift, lb.mapShift)
     assert torch.equal(a.atm._ext, b.atm._ext) or True          # positions differ (other canvas origin); values are compared through obs
+
+
+def test_frames_sequenced_by_the_library_equal_the_python_sequencing(dev):
+    """aoenv_atm_update (host-side C++: add_row plan per layer, grouping, canvas re-centring, tap weights) against the Python
+    methods it mirrors, on the same kernels: bit-identical OPD and identical bookkeeping over 400 frames of a three-layer
+    atmosphere with a small canvas slack (re-centring every 8 events) and a wind that changes on the way."""
+    from rlao_b200.Atmosphere import Atmosphere
+    from rlao_b200.Source import Source
+    from rlao_b200.Telescope import Telescope
+    B, R = 3, 48
+
+    def build(native):
+        tel = Telescope(R, 8.0, 1 / 500, n_envs=B, device=dev)
+        Source("I", 8) * tel
+        atm = Atmosphere(tel, 0.13, 25.0, [12.0, 31.0, 55.0], [0.5, 0.3, 0.2], [20.0, 200.0, 305.0], [0.0, 0.0, 0.0], seed=3,
+                         canvas_slack=8)
+        atm.native_update = native
+        atm.initializeAtmosphere(tel)
+        atm.generateNewPhaseScreen(11)
+        return atm
+    a, b = build(True), build(False)
+    assert a._cstate.warp_kernel == 0 and a._cstate.use_tc in (0, 1)
+    for k in range(400):
+        if k == 150:
+            a.windSpeed, b.windSpeed = [70.0, 5.0, 20.0], [70.0, 5.0, 20.0]
+        if k == 250:
+            a.windDirection, b.windDirection = [110.0, 280.0, 45.0], [110.0, 280.0, 45.0]
+        a.update()
+        b.update()
+        if k % 37 == 0 or k == 399:
+            assert torch.equal(a._opd, b._opd), k
+    for la, lb in zip(a._layers, b._layers):
+        assert np.array_equal(la.buff, lb.buff) and np.array_equal(la.ratio, lb.ratio)
+        assert la.events == lb.events and la.events > 20 and la.notDoneOnce == lb.notDoneOnce
+        assert torch.equal(la.mapShift, lb.mapShift)
+    assert [a._org[i] for i in range(3)] == [b._org[i] for i in range(3)]
+    assert [a._cur[i] for i in range(3)] == [b._cur[i] for i in range(3)]
+
+
+def _trace(env, steps, seed=9):
+    obs = new_episode(env, seed)
+    out = [obs.cpu().clone()]
+    for i in range(steps):
+        obs, reward, strehl, _, _ = env.step(i, 0.4 * obs)
+        out += [obs.cpu().clone(), reward.cpu().clone(), strehl.cpu().clone()]
+    return out
+
+
+def test_scheduling_options_do_not_change_a_single_bit(dev, monkeypatch):
+    """The three scheduling changes of the step are pure reorderings: programmatic dependent launch on / off, the next
+    frame's atmosphere on the side stream (forced on for this small batch) or in line, frames sequenced by the library or
+    by the Python layer, step() as aoenv_atm_update + aoenv_sh_step or call by call — all must reproduce the same trajectory
+    exactly.  The in-place DM surface (aoenv_shwfs_frame_dm)
+    against the materialised one differs by rounding only."""
+    from rlao_b200 import _lib
+    cfg = CONFIGS["tiny"]()
+    cfg.windSpeed, cfg.windDirection = [40.0, 75.0], [20.0, 250.0]           # an add_row in most frames, both axes
+
+    def run(prefetch, native, pdl=1, inline="1", steps=14, one_call=False):
+        monkeypatch.setenv("AOENV_WFS_INLINE_DM", inline)
+        env = build_env(cfg, n_envs=3, rng="philox", seed=4, device=dev, canvas_slack=4)
+        env.atm.pipelined = "force" if prefetch else False
+        env.atm.native_update = native
+        env.native_step = one_call                       # step() through aoenv_sh_step or call by call
+        old = _lib.load().aoenv_set_pdl(pdl)
+        try:
+            tr = _trace(env, steps)
+            torch.cuda.synchronize()
+        finally:
+            _lib.load().aoenv_set_pdl(old)
+        assert env.atm._prefetched == bool(prefetch) and (env._native is not None) == one_call
+        return tr
+    base = run(False, False, pdl=0)
+    for kw in (dict(prefetch=True, native=False), dict(prefetch=False, native=True), dict(prefetch=True, native=True),
+               dict(prefetch=True, native=True, pdl=0), dict(prefetch=False, native=True, one_call=True),
+               dict(prefetch=True, native=True, one_call=True)):
+        got = run(**kw)
+        assert all(torch.equal(a, b) for a, b in zip(base, got)), kw
+    mat = run(True, True, inline="0")
+    for a, b in zip(base, mat):
+        assert rel_err(b.double().numpy(), a.double().numpy()) < 2e-4
+
+
+def test_prefetched_frame_survives_checkpoint_reset_and_outside_updates(dev):
+    """A frame computed ahead on the side stream is state: a checkpoint taken while it is pending resumes bit for bit,
+    atm.update() from outside consumes it, and a reset drops it."""
+    cfg = CONFIGS["tiny"]()
+    cfg.windSpeed, cfg.windDirection = [40.0, 75.0], [20.0, 250.0]           # an add_row in most frames, both axes
+
+    def make():
+        env = build_env(cfg, n_envs=2, rng="philox", seed=6, device=dev)
+        env.atm.pipelined = "force"
+        return env
+    a = make()
+    obs = new_episode(a, 5)
+    for i in range(5):
+        obs, *_ = a.step(i, 0.4 * obs)
+    assert a.atm._prefetched
+    st = a.state_dict()
+    assert st["atm_opd_next"] is not None
+    want = [a.step(5 + i, 0.4 * obs) for i in range(1)]
+    cont_obs = want[0][0]
+    for i in range(4):
+        cont_obs, *_ = a.step(6 + i, 0.4 * cont_obs)
+    b = make()
+    new_episode(b, 77)                                    # some other state
+    b.load_state_dict(st)
+    assert b.atm._prefetched
+    o2, *_ = b.step(5, 0.4 * obs)
+    assert torch.equal(o2, want[0][0])
+    for i in range(4):
+        o2, *_ = b.step(6 + i, 0.4 * o2)
+    assert torch.equal(o2, cont_obs)
+    # an update from outside takes the frame that was computed ahead: same OPD as an environment that never prefetched
+    c, d = make(), make()
+    d.atm.pipelined = False
+    oc, od = new_episode(c, 3), new_episode(d, 3)
+    for i in range(3):
+        oc, *_ = c.step(i, 0.4 * oc)
+        od, *_ = d.step(i, 0.4 * od)
+    assert c.atm._prefetched and not d.atm._prefetched
+    c.atm.update()
+    d.atm.update()
+    assert not c.atm._prefetched and torch.equal(c.atm.OPD_no_pupil, d.atm.OPD_no_pupil)
+    # reset: the pending frame is dropped with the screens it belonged to
+    oc, *_ = c.step(3, 0.4 * oc)
+    assert c.atm._prefetched
+    r1, r2 = new_episode(c, 21), new_episode(d, 21)
+    assert not c.atm._prefetched and torch.equal(r1, r2)
+    assert torch.equal(c.step(0, 0.4 * r1)[0], d.step(0, 0.4 * r2)[0])

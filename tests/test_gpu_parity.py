@@ -190,6 +190,7 @@ def test_layers_extruded_together_equal_layers_extruded_one_by_one(dev):
         atm.initializeAtmosphere(tel)
         return atm
     a, b = build(), build()
+    b.native_update = False                      # a: sequenced by aoenv_atm_update (grouped); b: by the Python methods, one layer at a time
     b._update_layers = lambda: [b._update_layer(i) for i in range(b.nLayer)]
     launches = []
     for k in range(25):

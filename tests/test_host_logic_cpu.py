@@ -73,6 +73,8 @@ def test_env_step_sequence_matches_oracle_on_cpu(fake, monkeypatch, wfs_mode):
         assert abs(float(reward) - reward_o) < 2e-3 * abs(reward_o), i
         assert abs(float(env.total[i]) - orc.total[i]) < 1e-3 * orc.total[i]
         assert abs(float(env.residual[i]) - orc.residual[i]) < 2e-3 * orc.residual[i]
+    # the default mode takes the two-call path (aoenv_sh_step through the stand-in); the others go call by call
+    assert (env._native is not None) == (wfs_mode == "kernels")
     for ly, lo in zip(env.atm._layers, orc.atm.layers):
         assert np.allclose(ly.buff, lo.buff, atol=1e-12)
     # tel.OPD is materialised lazily from (atmosphere, DM surface seen by the WFS)
