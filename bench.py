@@ -429,10 +429,17 @@ def run_gpu_arm(args):
     roofline, kernels = None, None
     if rank == 0:
         n_prof = min(args.steps, 10)
+        # attribution needs the step call by call, on one stream: the library-sequenced entry points (aoenv_atm_update,
+        # aoenv_sh_step) and the side-stream atmosphere are switched off for this pass only
+        saved = (env.native_step, env.atm.native_update, env.atm.pipelined)
+        torch.cuda.synchronize()
+        env.atm._join_prefetch(consume=True)
+        env.native_step, env.atm.native_update, env.atm.pipelined = False, False, False
         with KernelTimer(_lib.load(), torch) as kt:
             o = env._sq(env._obs).clone()
             for i in range(n_prof):
                 o, *_ = env.step(None, gain * o)
+        env.native_step, env.atm.native_update, env.atm.pipelined = saved
         kernels = kt.summary(n_prof)
         roofline = dominant_roofline(kernels, env, B)
     if world > 1:
