@@ -164,6 +164,9 @@ int aoenv_atm_update(aoenv_atm_state_t* state, const void* w_planes, float* opd_
  * add_row's X = A Z + B xi (OOPAO/Atmosphere.py:308), reconstruction (MAIN/OOPAOEnv/OOPAOEnvRazor.py:496-499).
  * D[m][n] = alpha * sum_k X[m][k] * W[n][k]     (both operands K-contiguous; D row-major, ldd floats/row)
  * ------------------------------------------------------------------------------------------------------- */
+/* Up to AOENV_SKINNY_MAX_ROWS rows of X (a single or a few environments) take a warp-per-column kernel in exact FP32; the
+ * host layers route such products here instead of to the tensor-core kernel, whose set-up dominates at that size. */
+#define AOENV_SKINNY_MAX_ROWS 8
 int aoenv_gemm_tn(const float* X, int ldx, const float* W, int ldw, float* D, int ldd,
                   int M, int N, int K, float alpha, void* stream);
 
@@ -325,7 +328,9 @@ typedef struct {
   const void *act_pos, *wx, *j0x;                                     /* aoenv_dm_rows */
 } aoenv_sh_step_t;
 
-int aoenv_sh_step(const aoenv_sh_step_t* c, const float* opd_a, const float* dm_rows_cur, const aoenv_detector_t* det,
+/* part: 0 = the whole chain; 1 = spots + slopes only, 2 = the rest — the caller that runs the next frame's atmosphere on a
+ * side stream issues it between the two, so that it fills the SMs the small kernels of part 2 leave idle. */
+int aoenv_sh_step(const aoenv_sh_step_t* c, int part, const float* opd_a, const float* dm_rows_cur, const aoenv_detector_t* det,
                   const float* action, float* coefs_next, float* dm_rows_next, float* obs, float* reward, float* strehl,
                   float* total, float* residual, void* stream);
 

@@ -299,7 +299,7 @@ class Atmosphere:
         lib = _lib.load()
         B, M, pitch, S, G = self.n_envs, self._M, self._pitch, self._S, len(group)
         st = _lib.stream_ptr(self.device)
-        tc = gemm.uses_tensor_cores()
+        tc = gemm.uses_tensor_cores(G * B)
         xi = None
         wins, sxs, sys_, seeds, ids = [], [], [], [], []
         for i, sx, sy in group:
@@ -337,7 +337,8 @@ class Atmosphere:
                                                   (C.c_uint64 * G)(*ids), G, B, M, pitch, self._env_stride,
                                                   _lib.ptr(self._inner_rc), self._nI, self._nO, None, zx, self._K,
                                                   planes, self._W_op.parts, st), "atm_gather_multi")
-        gemm.gemm_tn(self._zx, self._W_op, self._X, G * B, self._nO, x_planes=self._zx_planes if tc else None)
+        gemm.gemm_tn(self._zx, self._W_op, self._X, G * B, self._nO, backend="tc" if tc else "simt",
+                     x_planes=self._zx_planes if tc else None)
         wins, offs, exts = [], [], []
         for i, sx, sy in group:
             oy, ox = self._org[i]

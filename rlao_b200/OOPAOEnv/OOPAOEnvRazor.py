@@ -237,7 +237,7 @@ class OOPAO:
         lib, st, B, nA = _lib.load(), _lib.stream_ptr(self.device), self.n_envs, self.dm.nValidAct
         sig = self.wfs._signal
         gemm.gemm_tn(sig, self._Rm_op, self._rec, B, nA,
-                     x_planes=self.wfs._signal_planes if gemm.uses_tensor_cores() else None)
+                     x_planes=self.wfs._signal_planes if gemm.uses_tensor_cores(B) else None)
         _lib.check(lib.aoenv_observe(_lib.ptr(self._rec), self._rec.stride(0), _lib.ptr(self._act_idx), B, nA,
                                      self.nActuator ** 2, _lib.ptr(self.wfs._stats) if with_stats else None,
                                      float(self.tel.pixelArea), self._phase_scale, _lib.ptr(self._obs), _lib.ptr(self._reward),
@@ -288,7 +288,7 @@ class OOPAO:
         win = wfs._dm_windows(tables) if tables is not None else None
         if win is None or 2 * math.pi / src.wavelength != self._phase_scale:
             return None
-        tc = gemm.uses_tensor_cores()
+        tc = gemm.uses_tensor_cores(self.n_envs)
         dm._rows_of(dm._slot)                             # allocates the T buffers, makes the current slot's rows valid
         c = _lib.ShStepStruct()
         c.B, c.nS, c.n, c.nV, c.lds = self.n_envs, wfs.nSubap, wfs.n_pix_subap, wfs.nValidSubaperture, wfs._signal.stride(0)
@@ -324,12 +324,18 @@ class OOPAO:
         reward = torch.empty((B,), dtype=torch.float32, device=dev)
         strehl = torch.empty((B,), dtype=torch.float32, device=dev)
         coefs = self._coefs_buf[self._coefs_slot]
-        _lib.check(_lib.load().aoenv_sh_step(ctypes.byref(c), atm._opd.data_ptr(), dm._rows[slot].data_ptr(),
-                                             ctypes.byref(det) if det is not None else None, a.data_ptr(), coefs.data_ptr(),
-                                             dm._rows[slot ^ 1].data_ptr(), obs.data_ptr(), reward.data_ptr(), strehl.data_ptr(),
-                                             self._total_now.data_ptr(), self._residual_now.data_ptr(), _lib.stream_ptr(dev)),
-                   "sh_step")
-        atm.prefetch()
+        args = (atm._opd.data_ptr(), dm._rows[slot].data_ptr(), ctypes.byref(det) if det is not None else None, a.data_ptr(),
+                coefs.data_ptr(), dm._rows[slot ^ 1].data_ptr(), obs.data_ptr(), reward.data_ptr(), strehl.data_ptr(),
+                self._total_now.data_ptr(), self._residual_now.data_ptr(), _lib.stream_ptr(dev))
+        step = _lib.load().aoenv_sh_step
+        if atm.can_prefetch():
+            # the next frame's atmosphere goes on the side stream right behind the spots and the slopes: it then fills the
+            # SMs that the small kernels of the second half (reconstruction, observation, command, T rows) leave idle
+            _lib.check(step(ctypes.byref(c), 1, *args), "sh_step")
+            atm.prefetch()
+            _lib.check(step(ctypes.byref(c), 2, *args), "sh_step")
+        else:
+            _lib.check(step(ctypes.byref(c), 0, *args), "sh_step")
         self._coefs_slot ^= 1
         dm._coefs, dm._multi, dm._coefs_matrix, dm._slot = coefs, None, None, slot ^ 1
         dm._coefs_of[slot ^ 1], dm._rows_valid[slot ^ 1], dm._valid[slot ^ 1] = coefs, True, False
@@ -573,7 +579,7 @@ class OOPAO:
     def sample_noise(self, sigma, use_torch=True):
         """OOPAOEnvRazor.py:616-619: F @ (sigma * N(0, I)), as an actuator image per environment."""
         lib, st, B, nA = _lib.load(), _lib.stream_ptr(self.device), self.n_envs, self.dm.nValidAct
-        tc = gemm.uses_tensor_cores()
+        tc = gemm.uses_tensor_cores(B)
         # Philox normals (counter = call number; environments of other shards sit at other rows of the stream) ...
         _lib.check(lib.aoenv_normal_fill(ctypes.c_uint64(self._noise_seed + (self.env_offset << 20)), ctypes.c_uint64(self._noise_calls),
                                          B, nA, self.dm._Kp, ctypes.c_float(float(sigma)), _lib.ptr(self._noise_z),

@@ -350,7 +350,7 @@ class ShackHartmann:
         env_offset = self.env_offset if env_offset is None else env_offset
         det = self.cam.as_struct(env_offset)
         scale = 2 * math.pi / tel.src.wavelength
-        planes = self._signal_planes if gemm.uses_tensor_cores() else None
+        planes = self._signal_planes if gemm.uses_tensor_cores(opd_a.shape[0]) else None
         if self._fused_ok(opd_a):
             keep = self.keep_frame or det is not None
             self._run_fused(opd_a, opd_b, scale, det, self._frame, self._envmax, self._stats, self._signal, self._ref_xy,

@@ -80,7 +80,7 @@ PROTOTYPES = {
     "aoenv_vk_screens": [_u64, C.c_uint32, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i,
                          _vp, _i, _i64, _vp],
     "aoenv_atm_update": [_vp, _vp, _vp, _vp],
-    "aoenv_sh_step": [_vp] * 13,
+    "aoenv_sh_step": [_vp, _i] + [_vp] * 12,
     "aoenv_atm_phase": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp],
     "aoenv_gemm_tn": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _f, _vp],
     "aoenv_split_bf16": [_vp, _i, _i, _i, _i, _vp, _i, _vp],

@@ -104,6 +104,40 @@ gemm_tn_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W
   }
 }
 
+// A handful of X rows (one or a few environments): the tiled kernel above would run three CTAs through ~100 barriers, and
+// the tensor-core kernel spends longer setting up than computing.  One warp per output column streams its W row once
+// (128-bit loads) against up to MR rows of X, then reduces across lanes.
+template <int MR>
+__global__ void __launch_bounds__(256)
+gemm_skinny_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw, float* __restrict__ D, int ldd,
+                   int M, int N, int K, float alpha) {
+  pdl_enter();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + warp;
+  const int m0 = blockIdx.y * MR;
+  if (n >= N) return;
+  float acc[MR];
+#pragma unroll
+  for (int r = 0; r < MR; ++r) acc[r] = 0.f;
+  const float4* __restrict__ w4 = reinterpret_cast<const float4*>(W + (size_t)n * ldw);
+  for (int k4 = lane; k4 < K / 4; k4 += 32) {
+    const float4 w = __ldg(w4 + k4);
+#pragma unroll
+    for (int r = 0; r < MR; ++r)
+      if (m0 + r < M) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(X + (size_t)(m0 + r) * ldx) + k4);
+        acc[r] = fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, acc[r]))));
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < MR; ++r) {
+    float v = acc[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && m0 + r < M) D[(size_t)(m0 + r) * ldd + n] = alpha * v;
+  }
+}
+
 }  // namespace aoenv
 
 using namespace aoenv;
@@ -115,6 +149,12 @@ extern "C" int aoenv_gemm_tn(const float* X, int ldx, const float* W, int ldw, f
   AOENV_CHECK_ARG(ldx % 4 == 0 && ldw % 4 == 0 && ldx >= K && ldw >= K, "gemm_tn: ldx=%d ldw=%d must be >= K and multiples of 4", ldx, ldw);
   AOENV_CHECK_ARG(((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W)) & 15) == 0, "gemm_tn: operands must be 16-byte aligned");
   AOENV_CHECK_ARG(ldd >= N, "gemm_tn: ldd=%d < N=%d", ldd, N);
+  if (M <= AOENV_SKINNY_MAX_ROWS) {
+    AOENV_LAUNCH(gemm_skinny_kernel<8>, dim3((N + 7) / 8, (M + 7) / 8), 256, 0, (cudaStream_t)stream, X, ldx, W, ldw, D, ldd, M, N,
+                 K, alpha);
+    AOENV_LAUNCH_CHECK("gemm_tn(skinny)");
+    return 0;
+  }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
   AOENV_CHECK_ARG(grid.y <= 65535, "gemm_tn: M too large");
   gemm_tn_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(X, ldx, W, ldw, D, ldd, M, N, K, alpha);

@@ -104,11 +104,12 @@ int extrude_group(aoenv_atm_state_t& st, const int* layers, const Step* steps, i
     ids[g] = ((ly.events << 8) | (uint64_t)i) + (st.env_offset << 40);
     ly.events += 1;
   }
+  const bool tc = st.use_tc && G * st.B > AOENV_SKINNY_MAX_ROWS;       // a few rows: exact FP32, one warp per ring pixel
   int rc = aoenv_atm_gather_multi(wins, sxs, sys_, seeds, ids, G, st.B, st.M, st.pitch, st.env_stride, (const int32_t*)st.inner_rc,
-                                  st.nI, st.nO, nullptr, st.use_tc ? nullptr : (float*)st.zx, st.ldz,
-                                  st.use_tc ? st.zx_planes : nullptr, st.parts, stream);
+                                  st.nI, st.nO, nullptr, tc ? nullptr : (float*)st.zx, st.ldz, tc ? st.zx_planes : nullptr,
+                                  st.parts, stream);
   if (rc) return rc;
-  if (st.use_tc)
+  if (tc)
     rc = aoenv_gemm_tn_tc(st.zx_planes, w_planes, st.ldz, st.parts, (float*)st.X, st.ldx, G * st.B, st.nO, st.ldz, 1.0f, stream);
   else
     rc = aoenv_gemm_tn((const float*)st.zx, st.ldz, (const float*)st.w_f32, st.ldz, (float*)st.X, st.ldx, G * st.B, st.nO, st.ldz,
@@ -188,23 +189,29 @@ int aoenv_atm_update(aoenv_atm_state_t* state, const void* w_planes, float* opd_
 // command.  Exactly the entry points rlao_b200/OOPAOEnv/OOPAOEnvRazor.py calls one by one (OOPAOEnvRazor.py:474-514 of
 // the reference), in the same order on the same stream.
 // ---------------------------------------------------------------------------------------------------------
-extern "C" int aoenv_sh_step(const aoenv_sh_step_t* c, const float* opd_a, const float* dm_rows_cur, const aoenv_detector_t* det,
-                             const float* action, float* coefs_next, float* dm_rows_next, float* obs, float* reward,
-                             float* strehl, float* total, float* residual, void* stream) {
-  AOENV_CHECK_ARG(c != nullptr && opd_a != nullptr && dm_rows_cur != nullptr && action != nullptr && coefs_next != nullptr &&
-                      dm_rows_next != nullptr && obs != nullptr && reward != nullptr && strehl != nullptr,
-                  "sh_step: null argument");
+extern "C" int aoenv_sh_step(const aoenv_sh_step_t* c, int part, const float* opd_a, const float* dm_rows_cur,
+                             const aoenv_detector_t* det, const float* action, float* coefs_next, float* dm_rows_next,
+                             float* obs, float* reward, float* strehl, float* total, float* residual, void* stream) {
+  AOENV_CHECK_ARG(c != nullptr && part >= 0 && part <= 2, "sh_step: bad arguments");
+  AOENV_CHECK_ARG(part == 2 || (opd_a != nullptr && dm_rows_cur != nullptr), "sh_step: null wavefront argument");
+  AOENV_CHECK_ARG(part == 1 || (action != nullptr && coefs_next != nullptr && dm_rows_next != nullptr && obs != nullptr &&
+                                reward != nullptr && strehl != nullptr), "sh_step: null command / output argument");
+  const bool tc = c->use_tc && c->B > AOENV_SKINNY_MAX_ROWS;
+  int rc = 0;
+  if (part != 2) {
   aoenv_dm_sep_t dm = c->dm;
   dm.rows = dm_rows_cur;
-  int rc = aoenv_shwfs_frame_dm(opd_a, nullptr, &dm, (const int32_t*)c->order, (const float*)c->pupil, (const float*)c->amp,
+  rc = aoenv_shwfs_frame_dm(opd_a, nullptr, &dm, (const int32_t*)c->order, (const float*)c->pupil, (const float*)c->amp,
                                 (const uint8_t*)c->valid, c->B, c->nS, c->n, c->phase_scale, det, 0, (float*)c->frame,
                                 (int32_t*)c->envmax, (double*)c->stats, stream);
   if (rc) return rc;
   rc = aoenv_shwfs_slopes((const float*)c->frame, (const int32_t*)c->envmax, 0, (const int32_t*)c->valid_idx, c->nV,
                           (const float*)c->ref_xy, c->inv_units, c->threshold_cog, c->B, c->nS, c->n, (float*)c->slopes, c->lds,
-                          c->use_tc ? c->slope_planes : nullptr, 2, stream);
+                          tc ? c->slope_planes : nullptr, 2, stream);
   if (rc) return rc;
-  if (c->use_tc)
+  }
+  if (part == 1) return 0;
+  if (tc)
     rc = aoenv_gemm_tn_tc(c->slope_planes, c->rec_planes, c->lds, c->rec_parts, (float*)c->rec, c->ldr, c->B, c->nA, c->lds, 1.0f,
                           stream);
   else

@@ -505,8 +505,11 @@ dm_rows_kernel(const float* __restrict__ coefs, int ldc, const int32_t* __restri
       const float4 v = __ldg(reinterpret_cast<const float4*>(wx + (size_t)x * W) + q);
       w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
     }
+    // gridDim.y CTAs share the rows of one environment (the whole command image is cheap to stage, the rows are the work)
+    const int per = (nAct + gridDim.y - 1) / gridDim.y;
+    const int i_lo = blockIdx.y * per, i_hi = min(nAct, i_lo + per);
 #pragma unroll 4
-    for (int i = 0; i < nAct; ++i) {                     // rows are independent: four FMA chains in flight
+    for (int i = i_lo; i < i_hi; ++i) {                  // rows are independent: four FMA chains in flight
       const float* __restrict__ c = sC + i * ldC + j0;
       float t = 0.f;
 #pragma unroll
@@ -560,8 +563,9 @@ int aoenv_dm_rows(const float* coefs, int ldc, const int32_t* act_pos, int nA, i
   cudaError_t e = W == 12 ? cudaFuncSetAttribute(dm_rows_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                           : cudaFuncSetAttribute(dm_rows_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(-3, "dm_rows smem attribute: %s", cudaGetErrorString(e));
-  if (W == 12) AOENV_LAUNCH(dm_rows_kernel<12>, dim3(B), 256, smem, s, coefs, ldc, act_pos, nA, nAct, nActP, wx, j0x, R, rows);
-  else AOENV_LAUNCH(dm_rows_kernel<16>, dim3(B), 256, smem, s, coefs, ldc, act_pos, nA, nAct, nActP, wx, j0x, R, rows);
+  const dim3 grid(B, nAct >= 16 ? 4 : 1);
+  if (W == 12) AOENV_LAUNCH(dm_rows_kernel<12>, grid, 256, smem, s, coefs, ldc, act_pos, nA, nAct, nActP, wx, j0x, R, rows);
+  else AOENV_LAUNCH(dm_rows_kernel<16>, grid, 256, smem, s, coefs, ldc, act_pos, nA, nAct, nActP, wx, j0x, R, rows);
   AOENV_LAUNCH_CHECK("dm_rows");
   return 0;
 }

@@ -48,14 +48,18 @@ def _x_planes(X, parts):
     return ws
 
 
-def uses_tensor_cores(backend=None):
-    return (backend or BACKEND) == "tc"
+SKINNY_MAX_ROWS = 8      # AOENV_SKINNY_MAX_ROWS (include/aoenv.h): this few rows of X go to the exact-FP32 warp-per-column kernel
+
+
+def uses_tensor_cores(rows=None, backend=None):
+    """Whether a product with `rows` rows of X (None: any large one) runs on the tcgen05 kernel."""
+    return (backend or BACKEND) == "tc" and (rows is None or rows > SKINNY_MAX_ROWS)
 
 
 def gemm_tn(X, op, D, M, N, alpha=1.0, backend=None, x_planes=None):
     """X [M, Kp] float32, op: Operator over W [N, Kp]; D [M, >=N] float32 (row stride D.stride(0)).
     x_planes: X already in split-bf16 form [op.parts, M, Kp] (written by the kernel that produced X)."""
-    backend = backend or BACKEND
+    backend = backend or ("tc" if uses_tensor_cores(M) else "simt")
     lib, st = _lib.load(), _lib.stream_ptr(X.device)
     Kp = op.W.stride(0)
     assert X.stride(0) == Kp, "operands must share the padded K"

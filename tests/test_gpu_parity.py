@@ -47,7 +47,8 @@ def test_extension_is_the_code_that_runs(dev):
     assert rel_err(_np(d[:, :5]), _np(x) @ _np(w).T) < 1e-5
 
 
-@pytest.mark.parametrize("M,N,K", [(1, 1, 16), (37, 131, 48), (300, 257, 1360), (128, 128, 16), (1024, 980, 2928)])
+@pytest.mark.parametrize("M,N,K", [(1, 1, 16), (37, 131, 48), (300, 257, 1360), (128, 128, 16), (1024, 980, 2928),
+                                   (1, 1353, 2528), (3, 500, 1488), (8, 357, 640), (9, 357, 640)])     # <= 8 rows: the warp-per-column kernel
 def test_gemm_tn_vs_float64(dev, M, N, K):
     from rlao_b200 import _lib
     g = torch.Generator(device=dev).manual_seed(M * 7 + N)
@@ -184,7 +185,9 @@ def test_layers_extruded_together_equal_layers_extruded_one_by_one(dev):
     speeds, dirs, frac = [47.0, 21.0, 12.0, 33.0], [10.0, 130.0, 250.0, 300.0], [0.4, 0.3, 0.2, 0.1]
 
     def build():
-        tel = Telescope(cfg.resolution, cfg.diameter, cfg.samplingTime, n_envs=3, device=dev)
+        # nine environments: more rows than AOENV_SKINNY_MAX_ROWS, so the grouped and the single-layer products both run on
+        # the tensor-core kernel (a product of <= 8 rows takes the exact-FP32 kernel and rounds differently)
+        tel = Telescope(cfg.resolution, cfg.diameter, cfg.samplingTime, n_envs=9, device=dev)
         Source(cfg.opticalBand, cfg.magnitude) * tel
         atm = Atmosphere(tel, cfg.r0, cfg.L0, speeds, frac, dirs, [0.0] * 4, rng="philox", seed=5, canvas_slack=6)
         atm.initializeAtmosphere(tel)
