@@ -328,9 +328,11 @@ typedef struct {
   const void *act_pos, *wx, *j0x;                                     /* aoenv_dm_rows */
 } aoenv_sh_step_t;
 
-/* part: 0 = the whole chain; 1 = spots + slopes only, 2 = the rest — the caller that runs the next frame's atmosphere on a
- * side stream issues it between the two, so that it fills the SMs the small kernels of part 2 leave idle. */
-int aoenv_sh_step(const aoenv_sh_step_t* c, int part, const float* opd_a, const float* dm_rows_cur, const aoenv_detector_t* det,
+/* parts: bit 0 = spots + slopes, bit 1 = reconstruction + observation / reward / Strehl, bit 2 = command update + T rows
+ * (7 = the whole chain).  A caller that runs the next frame's atmosphere on a side stream issues it after part 1, so that
+ * it fills the SMs the small kernels of the rest leave idle; a host-facing caller starts the download of the observation
+ * after part 2 and waits for the uploaded action before part 4. */
+int aoenv_sh_step(const aoenv_sh_step_t* c, int parts, const float* opd_a, const float* dm_rows_cur, const aoenv_detector_t* det,
                   const float* action, float* coefs_next, float* dm_rows_next, float* obs, float* reward, float* strehl,
                   float* total, float* residual, void* stream);
 

@@ -309,33 +309,42 @@ class OOPAO:
         self._native = (c, keep)
         return self._native
 
-    def _step_native(self, i, action, native):
+    def _step_native(self, i, action, native, action_ready=None, after_observe=None):
         """OOPAOEnvRazor.py:474-514 through aoenv_atm_update + aoenv_sh_step; the Python objects are kept in step (slots,
-        counters, lazy frames) exactly as the call-by-call path leaves them."""
+        counters, lazy frames) exactly as the call-by-call path leaves them.  action_ready / after_observe: see
+        _step_views."""
         c = native[0]
         dm, wfs, atm, B, dev = self.dm, self.wfs, self.atm, self.n_envs, self.device
         slot = dm._slot
         atm.update()                                                       # :482 (consumes a frame computed ahead)
         self.tel._set_lazy(atm._opd, DMSurfaceRef(dm, slot))               # :488 tel*dm, lazily
         det = wfs.cam.as_struct(self.env_offset)
-        a = self._action_tensor(action)
         nAct = self.nActuator
         obs = torch.empty((B, nAct, nAct), dtype=torch.float32, device=dev)
         reward = torch.empty((B,), dtype=torch.float32, device=dev)
         strehl = torch.empty((B,), dtype=torch.float32, device=dev)
         coefs = self._coefs_buf[self._coefs_slot]
-        args = (atm._opd.data_ptr(), dm._rows[slot].data_ptr(), ctypes.byref(det) if det is not None else None, a.data_ptr(),
+        args = [atm._opd.data_ptr(), dm._rows[slot].data_ptr(), ctypes.byref(det) if det is not None else None, None,
                 coefs.data_ptr(), dm._rows[slot ^ 1].data_ptr(), obs.data_ptr(), reward.data_ptr(), strehl.data_ptr(),
-                self._total_now.data_ptr(), self._residual_now.data_ptr(), _lib.stream_ptr(dev))
-        step = _lib.load().aoenv_sh_step
-        if atm.can_prefetch():
+                self._total_now.data_ptr(), self._residual_now.data_ptr(), _lib.stream_ptr(dev)]
+        step, cref = _lib.load().aoenv_sh_step, ctypes.byref(c)
+        if atm.can_prefetch() or after_observe is not None or action_ready is not None:
             # the next frame's atmosphere goes on the side stream right behind the spots and the slopes: it then fills the
-            # SMs that the small kernels of the second half (reconstruction, observation, command, T rows) leave idle
-            _lib.check(step(ctypes.byref(c), 1, *args), "sh_step")
+            # SMs that the small kernels of the rest (reconstruction, observation, command, T rows) leave idle; a host-facing
+            # caller starts its download once the observation is queued and has the command wait for its upload
+            _lib.check(step(cref, 1, *args), "sh_step")
             atm.prefetch()
-            _lib.check(step(ctypes.byref(c), 2, *args), "sh_step")
+            _lib.check(step(cref, 2, *args), "sh_step")
+            if after_observe is not None:
+                after_observe(self._sq(obs), self._sq(reward), self._sq(strehl))
+            if action_ready is not None:
+                torch.cuda.current_stream(dev).wait_event(action_ready)
+            args[3] = self._action_tensor(action).data_ptr()               # (after the wait: it may have to make a copy)
+            _lib.check(step(cref, 4, *args), "sh_step")
         else:
-            _lib.check(step(ctypes.byref(c), 0, *args), "sh_step")
+            act = self._action_tensor(action)
+            args[3] = act.data_ptr()
+            _lib.check(step(cref, 7, *args), "sh_step")
         self._coefs_slot ^= 1
         dm._coefs, dm._multi, dm._coefs_matrix, dm._slot = coefs, None, None, slot ^ 1
         dm._coefs_of[slot ^ 1], dm._rows_valid[slot ^ 1], dm._valid[slot ^ 1] = coefs, True, False
@@ -355,7 +364,8 @@ class OOPAO:
         native = self._native_cfg()
         if native is not None and self.dm._rows_valid[self.dm._slot]:
             return self._step_native(i, action, native)
-        obs, reward, strehl, done, info = self._step_views(i, action)
+        obs, reward, strehl, done, info = self._measure_frame(i)
+        self._apply_command(action)
         strehl = strehl.clone()
         self.SR[-1] = strehl
         return obs.clone(), reward.clone(), strehl, done, {"strehl": strehl}
@@ -368,6 +378,9 @@ class OOPAO:
         (`after_observe(obs, reward, strehl)` is called at that point of the stream) while the command update and the
         next DM surface are still being computed, and can upload the action on another stream (`action_ready`: CUDA
         event the command update waits for) while the atmosphere and the WFS run."""
+        native = self._native_cfg()
+        if native is not None and self.dm._rows_valid[self.dm._slot]:
+            return self._step_native(i, action, native, action_ready, after_observe)     # fresh tensors rather than views
         out = self._measure_frame(i, after_observe)
         self._apply_command(action, action_ready)
         return out

@@ -189,41 +189,45 @@ int aoenv_atm_update(aoenv_atm_state_t* state, const void* w_planes, float* opd_
 // command.  Exactly the entry points rlao_b200/OOPAOEnv/OOPAOEnvRazor.py calls one by one (OOPAOEnvRazor.py:474-514 of
 // the reference), in the same order on the same stream.
 // ---------------------------------------------------------------------------------------------------------
-extern "C" int aoenv_sh_step(const aoenv_sh_step_t* c, int part, const float* opd_a, const float* dm_rows_cur,
+extern "C" int aoenv_sh_step(const aoenv_sh_step_t* c, int parts, const float* opd_a, const float* dm_rows_cur,
                              const aoenv_detector_t* det, const float* action, float* coefs_next, float* dm_rows_next,
                              float* obs, float* reward, float* strehl, float* total, float* residual, void* stream) {
-  AOENV_CHECK_ARG(c != nullptr && part >= 0 && part <= 2, "sh_step: bad arguments");
-  AOENV_CHECK_ARG(part == 2 || (opd_a != nullptr && dm_rows_cur != nullptr), "sh_step: null wavefront argument");
-  AOENV_CHECK_ARG(part == 1 || (action != nullptr && coefs_next != nullptr && dm_rows_next != nullptr && obs != nullptr &&
-                                reward != nullptr && strehl != nullptr), "sh_step: null command / output argument");
+  AOENV_CHECK_ARG(c != nullptr && parts >= 1 && parts <= 7, "sh_step: bad arguments");
+  AOENV_CHECK_ARG(!(parts & 1) || (opd_a != nullptr && dm_rows_cur != nullptr), "sh_step: null wavefront argument");
+  AOENV_CHECK_ARG(!(parts & 2) || (obs != nullptr && reward != nullptr && strehl != nullptr), "sh_step: null output argument");
+  AOENV_CHECK_ARG(!(parts & 4) || (action != nullptr && coefs_next != nullptr && dm_rows_next != nullptr), "sh_step: null command argument");
   const bool tc = c->use_tc && c->B > AOENV_SKINNY_MAX_ROWS;
   int rc = 0;
-  if (part != 2) {
-  aoenv_dm_sep_t dm = c->dm;
-  dm.rows = dm_rows_cur;
-  rc = aoenv_shwfs_frame_dm(opd_a, nullptr, &dm, (const int32_t*)c->order, (const float*)c->pupil, (const float*)c->amp,
-                                (const uint8_t*)c->valid, c->B, c->nS, c->n, c->phase_scale, det, 0, (float*)c->frame,
-                                (int32_t*)c->envmax, (double*)c->stats, stream);
-  if (rc) return rc;
-  rc = aoenv_shwfs_slopes((const float*)c->frame, (const int32_t*)c->envmax, 0, (const int32_t*)c->valid_idx, c->nV,
-                          (const float*)c->ref_xy, c->inv_units, c->threshold_cog, c->B, c->nS, c->n, (float*)c->slopes, c->lds,
-                          tc ? c->slope_planes : nullptr, 2, stream);
-  if (rc) return rc;
+  if (parts & 1) {                  // spots (DM surface in place) + slopes
+    aoenv_dm_sep_t dm = c->dm;
+    dm.rows = dm_rows_cur;
+    rc = aoenv_shwfs_frame_dm(opd_a, nullptr, &dm, (const int32_t*)c->order, (const float*)c->pupil, (const float*)c->amp,
+                              (const uint8_t*)c->valid, c->B, c->nS, c->n, c->phase_scale, det, 0, (float*)c->frame,
+                              (int32_t*)c->envmax, (double*)c->stats, stream);
+    if (rc) return rc;
+    rc = aoenv_shwfs_slopes((const float*)c->frame, (const int32_t*)c->envmax, 0, (const int32_t*)c->valid_idx, c->nV,
+                            (const float*)c->ref_xy, c->inv_units, c->threshold_cog, c->B, c->nS, c->n, (float*)c->slopes, c->lds,
+                            tc ? c->slope_planes : nullptr, 2, stream);
+    if (rc) return rc;
   }
-  if (part == 1) return 0;
-  if (tc)
-    rc = aoenv_gemm_tn_tc(c->slope_planes, c->rec_planes, c->lds, c->rec_parts, (float*)c->rec, c->ldr, c->B, c->nA, c->lds, 1.0f,
-                          stream);
-  else
-    rc = aoenv_gemm_tn((const float*)c->slopes, c->lds, (const float*)c->rec_f32, c->lds, (float*)c->rec, c->ldr, c->B, c->nA,
-                       c->lds, 1.0f, stream);
-  if (rc) return rc;
-  rc = aoenv_observe((const float*)c->rec, c->ldr, (const int32_t*)c->act_idx, c->B, c->nA, c->nAct2, (const double*)c->stats,
-                     c->n_pupil, c->phase_scale, obs, reward, strehl, total, residual, stream);
-  if (rc) return rc;
-  rc = aoenv_command_update(action, (const int32_t*)c->act_idx, c->B, c->nA, c->nAct2, c->leak, coefs_next, (float*)c->dm_prev,
-                            c->ldc, stream);
-  if (rc) return rc;
-  return aoenv_dm_rows(coefs_next, c->ldc, (const int32_t*)c->act_pos, c->nA, c->nAct, c->dm.nActP, (const float*)c->wx,
+  if (parts & 2) {                  // reconstruction + observation / reward / Strehl
+    if (tc)
+      rc = aoenv_gemm_tn_tc(c->slope_planes, c->rec_planes, c->lds, c->rec_parts, (float*)c->rec, c->ldr, c->B, c->nA, c->lds,
+                            1.0f, stream);
+    else
+      rc = aoenv_gemm_tn((const float*)c->slopes, c->lds, (const float*)c->rec_f32, c->lds, (float*)c->rec, c->ldr, c->B, c->nA,
+                         c->lds, 1.0f, stream);
+    if (rc) return rc;
+    rc = aoenv_observe((const float*)c->rec, c->ldr, (const int32_t*)c->act_idx, c->B, c->nA, c->nAct2, (const double*)c->stats,
+                       c->n_pupil, c->phase_scale, obs, reward, strehl, total, residual, stream);
+    if (rc) return rc;
+  }
+  if (parts & 4) {                  // command update + T = C gx of the new command
+    rc = aoenv_command_update(action, (const int32_t*)c->act_idx, c->B, c->nA, c->nAct2, c->leak, coefs_next, (float*)c->dm_prev,
+                              c->ldc, stream);
+    if (rc) return rc;
+    rc = aoenv_dm_rows(coefs_next, c->ldc, (const int32_t*)c->act_pos, c->nA, c->nAct, c->dm.nActP, (const float*)c->wx,
                        (const int32_t*)c->j0x, c->W, c->B, c->nS * c->n, dm_rows_next, stream);
+  }
+  return rc;
 }

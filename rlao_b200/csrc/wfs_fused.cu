@@ -563,7 +563,7 @@ int aoenv_dm_rows(const float* coefs, int ldc, const int32_t* act_pos, int nA, i
   cudaError_t e = W == 12 ? cudaFuncSetAttribute(dm_rows_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                           : cudaFuncSetAttribute(dm_rows_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(-3, "dm_rows smem attribute: %s", cudaGetErrorString(e));
-  const dim3 grid(B, nAct >= 16 ? 4 : 1);
+  const dim3 grid(B, 1);        // (four CTAs per environment measured slower, 35.6 vs 27 us at cfg3: the staging is repeated)
   if (W == 12) AOENV_LAUNCH(dm_rows_kernel<12>, grid, 256, smem, s, coefs, ldc, act_pos, nA, nAct, nActP, wx, j0x, R, rows);
   else AOENV_LAUNCH(dm_rows_kernel<16>, grid, 256, smem, s, coefs, ldc, act_pos, nA, nAct, nActP, wx, j0x, R, rows);
   AOENV_LAUNCH_CHECK("dm_rows");

@@ -108,24 +108,25 @@ class FakeLib:
 
     def aoenv_sh_step(self, c, part, opd_a, rows_cur, det, action, coefs_next, rows_next, obs, reward, strehl, total, residual,
                       stream):
-        """The six calls of csrc/step.cu, in its order (part 1: the first two, part 2: the rest)."""
+        """The six calls of csrc/step.cu, in its order (parts: bit 0 the first two, bit 1 the next two, bit 2 the last two)."""
         from rlao_b200 import _lib as L
         c = c._obj if hasattr(c, "_obj") else c
-        if part != 2:
+        if part & 1:
             dm = L.DmSepStruct()
             dm.rows, dm.wlr, dm.ilr, dm.nActP, dm.WL = rows_cur, c.dm.wlr, c.dm.ilr, c.dm.nActP, c.dm.WL
             self.aoenv_shwfs_frame_dm(opd_a, None, dm, c.order, c.pupil, c.amp, c.valid, c.B, c.nS, c.n, c.phase_scale, det, 0,
                                       c.frame, c.envmax, c.stats, stream)
             self.aoenv_shwfs_slopes(c.frame, c.envmax, 0, c.valid_idx, c.nV, c.ref_xy, c.inv_units, c.threshold_cog, c.B, c.nS,
                                     c.n, c.slopes, c.lds, None, 2, stream)
-        if part == 1:
-            return 0
-        self.aoenv_gemm_tn(c.slopes, c.lds, c.rec_f32, c.lds, c.rec, c.ldr, c.B, c.nA, c.lds, 1.0, stream)
-        self.aoenv_observe(c.rec, c.ldr, c.act_idx, c.B, c.nA, c.nAct2, c.stats, c.n_pupil, c.phase_scale, obs, reward, strehl,
-                           total, residual, stream)
-        self.aoenv_command_update(action, c.act_idx, c.B, c.nA, c.nAct2, c.leak, coefs_next, c.dm_prev, c.ldc, stream)
-        return self.aoenv_dm_rows(coefs_next, c.ldc, c.act_pos, c.nA, c.nAct, c.dm.nActP, c.wx, c.j0x, c.W, c.B, c.nS * c.n,
-                                  rows_next, stream)
+        if part & 2:
+            self.aoenv_gemm_tn(c.slopes, c.lds, c.rec_f32, c.lds, c.rec, c.ldr, c.B, c.nA, c.lds, 1.0, stream)
+            self.aoenv_observe(c.rec, c.ldr, c.act_idx, c.B, c.nA, c.nAct2, c.stats, c.n_pupil, c.phase_scale, obs, reward,
+                               strehl, total, residual, stream)
+        if part & 4:
+            self.aoenv_command_update(action, c.act_idx, c.B, c.nA, c.nAct2, c.leak, coefs_next, c.dm_prev, c.ldc, stream)
+            self.aoenv_dm_rows(coefs_next, c.ldc, c.act_pos, c.nA, c.nAct, c.dm.nActP, c.wx, c.j0x, c.W, c.B, c.nS * c.n,
+                               rows_next, stream)
+        return 0
 
     def aoenv_atm_update(self, state, w_planes, opd_out, stream):
         raise AssertionError("the CPU stand-in sequences frames in Python (AOENV_ATM_NATIVE=0)")
