@@ -135,6 +135,10 @@ atm_ring_kernel(const __grid_constant__ AtmGroup grp, int M, int pitch, size_t e
 }
 
 // Exact extrema of the window interior for the flagged environments, merged into ext (which already holds the ring's).
+// A CTA scans `rows_per_block` interior rows with aligned 128-bit loads, four rows (64 bytes) per thread in flight; the
+// running extrema are kept as (value, position) pairs under plain float comparisons and packed once at the end.  Rows
+// start on arbitrary columns (the window origin moves pixel by pixel), so the first / last vector of a row is masked.
+// Needs pitch and env_stride to be multiples of 4 floats (then every row has the same misalignment).
 __global__ void __launch_bounds__(256)
 atm_rescan_kernel(const __grid_constant__ AtmGroup grp, int M, int pitch, size_t env_stride,
                   const int32_t* __restrict__ flag, int rows_per_block) {
@@ -146,23 +150,37 @@ atm_rescan_kernel(const __grid_constant__ AtmGroup grp, int M, int pitch, size_t
   const float* __restrict__ w = grp.win[g] + (size_t)b * env_stride;
   const int r_begin = 1 + blockIdx.x * rows_per_block;
   const int r_end = min(M - 1, r_begin + rows_per_block);
-  unsigned long long lo = ~0ull, hi = 0ull;
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;       // 64 threads x 4 columns per row, 4 rows in flight
-  for (int r = r_begin + ty; r < r_end; r += 4) {
-    const float* __restrict__ rowp = w + (size_t)r * pitch;
-    for (int c = 1 + 4 * tx; c < M - 1; c += 256) {
-      float v[4];
+  const int mis = (int)((reinterpret_cast<uintptr_t>(w) >> 2) & 3);      // window column 0 sits `mis` floats into a 16-byte line
+  const int nvec = (M - 1 + mis + 3) >> 2;                                // vectors covering columns -mis .. M-2
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  float vlo = INFINITY, vhi = -INFINITY;
+  uint32_t plo = 0, phi = 0;
+  constexpr int kRows = 4;
+  for (int r0 = r_begin + ty * kRows; r0 < r_end; r0 += 4 * kRows) {
+    for (int v4 = tx; v4 < nvec; v4 += 64) {
+      const int c0 = 4 * v4 - mis;
+      float4 q[kRows];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] = (c + k < M - 1) ? __ldg(rowp + c + k) : 0.f;
+      for (int i = 0; i < kRows; ++i)
+        q[i] = (r0 + i < r_end) ? __ldg(reinterpret_cast<const float4*>(w + (size_t)(r0 + i) * pitch + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (c + k < M - 1) {
-          const unsigned long long pk = pack(v[k], win_offset + (uint32_t)(r * pitch + c + k));
-          lo = pk < lo ? pk : lo;
-          hi = pk > hi ? pk : hi;
+      for (int i = 0; i < kRows; ++i) {
+        if (r0 + i >= r_end) break;
+        const uint32_t base = (uint32_t)((r0 + i) * pitch + c0);
+        const float e[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = c0 + k;
+          if (c >= 1 && c < M - 1) {
+            if (e[k] < vlo) { vlo = e[k]; plo = base + k; }
+            if (e[k] > vhi) { vhi = e[k]; phi = base + k; }
+          }
         }
+      }
     }
   }
+  unsigned long long lo = vlo < INFINITY ? pack(vlo, win_offset + plo) : ~0ull;
+  unsigned long long hi = vhi > -INFINITY ? pack(vhi, win_offset + phi) : 0ull;
   block_reduce_ext(lo, hi);
   if (threadIdx.x == 0 && r_begin < r_end) {
     atomicMin(&ext[2 * b], lo);
@@ -383,7 +401,8 @@ int aoenv_atm_gather(const float* win, int B, int M, int pitch, int64_t env_stri
 int aoenv_atm_ring_multi(void* const* wins, const int64_t* win_offsets, void* const* exts, int G, int B, int M, int pitch,
                          int64_t env_stride, int nO, const float* X, int ldx, int32_t* flag, int force_rescan, void* stream) {
   AOENV_CHECK_ARG(G > 0 && G <= AOENV_MAX_LAYERS, "atm_ring: %d layers in one group (max %d)", G, AOENV_MAX_LAYERS);
-  AOENV_CHECK_ARG(B > 0 && B <= 65535 && M > 6 && pitch >= M, "atm_ring: bad shape");
+  AOENV_CHECK_ARG(B > 0 && B <= 65535 && M > 6 && pitch >= M && pitch % 4 == 0 && env_stride % 4 == 0,
+                  "atm_ring: bad shape (pitch and env_stride must be multiples of 4 floats)");
   AOENV_CHECK_ARG(nO == 4 * M - 4 && ldx >= nO, "atm_ring: ring has %d pixels, got nO=%d ldx=%d", 4 * M - 4, nO, ldx);
   AtmGroup grp{};
   for (int g = 0; g < G; ++g) {

@@ -9,9 +9,21 @@ SRCS="api.cu atm.cu step.cu vk.cu gemm.cu wfs.cu wfs_fused.cu pyr.cu ctrl.cu dm.
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 TMP="$OUT.tmp.$$"
 set +e
-$NVCC -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
-      -Xcompiler -fPIC,-O2,-Wall -Xptxas -v --shared -o "$TMP" $SRCS > build.log 2>&1
-rc=$?
+# one object per source, compiled in parallel (the sources are independent translation units), then one link
+OBJ=$(mktemp -d)
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O2,-Wall -Xptxas -v"
+pids=""
+for f in $SRCS; do
+  $NVCC $FLAGS -c -o "$OBJ/${f%.cu}.o" "$f" > "$OBJ/${f%.cu}.log" 2>&1 &
+  pids="$pids $!"
+done
+rc=0
+for p in $pids; do wait $p || rc=1; done
+cat "$OBJ"/*.log > build.log
+if [ $rc -eq 0 ]; then
+  $NVCC -gencode arch=compute_100a,code=sm_100a --shared -o "$TMP" "$OBJ"/*.o >> build.log 2>&1 || rc=1
+fi
+rm -rf "$OBJ"
 set -e
 grep -E "error|warning|spill|Used" build.log || true
 if [ $rc -ne 0 ] || [ ! -f "$TMP" ]; then

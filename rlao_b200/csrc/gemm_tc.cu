@@ -92,6 +92,46 @@ __host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Work list of one CTA.  A segment is (output tile mn, k-blocks [kb0, kb1)).
+//   * tile mode: segments t = blockIdx.x, + gridDim.x, ... of num_mn * split_k; segment t covers slice t / num_mn of K;
+//   * stream-K mode (more tiles than SMs, not a multiple of them): the num_mn * num_kb units (tile-major) are cut into
+//     gridDim.x equal contiguous ranges, so every SM does the same number of k-blocks instead of one SM wave running
+//     nearly empty.  A range is at least num_kb long, hence a tile is shared by at most two CTAs; both add their partial
+//     sum to a zeroed D with float atomics, and two addends commute — the result stays bit-reproducible.
+struct Seg { int mn, kb0, kb1; };
+struct SegIter {
+  int stream, num_mn, num_kb, kb_per, t, t_end, stride;
+  __device__ SegIter(int stream_k, int num_mn_, int num_kb_, int split_k)
+      : stream(stream_k), num_mn(num_mn_), num_kb(num_kb_), kb_per((num_kb_ + split_k - 1) / split_k) {
+    if (stream) {
+      const long long units = (long long)num_mn * num_kb;
+      t = (int)(units * blockIdx.x / gridDim.x);
+      t_end = (int)(units * (blockIdx.x + 1) / gridDim.x);
+      stride = 0;
+    } else {
+      t = blockIdx.x;
+      t_end = num_mn * split_k;
+      stride = gridDim.x;
+    }
+  }
+  __device__ __forceinline__ bool next(Seg& s) {
+    if (t >= t_end) return false;
+    if (stream) {
+      s.mn = t / num_kb;
+      s.kb0 = t - s.mn * num_kb;
+      const int len = min(num_kb - s.kb0, t_end - t);
+      s.kb1 = s.kb0 + len;
+      t += len;
+    } else {
+      s.mn = t % num_mn;
+      s.kb0 = (t / num_mn) * kb_per;
+      s.kb1 = min(num_kb, s.kb0 + kb_per);
+      t += stride;
+    }
+    return true;
+  }
+};
+
 template <int kParts, int BLOCK_N>
 struct Cfg {
   static constexpr int kStages = 2;
@@ -111,7 +151,7 @@ struct Cfg {
 template <int kParts, int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ TensorMaps maps, float* __restrict__ D, int ldd, int MX, int NW, int K, float alpha,
-               int split_k) {
+               int split_k, int stream_k) {
   using C = Cfg<kParts, BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -126,9 +166,9 @@ gemm_tc_kernel(const __grid_constant__ TensorMaps maps, float* __restrict__ D, i
   const int num_m = (NW + BLOCK_M - 1) / BLOCK_M;
   const int num_n = (MX + BLOCK_N - 1) / BLOCK_N;
   const int num_mn = num_m * num_n;
-  const int num_tiles = num_mn * split_k;            // split-K: tile t covers k-blocks [kb0, kb1) of output tile t % num_mn
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
-  const int kb_per = (num_kb + split_k - 1) / split_k;
+  // The three roles walk the same list of segments (output tile, k-block range) — see SegIter.
+  const SegIter seg_begin(stream_k, num_mn, num_kb, split_k);
 
   pdl_trigger();                                   // the successor may be scheduled while this grid's last wave runs
   if (warp == 0 && lane == 0) {
@@ -165,11 +205,11 @@ gemm_tc_kernel(const __grid_constant__ TensorMaps maps, float* __restrict__ D, i
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int mn = t % num_mn, ks = t / num_mn;
-        const int m_blk = mn / num_n, n_blk = mn % num_n;
-        const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
-        for (int kb = kb0; kb < kb1; ++kb) {
+      SegIter it = seg_begin;
+      Seg sg;
+      while (it.next(sg)) {
+        const int m_blk = sg.mn / num_n, n_blk = sg.mn % num_n;
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * C::kStageBytes;
           mbar_expect_tx(&full_bar[stage], C::kStageBytes);
@@ -190,12 +230,13 @@ gemm_tc_kernel(const __grid_constant__ TensorMaps maps, float* __restrict__ D, i
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      SegIter it = seg_begin;
+      Seg sg;
+      while (it.next(sg)) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + acc * C::kAccPerBuf * BLOCK_N;
-        const int ks = t / num_mn;
-        const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+        const int kb0 = sg.kb0, kb1 = sg.kb1;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -234,9 +275,11 @@ gemm_tc_kernel(const __grid_constant__ TensorMaps maps, float* __restrict__ D, i
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int mn = t % num_mn;
-      const int m_blk = mn / num_n, n_blk = mn % num_n;
+    SegIter it = seg_begin;
+    Seg sg;
+    while (it.next(sg)) {
+      const int m_blk = sg.mn / num_n, n_blk = sg.mn % num_n;
+      const bool partial = sg.kb1 - sg.kb0 < num_kb;     // this CTA holds only part of the sum over K
       mbar_wait(&tmem_full[acc], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int w_row = m_blk * BLOCK_M + q * 32 + lane;
@@ -262,7 +305,7 @@ gemm_tc_kernel(const __grid_constant__ TensorMaps maps, float* __restrict__ D, i
             if (x0 + j < MX) {
               float* dst = &D[(size_t)(x0 + j) * ldd + w_row];
               const float val = alpha * __uint_as_float(v[j]);
-              if (split_k > 1) atomicAdd(dst, val);       // D was zeroed; two partials add commutatively -> deterministic
+              if (partial) atomicAdd(dst, val);           // D was zeroed; two partials add commutatively -> deterministic
               else *dst = val;
             }
         }
@@ -342,13 +385,16 @@ static int launch(const __nv_bfloat16* Xs, const __nv_bfloat16* Ws, int ldk, flo
   // small outputs leave most SMs idle: split K in two (two partial sums added with float atomics commute, so the
   // result stays bit-reproducible; more than two would not)
   const int split_k = (2 * num_mn <= kNumSMs && num_kb >= 8) ? 2 : 1;
-  if (split_k > 1) {
+  // more tiles than SMs and not a multiple of them: equal k-block ranges per SM (see SegIter)
+  const int stream_k = (num_mn > kNumSMs && num_mn % kNumSMs != 0) ? 1 : 0;
+  if (split_k > 1 || stream_k) {
     cudaError_t e = cudaMemset2DAsync(D, sizeof(float) * (size_t)ldd, 0, sizeof(float) * (size_t)NW, (size_t)MX, s);
     if (e != cudaSuccess) return fail(-3, "gemm_tc memset: %s", cudaGetErrorString(e));
   }
   const int num_tiles = num_mn * split_k;
   const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
-  AOENV_LAUNCH((gemm_tc_kernel<kParts, BLOCK_N>), dim3(grid), kThreads, C::kSmemBytes, s, maps, D, ldd, MX, NW, K, alpha, split_k);
+  AOENV_LAUNCH((gemm_tc_kernel<kParts, BLOCK_N>), dim3(grid), kThreads, C::kSmemBytes, s, maps, D, ldd, MX, NW, K, alpha, split_k,
+               stream_k);
   AOENV_LAUNCH_CHECK("gemm_tc");
   return 0;
 }

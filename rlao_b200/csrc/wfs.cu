@@ -75,40 +75,77 @@ constexpr RcpTable make_rcp() {
 }
 __constant__ RcpTable c_rcp_table = make_rcp();
 
-// Poisson(lambda) from the uniform words (w0, w1): inversion by sequential search below 12 (one word), Hormann's PTRS
-// transformed rejection above (two words per attempt; the algorithm numpy's legacy generator also uses for
-// lambda >= 10); attempts after the first take their words from block `retry_block + attempt` of the pixel's stream.
+// Poisson(lambda), lambda < 12, by inversion of the uniform u in (0, 1): sequential search from k = 0.  The first
+// sixteen terms are unrolled with literal reciprocals (four FP32 instructions and a branch per term, no table load); the
+// table loop takes over beyond (P(k > 16 | lambda < 12) < 8 %).
+__device__ __forceinline__ float poisson_small(float lam, float u) {
+  if (!(lam > 0.f)) return 0.f;
+  float p = __expf(-lam), F = p;
+#pragma unroll
+  for (int j = 1; j <= 16; ++j) {
+    if (!(u > F)) return (float)(j - 1);
+    p *= lam * (1.0f / (float)j);
+    F += p;
+  }
+  int k = 16;
+  while (u > F && k < 63) {              // P(k >= 63 | lambda < 12) < 1e-24
+    ++k;
+    p *= lam * c_rcp_table.v[k];
+    F += p;
+  }
+  return (float)k;
+}
+// the same search as a loop (rare call sites: the dark-current draw)
+__device__ __noinline__ float poisson_small_loop(float lam, float u) {
+  float p = __expf(-lam), F = p;
+  int k = 0;
+  while (u > F && k < 63) {
+    ++k;
+    p *= lam * c_rcp_table.v[k];
+    F += p;
+  }
+  return (float)k;
+}
+
+// Hormann's PTRS transformed rejection for lambda >= 12 (the algorithm numpy's legacy generator also uses for
+// lambda >= 10), one attempt at a time: two uniform words per attempt.
+struct Ptrs {
+  float lam, loglam, bb, a, invalpha, vr;
+  __device__ __forceinline__ explicit Ptrs(float l) : lam(l) {
+    const float slam = sqrtf(l);
+    loglam = __logf(l);
+    bb = 0.931f + 2.53f * slam;
+    a = -0.059f + 0.02483f * bb;
+    invalpha = 1.1239f + __fdividef(1.1328f, bb - 3.4f);
+    vr = 0.9277f - __fdividef(3.6224f, bb - 2.f);
+  }
+  // true: accepted, k holds the draw
+  __device__ __forceinline__ bool attempt(uint32_t w0, uint32_t w1, float& k) const {
+    const float U = u32_to_unit(w0) - 0.5f;
+    const float V = u32_to_unit(w1);
+    const float us = 0.5f - fabsf(U);
+    k = floorf((__fdividef(2.f * a, us) + bb) * U + lam + 0.43f);
+    if (us >= 0.07f && V <= vr) return true;
+    if (k < 0.f || (us < 0.013f && V > us)) return false;
+    return __logf(V * invalpha * __frcp_rn(__fdividef(a, us * us) + bb)) <= -lam + k * loglam - log_factorial(k);
+  }
+};
+constexpr int kPtrsMaxAttempts = 15;
+
+// Poisson(lambda) from the uniform words (w0, w1), any lambda, attempts after the first from block `retry_block + attempt`
+// of the pixel's stream (the in-lane form: used where the draws are too rare to be worth queueing)
 __device__ __forceinline__ float poisson_draw(float lam, uint32_t w0, uint32_t w1, const PixelRng& rng, uint32_t retry_block) {
   if (!(lam > 0.f)) return 0.f;
-  if (lam < 12.f) {
-    float p = __expf(-lam), F = p;
-    const float u = u32_to_unit(w0) * 0.99999994f;
-    int k = 0;
-    while (u > F && k < 63) {            // P(k >= 63 | lambda < 12) < 1e-24
-      ++k;
-      p *= lam * c_rcp_table.v[k];
-      F += p;
-    }
-    return (float)k;
-  }
-  const float slam = sqrtf(lam), loglam = __logf(lam);
-  const float bb = 0.931f + 2.53f * slam;
-  const float a = -0.059f + 0.02483f * bb;
-  const float invalpha = 1.1239f + __fdividef(1.1328f, bb - 3.4f);
-  const float vr = 0.9277f - __fdividef(3.6224f, bb - 2.f);
-  for (int it = 0; it < 15; ++it) {
+  if (lam < 12.f) return poisson_small_loop(lam, u32_to_unit(w0) * 0.99999994f);
+  const Ptrs pt(lam);
+  for (int it = 0; it < kPtrsMaxAttempts; ++it) {
     if (it > 0) {
       const uint4 r = rng.block(retry_block + (uint32_t)it);
       w0 = r.x;
       w1 = r.y;
     }
-    const float U = u32_to_unit(w0) - 0.5f;
-    const float V = u32_to_unit(w1);
-    const float us = 0.5f - fabsf(U);
-    const float k = floorf((__fdividef(2.f * a, us) + bb) * U + lam + 0.43f);
-    if (us >= 0.07f && V <= vr) return k;
-    if (k < 0.f || (us < 0.013f && V > us)) continue;
-    if (__logf(V * invalpha * __frcp_rn(__fdividef(a, us * us) + bb)) <= -lam + k * loglam - log_factorial(k)) return k;
+    float k;
+    if (pt.attempt(w0, w1, k)) return k;
   }
   return rintf(lam);
 }
@@ -142,13 +179,22 @@ __device__ __forceinline__ float detector_finish(float photons, float dark, floa
 // The camera as its own pass over the noise-free frame.  A warp walks kDetPerLane * 32 consecutive pixels (coalesced
 // loads and stores, no block barrier).  Every lane does the cheap, uniform part of a pixel — one Philox block, the
 // read-out normal, the dark-current draw, and the photon draw when the flux is below 12 (sequential inversion).  Pixels
-// in the transformed-rejection regime (the bright cores, ~10 % of the frame) are queued in the warp's shared-memory list
-// and drawn afterwards by consecutive lanes, so the long PTRS path runs on full warps instead of on the two or three
-// lanes per warp that need it (ncu before: 4 active threads on average in that code, a third of all instructions).
+// in the transformed-rejection regime (the bright cores, about a third of the lit pixels) are queued in the warp's
+// shared-memory list and drawn afterwards by consecutive lanes, so the PTRS path runs on full warps.  Rejected attempts
+// are not retried in the lane (one rejecting lane in 32 would make the whole warp pay for another Philox block and
+// another attempt — ncu: 550 instructions per queued pixel, 40 % of the kernel): they are compacted into the front of the
+// same list and the next round works on the rejected ones only, again on full warps.
 // The random stream of a pixel depends only on (pixel, env, frame counter): block 0 -> photon words x, y / normal z, w;
-// the dark current takes word y when the photon draw did not need it, block 1 otherwise; PTRS retries use blocks 16...
+// the four low bytes that u32_to_unit drops make a fifth independent word for the dark current; attempt i > 0 of the
+// rejection sampler uses block 16 + i; dark currents >= 12 e- take block 1 (retries: blocks 32..).
 constexpr int kDetPerLane = 8;
+// w0 / w1: the photon words; their low bytes (which u32_to_unit drops) carry the pixel's dark-current draw, a whole number
+// of electrons, as a 16-bit count — the entry stays at 20 bytes (40 KB of queues per CTA)
 struct DetQueued { float lam, ron; uint32_t w0, w1; int pix; };
+
+__device__ __forceinline__ uint32_t spare_word(const uint4& r) {
+  return (r.x & 0xffu) | ((r.y & 0xffu) << 8) | ((r.z & 0xffu) << 16) | (r.w << 24);
+}
 
 __global__ void __launch_bounds__(256)
 shwfs_detector_kernel(float* __restrict__ frame, const uint8_t* __restrict__ valid, int nS, int n, float inv_R, float inv_n,
@@ -176,54 +222,81 @@ shwfs_detector_kernel(float* __restrict__ frame, const uint8_t* __restrict__ val
     const int li = (int)(((float)y + 0.5f) * inv_n), lj = (int)(((float)x + 0.5f) * inv_n);
     return valid[li * nS + lj] != 0;
   };
+  // the maximum runs over the lit lenslets only; the lookup is needed for the few values that would raise it
+  auto track = [&](int pix, float val) {
+    if (val > vmax && is_lit(pix)) vmax = val;
+  };
+  // dark current of one pixel (Detector.py:232-238): almost always zero — one comparison against exp(-dark)
+  auto dark_draw = [&](const uint4& r0, const PixelRng& rng) {
+    if (!has_dark) return 0.f;
+    const uint32_t w = spare_word(r0);
+    const float u = u32_to_unit(w) * 0.99999994f;
+    if (!(u > dark_p0)) return 0.f;
+    if (det.dark_electrons < 12.f) return poisson_small_loop(det.dark_electrons, u);
+    const uint4 r1 = rng.block(1);
+    return poisson_draw(det.dark_electrons, r1.x, r1.y, rng, 32);
+  };
 
 #pragma unroll 2
   for (int j = 0; j < kDetPerLane; ++j) {
     const int pix = first + j * 32 + lane;
     const bool in = pix < P;
-    float lam = in ? img[pix] : 0.f;
+    const float lam = in ? img[pix] : 0.f;
     const PixelRng rng(det.seed, (uint32_t)pix, (uint32_t)b, det.frame_counter);
     const uint4 r0 = rng.block(0);
     float ron = 0.f;
     if (has_ron)                        // Box-Muller with the SFU logarithm / cosine: the draw is rounded to whole electrons
       ron = rintf(sqrtf(-2.0f * __logf(u32_to_unit(r0.z))) * __cosf(6.283185307179586f * u32_to_unit(r0.w)) * det.readout_noise);
+    const float dark = dark_draw(r0, rng);
     const bool ptrs = in && photon_noise && lam >= 12.f;
     if (!ptrs && in) {
-      const float photons = photon_noise ? poisson_draw(lam, r0.x, 0u, rng, 16) : lam;
-      float dark = 0.f;
-      if (has_dark) {                   // almost always zero: one comparison against exp(-dark)
-        const float u = u32_to_unit(r0.y) * 0.99999994f;
-        if (u > dark_p0) {
-          // small means: inversion continues from the same uniform; large means (PTRS) need two fresh words
-          if (det.dark_electrons < 12.f) {
-            dark = poisson_draw(det.dark_electrons, r0.y, 0u, rng, 32);
-          } else {
-            const uint4 r1 = rng.block(1);
-            dark = poisson_draw(det.dark_electrons, r1.x, r1.y, rng, 32);
-          }
-        }
-      }
+      const float photons = photon_noise ? poisson_small(lam, u32_to_unit(r0.x) * 0.99999994f) : lam;
       const float val = detector_finish(photons, dark, ron, det, stages);
       img[pix] = val;
-      if (is_lit(pix)) vmax = fmaxf(vmax, val);
+      track(pix, val);
     }
     const unsigned m = __ballot_sync(0xffffffffu, ptrs);
-    if (ptrs) q[queued + __popc(m & ((1u << lane) - 1u))] = {lam, ron, r0.x, r0.y, pix};
+    if (ptrs) {
+      const uint32_t dk = (uint32_t)fminf(dark, 65535.f);
+      q[queued + __popc(m & ((1u << lane) - 1u))] = {lam, ron, (r0.x & ~0xffu) | (dk & 0xffu), (r0.y & ~0xffu) | (dk >> 8), pix};
+    }
     queued += __popc(m);
   }
   __syncwarp();
-  for (int e = lane; e < queued; e += 32) {
-    const DetQueued it = q[e];
-    const PixelRng rng(det.seed, (uint32_t)it.pix, (uint32_t)b, det.frame_counter);
-    const float photons = poisson_draw(it.lam, it.w0, it.w1, rng, 16);
-    float dark = 0.f;
-    if (has_dark) {
-      const uint4 r1 = rng.block(1);
-      dark = poisson_draw(det.dark_electrons, r1.x, r1.y, rng, 32);
+  // rounds of one attempt per queued pixel; the rejected ones move to the front of the list for the next round
+  for (int round = 0; queued > 0; ++round) {
+    int kept = 0;                                   // warp-uniform
+    for (int e0 = 0; e0 < queued; e0 += 32) {
+      const int e = e0 + lane;
+      const bool have = e < queued;
+      DetQueued it = q[have ? e : 0];
+      bool rejected = false;
+      if (have) {
+        const float dark = (float)((it.w0 & 0xffu) | ((it.w1 & 0xffu) << 8));
+        if (round > 0) {
+          const PixelRng rng(det.seed, (uint32_t)it.pix, (uint32_t)b, det.frame_counter);
+          const uint4 r = rng.block(16u + (uint32_t)round);
+          it.w0 = (r.x & ~0xffu) | (it.w0 & 0xffu);
+          it.w1 = (r.y & ~0xffu) | (it.w1 & 0xffu);
+        }
+        const Ptrs pt(it.lam);
+        float photons;
+        bool ok = pt.attempt(it.w0, it.w1, photons);
+        if (!ok && round == kPtrsMaxAttempts - 1) { photons = rintf(it.lam); ok = true; }
+        if (ok) {
+          const float val = detector_finish(photons, dark, it.ron, det, stages);
+          img[it.pix] = val;
+          track(it.pix, val);
+        }
+        rejected = !ok;
+      }
+      __syncwarp();                                 // every lane has read its entry before the front of the list is rewritten
+      const unsigned m = __ballot_sync(0xffffffffu, rejected);
+      if (rejected) q[kept + __popc(m & ((1u << lane) - 1u))] = it;      // kept + rank <= e: never ahead of the reads
+      kept += __popc(m);
     }
-    const float val = detector_finish(photons, dark, it.ron, det, stages);
-    img[it.pix] = val;
-    if (is_lit(it.pix)) vmax = fmaxf(vmax, val);
+    __syncwarp();
+    queued = kept;
   }
   if (envmax != nullptr) {
     vmax = warp_max(vmax);

@@ -590,6 +590,49 @@ def test_poisson_sampler_matches_the_poisson_pmf(dev):
     assert min(checked) < 1.0 and max(checked) > 1000 and any(8 < c < 12 for c in checked) and any(12 < c < 20 for c in checked)
 
 
+def test_dark_current_draws_follow_the_poisson_pmf(dev):
+    """Dark-current shot noise (OOPAO/Detector.py:232-238) alone and on top of bright pixels: the draw comes from the
+    fifth word of the pixel's Philox block (means below 12) or from block 1 (PTRS, means >= 12); it must be Poisson,
+    independent of the photon draw of the same pixel, and survive the trip through the warp queue of the bright pixels."""
+    from scipy import stats
+    from rlao_b200.ShackHartmann import ShackHartmann
+    from rlao_b200.Source import Source
+    from rlao_b200.Telescope import Telescope
+    B = 512
+    tel = Telescope(48, 8, 1 / 500, n_envs=B, device=dev)
+    Source("I", 8) * tel
+    wfs = ShackHartmann(8, tel, 0.5)
+    tel.resetOPD()
+    tel * wfs
+    ideal = _np(wfs.cam.frame[0]).astype(np.float64)
+    wfs.cam.integrationTime = 1 / 500
+    for d in (0.05, 3.0, 20.0):
+        wfs.cam.photonNoise, wfs.cam.darkCurrent = False, d * 500
+        tel * wfs
+        x = _np(wfs.cam.frame).astype(np.float64) - ideal
+        assert np.abs(x - np.round(x)).max() < 2e-3 * max(1.0, ideal.max() * 1e-4) and x.min() > -0.5
+        x = np.round(x).reshape(-1)
+        assert abs(x.mean() - d) < 5 * np.sqrt(d / x.size), (d, x.mean())
+        assert abs(x.var() / d - 1) < 5 * np.sqrt((2 + 1 / d) / x.size), (d, x.var())
+        ks = np.arange(0, int(stats.poisson.ppf(1 - 1e-6, d)) + 1)
+        p = stats.poisson.pmf(ks, d)
+        obs = np.bincount(x.astype(np.int64), minlength=ks.size)[:ks.size]
+        keep = p * x.size >= 5
+        chi2 = (((obs[keep] - p[keep] * x.size) ** 2) / (p[keep] * x.size)).sum()
+        assert stats.chi2.sf(chi2, int(keep.sum()) - 1) > 1e-4, (d, chi2)
+    # with photon noise: mean and variance add, and the two draws of a pixel are uncorrelated (bright = queued pixels)
+    wfs.cam.photonNoise, wfs.cam.darkCurrent = True, 3.0 * 500
+    tel * wfs
+    y = _np(wfs.cam.frame).astype(np.float64)
+    assert (ideal > 100.0).sum() > 50
+    for sel in (ideal > 100.0, (ideal > 0.5) & (ideal < 10.0)):
+        if sel.sum() < 50:
+            continue
+        m, v = y.mean(axis=0)[sel], y.var(axis=0)[sel]
+        assert abs((m - ideal[sel]).mean() - 3.0) < 0.05 * np.sqrt(ideal[sel].mean() + 3.0) + 0.05
+        assert abs((v / (ideal[sel] + 3.0)).mean() - 1) < 0.05
+
+
 def test_extruded_screens_keep_the_von_karman_structure_function(dev):
     """After the window has been regenerated several times over by add_row (float32 maps, split-bf16 tensor-core GEMM for
     X = A Z + B xi), the phase structure function of the maps must still be the von Karman one the operators were
