@@ -57,9 +57,14 @@ atm_gather_kernel(const __grid_constant__ AtmGroup grp, int M, int pitch, size_t
 // ---------------------------------------------------------------------------------------------------------
 // Map extrema (the clip range of skimage.warp, tools/tools.py:215-217) are tracked WITH their position:
 // ext[b][0] = packed minimum, ext[b][1] = packed maximum, packed = (monotone 32-bit key of the value) << 32 | pos,
-// pos = element index inside the environment's canvas.  After an add_row the extremum survives iff its pixel is
-// still in the interior of the new window; then new = best(old, ring).  Otherwise that environment is flagged
-// and atm_rescan_kernel recomputes the window extrema exactly.
+// pos = element index inside the environment's canvas.  The array holds two such blocks per layer, [2][B][2]:
+// block 0 = extrema of the whole window (what atm_phase clips with), block 1 = extrema of the window INTERIOR (the
+// window without its outer ring).  The ring is redrawn at every add_row, so an extremum sitting on it (where a
+// von Karman screen likes to put them) says nothing about the next window; the interior pixels keep their values, and
+// an interior extremum survives an add_row unless its pixel leaves the interior on the trailing side.  Per add_row:
+// new interior extrema = best(old ones if they survive, the four edge lines of the new interior — which contain the
+// old-ring pixels that just became interior); window extrema = best(interior, new ring).  Only when an interior
+// extremum is lost is the environment flagged and atm_rescan_kernel recomputes the interior exactly.
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t key_of(float f) { return (uint32_t)float_to_ordered(f) ^ 0x80000000u; }
 __device__ __forceinline__ float value_of(unsigned long long packed) {
@@ -118,9 +123,24 @@ atm_ring_kernel(const __grid_constant__ AtmGroup grp, int M, int pitch, size_t e
     lo = pk < lo ? pk : lo;
     hi = pk > hi ? pk : hi;
   }
+  // edge lines of the new interior (rows 1 and M-2, columns 1 and M-2): whatever became interior with this step is on them
+  unsigned long long ilo = ~0ull, ihi = 0ull;
+  const int nE = 4 * (M - 2);
+  for (int k = threadIdx.x; k < nE; k += blockDim.x) {
+    const int side = k / (M - 2), t = 1 + k % (M - 2);
+    const int r = side == 0 ? 1 : (side == 1 ? M - 2 : t);
+    const int c = side == 2 ? 1 : (side == 3 ? M - 2 : t);
+    const uint32_t rel = (uint32_t)(r * pitch + c);
+    const unsigned long long pk = pack(w[rel], win_offset + rel);
+    ilo = pk < ilo ? pk : ilo;
+    ihi = pk > ihi ? pk : ihi;
+  }
   block_reduce_ext(lo, hi);
+  __syncthreads();                       // the reduction scratch is reused
+  block_reduce_ext(ilo, ihi);
   if (threadIdx.x == 0) {
-    const unsigned long long old_lo = ext[2 * b], old_hi = ext[2 * b + 1];
+    unsigned long long* __restrict__ ext_in = ext + 2 * (size_t)gridDim.x;      // block 1: interior extrema
+    const unsigned long long old_lo = ext_in[2 * b], old_hi = ext_in[2 * b + 1];
     const int oy = win_offset / pitch, ox = win_offset % pitch;
     auto retained = [&](unsigned long long pk) {
       const uint32_t pos = (uint32_t)pk;
@@ -128,8 +148,14 @@ atm_ring_kernel(const __grid_constant__ AtmGroup grp, int M, int pitch, size_t e
       return r >= 1 && r <= M - 2 && c >= 1 && c <= M - 2;
     };
     const bool ok = !force_rescan && retained(old_lo) && retained(old_hi);
-    ext[2 * b] = ok && old_lo < lo ? old_lo : lo;
-    ext[2 * b + 1] = ok && old_hi > hi ? old_hi : hi;
+    if (ok) {
+      ilo = old_lo < ilo ? old_lo : ilo;
+      ihi = old_hi > ihi ? old_hi : ihi;
+    }
+    ext_in[2 * b] = ilo;                  // not ok: the edge lines only, the rescan merges the rest
+    ext_in[2 * b + 1] = ihi;
+    ext[2 * b] = ilo < lo ? ilo : lo;
+    ext[2 * b + 1] = ihi > hi ? ihi : hi;
     flag[row] = ok ? 0 : 1;
   }
 }
@@ -183,6 +209,9 @@ atm_rescan_kernel(const __grid_constant__ AtmGroup grp, int M, int pitch, size_t
   unsigned long long hi = vhi > -INFINITY ? pack(vhi, win_offset + phi) : 0ull;
   block_reduce_ext(lo, hi);
   if (threadIdx.x == 0 && r_begin < r_end) {
+    unsigned long long* __restrict__ ext_in = ext + 2 * (size_t)gridDim.y;       // block 1: interior extrema
+    atomicMin(&ext_in[2 * b], lo);
+    atomicMax(&ext_in[2 * b + 1], hi);
     atomicMin(&ext[2 * b], lo);
     atomicMax(&ext[2 * b + 1], hi);
   }
@@ -213,9 +242,10 @@ atm_compact_kernel(const float* __restrict__ src, float* __restrict__ dst, int M
       }
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x < 2) {
-    const unsigned long long e = ext[2 * b + threadIdx.x];
-    ext[2 * b + threadIdx.x] = (e & 0xffffffff00000000ull) | (uint32_t)((int)(uint32_t)e + pos_delta);
+  if (blockIdx.x == 0 && threadIdx.x < 4) {     // both blocks of the extrema array: window and interior
+    const size_t i = (size_t)(threadIdx.x >> 1) * 2 * gridDim.y + 2 * b + (threadIdx.x & 1);
+    const unsigned long long e = ext[i];
+    ext[i] = (e & 0xffffffff00000000ull) | (uint32_t)((int)(uint32_t)e + pos_delta);
   }
 }
 

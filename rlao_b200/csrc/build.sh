@@ -2,7 +2,7 @@
 # Builds libaoenv_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU).
 set -euo pipefail
 cd "$(dirname "$0")"
-OUT=../libaoenv_b200.so
+OUT=${OUT:-../libaoenv_b200.so}
 SRCS="api.cu atm.cu step.cu vk.cu gemm.cu wfs.cu wfs_fused.cu pyr.cu ctrl.cu dm.cu"
 [ -f psf.cu ] && SRCS="$SRCS psf.cu"
 [ -f gemm_tc.cu ] && SRCS="$SRCS gemm_tc.cu"
@@ -11,7 +11,7 @@ TMP="$OUT.tmp.$$"
 set +e
 # one object per source, compiled in parallel (the sources are independent translation units), then one link
 OBJ=$(mktemp -d)
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O2,-Wall -Xptxas -v"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O2,-Wall -Xptxas -v ${NVCC_EXTRA:-}"
 pids=""
 for f in $SRCS; do
   $NVCC $FLAGS -c -o "$OBJ/${f%.cu}.o" "$f" > "$OBJ/${f%.cu}.log" 2>&1 &

@@ -166,12 +166,15 @@ def test_sliding_window_canvas_vs_oracle(dev):
     for i, lo in enumerate(orc.layers):
         got = _np(atm._layers[i].mapShift[0])
         assert rel_err(got, lo.map) < 3e-5
-        ext = atm._ext[i, 0].cpu().numpy().view(np.uint64)
+        ext = atm._ext[i, 0, 0].cpu().numpy().view(np.uint64)     # block 0: the whole window
+        ext_in = atm._ext[i, 1, 0].cpu().numpy().view(np.uint64)  # block 1: its interior
         pitch, (oy, ox) = atm._pitch, atm._org[i]
-        for packed, want_pos in ((ext[0], np.argmin(got)), (ext[1], np.argmax(got))):
+        inner = np.full_like(got, np.nan)
+        inner[1:-1, 1:-1] = got[1:-1, 1:-1]
+        for packed, want in ((ext[0], got.min()), (ext[1], got.max()), (ext_in[0], np.nanmin(inner)), (ext_in[1], np.nanmax(inner))):
             pos = int(packed) & 0xffffffff
             r, c = pos // pitch - oy, pos % pitch - ox
-            assert got[r, c] == got.reshape(-1)[want_pos]        # tracked extremum is the window's true extremum
+            assert got[r, c] == want                             # tracked extremum is the true extremum, at its true position
     assert sum(ly.events for ly in atm._layers) > 8 * atm._S        # the canvases were re-centred many times
 
 
