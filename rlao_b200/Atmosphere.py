@@ -135,6 +135,7 @@ class Atmosphere:
         self.native_update = os.environ.get("AOENV_ATM_NATIVE", "1") != "0"     # frames sequenced by aoenv_atm_update
         self.pipelined = False           # set by the environment: update() of the next frame runs ahead on a side stream
         self._prefetched, self._prefetch_event, self._side_stream, self._opd_next = False, None, None, None
+        self.sm_partition = None             # rlao_b200.sm_partition.SMPartition: the side stream runs on its own SMs
         self.mode = mode
         self.seeingArcsec = 206265 * (self.wavelength / r0)
         self.rng = rng
@@ -465,9 +466,13 @@ class Atmosphere:
             return False
         dev = self.device
         if self._side_stream is None:
-            # same priority as the main stream (measured: a higher one, -1, lets the atmosphere push the WFS kernel aside
-            # and the step gets slower, 0.802 vs 0.779 ms; the host-facing loop drops from 1.29 M to 0.98 M env-steps/s)
-            self._side_stream = torch.cuda.Stream(dev, priority=int(os.environ.get("AOENV_ATM_PREFETCH_PRIORITY", "0")))
+            if self.sm_partition is not None:
+                # a stream of the green context that owns the atmosphere's share of the SMs (rlao_b200/sm_partition.py)
+                self._side_stream = self.sm_partition.side
+            else:
+                # same priority as the main stream (measured: a higher one, -1, lets the atmosphere push the WFS kernel
+                # aside and the step gets slower, 0.802 vs 0.779 ms; the host-facing loop drops from 1.29 M to 0.98 M)
+                self._side_stream = torch.cuda.Stream(dev, priority=int(os.environ.get("AOENV_ATM_PREFETCH_PRIORITY", "0")))
             self._opd_next = torch.empty_like(self._opd)
         main, side = torch.cuda.current_stream(dev), self._side_stream
         # the other OPD buffer was read by the WFS of the previous frame, the canvases by nothing else: everything already

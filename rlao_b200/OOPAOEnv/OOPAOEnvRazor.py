@@ -69,6 +69,8 @@ class OOPAO:
         self.device = None
         self.psf_reward = None        # (zeroPaddingFactor, window) -> Strehl from the PSF peak each step
         self.native_step = os.environ.get("AOENV_STEP_NATIVE", "1") != "0"   # step() as two library calls when it can
+        # device-resident steps issue the next frame's atmosphere before the spots of this frame (see _step_native)
+        self.prefetch_early = os.environ.get("AOENV_PREFETCH_EARLY", "1") != "0"
         self._native_key, self._native = None, None
 
     # ---- configuration ------------------------------------------------------------------------------------
@@ -332,8 +334,18 @@ class OOPAO:
             # the next frame's atmosphere goes on the side stream right behind the spots and the slopes: it then fills the
             # SMs that the small kernels of the rest (reconstruction, observation, command, T rows) leave idle; a host-facing
             # caller starts its download once the observation is queued and has the command wait for its upload
+            # Where the next frame's atmosphere is issued.  Behind the spots and the slopes it fills the SMs that the small
+            # kernels of the rest leave idle and never delays the observation — what a caller that waits for the
+            # observation on the host needs (issued before the spots, the strict host loop drops from 1.32 M to 0.95 M
+            # env-steps/s at cfg3: the observation arrives later by the atmosphere's share of the SMs).  A device-resident
+            # loop only sees throughput, and there the earlier issue lets the HBM-bound atmosphere kernels slip into the
+            # FP32-bound spots kernel's tail and gaps: 0.748 -> 0.735 ms per step, bit-identical results.
+            early = atm.sm_partition is not None or (self.prefetch_early and after_observe is None and action_ready is None)
+            if early:
+                atm.prefetch()
             _lib.check(step(cref, 1, *args), "sh_step")
-            atm.prefetch()
+            if not early:
+                atm.prefetch()
             _lib.check(step(cref, 2, *args), "sh_step")
             if after_observe is not None:
                 after_observe(self._sq(obs), self._sq(reward), self._sq(strehl))

@@ -491,14 +491,20 @@ int aoenv_atm_phase(const float* const* h_canvas, const uint64_t* const* h_ext, 
     const int lo_c = fp_off + h_col_off[l], hi_c = fp_off + R - 1 + h_col_off[l] + 3;
     AOENV_CHECK_ARG(lo_r >= 0 && lo_c >= 0 && hi_r < M && hi_c < M, "atm_phase: taps of layer %d leave the map", l);
     AOENV_CHECK_ARG((reinterpret_cast<uintptr_t>(h_canvas[l]) & 15) == 0, "atm_phase: canvas must be 16-byte aligned");
-    cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)Mc, (cuuint64_t)B};
-    cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)Mc * pitch * 4};
-    cuuint32_t box[3] = {(cuuint32_t)kPhBoxW, (cuuint32_t)kPhBoxH, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&p.map[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(h_canvas[l]), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(-4, "atm_phase: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    static thread_local tma::MapCache<2 * AOENV_MAX_LAYERS> cache;       // two canvas buffers per layer
+    const tma::MapKey key{h_canvas[l], ((unsigned long long)(unsigned)pitch << 32) | (unsigned)Mc, (unsigned long long)(unsigned)B};
+    const int mrc = cache.get(key, &p.map[l], [&](CUtensorMap* out) {
+      cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)Mc, (cuuint64_t)B};
+      cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)Mc * pitch * 4};
+      cuuint32_t box[3] = {(cuuint32_t)kPhBoxW, (cuuint32_t)kPhBoxH, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(h_canvas[l]), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(-4, "atm_phase: cuTensorMapEncodeTiled failed (%d)", (int)r);
+      return 0;
+    });
+    if (mrc) return mrc;
     p.ext[l] = reinterpret_cast<const unsigned long long*>(h_ext[l]);
     p.row0[l] = oy + fp_off + h_row_off[l];
     p.col0[l] = ox + fp_off + h_col_off[l];

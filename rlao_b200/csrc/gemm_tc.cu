@@ -347,17 +347,22 @@ using tma::EncodeTiledFn;
 static EncodeTiledFn get_encode() { return tma::get_encode(); }
 
 static int make_map(CUtensorMap* m, const void* base, int rows, int K, int ldk, int box_rows) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return fail(-4, "cuTensorMapEncodeTiled is not available from the CUDA driver");
-  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ldk * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(-4, "cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ldk=%d", (int)r, rows, K, ldk);
-  return 0;
+  static thread_local tma::MapCache<32> cache;
+  const tma::MapKey key{base, ((unsigned long long)(unsigned)rows << 32) | (unsigned)K,
+                        ((unsigned long long)(unsigned)ldk << 32) | (unsigned)box_rows};
+  return cache.get(key, m, [&](CUtensorMap* out) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return fail(-4, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ldk * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-4, "cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ldk=%d", (int)r, rows, K, ldk);
+    return 0;
+  });
 }
 
 template <int kParts, int BLOCK_N>

@@ -57,5 +57,31 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode();
 
+// Encoded tensor maps are pure functions of (base address, shape, box): the step re-encodes the same handful at every
+// launch (six per GEMM, one per layer of atm_phase — microseconds of host time each), so each calling thread keeps the
+// last few.  `make(CUtensorMap*)` is called on a miss and returns 0 on success.
+struct MapKey {
+  const void* base;
+  unsigned long long a, b;
+  bool operator==(const MapKey& o) const { return base == o.base && a == o.a && b == o.b; }
+};
+template <int kSlots>
+struct MapCache {
+  MapKey key[kSlots];
+  CUtensorMap map[kSlots];
+  int used = 0, next = 0;
+  template <class Make>
+  int get(const MapKey& k, CUtensorMap* out, Make make) {
+    for (int i = 0; i < used; ++i)
+      if (key[i] == k) { *out = map[i]; return 0; }
+    const int rc = make(out);
+    if (rc) return rc;
+    const int slot = used < kSlots ? used++ : (next = (next + 1) % kSlots);
+    key[slot] = k;
+    map[slot] = *out;
+    return 0;
+  }
+};
+
 }  // namespace tma
 }  // namespace aoenv

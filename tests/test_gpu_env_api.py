@@ -398,12 +398,13 @@ def test_scheduling_options_do_not_change_a_single_bit(dev, monkeypatch):
     cfg = CONFIGS["tiny"]()
     cfg.windSpeed, cfg.windDirection = [40.0, 75.0], [20.0, 250.0]           # an add_row in most frames, both axes
 
-    def run(prefetch, native, pdl=1, inline="1", steps=14, one_call=False):
+    def run(prefetch, native, pdl=1, inline="1", steps=14, one_call=False, early=True):
         monkeypatch.setenv("AOENV_WFS_INLINE_DM", inline)
         env = build_env(cfg, n_envs=3, rng="philox", seed=4, device=dev, canvas_slack=4)
         env.atm.pipelined = "force" if prefetch else False
         env.atm.native_update = native
         env.native_step = one_call                       # step() through aoenv_sh_step or call by call
+        env.prefetch_early = early                       # the next frame's atmosphere before / behind the spots of this one
         old = _lib.load().aoenv_set_pdl(pdl)
         try:
             tr = _trace(env, steps)
@@ -415,7 +416,7 @@ def test_scheduling_options_do_not_change_a_single_bit(dev, monkeypatch):
     base = run(False, False, pdl=0)
     for kw in (dict(prefetch=True, native=False), dict(prefetch=False, native=True), dict(prefetch=True, native=True),
                dict(prefetch=True, native=True, pdl=0), dict(prefetch=False, native=True, one_call=True),
-               dict(prefetch=True, native=True, one_call=True)):
+               dict(prefetch=True, native=True, one_call=True), dict(prefetch=True, native=True, one_call=True, early=False)):
         got = run(**kw)
         assert all(torch.equal(a, b) for a, b in zip(base, got)), kw
     mat = run(True, True, inline="0")
