@@ -43,10 +43,12 @@ int aoenv_set_pdl(int enabled);
  * movable origin.  The reference shifts the whole map by one pixel at every add_row (Atmosphere.py:301-311); here the
  * window origin moves by -step instead and only the 4M-4 ring pixels are written.  A window is passed as a pointer
  * to its origin pixel plus `pitch` (floats per canvas row) and `env_stride` (floats per environment canvas).
- * `ext` [2][B][2] (uint64) tracks minimum / maximum WITH position — (monotone key of the float) << 32 | element
+ * `ext` [3][B][2] (uint64) tracks minimum / maximum WITH position — (monotone key of the float) << 32 | element
  * index in the canvas.  Block 0 [B][2]: the whole window, which is the clip range of skimage.warp
  * (tools/tools.py:215-217) and all that aoenv_atm_phase reads; block 1 [B][2]: the window interior (the window without
- * its outer ring), which is what survives an add_row — the ring is redrawn every time.
+ * its outer ring), which is what survives an add_row — the ring is redrawn every time; block 2 [B][2]: entry 0 =
+ * (1 << 32) | window origin at the previous add_row (0: none), from which the ring kernel knows which lines became
+ * interior.
  * ------------------------------------------------------------------------------------------------------- */
 
 /* add_row, step 1 (Atmosphere.py:303-307): gathers, for every environment, the two inner rings Z of the map
@@ -63,7 +65,7 @@ int aoenv_atm_gather(const float* win, int B, int M, int pitch, int64_t env_stri
 /* add_row, step 3 (Atmosphere.py:309-310): writes the freshly extruded outer ring X [B][ldx] (X = A Z + B xi, from
  * the GEMM on zx and the stacked operator [A | B]) on the border of `win`, the window AFTER the shift, ring pixels in
  * the order of numpy's boolean mask `outerMask` (row 0, then the (r,0),(r,M-1) pairs, then row M-1; nO = 4M-4).
- * win_offset = element index of the window origin inside the canvas.  Updates ext [2][B][2]: interior extrema whose
+ * win_offset = element index of the window origin inside the canvas.  Updates ext [3][B][2]: interior extrema whose
  * pixel is still in the interior of the new window are kept and merged with the pixels that just became interior;
  * otherwise (or when force_rescan) the environment is flagged in flag [B] and its interior is rescanned exactly; the
  * window extrema are the better of the interior's and the new ring's. */
@@ -83,7 +85,7 @@ int aoenv_atm_ring_multi(void* const* wins, const int64_t* win_offsets, void* co
                          int force_rescan, void* stream);
 
 /* Canvas re-centring: copies the window from src_win to dst_win (another canvas buffer, origin 16-byte aligned) and
- * adds pos_delta to the positions stored in ext [2][B][2]. */
+ * adds pos_delta to the positions stored in ext [3][B][2]. */
 int aoenv_atm_compact(const float* src_win, float* dst_win, int B, int M, int pitch, int64_t env_stride, uint64_t* ext,
                       int64_t pos_delta, void* stream);
 
@@ -127,7 +129,7 @@ int aoenv_atm_phase(const float* const* h_canvas, const uint64_t* const* h_ext, 
  * inject innovations); it is read AND updated: ratio / buff / not_done_once / events / cur / org.
  *   ratio, buff: pixels per frame and accumulated sub-pixel shift along (x = columns, y = rows); vX, vY wind (m/s);
  *   events: add_row count so far (Philox stream id); cur: canvas buffer in use; org: window origin (row, col).
- *   maps[l][2]: the two canvas buffers [B][Mc][pitch] of layer l; ext[l]: extrema [2][B][2]; S: canvas slack (Mc = M + S);
+ *   maps[l][2]: the two canvas buffers [B][Mc][pitch] of layer l; ext[l]: extrema [3][B][2]; S: canvas slack (Mc = M + S);
  *   zx / zx_planes / X / flag: the add_row workspaces for group_max * B rows; w_f32 [nO][ldz]: [A | B] (SIMT back end,
  *   use_tc = 0); w_planes (argument: it is rebuilt when r0 changes): its split-bf16 planes [parts][nO][ldz];
  *   weight[l] = sqrt(fractionalR0); warp_kernel: 0 = scikit-image 0.18.3 cubic, 1 = Catmull-Rom. */

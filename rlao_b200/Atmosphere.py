@@ -177,8 +177,9 @@ class Atmosphere:
             self._cstate = _lib.AtmState()
             self._cur = _CurView(self._cstate)
             self._org = _OrgView(self._cstate)                       # window origin (row, col) inside the canvas
-            # per layer [2][B][2]: block 0 = extrema of the window, block 1 = of its interior (csrc/atm.cu)
-            self._ext = torch.zeros((self.nLayer, 2, B, 2), dtype=torch.int64, device=dev)
+            # per layer [3][B][2]: block 0 = extrema of the window, block 1 = of its interior, block 2 = previous origin
+            # (csrc/atm.cu)
+            self._ext = torch.zeros((self.nLayer, 3, B, 2), dtype=torch.int64, device=dev)
             # add_row workspaces hold one row per (layer of a group, environment): layers that extrude in the same
             # round of a step share the operator [A | B] and go through ONE gather / GEMM / ring sequence
             G = self._group_max = min(self.nLayer, _lib.MAX_LAYERS)

@@ -57,13 +57,13 @@ atm_gather_kernel(const __grid_constant__ AtmGroup grp, int M, int pitch, size_t
 // ---------------------------------------------------------------------------------------------------------
 // Map extrema (the clip range of skimage.warp, tools/tools.py:215-217) are tracked WITH their position:
 // ext[b][0] = packed minimum, ext[b][1] = packed maximum, packed = (monotone 32-bit key of the value) << 32 | pos,
-// pos = element index inside the environment's canvas.  The array holds two such blocks per layer, [2][B][2]:
+// pos = element index inside the environment's canvas.  The array holds three blocks per layer, [3][B][2]:
 // block 0 = extrema of the whole window (what atm_phase clips with), block 1 = extrema of the window INTERIOR (the
-// window without its outer ring).  The ring is redrawn at every add_row, so an extremum sitting on it (where a
+// window without its outer ring), block 2 = [b][0]: (1 << 32) | window origin at the previous add_row (0 = none yet).  The ring is redrawn at every add_row, so an extremum sitting on it (where a
 // von Karman screen likes to put them) says nothing about the next window; the interior pixels keep their values, and
 // an interior extremum survives an add_row unless its pixel leaves the interior on the trailing side.  Per add_row:
-// new interior extrema = best(old ones if they survive, the four edge lines of the new interior — which contain the
-// old-ring pixels that just became interior); window extrema = best(interior, new ring).  Only when an interior
+// new interior extrema = best(old ones if they survive, the one or two edge lines of the new interior that were ring
+// pixels before the step); window extrema = best(interior, new ring).  Only when an interior
 // extremum is lost is the environment flagged and atm_rescan_kernel recomputes the interior exactly.
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t key_of(float f) { return (uint32_t)float_to_ordered(f) ^ 0x80000000u; }
@@ -110,6 +110,41 @@ atm_ring_kernel(const __grid_constant__ AtmGroup grp, int M, int pitch, size_t e
   float* __restrict__ w = grp.win[g] + (size_t)b * env_stride;
   const float* __restrict__ xb = X + row * ldx;
   const int nO = 4 * M - 4;
+  // Which lines became interior with this step: the window moved by (dy, dx) = new origin - previous origin (block 2 of
+  // the extrema array remembers the previous one); origin - 1 along an axis exposes line 1 of that axis, + 1 line M - 2.
+  // Unknown history (first call, forced rescan) -> all four edge lines of the interior.
+  unsigned long long* __restrict__ ext_prev = ext + 4 * (size_t)gridDim.x + 2 * b;
+  const unsigned long long prev = *ext_prev;
+  const int oy = win_offset / pitch, ox = win_offset % pitch;
+  int line_r[2], line_c[2], nr = 0, nc = 0;                     // rows / columns of the window to merge
+  {
+    const int py = (int)((uint32_t)prev / (uint32_t)pitch), px = (int)((uint32_t)prev % (uint32_t)pitch);
+    const int dy = oy - py, dx = ox - px;
+    if ((prev >> 32) != 1ull || force_rescan || dy < -1 || dy > 1 || dx < -1 || dx > 1) {
+      line_r[0] = 1; line_r[1] = M - 2; nr = 2;
+      line_c[0] = 1; line_c[1] = M - 2; nc = 2;
+    } else {
+      if (dy != 0) line_r[nr++] = dy < 0 ? 1 : M - 2;
+      if (dx != 0) line_c[nc++] = dx < 0 ? 1 : M - 2;
+    }
+  }
+  const int nE = (nr + nc) * (M - 2);
+  // their loads go first (the column ones are one 32-byte sector each), the ring is written while they are in flight
+  constexpr int kEdge = 8;
+  float ev[kEdge];
+  uint32_t erel[kEdge];
+#pragma unroll
+  for (int i = 0; i < kEdge; ++i) {
+    const int k = threadIdx.x + i * 256;
+    erel[i] = 0;
+    ev[i] = 0.f;
+    if (k < nE) {
+      const int side = k / (M - 2), t = 1 + k % (M - 2);
+      const int r = side < nr ? line_r[side] : t, c = side < nr ? t : line_c[side - nr];
+      erel[i] = (uint32_t)(r * pitch + c);
+      ev[i] = w[erel[i]];
+    }
+  }
   unsigned long long lo = ~0ull, hi = 0ull;
   for (int k = threadIdx.x; k < nO; k += blockDim.x) {
     int r, c;
@@ -123,13 +158,18 @@ atm_ring_kernel(const __grid_constant__ AtmGroup grp, int M, int pitch, size_t e
     lo = pk < lo ? pk : lo;
     hi = pk > hi ? pk : hi;
   }
-  // edge lines of the new interior (rows 1 and M-2, columns 1 and M-2): whatever became interior with this step is on them
   unsigned long long ilo = ~0ull, ihi = 0ull;
-  const int nE = 4 * (M - 2);
-  for (int k = threadIdx.x; k < nE; k += blockDim.x) {
+#pragma unroll
+  for (int i = 0; i < kEdge; ++i) {
+    if (threadIdx.x + i * 256 < nE) {
+      const unsigned long long pk = pack(ev[i], win_offset + erel[i]);
+      ilo = pk < ilo ? pk : ilo;
+      ihi = pk > ihi ? pk : ihi;
+    }
+  }
+  for (int k = threadIdx.x + kEdge * 256; k < nE; k += 256) {   // windows wider than 514 pixels with all four lines
     const int side = k / (M - 2), t = 1 + k % (M - 2);
-    const int r = side == 0 ? 1 : (side == 1 ? M - 2 : t);
-    const int c = side == 2 ? 1 : (side == 3 ? M - 2 : t);
+    const int r = side < nr ? line_r[side] : t, c = side < nr ? t : line_c[side - nr];
     const uint32_t rel = (uint32_t)(r * pitch + c);
     const unsigned long long pk = pack(w[rel], win_offset + rel);
     ilo = pk < ilo ? pk : ilo;
@@ -141,7 +181,7 @@ atm_ring_kernel(const __grid_constant__ AtmGroup grp, int M, int pitch, size_t e
   if (threadIdx.x == 0) {
     unsigned long long* __restrict__ ext_in = ext + 2 * (size_t)gridDim.x;      // block 1: interior extrema
     const unsigned long long old_lo = ext_in[2 * b], old_hi = ext_in[2 * b + 1];
-    const int oy = win_offset / pitch, ox = win_offset % pitch;
+    *ext_prev = (1ull << 32) | win_offset;
     auto retained = [&](unsigned long long pk) {
       const uint32_t pos = (uint32_t)pk;
       const int r = (int)(pos / pitch) - oy, c = (int)(pos % pitch) - ox;
@@ -242,7 +282,7 @@ atm_compact_kernel(const float* __restrict__ src, float* __restrict__ dst, int M
       }
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x < 4) {     // both blocks of the extrema array: window and interior
+  if (blockIdx.x == 0 && threadIdx.x < 5) {     // the three blocks of the extrema array: window, interior, previous origin
     const size_t i = (size_t)(threadIdx.x >> 1) * 2 * gridDim.y + 2 * b + (threadIdx.x & 1);
     const unsigned long long e = ext[i];
     ext[i] = (e & 0xffffffff00000000ull) | (uint32_t)((int)(uint32_t)e + pos_delta);
