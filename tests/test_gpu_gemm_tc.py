@@ -46,6 +46,24 @@ def test_tc_gemm_three_parts(dev, M, N, K):
     assert _run(dev, M, N, K, 3) < 2.0 ** -18
 
 
+@pytest.mark.parametrize("M,N,K,parts", [(3072, 980, 2928, 3), (5000, 1300, 200, 2), (2400, 1000, 64, 3)])
+def test_tc_gemm_stream_k_order(dev, M, N, K, parts):
+    """More output tiles than SMs (192, 220, 152): the kernel cuts tiles x k-blocks into equal ranges per SM, tiles shared
+    by two CTAs are summed with float atomics on a zeroed D — accuracy as in tile order, and two runs agree bit for bit
+    (three layers of cfg3 extruded together are the first shape)."""
+    from rlao_b200 import gemm
+    assert _run(dev, M, N, K, parts) < (2.0 ** -16 if parts == 2 else 2.0 ** -18)
+    Kp = (K + 15) // 16 * 16
+    g = torch.Generator(device=dev).manual_seed(7)
+    X, W = torch.randn(M, Kp, device=dev, generator=g), torch.randn(N, Kp, device=dev, generator=g)
+    op = gemm.Operator(W, parts=parts)
+    ldd = (N + 3) // 4 * 4
+    D1, D2 = torch.zeros(M, ldd, device=dev), torch.ones(M, ldd, device=dev)
+    gemm.gemm_tn(X, op, D1, M, N, backend="tc")
+    gemm.gemm_tn(X, op, D2, M, N, backend="tc")
+    assert torch.equal(D1[:, :N], D2[:, :N])
+
+
 def test_tc_gemm_wide_dynamic_range(dev):
     assert _run(dev, 64, 4096, 368, 2, scale_rows=True) < 2.0 ** -15
 

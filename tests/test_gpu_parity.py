@@ -178,6 +178,49 @@ def test_sliding_window_canvas_vs_oracle(dev):
     assert sum(ly.events for ly in atm._layers) > 8 * atm._S        # the canvases were re-centred many times
 
 
+def test_tracked_extrema_stay_exact_through_wind_reversals(dev):
+    """The clip range of every window (block 0 of the extrema array) and the extrema of its interior (block 1) against
+    the canvas itself, after every frame, for 24 environments: diagonal wind, canvas re-centring every few events, and a
+    reversal of the wind in mid-run (the ring kernel infers from the previous window origin which lines became interior;
+    a wrong line would leave a stale interior extremum behind)."""
+    from rlao_b200.Atmosphere import Atmosphere
+    from rlao_b200.Source import Source
+    from rlao_b200.Telescope import Telescope
+    cfg = CONFIGS["tiny"]()
+    cfg.windSpeed, cfg.windDirection = [70.0, 50.0], [30.0, 250.0]
+    B = 24
+    tel = Telescope(cfg.resolution, cfg.diameter, cfg.samplingTime, n_envs=B, device=dev)
+    Source(cfg.opticalBand, cfg.magnitude) * tel
+    atm = Atmosphere(tel, cfg.r0, cfg.L0, cfg.windSpeed, cfg.fractionalR0, cfg.windDirection, cfg.altitude,
+                     rng="philox", canvas_slack=3)
+    atm.initializeAtmosphere(tel)
+    M, pitch = atm._M, atm._pitch
+    rescans = 0
+    for k in range(36):
+        if k == 12:
+            atm.windDirection = [210.0, 70.0]          # both layers turn around
+        if k == 24:
+            atm.windDirection = [90.0, 180.0]          # pure +y / pure -x
+        atm.update()
+        torch.cuda.synchronize()
+        rescans += int(atm._flag.sum())
+        for i in range(atm.nLayer):
+            oy, ox = atm._org[i]
+            win = atm._maps[i, atm._cur[i], :, oy:oy + M, ox:ox + M]
+            ext = atm._ext[i].cpu().numpy().view(np.uint64)
+            w = win.cpu().numpy()
+            for b in range(B):
+                inner = w[b, 1:-1, 1:-1]
+                for blk, ref in ((0, w[b]), (1, inner)):
+                    for e, want in ((ext[blk, b, 0], ref.min()), (ext[blk, b, 1], ref.max())):
+                        pos = int(e) & 0xffffffff
+                        r, c = pos // pitch - oy, pos % pitch - ox
+                        assert 0 <= r < M and 0 <= c < M and w[b, r, c] == want, (k, i, b, blk)
+                        if blk == 1:
+                            assert 1 <= r <= M - 2 and 1 <= c <= M - 2, (k, i, b)
+    assert sum(ly.events for ly in atm._layers) > 30 and rescans > 0
+
+
 def test_layers_extruded_together_equal_layers_extruded_one_by_one(dev):
     """Counter-based innovations depend on (layer, event, environment) only: the grouped add_row (one gather / GEMM /
     ring for all layers of a round) must give bit-identical maps, extrema and OPD to the layer-by-layer sequence."""
