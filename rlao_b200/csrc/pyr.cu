@@ -167,12 +167,23 @@ pyr_rows_kernel(const float2* __restrict__ X1, const float2* __restrict__ mask_s
     float2* __restrict__ dst = tile + (size_t)r * T::LD;
     const float2* __restrict__ src = X1 + (img * N + u0 + r) * R;
     if (((lo | R) & 1) == 0) {                      // two complex numbers per 128-bit load (lo, R even; rows 16-byte aligned)
-      for (int i = 2 * lane; i < N; i += 64) {
-        const int xx = i - lo;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (xx >= 0 && xx < R) v = __ldg(reinterpret_cast<const float4*>(src + xx));
-        dst[i] = make_float2(v.x, v.y);
-        dst[i + 1] = make_float2(v.z, v.w);
+      // all loads of the row first, then the stores: one load in flight per warp made this loop the top stall of the
+      // kernel (ncu: 15 % of the samples on the first shared store, waiting for its load)
+      constexpr int kIt = (N + 63) / 64;
+      float4 v[kIt];
+#pragma unroll
+      for (int it = 0; it < kIt; ++it) {
+        const int xx = 2 * lane + 64 * it - lo;
+        v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (2 * lane + 64 * it < N && xx >= 0 && xx < R) v[it] = __ldg(reinterpret_cast<const float4*>(src + xx));
+      }
+#pragma unroll
+      for (int it = 0; it < kIt; ++it) {
+        const int i = 2 * lane + 64 * it;
+        if (i < N) {
+          dst[i] = make_float2(v[it].x, v[it].y);
+          dst[i + 1] = make_float2(v[it].z, v[it].w);
+        }
       }
     } else {
       for (int i = lane; i < N; i += 32) {
@@ -187,13 +198,19 @@ pyr_rows_kernel(const float2* __restrict__ X1, const float2* __restrict__ mask_s
   __syncthreads();
   if (warp < N1) {
     // forward stage 2 -> mask (stored in the same scrambled order) -> inverse stage 2, all in registers
+    // the mask values of this lane's row segment (N2 consecutive complex numbers, 16-byte aligned: N2 is even) are requested
+    // before the transform that precedes their use — issued right before the multiplication they were a quarter of the
+    // kernel's samples (L2 latency, one consumer after the other)
+    const float4* __restrict__ mk4 = reinterpret_cast<const float4*>(mask_s + (size_t)(u0 + lane) * N + N2 * warp);
+    float4 m4[N2 / 2];
+#pragma unroll
+    for (int j = 0; j < N2 / 2; ++j) m4[j] = __ldg(mk4 + j);
     cpx v[N2];
     T::fwd2_load(row, warp, v);
-    const float2* __restrict__ mk_ = mask_s + (size_t)(u0 + lane) * N + N2 * warp;
 #pragma unroll
     for (int j2 = 0; j2 < N2; ++j2) {
-      const float2 w = __ldg(mk_ + j2);
-      v[j2] = fftc::cmul(v[j2], w.x, w.y);
+      const float wx = (j2 & 1) ? m4[j2 >> 1].z : m4[j2 >> 1].x, wy = (j2 & 1) ? m4[j2 >> 1].w : m4[j2 >> 1].y;
+      v[j2] = fftc::cmul(v[j2], wx, wy);
     }
     T::inv2_store(row, warp, v);
   }
@@ -207,6 +224,7 @@ pyr_rows_kernel(const float2* __restrict__ X1, const float2* __restrict__ mask_s
   __syncthreads();
   // transposed store: Yt[b][th][q][u0 + lane], lanes = consecutive u'
   float2* __restrict__ out = Yt + (img * N) * N + u0 + lane;
+#pragma unroll 4
   for (int q = warp; q < N; q += T::kWarps) out[(size_t)q * N] = row[q];
 }
 
@@ -225,13 +243,25 @@ pyr_image_kernel(const float2* __restrict__ Yt, int nTheta, float scale, float* 
   float2* __restrict__ row = tile + (size_t)lane * T::LD;
   for (int th = 0; th < nTheta; ++th) {
     const size_t img = (size_t)b * nTheta + th;
+    // all loads of a row first, then its stores (N is even and the rows are 16-byte aligned): with one load in flight per
+    // warp this loop held 47 % of the kernel's samples
+    constexpr int kIt = (N + 63) / 64;
     for (int r = warp; r < 32; r += T::kWarps) {
       float2* __restrict__ dst = tile + (size_t)r * T::LD;
       const float2* __restrict__ src = Yt + (img * N + q0 + r) * N;
-      for (int i = 2 * lane; i < N; i += 64) {        // N is even and the rows are 16-byte aligned
-        const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
-        dst[i] = make_float2(v.x, v.y);
-        dst[i + 1] = make_float2(v.z, v.w);
+      float4 v[kIt];
+#pragma unroll
+      for (int it = 0; it < kIt; ++it) {
+        const int i = 2 * lane + 64 * it;
+        if (i < N) v[it] = __ldg(reinterpret_cast<const float4*>(src + i));
+      }
+#pragma unroll
+      for (int it = 0; it < kIt; ++it) {
+        const int i = 2 * lane + 64 * it;
+        if (i < N) {
+          dst[i] = make_float2(v[it].x, v[it].y);
+          dst[i + 1] = make_float2(v[it].z, v[it].w);
+        }
       }
     }
     __syncthreads();
