@@ -388,15 +388,18 @@ def run_gpu_arm(args):
     torch.set_num_threads(max(1, min(16, len(os.sched_getaffinity(0)) if world > 1 else (os.cpu_count() or 1))))
     wrapped = TorchWrapper(env, host_io=True)
     obs_h = wrapped.reset_soft()
-    act_h = torch.empty(obs_h.shape, dtype=torch.float32, pin_memory=True)
+    # The policy works IN PLACE on the pinned observation the wrapper returned (the caller owns it until step t+2) and hands
+    # it back as the action: a separate output array makes the multiply move 3 x 6.9 MB per rank and step (read, write-
+    # allocate, write) instead of 2 x, and eight ranks doing that on one host are bound by its memory bandwidth — measured
+    # at N = 8 with 4 threads per rank: 0.54 ms of the 1.38 ms step were this multiply (profiles/r2_v8_e2e_sweep_8gpu.json).
     for i in range(max(3, args.warmup)):
-        torch.mul(obs_h, gain, out=act_h)
-        obs_h, reward_h, strehl_h, _, _ = wrapped.step(None, act_h)
+        torch.mul(obs_h, gain, out=obs_h)
+        obs_h, reward_h, strehl_h, _, _ = wrapped.step(None, obs_h)
     barrier()
     e0.record()
     for i in range(args.steps):
-        torch.mul(obs_h, gain, out=act_h)
-        obs_h, reward_h, strehl_h, _, _ = wrapped.step(None, act_h)
+        torch.mul(obs_h, gain, out=obs_h)
+        obs_h, reward_h, strehl_h, _, _ = wrapped.step(None, obs_h)
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -404,17 +407,41 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / (float(t[0]) * 1e-3)
 
+    # experiment hook (AOENV_BENCH_E2E_SWEEP="1,2,4"): the strict loop again with other thread counts for the host policy
+    e2e_sweep = None
+    if os.environ.get("AOENV_BENCH_E2E_SWEEP"):
+        e2e_sweep = {}
+        for nt in [int(v) for v in os.environ["AOENV_BENCH_E2E_SWEEP"].split(",")]:
+            torch.set_num_threads(nt)
+            for i in range(5):
+                torch.mul(obs_h, gain, out=obs_h)
+                obs_h, reward_h, strehl_h, _, _ = wrapped.step(None, obs_h)
+            barrier()
+            t_host = 0.0
+            e0.record()
+            for i in range(args.steps):
+                th0 = time.perf_counter()
+                torch.mul(obs_h, gain, out=obs_h)
+                t_host += time.perf_counter() - th0
+                obs_h, reward_h, strehl_h, _, _ = wrapped.step(None, obs_h)
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1), t_host * 1e3], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_sweep[str(nt)] = {"value": world * B * args.steps / (float(t[0]) * 1e-3), "policy_ms_per_step": float(t[1]) / args.steps}
+
     # same loop with the opt-in lookahead wrapper (frame t+1 is measured while the host works on step t)
     ahead = TorchWrapper(env, host_io=True, lookahead=True)
     obs_h = ahead.reset_soft()
     for i in range(max(3, args.warmup)):
-        torch.mul(obs_h, gain, out=act_h)
-        obs_h, reward_h, strehl_h, _, _ = ahead.step(None, act_h)
+        torch.mul(obs_h, gain, out=obs_h)
+        obs_h, reward_h, strehl_h, _, _ = ahead.step(None, obs_h)
     barrier()
     e0.record()
     for i in range(args.steps):
-        torch.mul(obs_h, gain, out=act_h)
-        obs_h, reward_h, strehl_h, _, _ = ahead.step(None, act_h)
+        torch.mul(obs_h, gain, out=obs_h)
+        obs_h, reward_h, strehl_h, _, _ = ahead.step(None, obs_h)
     e1.record()
     barrier()
     ahead.flush()
@@ -470,10 +497,12 @@ def run_gpu_arm(args):
                            env.atm._maps.numel() * 4 / 2 / 1e6),
                        "mean_strehl_last_step": sr_mean, "host_affinity": pinned},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "host_policy": "action = gainCL * obs, in place on the pinned observation returned by the previous step"},
             "e2e_lookahead": {"value": e2e_ahead, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                               "note": "TorchWrapper(lookahead=True), opt-in; `e2e` is the strict wrapper"},
             "gpu_launches": launches,
+            **({"e2e_sweep": e2e_sweep} if e2e_sweep else {}),
             "roofline": roofline,
             "step_roofline": step_roofline(env, B, ms_max / args.steps),
             "cpu_baseline": cpu_baseline,
